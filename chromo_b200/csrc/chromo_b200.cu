@@ -1,0 +1,663 @@
+// chromo_b200.cu -- host side of the C ABI declared in include/chromo_b200.h.
+// One context = R replicas resident in the HBM of one B200; every compute entry
+// point launches hand-written sm_100a kernels on the context's stream.  There is
+// no CPU fallback: if CUDA is unavailable every call fails with CHROMO_ERR_CUDA.
+#include "launch.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/chromo_b200.h"
+#include "field_kernels.cuh"
+#include "rng.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(CHROMO_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+struct chromo_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    chromo_shape shape{};
+    DevCtx d{};
+    std::vector<void *> allocs;
+    int64_t bytes = 0;
+    // owned device buffers that can be replaced
+    double *d_bond = nullptr, *d_chi = nullptr, *d_mu = nullptr, *d_bindF = nullptr, *d_access = nullptr;
+    double *d_partial = nullptr, *d_out = nullptr;
+    int *d_dcount = nullptr;
+    long long *d_stage = nullptr;
+    int64_t stage_elems = 0;
+    DebugOut *d_dbg = nullptr;
+    long long *d_dbg_inds = nullptr, *d_dbg_touched = nullptr;
+    double *d_dbg_rows = nullptr, *d_dbg_dtrial = nullptr;
+    int64_t dbg_inds_cap = 0, dbg_touched_cap = 0;
+    int nblk_bins = 1, nblk_bonds = 1;
+    int cap = 0;           // hash-table capacity (slots) of the MC kernel
+    size_t smem_bytes = 0;
+    double roundK = 0.0;
+    bool have_binders = false, have_bonds = false, have_state = false;
+    int64_t last_attempts = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+};
+
+extern "C" const char *chromo_last_error(void) { return g_err.c_str(); }
+extern "C" int chromo_version(void) { return 100; }
+
+template <class T>
+static int dev_alloc(chromo_ctx *c, T **p, size_t n) {
+    void *q = nullptr;
+    size_t b = n * sizeof(T);
+    if (b == 0) b = sizeof(T);
+    CK(cudaMalloc(&q, b));
+    CK(cudaMemsetAsync(q, 0, b, c->stream));
+    c->allocs.push_back(q);
+    c->bytes += (int64_t)b;
+    *p = (T *)q;
+    return 0;
+}
+
+// shared-memory footprint of the MC kernel (must match mc_kernel.cuh)
+static inline size_t table_bytes(int cap, int ncol) {
+    return (size_t)cap * (ncol * sizeof(double) + 2 * sizeof(int));
+}
+static const size_t kWarpShBytes = 2048; // >= sizeof(WarpSh), checked in mc_kernel.cuh
+
+static int choose_table(chromo_ctx *c) {
+    // Shared memory per replica-warp = static WarpSh + the delta-density hash.
+    // Pick the largest power-of-two capacity (<= 2048 slots) that still lets
+    // every replica be resident at once (one wave); never below 128 slots.
+    const int ncol = c->d.ncol;
+    const int R = c->d.R;
+    int want_per_sm = (R + c->sm_count - 1) / c->sm_count;
+    if (want_per_sm > 32) want_per_sm = 32; // resident-block limit per SM
+    size_t budget = c->smem_optin ? c->smem_optin : 227 * 1024;
+    size_t per_block = budget / (size_t)want_per_sm;
+    int cap = 2048;
+    while (cap > 128 && table_bytes(cap, ncol) + kWarpShBytes + 1024 > per_block) cap >>= 1;
+    c->cap = cap;
+    c->smem_bytes = table_bytes(cap, ncol);
+    return 0;
+}
+
+extern "C" int chromo_ctx_create(chromo_ctx **out, int device, const chromo_shape *s) {
+    if (!out || !s) return fail(CHROMO_ERR_ARG, "null argument");
+    if (s->n_replicas < 1 || s->num_beads < 2 || s->num_binders < 1 || s->num_binders > CHROMO_MAX_BINDERS)
+        return fail(CHROMO_ERR_ARG, "bad shape: R=%lld N=%lld nb=%lld (nb must be 1..%d)",
+                    (long long)s->n_replicas, (long long)s->num_beads, (long long)s->num_binders,
+                    CHROMO_MAX_BINDERS);
+    if (s->num_beads > 0x3fffffff) return fail(CHROMO_ERR_ARG, "N too large");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(CHROMO_ERR_CUDA, "no CUDA device %d (have %d)", device, ndev);
+    CK(cudaSetDevice(device));
+    chromo_ctx *c = new chromo_ctx();
+    c->device = device;
+    c->shape = *s;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    DevCtx &d = c->d;
+    d.R = (int)s->n_replicas;
+    d.N = (int)s->num_beads;
+    d.nb = (int)s->num_binders;
+    d.ncol = d.nb + 1;
+    d.nx = (int)s->nx;
+    d.ny = (int)s->ny;
+    d.nz = (int)s->nz;
+    long long nbins = (long long)s->nx * s->ny * s->nz;
+    if (nbins > 0x7fffffffLL) return fail(CHROMO_ERR_ARG, "grid too large");
+    d.n_bins = (int)nbins;
+    d.field_active = nbins > 0;
+    d.confine_type = s->confine_type;
+    d.confine_length = s->confine_length;
+    d.vf_limit = (double)s->vf_limit; // C float -> double, as the reference's comparisons do
+    d.bead_vol = s->bead_vol;
+    d.max_binders = s->max_binders;
+    if (d.field_active) {
+        int n3[3] = {d.nx, d.ny, d.nz};
+        for (int j = 0; j < 3; j++) { // init_grid fields.pyx:536-575
+            d.width[j] = s->width[j];
+            d.dxyz[j] = s->width[j] / n3[j];
+            d.half_width[j] = 0.5 * s->width[j];
+            d.half_step[j] = 0.5 * d.dxyz[j];
+        }
+        d.vol_bin = s->width[0] * s->width[1] * s->width[2] / (double)d.n_bins;
+        // smallest hundredth K with double(K/100) > vf_limit (see round2_exceeds)
+        double K = 0.0;
+        while (K / 100.0 <= d.vf_limit && K < 1e7) K += 1.0;
+        c->roundK = K;
+    }
+    size_t RN = (size_t)d.R * d.N;
+    int rc;
+    if ((rc = dev_alloc(c, &d.r, RN * 3))) return rc;
+    if ((rc = dev_alloc(c, &d.t3, RN * 3))) return rc;
+    if ((rc = dev_alloc(c, &d.t2, RN * 3))) return rc;
+    if ((rc = dev_alloc(c, &d.states, RN * d.nb))) return rc;
+    if ((rc = dev_alloc(c, &d.mods, RN * d.nb))) return rc;
+    if ((rc = dev_alloc(c, &d.density, (size_t)d.R * (d.n_bins > 0 ? d.n_bins : 1) * d.ncol))) return rc;
+    if ((rc = dev_alloc(c, &d.moves, (size_t)d.R * CHROMO_NUM_MOVES))) return rc;
+    if ((rc = dev_alloc(c, &d.glibc, (size_t)d.R * CB_GLIBC_WORDS))) return rc;
+    if ((rc = dev_alloc(c, &d.mt, (size_t)d.R * CB_MT_WORDS))) return rc;
+    if ((rc = dev_alloc(c, &d.philox_ctr, (size_t)d.R))) return rc;
+    if ((rc = dev_alloc(c, &d.tan_inds, RN))) return rc;
+    if ((rc = dev_alloc(c, &d.sel_bits, (size_t)d.R * ((d.N + 31) / 32)))) return rc;
+    if ((rc = dev_alloc(c, &d.st_new, RN))) return rc;
+    if ((rc = dev_alloc(c, &d.attempts, (size_t)d.R))) return rc;
+    if ((rc = dev_alloc(c, &c->d_chi, (size_t)d.R))) return rc;
+    if ((rc = dev_alloc(c, &c->d_mu, (size_t)d.R * d.nb))) return rc;
+    d.chi = c->d_chi;
+    d.mu = c->d_mu;
+    // reduction scratch
+    c->nblk_bins = d.n_bins > 0 ? std::min(64, (d.n_bins + FK_THREADS - 1) / FK_THREADS) : 1;
+    c->nblk_bonds = std::min(64, (d.N - 1 + FK_THREADS - 1) / FK_THREADS);
+    int nblk = std::max(c->nblk_bins, c->nblk_bonds);
+    if ((rc = dev_alloc(c, &c->d_partial, (size_t)d.R * nblk * (d.ncol + 1)))) return rc;
+    if ((rc = dev_alloc(c, &c->d_out, (size_t)d.R * (d.ncol + 1)))) return rc;
+    if ((rc = dev_alloc(c, &c->d_dcount, (size_t)d.R * d.nb))) return rc;
+    // staging for int64 <-> int8 conversion
+    c->stage_elems = (int64_t)std::min<size_t>(RN * d.nb, (size_t)1 << 24);
+    if ((rc = dev_alloc(c, &c->d_stage, (size_t)c->stage_elems))) return rc;
+    // single-step instrumentation
+    c->dbg_inds_cap = d.N;
+    c->dbg_touched_cap = d.n_bins > 0 ? std::min<int64_t>(d.n_bins, 16LL * d.N) : 1;
+    if ((rc = dev_alloc(c, &c->d_dbg, 1))) return rc;
+    if ((rc = dev_alloc(c, &c->d_dbg_inds, (size_t)c->dbg_inds_cap))) return rc;
+    if ((rc = dev_alloc(c, &c->d_dbg_rows, (size_t)c->dbg_inds_cap * (9 + d.nb)))) return rc;
+    if ((rc = dev_alloc(c, &c->d_dbg_touched, (size_t)c->dbg_touched_cap))) return rc;
+    if ((rc = dev_alloc(c, &c->d_dbg_dtrial, (size_t)c->dbg_touched_cap * d.ncol))) return rc;
+    // defaults: chi = 1, seeds as a fresh process (glibc seed 1, numpy seed 0)
+    {
+        std::vector<double> chi(d.R, 1.0);
+        CK(cudaMemcpyAsync(c->d_chi, chi.data(), sizeof(double) * d.R, cudaMemcpyHostToDevice, c->stream));
+        std::vector<uint32_t> g((size_t)d.R * CB_GLIBC_WORDS, 0), m((size_t)d.R * CB_MT_WORDS, 0);
+        glibc_srand_host(g.data(), 1);
+        mt_seed_host(m.data(), 0);
+        for (int r = 1; r < d.R; r++) {
+            memcpy(&g[(size_t)r * CB_GLIBC_WORDS], g.data(), sizeof(uint32_t) * CB_GLIBC_WORDS);
+            memcpy(&m[(size_t)r * CB_MT_WORDS], m.data(), sizeof(uint32_t) * CB_MT_WORDS);
+        }
+        CK(cudaMemcpyAsync(d.glibc, g.data(), g.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d.mt, m.data(), m.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    choose_table(c);
+    *out = c;
+    return CHROMO_OK;
+}
+
+extern "C" int chromo_ctx_destroy(chromo_ctx *c) {
+    if (!c) return CHROMO_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (void *p : c->allocs) cudaFree(p);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return CHROMO_OK;
+}
+extern "C" int chromo_ctx_sync(chromo_ctx *c) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+extern "C" void *chromo_ctx_stream(chromo_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int64_t chromo_ctx_bytes(chromo_ctx *c) { return c ? c->bytes : 0; }
+
+// ------------------------------------------------------------- parameters
+template <class T>
+static int replace_buf(chromo_ctx *c, T **slot, const T *host, size_t n) {
+    if (!*slot) {
+        int rc = dev_alloc(c, slot, n);
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(*slot, host, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int chromo_set_binders(chromo_ctx *c, const int64_t *sites, const double *pref,
+                                  const double *e_intra, const double *xpref, const double *bind_F,
+                                  int64_t S) {
+    if (!c || !sites || !pref || !e_intra || !xpref || !bind_F) return fail(CHROMO_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    DevCtx &d = c->d;
+    for (int a = 0; a < d.nb; a++) {
+        if (sites[a] < 0 || sites[a] > S || S > 126) return fail(CHROMO_ERR_ARG, "bad sites_per_bead");
+        d.sites[a] = (int)sites[a];
+        d.pref[a] = pref[a];
+        d.e_intra[a] = e_intra[a];
+        for (int b = 0; b < d.nb; b++) d.xpref[a * d.nb + b] = xpref[a * d.nb + b];
+    }
+    d.S1 = (int)S + 1;
+    if (c->d_bindF) return fail(CHROMO_ERR_STATE, "binders already set for this context");
+    int rc = replace_buf(c, &c->d_bindF, bind_F, (size_t)d.nb * d.S1 * d.S1);
+    if (rc) return rc;
+    d.bindF = c->d_bindF;
+    c->have_binders = true;
+    return CHROMO_OK;
+}
+
+extern "C" int chromo_set_replica_params(chromo_ctx *c, const double *chi, const double *mu) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    if (chi) CK(cudaMemcpyAsync(c->d_chi, chi, sizeof(double) * c->d.R, cudaMemcpyHostToDevice, c->stream));
+    if (mu) CK(cudaMemcpyAsync(c->d_mu, mu, sizeof(double) * c->d.R * c->d.nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+
+extern "C" int chromo_set_bond_params(chromo_ctx *c, int64_t n_sets, const double *eps_bend,
+                                      const double *eps_par, const double *eps_perp,
+                                      const double *gamma, const double *eta) {
+    if (!c || !eps_bend || !eps_par || !eps_perp || !gamma || !eta) return fail(CHROMO_ERR_ARG, "null argument");
+    if (n_sets != 1 && n_sets != c->d.R) return fail(CHROMO_ERR_ARG, "n_sets must be 1 or R");
+    if (c->d_bond) return fail(CHROMO_ERR_STATE, "bond parameters already set for this context");
+    CK(cudaSetDevice(c->device));
+    size_t nbonds = (size_t)c->d.N - 1;
+    std::vector<double> packed((size_t)n_sets * nbonds * 5);
+    for (size_t s = 0; s < (size_t)n_sets; s++)
+        for (size_t b = 0; b < nbonds; b++) {
+            double *o = &packed[(s * nbonds + b) * 5];
+            o[0] = eps_bend[s * nbonds + b];
+            o[1] = eps_par[s * nbonds + b];
+            o[2] = eps_perp[s * nbonds + b];
+            o[3] = gamma[s * nbonds + b];
+            o[4] = eta[s * nbonds + b];
+        }
+    int rc = replace_buf(c, &c->d_bond, packed.data(), packed.size());
+    if (rc) return rc;
+    c->d.bond = c->d_bond;
+    c->d.bond_stride = (n_sets == 1) ? 0 : (long long)nbonds * 5;
+    c->have_bonds = true;
+    return CHROMO_OK;
+}
+
+extern "C" int chromo_set_access_volumes(chromo_ctx *c, const double *access_vol) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    if (!access_vol) {
+        c->d.access_vol = nullptr;
+        return CHROMO_OK;
+    }
+    if (!c->d.field_active) return fail(CHROMO_ERR_STATE, "context has no field");
+    int rc = replace_buf(c, &c->d_access, access_vol, (size_t)c->d.n_bins);
+    if (rc) return rc;
+    c->d.access_vol = c->d_access;
+    return CHROMO_OK;
+}
+
+// ------------------------------------------------------------------ state
+static int check_range(chromo_ctx *c, int64_t first, int64_t n) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    if (first < 0 || n < 0 || first + n > c->d.R)
+        return fail(CHROMO_ERR_ARG, "replica range [%lld, %lld) outside [0, %d)", (long long)first,
+                    (long long)(first + n), c->d.R);
+    return 0;
+}
+
+static int upload_i64_as_i8(chromo_ctx *c, signed char *dst, const int64_t *src, size_t n) {
+    for (size_t o = 0; o < n; o += (size_t)c->stage_elems) {
+        size_t m = std::min(n - o, (size_t)c->stage_elems);
+        CK(cudaMemcpyAsync(c->d_stage, src + o, m * 8, cudaMemcpyHostToDevice, c->stream));
+        CB_LAUNCH(narrow_i64_kernel, (unsigned)((m + 255) / 256), 256, 0, c->stream, (const long long *)c->d_stage, dst + o, (long long)m);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+static int download_i8_as_i64(chromo_ctx *c, int64_t *dst, const signed char *src, size_t n) {
+    for (size_t o = 0; o < n; o += (size_t)c->stage_elems) {
+        size_t m = std::min(n - o, (size_t)c->stage_elems);
+        CB_LAUNCH(widen_i8_kernel, (unsigned)((m + 255) / 256), 256, 0, c->stream, src + o, c->d_stage, (long long)m);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(dst + o, c->d_stage, m * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+extern "C" int chromo_upload_state(chromo_ctx *c, int64_t first, int64_t n, const double *r,
+                                   const double *t3, const double *t2, const int64_t *states,
+                                   const int64_t *mods) {
+    int rc = check_range(c, first, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    DevCtx &d = c->d;
+    size_t off = (size_t)first * d.N, cnt = (size_t)n * d.N;
+    if (r) CK(cudaMemcpyAsync(d.r + off * 3, r, cnt * 24, cudaMemcpyHostToDevice, c->stream));
+    if (t3) CK(cudaMemcpyAsync(d.t3 + off * 3, t3, cnt * 24, cudaMemcpyHostToDevice, c->stream));
+    if (t2) CK(cudaMemcpyAsync(d.t2 + off * 3, t2, cnt * 24, cudaMemcpyHostToDevice, c->stream));
+    if (states && (rc = upload_i64_as_i8(c, d.states + off * d.nb, states, cnt * d.nb))) return rc;
+    if (mods && (rc = upload_i64_as_i8(c, d.mods + off * d.nb, mods, cnt * d.nb))) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_state = true;
+    return CHROMO_OK;
+}
+
+extern "C" int chromo_download_state(chromo_ctx *c, int64_t first, int64_t n, double *r, double *t3,
+                                     double *t2, int64_t *states) {
+    int rc = check_range(c, first, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    DevCtx &d = c->d;
+    size_t off = (size_t)first * d.N, cnt = (size_t)n * d.N;
+    if (r) CK(cudaMemcpyAsync(r, d.r + off * 3, cnt * 24, cudaMemcpyDeviceToHost, c->stream));
+    if (t3) CK(cudaMemcpyAsync(t3, d.t3 + off * 3, cnt * 24, cudaMemcpyDeviceToHost, c->stream));
+    if (t2) CK(cudaMemcpyAsync(t2, d.t2 + off * 3, cnt * 24, cudaMemcpyDeviceToHost, c->stream));
+    if (states && (rc = download_i8_as_i64(c, states, d.states + off * d.nb, cnt * d.nb))) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+
+extern "C" int chromo_download_density(chromo_ctx *c, int64_t first, int64_t n, double *density) {
+    int rc = check_range(c, first, n);
+    if (rc) return rc;
+    if (!density) return fail(CHROMO_ERR_ARG, "null argument");
+    if (!c->d.field_active) return fail(CHROMO_ERR_STATE, "context has no field");
+    CK(cudaSetDevice(c->device));
+    size_t per = (size_t)c->d.n_bins * c->d.ncol;
+    CK(cudaMemcpyAsync(density, c->d.density + first * per, n * per * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+extern "C" int chromo_upload_density(chromo_ctx *c, int64_t first, int64_t n, const double *density) {
+    int rc = check_range(c, first, n);
+    if (rc) return rc;
+    if (!density) return fail(CHROMO_ERR_ARG, "null argument");
+    if (!c->d.field_active) return fail(CHROMO_ERR_STATE, "context has no field");
+    CK(cudaSetDevice(c->device));
+    size_t per = (size_t)c->d.n_bins * c->d.ncol;
+    CK(cudaMemcpyAsync(c->d.density + first * per, density, n * per * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+
+// -------------------------------------------------------- full recompute
+#define DISPATCH_NB(nb, ...)                              \
+    switch (nb) {                                         \
+    case 1: { constexpr int NB = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int NB = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int NB = 3; __VA_ARGS__; } break; \
+    default: { constexpr int NB = 4; __VA_ARGS__; } break; \
+    }
+
+static int launch_recompute(chromo_ctx *c, int clamp) {
+    DevCtx &d = c->d;
+    if (!d.field_active) return fail(CHROMO_ERR_STATE, "context has no field");
+    if (!c->have_state) return fail(CHROMO_ERR_STATE, "upload the polymer state first");
+    size_t n = (size_t)d.R * d.n_bins * d.ncol;
+    CK(cudaMemsetAsync(d.density, 0, n * 8, c->stream));
+    dim3 grid((d.N + FK_THREADS - 1) / FK_THREADS, d.R);
+    DISPATCH_NB(d.nb, { auto k = density_scatter_kernel<NB>; CB_LAUNCH(k, grid, FK_THREADS, 0, c->stream, d); });
+    CK(cudaGetLastError());
+    if (clamp) {
+        CB_LAUNCH(density_clamp_kernel, (unsigned)((n + 255) / 256), 256, 0, c->stream, d.density, (long long)n);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int chromo_field_recompute(chromo_ctx *c, int clamp) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    return launch_recompute(c, clamp);
+}
+
+static int field_reduce(chromo_ctx *c, int chi_observable) {
+    DevCtx &d = c->d;
+    CK(cudaMemsetAsync(c->d_dcount, 0, sizeof(int) * d.R * d.nb, c->stream));
+    dim3 grid(c->nblk_bins, d.R);
+    DISPATCH_NB(d.nb, {
+        auto k = field_energy_kernel<NB>;
+        CB_LAUNCH(k, grid, FK_THREADS, 0, c->stream, d, c->roundK, c->d_partial, c->d_dcount, chi_observable);
+    });
+    CK(cudaGetLastError());
+    int tot = d.R * d.ncol;
+    CB_LAUNCH(partial_finish_kernel, (tot + 127) / 128, 128, 0, c->stream, (const double *)c->d_partial, c->d_out, d.R, c->nblk_bins, d.ncol);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int chromo_field_energy(chromo_ctx *c, double *E, double *sum_sq, int64_t *doubly,
+                                   double *nonspecific) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    if (!c->have_binders) return fail(CHROMO_ERR_STATE, "call chromo_set_binders first");
+    CK(cudaSetDevice(c->device));
+    DevCtx &d = c->d;
+    int rc = launch_recompute(c, 0); // compute_E recomputes the densities (fields.pyx:1962-1964)
+    if (rc) return rc;
+    if ((rc = field_reduce(c, 0))) return rc;
+    std::vector<double> out((size_t)d.R * d.ncol);
+    std::vector<int> dc((size_t)d.R * d.nb);
+    CK(cudaMemcpyAsync(out.data(), c->d_out, out.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(dc.data(), c->d_dcount, dc.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < d.R; r++) {
+        double e = 0.0; // get_E_binders_and_beads fields.pyx:2236-2253
+        for (int a = 0; a < d.nb; a++) {
+            e += d.pref[a] * out[(size_t)r * d.ncol + a];
+            e += d.e_intra[a] * (double)dc[(size_t)r * d.nb + a];
+            if (sum_sq) sum_sq[(size_t)r * d.nb + a] = out[(size_t)r * d.ncol + a];
+            if (doubly) doubly[(size_t)r * d.nb + a] = dc[(size_t)r * d.nb + a];
+        }
+        e += out[(size_t)r * d.ncol + d.nb];
+        if (nonspecific) nonspecific[r] = out[(size_t)r * d.ncol + d.nb];
+        if (E) E[r] = e;
+    }
+    return CHROMO_OK;
+}
+
+extern "C" int chromo_chi_observable(chromo_ctx *c, double *Phi) {
+    if (!c || !Phi) return fail(CHROMO_ERR_ARG, "null argument");
+    if (!c->d.field_active) return fail(CHROMO_ERR_STATE, "context has no field");
+    CK(cudaSetDevice(c->device));
+    DevCtx &d = c->d;
+    int rc = field_reduce(c, 1);
+    if (rc) return rc;
+    std::vector<double> out((size_t)d.R * d.ncol);
+    CK(cudaMemcpyAsync(out.data(), c->d_out, out.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < d.R; r++) Phi[r] = out[(size_t)r * d.ncol + d.nb];
+    return CHROMO_OK;
+}
+
+extern "C" int chromo_elastic_energy(chromo_ctx *c, double *E) {
+    if (!c || !E) return fail(CHROMO_ERR_ARG, "null argument");
+    if (!c->have_bonds || !c->have_state) return fail(CHROMO_ERR_STATE, "set bond parameters and state first");
+    CK(cudaSetDevice(c->device));
+    DevCtx &d = c->d;
+    dim3 grid(c->nblk_bonds, d.R);
+    CB_LAUNCH(elastic_energy_kernel, grid, FK_THREADS, 0, c->stream, d, c->d_partial);
+    CK(cudaGetLastError());
+    CB_LAUNCH(partial_finish_kernel, (d.R + 127) / 128, 128, 0, c->stream, (const double *)c->d_partial, c->d_out, d.R, c->nblk_bonds, 1);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(E, c->d_out, sizeof(double) * d.R, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+
+// -------------------------------------------------------------------- RNG
+extern "C" int chromo_srand(chromo_ctx *c, const uint32_t *seeds) {
+    if (!c || !seeds) return fail(CHROMO_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    std::vector<uint32_t> g((size_t)c->d.R * CB_GLIBC_WORDS, 0);
+    for (int r = 0; r < c->d.R; r++) glibc_srand_host(&g[(size_t)r * CB_GLIBC_WORDS], seeds[r]);
+    CK(cudaMemcpyAsync(c->d.glibc, g.data(), g.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+extern "C" int chromo_numpy_seed(chromo_ctx *c, const uint32_t *seeds) {
+    if (!c || !seeds) return fail(CHROMO_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    std::vector<uint32_t> m((size_t)c->d.R * CB_MT_WORDS, 0);
+    for (int r = 0; r < c->d.R; r++) mt_seed_host(&m[(size_t)r * CB_MT_WORDS], seeds[r]);
+    CK(cudaMemcpyAsync(c->d.mt, m.data(), m.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+
+// ----------------------------------------------------------- the hot path
+static int check_ready(chromo_ctx *c) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    if (!c->have_binders) return fail(CHROMO_ERR_STATE, "call chromo_set_binders first");
+    if (!c->have_bonds) return fail(CHROMO_ERR_STATE, "call chromo_set_bond_params first");
+    if (!c->have_state) return fail(CHROMO_ERR_STATE, "call chromo_upload_state first");
+    return 0;
+}
+
+static int validate_moves(chromo_ctx *c, const chromo_move_state *mv) {
+    const int N = c->d.N;
+    for (int r = 0; r < c->d.R; r++)
+        for (int m = 0; m < CHROMO_NUM_MOVES; m++) {
+            const chromo_move_state &s = mv[(size_t)r * CHROMO_NUM_MOVES + m];
+            if (!s.move_on) continue;
+            // bead_selection.pyx:85-88,138-141: a window larger than the chain raises
+            if (s.amp_bead > N || s.bead_amp_hi > N)
+                return fail(CHROMO_ERR_ARG, "Bead selection window size must be less than polymer length"
+                                            " (replica %d move %d: amp_bead %d, N %d)", r, m, s.amp_bead, N);
+            if (m == CHROMO_TANGENT_ROTATION && s.amp_bead < 1)
+                return fail(CHROMO_ERR_ARG, "tangent_rotation needs amp_bead >= 1");
+            if (m == CHROMO_END_PIVOT && s.amp_bead < 1)
+                return fail(CHROMO_ERR_ARG, "end_pivot needs amp_bead >= 1");
+            if (s.num_per_cycle < 0) return fail(CHROMO_ERR_ARG, "negative num_per_cycle");
+        }
+    return 0;
+}
+
+extern "C" int chromo_set_moves(chromo_ctx *c, const chromo_move_state *mv) {
+    if (!c || !mv) return fail(CHROMO_ERR_ARG, "null argument");
+    int rc = validate_moves(c, mv);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->d.moves, mv, sizeof(chromo_move_state) * c->d.R * CHROMO_NUM_MOVES,
+                       cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+extern "C" int chromo_get_moves(chromo_ctx *c, chromo_move_state *mv) {
+    if (!c || !mv) return fail(CHROMO_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(mv, c->d.moves, sizeof(chromo_move_state) * c->d.R * CHROMO_NUM_MOVES,
+                       cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+
+extern "C" int chromo_mc_sim(chromo_ctx *c, int64_t num_mc_steps, chromo_move_state *moves,
+                             double mu_adjust_factor, uint64_t seed, int rng_mode,
+                             const uint32_t *numpy_seeds) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (num_mc_steps < 0) return fail(CHROMO_ERR_ARG, "negative num_mc_steps");
+    CK(cudaSetDevice(c->device));
+    DevCtx &d = c->d;
+    if (moves && (rc = chromo_set_moves(c, moves))) return rc;
+    if (rng_mode == CHROMO_RNG_REPLAY && numpy_seeds && (rc = chromo_numpy_seed(c, numpy_seeds))) return rc;
+    McSimArgs a{d, (long long)num_mc_steps, mu_adjust_factor, (unsigned long long)seed, c->cap, c->smem_bytes, c->stream};
+    int e;
+    if (rng_mode == CHROMO_RNG_REPLAY) e = d.nb <= 2 ? cb_mc_sim_replay_12(a) : cb_mc_sim_replay_34(a);
+    else if (rng_mode == CHROMO_RNG_PHILOX) e = d.nb <= 2 ? cb_mc_sim_philox_12(a) : cb_mc_sim_philox_34(a);
+    else return fail(CHROMO_ERR_ARG, "unknown rng_mode %d", rng_mode);
+    if (e) return fail(CHROMO_ERR_CUDA, "mc_sim launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    CK(cudaGetLastError());
+    if (moves) {
+        CK(cudaMemcpyAsync(moves, d.moves, sizeof(chromo_move_state) * d.R * CHROMO_NUM_MOVES,
+                           cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return CHROMO_OK;
+}
+
+extern "C" int64_t chromo_last_attempts(chromo_ctx *c) {
+    if (!c) return -1;
+    cudaSetDevice(c->device);
+    std::vector<unsigned long long> a(c->d.R);
+    if (cudaMemcpyAsync(a.data(), c->d.attempts, a.size() * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+        return -1;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    int64_t t = 0;
+    for (auto v : a) t += (int64_t)v;
+    return t;
+}
+
+extern "C" int chromo_mc_step(chromo_ctx *c, int64_t replica, int move, double amp_move,
+                              int64_t amp_bead, double mu_adjust_factor, int rng_mode, uint64_t seed,
+                              int force_accept, chromo_step_report *report, int64_t *inds,
+                              int64_t inds_cap, double *trial_rows, int64_t rows_cap, int64_t *touched,
+                              double *dtrial, int64_t touched_cap) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    DevCtx &d = c->d;
+    if (replica < 0 || replica >= d.R) return fail(CHROMO_ERR_ARG, "replica out of range");
+    if (move < 0 || move >= CHROMO_NUM_MOVES) return fail(CHROMO_ERR_ARG, "unknown move %d", move);
+    if (amp_bead > d.N) // bead_selection.pyx:85-88,138-141
+        return fail(CHROMO_ERR_ARG, "Bead selection window size must be less than polymer length");
+    if ((move == CHROMO_TANGENT_ROTATION || move == CHROMO_END_PIVOT) && amp_bead < 1)
+        return fail(CHROMO_ERR_ARG, "amp_bead must be >= 1 for this move");
+    CK(cudaSetDevice(c->device));
+    DebugOut h{};
+    h.inds_cap = c->dbg_inds_cap;
+    h.rows_cap = c->dbg_inds_cap;
+    h.touched_cap = c->dbg_touched_cap;
+    h.inds = c->d_dbg_inds;
+    h.rows = c->d_dbg_rows;
+    h.touched = c->d_dbg_touched;
+    h.dtrial = c->d_dbg_dtrial;
+    CK(cudaMemcpyAsync(c->d_dbg, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+    McStepArgs a{d, (int)replica, move, amp_move, (int)amp_bead, mu_adjust_factor, (unsigned long long)seed,
+                 force_accept, c->d_dbg, c->cap, c->smem_bytes, c->stream};
+    int e;
+    if (rng_mode == CHROMO_RNG_REPLAY) e = d.nb <= 2 ? cb_mc_step_replay_12(a) : cb_mc_step_replay_34(a);
+    else if (rng_mode == CHROMO_RNG_PHILOX) e = d.nb <= 2 ? cb_mc_step_philox_12(a) : cb_mc_step_philox_34(a);
+    else return fail(CHROMO_ERR_ARG, "unknown rng_mode %d", rng_mode);
+    if (e) return fail(CHROMO_ERR_CUDA, "mc_step launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&h, c->d_dbg, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (report) {
+        report->n_inds = h.n_inds;
+        report->n_touched = h.n_touched;
+        report->dE_poly = h.dE_poly;
+        report->dE_field = h.dE_field;
+        report->u = h.u;
+        report->accepted = h.accepted;
+        report->passes = h.passes;
+    }
+    int64_t ni = std::min<int64_t>(h.n_inds, c->dbg_inds_cap);
+    int64_t nt = std::min<int64_t>(h.n_touched, c->dbg_touched_cap);
+    if (inds && ni > 0)
+        CK(cudaMemcpyAsync(inds, c->d_dbg_inds, 8 * std::min(ni, inds_cap), cudaMemcpyDeviceToHost, c->stream));
+    if (trial_rows && ni > 0)
+        CK(cudaMemcpyAsync(trial_rows, c->d_dbg_rows, 8 * (9 + d.nb) * std::min(ni, rows_cap),
+                           cudaMemcpyDeviceToHost, c->stream));
+    if (touched && nt > 0)
+        CK(cudaMemcpyAsync(touched, c->d_dbg_touched, 8 * std::min(nt, touched_cap), cudaMemcpyDeviceToHost, c->stream));
+    if (dtrial && nt > 0)
+        CK(cudaMemcpyAsync(dtrial, c->d_dbg_dtrial, 8 * d.ncol * std::min(nt, touched_cap),
+                           cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}

@@ -1,0 +1,177 @@
+// field_kernels.cuh -- whole-replica kernels (A8): full density binning,
+// total field energy, total elastic energy, the chi-conjugate observable.
+// These are the HBM-streaming kernels of the path: every bead / voxel is read
+// once, coalesced; per-replica results come from fixed-order block partials so
+// they are bit-reproducible run to run.
+#pragma once
+#include "geometry.cuh"
+#include "launch.cuh"
+#include "params.cuh"
+
+#define FK_THREADS 256
+
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += sh[i];
+    return t; // valid on thread 0
+}
+
+// update_all_densities fields.pyx:1977-2039: scatter every bead into its 8
+// voxels (rho += w / V_access * {1, state}).  One thread per bead; a warp's
+// 32 beads are one contiguous 768-byte run of r.  Accumulation is a native
+// fp64 reduction at L2 (RED.E.ADD.F64); the grid was zeroed by the caller.
+template <int NB>
+__global__ void __launch_bounds__(FK_THREADS) density_scatter_kernel(DevCtx C) {
+    constexpr int NCOL = NB + 1;
+    const int rep = blockIdx.y;
+    const int bead = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bead >= C.N) return;
+    const double *p = C.r + ((long long)rep * C.N + bead) * 3;
+    const signed char *st = C.states + ((long long)rep * C.N + bead) * NB;
+    double *dens = C.density + (long long)rep * C.n_bins * NCOL;
+    int idx[8];
+    double w[8];
+    bin_point(C, p[0], p[1], p[2], idx, w);
+    double s[NB];
+#pragma unroll
+    for (int m = 0; m < NB; m++) s[m] = (double)st[m];
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+        double V = C.access_vol ? C.access_vol[idx[l]] : C.vol_bin;
+        double d = w[l] / V;
+        double *row = dens + (long long)idx[l] * NCOL;
+        atomicAdd(row, d);
+#pragma unroll
+        for (int m = 0; m < NB; m++)
+            if (s[m] != 0.0) atomicAdd(row + 1 + m, d * s[m]);
+    }
+}
+
+// the |rho| < 1e-18 -> 0 pass of update_all_densities_for_all_polymers
+// (fields.pyx:2101-2105)
+__global__ void density_clamp_kernel(double *d, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && fabs(d[i]) < 1E-18) d[i] = 0.0;
+}
+
+// Python's round(x, 2) > limit, exactly: round-half-even of the EXACT decimal
+// value of x (float.__round__), compared through the smallest hundredth K
+// whose double K/100 exceeds the limit (K computed on the host).
+__device__ __forceinline__ bool round2_exceeds(double x, double K) {
+    double T = K - 0.5;
+    double p = 100.0 * x;
+    if (p > T) return true;
+    if (p < T) return false;
+    if (!(p == T)) return false;     // NaN
+    double e = fma(100.0, x, -p);    // exact rounding error of p
+    if (e > 0.0) return true;
+    if (e < 0.0) return false;
+    return fmod(K, 2.0) == 0.0;      // exact tie: to even
+}
+
+// get_E_binders_and_beads + nonspecific_interact_E fields.pyx:2208-2315.
+// partial[rep][blk][0..NB-1] = sum rho_a^2, [NB] = nonspecific, over the
+// block's voxels;  dcount[rep][a] += # beads with state == 2.
+template <int NB>
+__global__ void __launch_bounds__(FK_THREADS) field_energy_kernel(DevCtx C, double roundK,
+                                                                  double *partial, int *dcount,
+                                                                  int chi_observable) {
+    constexpr int NCOL = NB + 1;
+    __shared__ double sh[FK_THREADS / 32];
+    const int rep = blockIdx.y;
+    const double *dens = C.density + (long long)rep * C.n_bins * NCOL;
+    const double chi = C.chi[rep];
+    double sq[NB], ns = 0.0;
+#pragma unroll
+    for (int a = 0; a < NB; a++) sq[a] = 0.0;
+    for (int bin = blockIdx.x * blockDim.x + threadIdx.x; bin < C.n_bins; bin += gridDim.x * blockDim.x) {
+        const double *row = dens + (long long)bin * NCOL;
+#pragma unroll
+        for (int a = 0; a < NB; a++) sq[a] += row[a + 1] * row[a + 1];
+        double V = C.access_vol ? C.access_vol[bin] : C.vol_bin;
+        double vf = row[0] * C.bead_vol;
+        if (chi_observable) ns += (V / C.bead_vol) * (vf * vf);
+        else if (round2_exceeds(vf, roundK)) ns += CB_E_HUGE_FIELD * vf;
+        else ns += chi * (V / C.bead_vol) * vf * (1.0 - vf);
+    }
+    double *out = partial + ((long long)rep * gridDim.x + blockIdx.x) * NCOL;
+#pragma unroll
+    for (int a = 0; a < NB; a++) {
+        double t = block_sum(sq[a], sh);
+        if (threadIdx.x == 0) out[a] = t;
+    }
+    double t = block_sum(ns, sh);
+    if (threadIdx.x == 0) out[NB] = t;
+    if (!chi_observable) {
+        const signed char *st = C.states + (long long)rep * C.N * NB;
+        int cnt[NB];
+#pragma unroll
+        for (int a = 0; a < NB; a++) cnt[a] = 0;
+        for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < C.N; b += gridDim.x * blockDim.x)
+#pragma unroll
+            for (int a = 0; a < NB; a++) cnt[a] += (st[(long long)b * NB + a] == 2);
+#pragma unroll
+        for (int a = 0; a < NB; a++) {
+            int v = cnt[a];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0 && v) atomicAdd(&dcount[rep * NB + a], v);
+        }
+    }
+}
+
+// SSWLC.compute_E polymers.pyx:1348-1381: one thread per bond, fixed-order
+// block partials.  Note the reference builds `bend` here as
+// t3_1 + (-t3_0 - eta*dr_perp), not as in the dE routines.
+__global__ void __launch_bounds__(FK_THREADS) elastic_energy_kernel(DevCtx C, double *partial) {
+    __shared__ double sh[FK_THREADS / 32];
+    const int rep = blockIdx.y;
+    const double *Rr = C.r + (long long)rep * C.N * 3;
+    const double *T3 = C.t3 + (long long)rep * C.N * 3;
+    double e = 0.0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < C.N - 1; b += gridDim.x * blockDim.x) {
+        double r0[3], r1[3], t0[3], t1[3], dr[3], perp[3], bend[3];
+        load3(Rr + 3 * (long long)b, r0);
+        load3(Rr + 3 * (long long)(b + 1), r1);
+        load3(T3 + 3 * (long long)b, t0);
+        load3(T3 + 3 * (long long)(b + 1), t1);
+        Bond B = load_bond(C, rep, b);
+        for (int i = 0; i < 3; i++) dr[i] = r1[i] - r0[i];
+        double par = dot3(t0, dr);
+        for (int i = 0; i < 3; i++) {
+            perp[i] = dr[i] - t0[i] * par;
+            bend[i] = t1[i] + (-t0[i] - B.eta * perp[i]);
+        }
+        double tp = par - B.gamma;
+        e += (0.5 * B.eps_bend * dot3(bend, bend) + 0.5 * B.eps_par * (tp * tp)) +
+             0.5 * B.eps_perp * dot3(perp, perp);
+    }
+    double t = block_sum(e, sh);
+    if (threadIdx.x == 0) partial[(long long)rep * gridDim.x + blockIdx.x] = t;
+}
+
+// out[rep][c] = sum_blk partial[rep][blk][c], in block order
+__global__ void partial_finish_kernel(const double *partial, double *out, int R, int nblk, int ncomp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * ncomp) return;
+    int rep = i / ncomp, c = i % ncomp;
+    double t = 0.0;
+    for (int b = 0; b < nblk; b++) t += partial[((long long)rep * nblk + b) * ncomp + c];
+    out[i] = t;
+}
+
+// int64 host layout <-> int8 device layout for states / chemical_mods
+__global__ void widen_i8_kernel(const signed char *src, long long *dst, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+__global__ void narrow_i64_kernel(const long long *src, signed char *dst, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (signed char)src[i];
+}

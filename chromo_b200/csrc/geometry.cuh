@@ -1,0 +1,161 @@
+// geometry.cuh -- per-bead device functions: trilinear binning, affine
+// transforms, SSWLC pair energy.  Compiled with -fmad=false: the reference is
+// built for generic x86-64 (no FMA contraction), and a contracted
+// `x/dx - ind` could flip the last ulp of a weight or a floor().
+#pragma once
+#include "params.cuh"
+
+// ---------------------------------------------------------------- binning
+// Reference: UniformDensityField.get_change_in_density fields.pyx:1437-1462
+// (wrap, lower index, lower weight), _generate_weight_vector_with_trial
+// 1524-1598 (8 weights), _generate_index_vector_with_trial 1600-1673 and the
+// wrap table 673-685 (8 super-indices  ix + nx*iy + nx*ny*iz).
+//
+// Bit-exact contract: `%` is Python-modulo on doubles (cdivision=False,
+// setup.py:89): fmod, then +W when the remainder is negative.  The weight uses
+// the UNPATCHED floor index even when it is -1 (fields.pyx:1451-1462).
+__device__ __forceinline__ void bin_axis(double x, double half_width, double width,
+                                         double half_step, double d, int n, int &ind_lo,
+                                         int &ind_hi, double &w_lo) {
+    double a = x + half_width;
+    double m = fmod(a, width); // exact (fmod has no rounding error)
+    if (m != 0.0 && m < 0.0) m = m + width;
+    double xs = m - half_step;
+    double q = xs / d; // IEEE division
+    double fl = floor(q);
+    int ind = (int)fl;
+    w_lo = 1.0 - (q - fl);
+    ind_lo = (ind == -1) ? n - 1 : ind;
+    ind_hi = (ind_lo + 1 >= n) ? ind_lo + 1 - n : ind_lo + 1;
+}
+
+__device__ __forceinline__ void bin_point(const DevCtx &C, double x, double y, double z,
+                                          int idx[8], double w[8]) {
+    int x0, x1, y0, y1, z0, z1;
+    double wx, wy, wz;
+    bin_axis(x, C.half_width[0], C.width[0], C.half_step[0], C.dxyz[0], C.nx, x0, x1, wx);
+    bin_axis(y, C.half_width[1], C.width[1], C.half_step[1], C.dxyz[1], C.ny, y0, y1, wy);
+    bin_axis(z, C.half_width[2], C.width[2], C.half_step[2], C.dxyz[2], C.nz, z0, z1, wz);
+    double ux = 1.0 - wx, uy = 1.0 - wy, uz = 1.0 - wz;
+    // l = bit0:x, bit1:y, bit2:z ; products in the reference's order (x*y)*z
+    w[0] = wx * wy * wz;
+    w[1] = ux * wy * wz;
+    w[2] = wx * uy * wz;
+    w[3] = ux * uy * wz;
+    w[4] = wx * wy * uz;
+    w[5] = ux * wy * uz;
+    w[6] = wx * uy * uz;
+    w[7] = ux * uy * uz;
+    int nxy = C.nx * C.ny;
+    int r00 = C.nx * y0 + nxy * z0, r10 = C.nx * y1 + nxy * z0;
+    int r01 = C.nx * y0 + nxy * z1, r11 = C.nx * y1 + nxy * z1;
+    idx[0] = x0 + r00;
+    idx[1] = x1 + r00;
+    idx[2] = x0 + r10;
+    idx[3] = x1 + r10;
+    idx[4] = x0 + r01;
+    idx[5] = x1 + r01;
+    idx[6] = x0 + r11;
+    idx[7] = x1 + r11;
+}
+
+// ------------------------------------------------------------- transforms
+// arbitrary_axis_rotation linalg.pyx:62-139.  M is 3x4 row-major (M[4*j+3] is
+// the translation column).
+__device__ __forceinline__ void rotation_matrix(const double ax[3], const double pt[3],
+                                                double ang, double M[12]) {
+    double sn, c;
+    sincos(ang, &sn, &c);
+    double omc = 1.0 - c;
+    M[0] = ax[0] * ax[0] + (ax[1] * ax[1] + ax[2] * ax[2]) * c;
+    M[1] = ax[0] * ax[1] * omc - ax[2] * sn;
+    M[2] = ax[0] * ax[2] * omc + ax[1] * sn;
+    M[4] = ax[0] * ax[1] * omc + ax[2] * sn;
+    M[5] = ax[1] * ax[1] + (ax[0] * ax[0] + ax[2] * ax[2]) * c;
+    M[6] = ax[1] * ax[2] * omc - ax[0] * sn;
+    M[8] = ax[0] * ax[2] * omc - ax[1] * sn;
+    M[9] = ax[1] * ax[2] * omc + ax[0] * sn;
+    M[10] = ax[2] * ax[2] + (ax[0] * ax[0] + ax[1] * ax[1]) * c;
+    double r0 = (pt[1] * ax[2] - pt[2] * ax[1]) * sn;
+    double r1 = (pt[2] * ax[0] - pt[0] * ax[2]) * sn;
+    double r2 = (pt[0] * ax[1] - pt[1] * ax[0]) * sn;
+    r0 += (pt[0] * (1.0 - ax[0] * ax[0]) - ax[0] * (pt[1] * ax[1] + pt[2] * ax[2])) * omc;
+    r1 += (pt[1] * (1.0 - ax[1] * ax[1]) - ax[1] * (pt[0] * ax[0] + pt[2] * ax[2])) * omc;
+    r2 += (pt[2] * (1.0 - ax[2] * ax[2]) - ax[2] * (pt[0] * ax[0] + pt[1] * ax[1])) * omc;
+    M[3] = r0;
+    M[7] = r1;
+    M[11] = r2;
+}
+
+// transform_r_t3_t2 move_funcs.pyx:121-154: ((m0 x + m1 y) + m2 z) (+ t)
+__device__ __forceinline__ void apply_rot(const double *M, const double v[3], double o[3]) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) o[j] = (M[4 * j] * v[0] + M[4 * j + 1] * v[1]) + M[4 * j + 2] * v[2];
+}
+__device__ __forceinline__ void apply_affine(const double *M, const double v[3], double o[3]) {
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+        o[j] = ((M[4 * j] * v[0] + M[4 * j + 1] * v[1]) + M[4 * j + 2] * v[2]) + M[4 * j + 3];
+}
+
+// uniform_sample_unit_sphere linalg.pyx:23-59 from two rand() outputs
+__device__ __forceinline__ void sphere_from_draws(uint32_t d1, uint32_t d2, double v[3]) {
+    double phi = (double)d1 / CB_RAND_MAX * (2.0 * 3.14159265358979323846);
+    double theta = acos(((double)d2 / CB_RAND_MAX) * 2.0 - 1.0);
+    double sp, cp, st, ct;
+    sincos(phi, &sp, &cp);
+    sincos(theta, &st, &ct);
+    v[0] = cp * st;
+    v[1] = sp * st;
+    v[2] = ct;
+}
+
+// ---------------------------------------------------------- SSWLC energy
+struct Bond {
+    double eps_bend, eps_par, eps_perp, gamma, eta;
+};
+__device__ __forceinline__ Bond load_bond(const DevCtx &C, int rep, int b) {
+    const double *p = C.bond + (long long)rep * C.bond_stride + (long long)b * 5;
+    Bond o;
+    o.eps_bend = p[0];
+    o.eps_par = p[1];
+    o.eps_perp = p[2];
+    o.gamma = p[3];
+    o.eta = p[4];
+    return o;
+}
+
+__device__ __forceinline__ double dot3(const double a[3], const double b[3]) {
+    return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; // ((0+p0)+p1)+p2, linalg.pyx:374-395
+}
+
+// E of one bond given the tangent of its first bead, polymers.pyx:1148-1175
+// with dr / dr_par / dr_perp / bend built as in bead_pair_dE_poly_forward
+// (polymers.pyx:1253-1271).
+__device__ __forceinline__ double bond_energy(const Bond &B, const double r0[3],
+                                              const double r1[3], const double t0[3],
+                                              const double t1[3]) {
+    double dr[3], perp[3], bend[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) dr[i] = r1[i] - r0[i];
+    double par = dot3(t0, dr);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        perp[i] = dr[i] - t0[i] * par;
+        bend[i] = (t1[i] - t0[i]) - perp[i] * B.eta;
+    }
+    double tp = par - B.gamma;
+    return (0.5 * B.eps_bend * dot3(bend, bend) + 0.5 * B.eps_par * (tp * tp)) +
+           0.5 * B.eps_perp * dot3(perp, perp);
+}
+
+__device__ __forceinline__ void load3(const double *p, double v[3]) {
+    v[0] = p[0];
+    v[1] = p[1];
+    v[2] = p[2];
+}
+__device__ __forceinline__ void store3(double *p, const double v[3]) {
+    p[0] = v[0];
+    p[1] = v[1];
+    p[2] = v[2];
+}

@@ -1,0 +1,44 @@
+// mc_inst.cu -- instantiates the fused MC kernels for one RNG mode and one pair
+// of binder counts.  Compile with
+//   -DCB_INST_REPLAY=0|1  -DCB_INST_HI=0|1     (HI: nb in {3,4}, else {1,2})
+#include "launch.cuh"
+#include "mc_kernel.cuh"
+
+#ifndef CB_INST_REPLAY
+#error "define CB_INST_REPLAY"
+#endif
+#if CB_INST_REPLAY
+typedef ReplayRng InstRng;
+#define NAME2(a, b) cb_mc_##a##_replay_##b
+#else
+typedef PhiloxRng InstRng;
+#define NAME2(a, b) cb_mc_##a##_philox_##b
+#endif
+#if CB_INST_HI
+#define NAME(a) NAME2(a, 34)
+constexpr int NB_A = 3, NB_B = 4;
+#else
+#define NAME(a) NAME2(a, 12)
+constexpr int NB_A = 1, NB_B = 2;
+#endif
+
+template <int NB>
+static int sim_one(const McSimArgs &a) {
+    auto k = mc_sim_kernel<InstRng, NB>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
+    if (e != cudaSuccess) return (int)e;
+    CB_LAUNCH(k, a.d.R, 32, a.smem, a.stream, a.d, a.num_mc_steps, a.mu_adjust, a.seed, a.cap);
+    return (int)cudaGetLastError();
+}
+template <int NB>
+static int step_one(const McStepArgs &a) {
+    auto k = mc_step_kernel<InstRng, NB>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
+    if (e != cudaSuccess) return (int)e;
+    CB_LAUNCH(k, 1, 32, a.smem, a.stream, a.d, a.replica, a.move, a.amp_move, a.amp_bead, a.mu_adjust,
+              a.seed, a.force_accept, a.dbg, a.cap);
+    return (int)cudaGetLastError();
+}
+
+int NAME(sim)(const McSimArgs &a) { return a.d.nb == NB_A ? sim_one<NB_A>(a) : sim_one<NB_B>(a); }
+int NAME(step)(const McStepArgs &a) { return a.d.nb == NB_A ? step_one<NB_A>(a) : step_one<NB_B>(a); }

@@ -1,0 +1,64 @@
+// params.cuh -- device-side view of a context (R replicas resident in HBM).
+//
+// HBM layout (one context = one GPU):
+//   r, t3, t2   [R][N][3]  fp64   AoS xyz, the reference's own layout
+//                                 (polymers.pxd:21) so a move segment
+//                                 [ind0, indf) is ONE contiguous 24n-byte run
+//                                 per array -> fully coalesced warp loads
+//   states,mods [R][N][nb] int8   (int64 in the reference; values 0..sites)
+//   density     [R][n_bins][nb+1] fp64, row = one voxel (fields.pxd:54), so a
+//                                 touched voxel is one 16/24/32-byte gather
+//   bond        [sets][N-1][5]    eps_bend, eps_par, eps_perp, gamma, eta
+//   moves       [R][5]            controller / tracker state
+#pragma once
+#include <cstdint>
+#include "../../include/chromo_b200.h"
+
+#define CB_MAXNB CHROMO_MAX_BINDERS
+#define CB_E_HUGE_FIELD 1E99 /* fields.pyx:32 */
+#define CB_E_HUGE_POLY 1E25  /* polymers.pyx:35 */
+#define CB_RAND_MAX 2147483647.0
+
+struct DevCtx {
+    int R, N, nb, ncol;
+    int nx, ny, nz, n_bins;
+    int field_active, confine_type;
+    double width[3], dxyz[3], half_width[3], half_step[3];
+    double vol_bin, bead_vol, confine_length, vf_limit;
+    long long max_binders;
+    double *r, *t3, *t2;
+    signed char *states, *mods;
+    double *density;
+    const double *access_vol; // nullptr -> vol_bin
+    const double *bond;
+    long long bond_stride; // 0 (shared) or (N-1)*5
+    const double *chi;     // [R]
+    const double *mu;      // [R][nb]
+    double pref[CB_MAXNB], e_intra[CB_MAXNB], xpref[CB_MAXNB * CB_MAXNB];
+    int sites[CB_MAXNB];
+    const double *bindF; // [nb][S1][S1]
+    int S1;
+    chromo_move_state *moves;        // [R][5]
+    uint32_t *glibc;                 // [R][GLIBC_WORDS]
+    uint32_t *mt;                    // [R][MT_WORDS]
+    unsigned long long *philox_ctr;  // [R]
+    int *tan_inds;                   // [R][N]   tangent-rotation large path
+    uint32_t *sel_bits;              // [R][ceil(N/32)]
+    signed char *st_new;             // [R][N]   binding large path
+    unsigned long long *attempts;    // [R]
+};
+
+#define CB_GLIBC_WORDS 36 // r[31], f, b (+pad)
+#define CB_MT_WORDS 628   // mt[624], pos (+pad)
+
+// instrumentation written by the single-step parity kernel (chromo_mc_step)
+struct DebugOut {
+    long long n_inds, n_touched;
+    double dE_poly, dE_field, u;
+    int accepted, passes;
+    long long inds_cap, rows_cap, touched_cap;
+    long long *inds;    // [inds_cap]
+    double *rows;       // [rows_cap][9+nb]
+    long long *touched; // [touched_cap]
+    double *dtrial;     // [touched_cap][ncol]
+};

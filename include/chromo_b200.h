@@ -1,0 +1,225 @@
+/*
+ * chromo_b200.h -- C ABI of the B200-native Monte-Carlo energy-evaluation path.
+ *
+ * This is the drop-in boundary for chromo's hot path.  The
+ * reference has no FFI for this path: the seam is the Cython entry point
+ *
+ *   cpdef void mc_sim(list polymers, readerproteins, long num_mc_steps,
+ *                     list mc_move_controllers, FieldBase field,
+ *                     double mu_adjust_factor, long random_seed)
+ *                                   (chromo/mc/mc_sim.pyx:26-30, mc_sim.pxd:11-15)
+ *
+ * plus the fine-grained cdef/cpdef methods it calls.  Every entry point below
+ * names the reference interface it replaces (file:line under
+ * /root/reference/chromo/).  INTEGRATION.md shows the ctypes stub a chromo
+ * maintainer would add to bind them.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types in any signature;
+ *   - a context (`chromo_ctx`) holds R independent replicas of one problem
+ *     shape (N beads, nb binders, one nx*ny*nz grid) resident in HBM on ONE
+ *     device; replica i of a multi-GPU job lives on rank i % world_size;
+ *   - all array arguments are caller-owned HOST buffers unless the name ends in
+ *     `_dev`; layouts are the reference's (C-contiguous, fp64 / int64);
+ *   - every function returns 0 on success or a negative code; the message is
+ *     available from chromo_last_error() (thread-local);
+ *   - one CUDA stream per context; calls on one context are not re-entrant;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with CHROMO_ERR_CUDA.
+ */
+#ifndef CHROMO_B200_H
+#define CHROMO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHROMO_OK 0
+#define CHROMO_ERR_ARG -1
+#define CHROMO_ERR_CUDA -2
+#define CHROMO_ERR_STATE -3
+
+#define CHROMO_MAX_BINDERS 4
+
+/* move order = controller order in mc_sim (mc_controller.py:255-258) */
+enum chromo_move_id {
+    CHROMO_CRANK_SHAFT = 0,          /* move_funcs.pyx:39  */
+    CHROMO_END_PIVOT = 1,            /* move_funcs.pyx:285 */
+    CHROMO_SLIDE = 2,                /* move_funcs.pyx:403 */
+    CHROMO_TANGENT_ROTATION = 3,     /* move_funcs.pyx:470 */
+    CHROMO_CHANGE_BINDING_STATE = 4, /* move_funcs.pyx:717 */
+    CHROMO_NUM_MOVES = 5
+};
+
+enum chromo_confine { CHROMO_CONFINE_NONE = 0, CHROMO_CONFINE_SPHERICAL = 1,
+                      CHROMO_CONFINE_CUBICAL = 2 }; /* fields.pyx:160-202 */
+
+/* RNG behind the proposals and the Metropolis test.
+ *   PHILOX: production; Philox4x32-10 keyed by (seed, replica).
+ *   REPLAY: restates the reference's generators -- glibc rand() (never seeded
+ *           by the reference, mc_sim.pyx:52-56) and numpy's legacy MT19937
+ *           (np.random.seed(random_seed), mc_sim.pyx:81) -- so that a run can
+ *           be compared draw for draw with the reference. */
+enum chromo_rng_mode { CHROMO_RNG_PHILOX = 0, CHROMO_RNG_REPLAY = 1 };
+
+/* One MCAdapter + its controller + its AcceptanceTracker, per replica and move
+ * (moves.pyx:58-135; mc_controller.py:89-213; mc_stat.py:72,190-207). In/out. */
+typedef struct chromo_move_state {
+    double amp_move;        /* MCAdapter.amp_move */
+    double move_amp_lo;     /* Controller.move_amp_bounds */
+    double move_amp_hi;
+    double bead_amp_lo;     /* Controller.bead_amp_bounds (may be fractional:  */
+    double bead_amp_hi;     /*  end_pivot lower bound is min(50, N/4))         */
+    double acceptance_rate; /* AcceptanceTracker.acceptance_rate (EWMA)        */
+    double alpha;           /* 2 / (moves_in_average + 1)                      */
+    int64_t num_attempt;    /* MCAdapter.num_attempt */
+    int64_t num_success;    /* MCAdapter.num_success */
+    int32_t amp_bead;       /* MCAdapter.amp_bead */
+    int32_t num_per_cycle;  /* MCAdapter.num_per_cycle */
+    int32_t move_on;        /* MCAdapter.move_on */
+    int32_t controller;     /* 0 = NoControl, 1 = SimpleControl */
+} chromo_move_state;
+
+/* Problem shape shared by all replicas of a context.
+ * Replaces the constructor state of UniformDensityField (fields.pyx:453-575)
+ * and PolymerBase/SSWLC (polymers.pyx:186-300, 959-1012). */
+typedef struct chromo_shape {
+    int64_t n_replicas;
+    int64_t num_beads;      /* N */
+    int64_t num_binders;    /* nb >= 1 (null_reader counts, polymers.pyx:322) */
+    int64_t nx, ny, nz;     /* 0,0,0 = NullField (fields.pyx:280) */
+    double width[3];        /* x_width, y_width, z_width */
+    int32_t confine_type;   /* enum chromo_confine */
+    double confine_length;
+    float vf_limit;         /* stored as C float by the reference (fields.pxd:61) */
+    double bead_vol;        /* beads[0].vol = 4/3*pi*rad^3 (beads.py:415) */
+    int64_t max_binders;    /* PolymerBase.max_binders, -1 = no limit */
+} chromo_shape;
+
+typedef struct chromo_ctx chromo_ctx;
+
+const char *chromo_last_error(void);
+int chromo_version(void);
+
+/* ---- lifetime ---------------------------------------------------------- */
+int chromo_ctx_create(chromo_ctx **out, int device, const chromo_shape *shape);
+int chromo_ctx_destroy(chromo_ctx *ctx);
+int chromo_ctx_sync(chromo_ctx *ctx);
+/* the context's cudaStream_t, for CUDA-event timing by the caller */
+void *chromo_ctx_stream(chromo_ctx *ctx);
+/* bytes of HBM held by the context */
+int64_t chromo_ctx_bytes(chromo_ctx *ctx);
+
+/* ---- parameters -------------------------------------------------------- */
+/* Reader-protein tables.
+ *  sites_per_bead[nb]                    binders.pyx:38-49
+ *  field_pref[nb], e_intra[nb], xpref[nb*nb]
+ *                                        init_field_energy_prefactors fields.pyx:687-712
+ *  bind_F[nb][S+1][S+1]  with S = max sites_per_bead:
+ *      bind_F[b][Nm][s] = -ln sum_i C(Nm,i) C(Nn-Nm,s-i) exp(-(i e_mod + (s-i) e_nomod))
+ *                                        bead_binding_dE polymers.pyx:1493-1517 */
+int chromo_set_binders(chromo_ctx *ctx, const int64_t *sites_per_bead, const double *field_pref,
+                       const double *e_intra, const double *xpref, const double *bind_F,
+                       int64_t S);
+/* Per-replica sweep parameters: chi[R] (UniformDensityField.chi, fields.pyx:526)
+ * and chemical_potential[R][nb] (ReaderProtein.chemical_potential). */
+int chromo_set_replica_params(chromo_ctx *ctx, const double *chi, const double *mu);
+/* SSWLC bond parameters [n_sets][N-1] each (SSWLC._find_parameters
+ * polymers.pyx:1545-1601); n_sets is 1 (shared by all replicas) or R. */
+int chromo_set_bond_params(chromo_ctx *ctx, int64_t n_sets, const double *eps_bend,
+                           const double *eps_par, const double *eps_perp, const double *gamma,
+                           const double *eta);
+/* access_vols[n_bins] (fields.pyx:523-525, 714-770); NULL = vol_bin everywhere */
+int chromo_set_access_volumes(chromo_ctx *ctx, const double *access_vol);
+
+/* ---- state ------------------------------------------------------------- */
+/* r, t3, t2: [n][N][3] fp64; states, chemical_mods: [n][N][nb] int64
+ * (polymers.pxd:21-24) for replicas first .. first+n-1.  NULL = leave as is. */
+int chromo_upload_state(chromo_ctx *ctx, int64_t first, int64_t n, const double *r,
+                        const double *t3, const double *t2, const int64_t *states,
+                        const int64_t *chemical_mods);
+int chromo_download_state(chromo_ctx *ctx, int64_t first, int64_t n, double *r, double *t3,
+                          double *t2, int64_t *states);
+/* density[n][n_bins][nb+1] (UniformDensityField.density, fields.pxd:54) */
+int chromo_download_density(chromo_ctx *ctx, int64_t first, int64_t n, double *density);
+int chromo_upload_density(chromo_ctx *ctx, int64_t first, int64_t n, const double *density);
+
+/* ---- full recompute (A8) ---------------------------------------------- */
+/* update_all_densities (fields.pyx:1977-2039) for every replica; clamp != 0
+ * also applies the |rho| < 1e-18 -> 0 pass of
+ * update_all_densities_for_all_polymers (fields.pyx:2041-2106). */
+int chromo_field_recompute(chromo_ctx *ctx, int clamp);
+/* UniformDensityField.compute_E (fields.pyx:1939-1966, 2208-2315): recomputes
+ * the densities, then returns per replica
+ *   sum_sq[R][nb]   = sum_bins rho_a^2
+ *   doubly[R][nb]   = # beads with state == 2
+ *   nonspecific[R]  = sum_bins (round(phi,2) > vf_limit ? 1e99 phi : chi (V/v) phi (1-phi))
+ *   E[R]            = sum_a (pref_a sum_sq_a + e_intra_a doubly_a) + nonspecific  */
+int chromo_field_energy(chromo_ctx *ctx, double *E, double *sum_sq, int64_t *doubly,
+                        double *nonspecific);
+/* SSWLC.compute_E (polymers.pyx:1348-1381): E[R] */
+int chromo_elastic_energy(chromo_ctx *ctx, double *E);
+/* chi-conjugate observable used by the replica-exchange step (new functionality,
+ * SURVEY.md 8e): Phi[R] = sum_bins (V/v) phi^2, i.e. dE_chi-term / chi
+ * (nonspecific_interact_dE fields.pyx:1829-1840).  Uses the current densities. */
+int chromo_chi_observable(chromo_ctx *ctx, double *Phi);
+
+/* ---- RNG --------------------------------------------------------------- */
+/* REPLAY: seed each replica's glibc rand() state, as srand(seed) would. */
+int chromo_srand(chromo_ctx *ctx, const uint32_t *seeds /* [R] */);
+/* REPLAY: np.random.seed(seed) for each replica (mc_sim.pyx:81 does this once
+ * per mc_sim call; chromo_mc_sim does it too when reseed_numpy != 0). */
+int chromo_numpy_seed(chromo_ctx *ctx, const uint32_t *seeds /* [R] */);
+
+/* ---- the hot path (A1-A7, A9-A12) -------------------------------------- */
+/* mc_sim (mc_sim.pyx:26-103) for all replicas at once: num_mc_steps sweeps of
+ * the five move types, num_per_cycle attempts each, Metropolis accept/reject,
+ * incremental density update, amplitude controller once per type per sweep.
+ *   moves[R][5]      in/out (NULL = keep the context's current controllers)
+ *   numpy_seeds[R]   REPLAY only: per-replica np.random.seed value (NULL = keep)
+ *   seed             PHILOX key
+ * Asynchronous on the context's stream when `moves` is NULL; otherwise the
+ * call returns after the controllers have been copied back. */
+int chromo_mc_sim(chromo_ctx *ctx, int64_t num_mc_steps, chromo_move_state *moves,
+                  double mu_adjust_factor, uint64_t seed, int rng_mode,
+                  const uint32_t *numpy_seeds);
+int chromo_get_moves(chromo_ctx *ctx, chromo_move_state *moves /* [R][5] */);
+int chromo_set_moves(chromo_ctx *ctx, const chromo_move_state *moves /* [R][5] */);
+/* attempts executed by the last chromo_mc_sim call, summed over replicas */
+int64_t chromo_last_attempts(chromo_ctx *ctx);
+
+/* One mc_step (mc_sim.pyx:106-182) of ONE replica through the same device code
+ * as chromo_mc_sim, with everything the reference exposes after a step
+ * written back for parity checks:
+ *   MCAdapter.propose (moves.pyx:137-154)       -> inds, trial rows
+ *   PolymerBase.compute_dE (polymers.pxd:33-38)  -> dE_poly
+ *   FieldBase.compute_dE (fields.pxd:16-19)      -> dE_field, touched bins
+ *                                                   (affected_bins_last_move),
+ *                                                   density_trial rows
+ *   accept / reject (moves.pxd:24-33), update_affected_densities (fields.pxd:20)
+ * force_accept: -1 = Metropolis with one RNG draw (mc_sim.pyx:171),
+ *                0 / 1 = forced reject / accept without consuming a draw. */
+typedef struct chromo_step_report {
+    int64_t n_inds;
+    int64_t n_touched;
+    double dE_poly;
+    double dE_field;
+    double u;             /* Metropolis uniform (NaN when forced) */
+    int32_t accepted;
+    int32_t passes;       /* hash-partition passes the field dE needed */
+} chromo_step_report;
+
+int chromo_mc_step(chromo_ctx *ctx, int64_t replica, int move, double amp_move,
+                   int64_t amp_bead, double mu_adjust_factor, int rng_mode, uint64_t seed,
+                   int force_accept, chromo_step_report *report,
+                   int64_t *inds, int64_t inds_cap,            /* [n_inds] */
+                   double *trial_rows, int64_t rows_cap,       /* [n_inds][9+nb]: r,t3,t2,states */
+                   int64_t *touched, double *dtrial, int64_t touched_cap /* [n_touched],[..][nb+1] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHROMO_B200_H */

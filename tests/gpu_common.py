@@ -1,0 +1,43 @@
+"""Helpers shared by the GPU parity tests, the emulator tests, smoke() and bench."""
+import numpy as np
+
+import oracle as O
+from chromo_b200._lib import MOVE_DTYPE
+from chromo_b200.engine import Engine
+
+_MV_FIELDS = ("amp_move", "move_amp_lo", "move_amp_hi", "bead_amp_lo", "bead_amp_hi", "acceptance_rate",
+              "alpha", "num_attempt", "num_success", "amp_bead", "num_per_cycle", "move_on", "controller")
+
+
+def engine_from_spec(spec, R=1, device=0, chi=None, mu=None):
+    """R identical replicas of `spec` on one device, densities initialised as
+    UniformDensityField.__init__ does (fields.pyx:532)."""
+    N, nb = spec["N"], spec["nb"]
+    f = spec["field"]
+    bead_vol = (4 / 3) * np.pi * spec["bead_rad"] ** 3
+    e = Engine(R, N, nb, grid=f, bead_vol=bead_vol, max_binders=spec.get("max_binders", -1), device=device)
+    if f is not None:
+        vol_bin = f["x_width"] * f["y_width"] * f["z_width"] / (f["nx"] * f["ny"] * f["nz"])
+    else:
+        vol_bin = 1.0
+    pref, e_intra, xpref = O.field_prefactors(spec["binders"], vol_bin)
+    e.set_binders(spec["binders"], pref, e_intra, xpref)
+    bp = O.bond_params(spec["bead_length"], spec["lp"])
+    e.set_bond_params(bp["eps_bend"], bp["eps_par"], bp["eps_perp"], bp["gamma"], bp["eta"])
+    e.set_replica_params(chi=(f["chi"] if f is not None else 1.0) if chi is None else chi,
+                         mu=[b["chemical_potential"] for b in spec["binders"]] if mu is None else mu)
+    tile = lambda a: np.broadcast_to(np.asarray(a), (R,) + np.asarray(a).shape).copy()
+    e.upload(tile(spec["r"]), tile(spec["t3"]), tile(spec["t2"]), tile(spec["states"]), tile(spec["mods"]))
+    if f is not None:
+        e.field_recompute(clamp=True)
+    return e
+
+
+def moves_array(spec, R, per_cycle=(30, 1, 60, 60, 10), controller=1, move_on=(1, 1, 1, 1, 1)):
+    mv = O.make_moves(spec["N"], float(np.min(spec["bead_length"])), per_cycle=per_cycle,
+                      controller=controller, move_on=move_on)
+    a = np.zeros((R, 5), dtype=MOVE_DTYPE)
+    for i in range(5):
+        for f in _MV_FIELDS:
+            a[f][:, i] = getattr(mv[i], f)
+    return a

@@ -1,0 +1,174 @@
+// cuda_emu.h -- a lockstep-warp CPU emulator of the handful of CUDA features the
+// chromo_b200 kernels use.  TEST TOOL ONLY: it lets the kernel LOGIC (hash table,
+// warp collectives, proposal code, the C ABI host side) be exercised against the
+// oracle in a container without a GPU (tests/test_emu_*.py).  It is never built
+// into, shipped with, or loaded by the chromo_b200 package; the product library
+// is compiled by nvcc for sm_100a and has no CPU path.
+//
+// Model: each thread block runs as blockDim.x OS threads; warp collectives
+// (__shfl*_sync, __any_sync, __syncwarp) rendezvous on a per-warp barrier,
+// __syncthreads on a per-block barrier; blocks of a grid run one after another.
+// All collectives in the kernels are called with warp-uniform control flow and a
+// full mask, which is what this model requires.
+#pragma once
+#include <pthread.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __align__(x) alignas(x)
+#define __shared__ static
+
+using std::max;
+using std::min;
+
+struct emu_dim3 {
+    unsigned x = 1, y = 1, z = 1;
+    emu_dim3() {}
+    emu_dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+typedef emu_dim3 dim3;
+static thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+struct EmuBlock {
+    pthread_barrier_t block_bar;
+    std::vector<pthread_barrier_t> warp_bar;
+    std::vector<uint64_t> slots; // one per thread
+    unsigned char *dyn = nullptr;
+};
+static thread_local EmuBlock *emu_blk = nullptr;
+
+static inline void emu_warp_wait() { pthread_barrier_wait(&emu_blk->warp_bar[threadIdx.x >> 5]); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_wait(); }
+static inline void __syncthreads() { pthread_barrier_wait(&emu_blk->block_bar); }
+
+template <class T>
+static inline T emu_exchange(T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "");
+    uint64_t bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    unsigned base = threadIdx.x & ~31u;
+    emu_blk->slots[threadIdx.x] = bits;
+    emu_warp_wait();
+    uint64_t got = emu_blk->slots[base + (unsigned)(src_lane & 31)];
+    emu_warp_wait();
+    T r;
+    memcpy(&r, &got, sizeof(T));
+    return r;
+}
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, src); }
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_exchange(v, (int)((threadIdx.x & 31) ^ (unsigned)m)); }
+static inline int __any_sync(unsigned, int pred) {
+    unsigned base = threadIdx.x & ~31u;
+    emu_blk->slots[threadIdx.x] = pred ? 1 : 0;
+    emu_warp_wait();
+    int r = 0;
+    for (int i = 0; i < 32 && base + i < blockDim.x; i++) r |= (int)emu_blk->slots[base + i];
+    emu_warp_wait();
+    return r;
+}
+
+static inline int atomicCAS(int *a, int cmp, int val) {
+    __atomic_compare_exchange_n(a, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return cmp;
+}
+static inline int atomicAdd(int *a, int v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
+static inline double atomicAdd(double *a, double v) {
+    uint64_t *p = (uint64_t *)a, old = __atomic_load_n(p, __ATOMIC_SEQ_CST), nw;
+    double o;
+    do {
+        memcpy(&o, &old, 8);
+        double n = o + v;
+        memcpy(&nw, &n, 8);
+    } while (!__atomic_compare_exchange_n(p, &old, nw, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+    return o;
+}
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline double __longlong_as_double(long long v) {
+    double d;
+    memcpy(&d, &v, 8);
+    return d;
+}
+
+#define CB_DYN_SMEM(name) unsigned char *name = emu_blk->dyn
+
+// ---- minimal CUDA runtime ------------------------------------------------
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaStreamNonBlocking = 1 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+struct cudaDeviceProp {
+    int multiProcessorCount;
+    size_t sharedMemPerBlockOptin;
+};
+static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
+    p->multiProcessorCount = 148;
+    p->sharedMemPerBlockOptin = 227 * 1024;
+    return 0;
+}
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, int) { *s = (void *)1; return 0; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n); return *p ? 0 : 2; }
+static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
+static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) {
+    memcpy(d, s, n);
+    return 0;
+}
+static inline cudaError_t cudaGetLastError() { return 0; }
+template <class K>
+static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return 0; }
+
+// ---- kernel launch ---------------------------------------------------------
+template <class K, class... A>
+static void emu_launch(K kernel, dim3 grid, dim3 block, size_t smem, A... args) {
+    const unsigned nt = block.x;
+    const unsigned nw = (nt + 31) / 32;
+    EmuBlock blk;
+    blk.slots.assign(nw * 32, 0);
+    blk.warp_bar.resize(nw);
+    std::vector<unsigned char> dyn(smem + 64);
+    blk.dyn = (unsigned char *)(((uintptr_t)dyn.data() + 15) & ~(uintptr_t)15);
+    pthread_barrier_init(&blk.block_bar, nullptr, nt);
+    for (unsigned w = 0; w < nw; w++) pthread_barrier_init(&blk.warp_bar[w], nullptr, std::min(32u, nt - 32 * w));
+    for (unsigned by = 0; by < grid.y; by++)
+        for (unsigned bx = 0; bx < grid.x; bx++) {
+            std::vector<std::thread> th;
+            th.reserve(nt);
+            for (unsigned t = 0; t < nt; t++)
+                th.emplace_back([&, t]() {
+                    threadIdx = emu_dim3(t);
+                    blockIdx = emu_dim3(bx, by);
+                    blockDim = block;
+                    gridDim = grid;
+                    emu_blk = &blk;
+                    kernel(args...);
+                });
+            for (auto &x : th) x.join();
+        }
+    pthread_barrier_destroy(&blk.block_bar);
+    for (unsigned w = 0; w < nw; w++) pthread_barrier_destroy(&blk.warp_bar[w]);
+}
+#define CB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emu_launch(kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
