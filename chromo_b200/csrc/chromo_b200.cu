@@ -15,6 +15,10 @@
 #include "field_kernels.cuh"
 #include "rng.cuh"
 
+static_assert(sizeof(chromo_move_state) == 88, "ABI: chromo_move_state");
+static_assert(sizeof(chromo_shape) == 112, "ABI: chromo_shape");
+static_assert(sizeof(chromo_step_report) == 48, "ABI: chromo_step_report");
+
 static thread_local std::string g_err;
 
 static int fail(int code, const char *fmt, ...) {
@@ -221,6 +225,20 @@ extern "C" int chromo_ctx_sync(chromo_ctx *c) {
     if (!c) return fail(CHROMO_ERR_ARG, "null context");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+extern "C" int chromo_ctx_set_table_capacity(chromo_ctx *c, int64_t cap, int64_t *cap_out) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    if (cap == 0) {
+        choose_table(c);
+    } else {
+        if (cap < 128 || cap > 4096 || (cap & (cap - 1))) return fail(CHROMO_ERR_ARG, "capacity must be a power of two in [128, 4096]");
+        if (table_bytes((int)cap, c->d.ncol) + kWarpShBytes + 1024 > (c->smem_optin ? c->smem_optin : 227 * 1024))
+            return fail(CHROMO_ERR_ARG, "capacity does not fit in shared memory");
+        c->cap = (int)cap;
+        c->smem_bytes = table_bytes((int)cap, c->d.ncol);
+    }
+    if (cap_out) *cap_out = c->cap;
     return CHROMO_OK;
 }
 extern "C" void *chromo_ctx_stream(chromo_ctx *c) { return c ? (void *)c->stream : nullptr; }

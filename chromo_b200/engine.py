@@ -207,6 +207,12 @@ class Engine:
         check(self._L.chromo_mc_sim(self._h, int(num_mc_steps), mp, float(mu_adjust_factor),
                                     int(seed) & 0xFFFFFFFFFFFFFFFF, int(rng_mode), _lib.uptr(ns)))
 
+    def set_table_capacity(self, cap: int = 0) -> int:
+        """Slots of the per-replica shared-memory delta-density hash (0 = auto)."""
+        out = C.c_int64(0)
+        check(self._L.chromo_ctx_set_table_capacity(self._h, int(cap), C.byref(out)))
+        return int(out.value)
+
     def sync(self):
         check(self._L.chromo_ctx_sync(self._h))
 

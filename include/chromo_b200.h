@@ -112,6 +112,12 @@ int chromo_ctx_sync(chromo_ctx *ctx);
 void *chromo_ctx_stream(chromo_ctx *ctx);
 /* bytes of HBM held by the context */
 int64_t chromo_ctx_bytes(chromo_ctx *ctx);
+/* Tuning knob: slots (power of two, 128..4096) of the per-replica shared-memory
+ * delta-density hash used by the MC kernel; 0 = choose from the replica count so
+ * that all replicas are resident at once.  Moves that touch more voxels than fit
+ * are evaluated in several hash-partition passes (same result).  Returns the
+ * capacity in effect through *cap_out (may be NULL). */
+int chromo_ctx_set_table_capacity(chromo_ctx *ctx, int64_t cap, int64_t *cap_out);
 
 /* ---- parameters -------------------------------------------------------- */
 /* Reader-protein tables.

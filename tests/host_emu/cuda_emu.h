@@ -41,7 +41,7 @@ struct emu_dim3 {
     emu_dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 typedef emu_dim3 dim3;
-static thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+inline thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim; // one instance across TUs
 
 struct EmuBlock {
     pthread_barrier_t block_bar;
@@ -49,7 +49,7 @@ struct EmuBlock {
     std::vector<uint64_t> slots; // one per thread
     unsigned char *dyn = nullptr;
 };
-static thread_local EmuBlock *emu_blk = nullptr;
+inline thread_local EmuBlock *emu_blk = nullptr;
 
 static inline void emu_warp_wait() { pthread_barrier_wait(&emu_blk->warp_bar[threadIdx.x >> 5]); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_wait(); }

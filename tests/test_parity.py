@@ -1,0 +1,253 @@
+"""Parity of the CUDA path with the reference, through the C ABI.
+
+Every test runs twice: on the lockstep CPU emulation of the kernels ("emu",
+the not-gpu suite: checks the kernel logic in this container) and on the real
+sm_100a library ("cuda", marked gpu).  Golden vectors come from the reference's
+own Cython build (tests/golden/make_golden.py); the oracle is
+oracle/chromo_oracle.c.
+
+Bars (north_star): bin indices / touched-bin sets bit-exact; energies and dE
+within 1e-9 relative in fp64; with replayed RNG draws identical accept/reject
+sequences.  Trial coordinates are bit-exact under emulation (same libm) and
+within 1e-9 nm on the GPU (CUDA's sin/cos/acos/log10 differ from glibc's in the
+last ulp)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import close, close_dE, huge_scale, load_golden, split
+from gpu_common import engine_from_spec, moves_array
+
+STATIC = ["static_c1", "static_c2", "static_c3", "static_c4"]
+MOVES = ["moves_c1", "moves_c2", "moves_c3", "moves_c4"]
+MCSIM = ["mcsim_c1", "mcsim_c2", "mcsim_c3"]
+REPLAY, PHILOX = 1, 0
+
+
+@pytest.mark.parametrize("name", STATIC)
+def test_full_recompute_and_total_energies(backend, name):
+    """A8: update_all_densities, compute_E (field) and SSWLC.compute_E."""
+    spec, g = load_golden(name)
+    e = engine_from_spec(spec, R=3)
+    d = e.density()
+    for rep in range(3):
+        assert np.array_equal(d[rep] != 0, g["density"] != 0)  # occupied-bin set, bit-exact
+        assert np.allclose(d[rep], g["density"], rtol=1e-12, atol=0)
+    E, sq, dbl, ns = e.field_energy()
+    Ep = e.elastic_energy()
+    for rep in range(3):
+        assert close(E[rep], float(g["E_field"]))
+        assert close(Ep[rep], float(g["E_poly"]))
+    vol_bin = float(g["vol_bin"])
+    assert np.allclose(d[..., 0].sum(axis=1) * vol_bin, spec["N"], rtol=1e-12)  # mass conservation
+    e.close()
+
+
+@pytest.mark.parametrize("name", MOVES)
+def test_single_move_chain(backend, name):
+    """A1-A7, A9-A11: a chain of mc_steps replaying the reference's RNG draws:
+    proposal indices, trial rows, elastic dE, field dE, touched bins,
+    density_trial rows; accept/reject forced to the golden decision."""
+    exact = backend == "emu"
+    spec, g = load_golden(name)
+    e = engine_from_spec(spec, R=2)
+    seed = int(g["seed"])
+    e.srand(seed)
+    e.numpy_seed(seed)
+    inds_l = split(g["inds"], g["n"])
+    touched_l = split(g["touched"], g["n_touched"])
+    dtrial_l = split(g["dtrial"], g["n_touched"])
+    rows_l = split(g["trial_rows"], g["n"])
+    vol_bin = spec["field"]["x_width"] ** 3 / spec["field"]["nx"] ** 3
+    bead_vol = (4 / 3) * np.pi * spec["bead_rad"] ** 3
+    for it in range(len(g["move"])):
+        m = int(g["move"][it])
+        dens = e.density(1, 1)[0] if (m != 3 and abs(float(g["dE_field"][it])) > 1e50) else None
+        out = e.mc_step(1, m, float(g["amp_move"][it]), int(g["amp_bead"][it]), 1.0, REPLAY, 0,
+                        int(g["accept"][it]))
+        assert np.array_equal(out["inds"], inds_l[it]), (it, m)
+        if exact:
+            assert np.array_equal(out["rows"], rows_l[it]), (it, m)
+        else:
+            assert np.allclose(out["rows"], rows_l[it], rtol=0, atol=1e-9), (it, m)
+        assert close(out["dE_poly"], float(g["dE_poly"][it]), 1e-9, 1e-9), (it, m)
+        if m != 3:
+            order = np.argsort(out["touched"])
+            assert np.array_equal(out["touched"][order], touched_l[it]), (it, m)  # bit-exact set
+            assert np.allclose(out["dtrial"][order], dtrial_l[it], rtol=1e-9, atol=1e-9 / vol_bin), (it, m)
+            sc = 0.0
+            if dens is not None:
+                sc = huge_scale(dens, _scatter(dens.shape, touched_l[it], dtrial_l[it]), touched_l[it],
+                                bead_vol, spec["field"]["vf_limit"])
+            assert close_dE(out["dE_field"], float(g["dE_field"][it]), sc), (it, m)
+        assert out["accepted"] == bool(g["accept"][it])
+    r, t3, t2, st = e.download()
+    tol = 0 if exact else 1e-8
+    assert np.allclose(r[1], g["final_r"], rtol=0, atol=tol)
+    assert np.allclose(t3[1], g["final_t3"], rtol=0, atol=tol)
+    assert np.allclose(t2[1], g["final_t2"], rtol=0, atol=tol)
+    assert np.array_equal(st[1], g["final_states"])
+    assert np.allclose(e.density(1, 1)[0], g["final_density"], rtol=1e-9, atol=1e-9 / vol_bin)
+    # replica 0 was never stepped
+    assert np.array_equal(r[0], spec["r"])
+    e.close()
+
+
+def _scatter(shape, touched, rows):
+    a = np.zeros(shape)
+    a[touched] = rows
+    return a
+
+
+@pytest.mark.parametrize("name", MCSIM)
+def test_mc_sim_replay(backend, name):
+    """A12 + the whole loop: a full mc_sim under the reference's RNG streams
+    reproduces the reference's accept/reject sequence, controller state and
+    final configuration."""
+    exact = backend == "emu"
+    spec, g = load_golden(name)
+    R = 2
+    e = engine_from_spec(spec, R=R)
+    mv = moves_array(spec, R, tuple(int(x) for x in g["per_cycle"]))
+    e.srand(int(g["srand_seed"]))
+    e.mc_sim(int(g["steps"]), mv, float(g["mu_adjust"]), 0, REPLAY, numpy_seeds=int(g["np_seed"]))
+    r, t3, t2, st = e.download()
+    for rep in range(R):
+        assert list(mv["num_attempt"][rep]) == list(g["num_attempt"])
+        assert list(mv["num_success"][rep]) == list(g["num_success"])  # same accept/reject sequence
+        assert list(mv["amp_bead"][rep]) == list(g["amp_bead"])
+        assert np.array_equal(mv["amp_move"][rep], g["amp_move"])
+        assert np.array_equal(mv["acceptance_rate"][rep], g["acceptance_rate"])
+        tol = 0 if exact else 1e-7
+        assert np.allclose(r[rep], g["final_r"], rtol=0, atol=tol)
+        assert np.allclose(t3[rep], g["final_t3"], rtol=0, atol=tol)
+        assert np.array_equal(st[rep], g["final_states"])
+    assert e.last_attempts() == R * int(np.sum(g["num_attempt"]))
+    vol_bin = spec["field"]["x_width"] ** 3 / spec["field"]["nx"] ** 3
+    assert np.allclose(e.density()[0], g["final_density"], rtol=1e-9, atol=1e-9 / vol_bin)
+    E, _, _, _ = e.field_energy()
+    assert close(E[0], float(g["E_field"]), 1e-9 if exact else 1e-7)
+    assert close(e.elastic_energy()[1], float(g["E_poly"]), 1e-9 if exact else 1e-7)
+    e.close()
+
+
+def test_large_moves_take_partition_passes(backend, oracle_mod):
+    """Moves whose touched-voxel set overflows the shared-memory table are
+    evaluated in hash-partition passes; results must not change."""
+    O = oracle_mod
+    spec = O.make_spec(N=300, nb=2, seed=5, grid=24, cross_talk=-0.7)
+    e = engine_from_spec(spec, R=1)
+    assert e.set_table_capacity(128) == 128
+    o = O.OracleSim(spec)
+    e.srand(3), o.srand(3), e.numpy_seed(3), o.np_seed(3)
+    mvs = O.make_moves(spec["N"], 16.5)
+    rng = np.random.default_rng(0)
+    maxp = 0
+    for it in range(40):
+        m = int(rng.integers(0, 5))
+        amp_bead, amp_move = int(rng.integers(40, 150)), 0.3 * (1 + m)
+        inds = o.propose(m, amp_move, amp_bead)
+        dEp = o.poly_dE(m, inds)
+        dEf, touched = (0.0, np.zeros(0, dtype=np.int64)) if m == 3 else o.field_dE(inds, m == 4)
+        with np.errstate(over="ignore"):
+            acc = int(rng.uniform() < np.exp(-(dEp + dEf)))
+        out = e.mc_step(0, m, amp_move, amp_bead, 1.0, REPLAY, 0, acc)
+        maxp = max(maxp, out["passes"])
+        assert np.array_equal(out["inds"], inds)
+        assert close(out["dE_poly"], dEp, 1e-9, 1e-9)
+        if m != 3:
+            assert np.array_equal(np.sort(out["touched"]), np.sort(touched))
+            a = out["dtrial"][np.argsort(out["touched"])]
+            b = o.density_trial[np.sort(touched)]
+            assert np.allclose(a, b, rtol=1e-9, atol=1e-9 / o.s.vol_bin)
+            assert close_dE(out["dE_field"], dEf)
+        ip = inds.ctypes.data_as(O._pl)
+        if acc:
+            O.lib().oc_accept(C.byref(o.s), C.byref(mvs[m]), m, ip, len(inds))
+            if m != 3:
+                o.commit_field()
+        else:
+            O.lib().oc_reject(C.byref(o.s), C.byref(mvs[m]), m, ip, len(inds))
+    assert maxp >= 4
+    r, t3, t2, st = e.download()
+    assert np.allclose(r[0], o.r, rtol=0, atol=1e-8) and np.array_equal(st[0], o.states)
+    assert np.allclose(e.density()[0], o.density, rtol=1e-9, atol=1e-9 / o.s.vol_bin)
+    e.close()
+
+
+def test_binning_edge_cases(backend, oracle_mod):
+    """Beads exactly on voxel faces, on the box faces, several box widths away
+    and a hair below zero (Python-modulo result == W): bin sets bit-exact."""
+    O = oracle_mod
+    spec = O.make_spec(N=64, nb=1, seed=9, confine="", grid=6, random_states=True)
+    W = spec["field"]["x_width"]
+    d = W / 6
+    pts = [0.0, -0.0, d, -d, d / 2, -d / 2, W / 2, -W / 2, W, -W, 3 * W + d / 2, -5 * W - d / 2,
+           np.nextafter(-W / 2, -np.inf), np.nextafter(-W / 2, np.inf), -W / 2 - 1e-17, 1e-300, -1e-300,
+           np.nextafter(W / 2, np.inf), np.nextafter(d / 2, 0), np.nextafter(d / 2, W)]
+    rng = np.random.default_rng(1)
+    r = rng.choice(pts, size=(64, 3))
+    spec["r"] = r
+    e = engine_from_spec(spec, R=1)
+    o = O.OracleSim(spec)
+    dd = e.density()[0]
+    assert np.array_equal(dd != 0, o.density != 0)
+    assert np.allclose(dd, o.density, rtol=1e-12, atol=0)
+    E, _, _, _ = e.field_energy()
+    assert close(E[0], o.field_E())
+    e.close()
+
+
+def test_philox_is_deterministic_and_consistent(backend, oracle_mod):
+    """Production RNG: same seed -> identical trajectory; different replicas
+    decorrelate; the incrementally updated density equals a full recompute;
+    mass is conserved; states stay within [0, sites]."""
+    O = oracle_mod
+    spec = O.make_spec(N=150, nb=2, seed=12, cross_talk=-0.5, random_states=False)
+    R = 3
+    runs = []
+    for _ in range(2):
+        e = engine_from_spec(spec, R=R)
+        mv = moves_array(spec, R)
+        e.mc_sim(4, mv, 1.0, 77, PHILOX)
+        r, t3, t2, st = e.download()
+        dens = e.density()
+        runs.append((r, st, dens, mv.copy()))
+        if _ == 0:
+            e.field_recompute(clamp=False)
+            assert np.allclose(e.density(), dens, rtol=1e-9, atol=1e-12 * dens.max())
+            o = O.OracleSim(spec)
+            assert np.allclose(dens[..., 0].sum(axis=1) * o.s.vol_bin, spec["N"], rtol=1e-9)
+            assert st.min() >= 0 and st.max() <= 2
+            assert np.all(np.linalg.norm(r, axis=2) <= spec["field"]["confine_length"] + 1e-9)
+            n3 = np.linalg.norm(t3, axis=2)
+            assert np.allclose(n3, 1.0, atol=1e-9)
+        e.close()
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    # densities are accumulated with atomics: equal up to summation order
+    assert np.allclose(runs[0][2], runs[1][2], rtol=1e-12, atol=1e-15 * runs[0][2].max())
+    assert not np.array_equal(runs[0][0][0], runs[0][0][1])
+    acc = runs[0][3]["num_success"].sum() / runs[0][3]["num_attempt"].sum()
+    assert 0.2 < acc < 0.95
+
+
+def test_error_behaviour(backend, oracle_mod):
+    """Argument checks mirror the reference's exceptions."""
+    from chromo_b200 import _lib
+    from chromo_b200.engine import Engine
+    O = oracle_mod
+    spec = O.make_spec(N=50, nb=1, seed=2)
+    e = engine_from_spec(spec, R=1)
+    mv = moves_array(spec, 1)
+    mv["amp_bead"][0, 0] = 51  # bead_selection.pyx:85-88: window larger than the chain
+    with pytest.raises(_lib.ChromoError, match="window size"):
+        e.mc_sim(1, mv, 1.0, 0, PHILOX)
+    with pytest.raises(_lib.ChromoError):
+        e.mc_step(5, 0, 0.1, 3)
+    with pytest.raises(ValueError, match="Confinement type"):
+        Engine(1, 10, 1, grid=dict(spec["field"], confine_type="Ellipsoidal"), bead_vol=1.0)
+    e2 = Engine(1, 10, 1, grid=None, bead_vol=1.0)
+    with pytest.raises(_lib.ChromoError, match="set_binders"):
+        e2.mc_sim(1, None, 1.0, 0, PHILOX)
+    e.close(), e2.close()
