@@ -66,7 +66,8 @@ def golden_moves(name, spec, nmoves, seed):
     inds_all, touched_all, dtrial_all, trial_rows = [], [], [], []
     for it in range(nmoves):
         m = int(rng.integers(0, 5))
-        amp_move = float(cs[m].move.amp_move * rng.uniform(0.5, 3))
+        # bounded amplitudes: 0.5x .. 3x the controller's lower bound
+        amp_move = float(mb.bounds[O.MOVE_NAMES[m]][0] * rng.uniform(0.5, 3))
         amp_bead = int(rng.integers(1, 40))
         cs[m].move.amp_move, cs[m].move.amp_bead = amp_move, amp_bead
         inds = np.asarray(sh.propose(cs[m].move, poly)).copy()
