@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- MC move attempts/s of the hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): chromatin, 10,000 beads
+per replica, HP1 on synthetic H3K9me3 marks, chi = 1, mu = -1.2, spherical
+confinement, 21^3 voxel grid, canonical 161-attempt sweep (30 crank-shaft, 1
+end-pivot, 60 slide, 60 tangent-rotation, 10 binding) with SimpleControl, and
+1,024 replicas PER GPU (weak scaling: replicas shard across ranks, no data-path
+collective).  One bench "step" = one `mc_sim` call of --sweeps MC sweeps over
+every replica = R * sweeps * 161 move attempts.
+
+value : attempts/s with the state resident in HBM (CUDA events on the kernel's
+        stream around K back-to-back mc_sim launches, max over ranks).
+e2e   : the same metric through the host-facing call (ReplicaEnsemble.mc_sim with
+        sync_host=True): per step the r/t3/t2/states arrays go pinned-host ->
+        device, the kernel runs, and they come back -- like handing the
+        reference its numpy arrays.
+roofline : dominant kernel = mc_sim_kernel; achieved = algorithmic bytes
+        (counted in-kernel with SURVEY.md 8d's per-attempt formula) / kernel time.
+cpu_baseline : the reference's own Cython mc_sim (oracle/_ref, kind "reference";
+        or the C port of it when that build is absent), one process per host
+        core, each an independent replica of the same config, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ATTEMPTS_PER_SWEEP = 161
+METRIC = "MC move attempts/sec (field+elastic dE)"
+UNIT = "attempts/s"
+
+
+# ------------------------------------------------------------------ workload
+def workload_params(N: int):
+    """Geometry of SURVEY.md 8(d): bead density of the 393,216-bead / 900 nm
+    nucleus, voxel ~28.6 nm (one_mark_coarse.py:79,93,117-120)."""
+    dens = 393216 / (4.0 / 3.0 * math.pi * 900.0 ** 3)
+    Rc = (N / dens / (4.0 * math.pi / 3.0)) ** (1.0 / 3.0)
+    n_acc = max(int(round(63 * Rc / 900.0)), 2)
+    nx = n_acc + 2
+    W = 2 * Rc * (1 + 2.0 / n_acc)
+    return Rc, nx, W
+
+
+HP1 = dict(name="HP1", sites_per_bead=2, bind_energy_mod=-0.01, bind_energy_no_mod=1.52,
+           interaction_energy=-4.0, chemical_potential=-1.2, interaction_radius=3.0, cross_talk={"PRC1": 0.0})
+
+
+def make_inputs(R: int, N: int, seed: int, pinned: bool):
+    """Synthetic replicas: confined Gaussian-direction walks, central-difference
+    tangents, blocky 0/1/2 marks, all binding states 0."""
+    import numpy as np
+    from chromo_b200.util import poly_paths as paths
+    rng = np.random.default_rng(seed)
+    Rc, nx, W = workload_params(N)
+    r = paths.confined_gaussian_walk(N, np.full(N - 1, 16.5), "Spherical", Rc, rng, replicas=R)
+    t3, t2 = paths.estimate_tangents_from_coordinates(r)
+    mods = paths.synthetic_marks(N, 1, rng, replicas=R)
+    states = np.zeros((R, N, 1), dtype=np.int64)
+    if pinned:
+        import torch
+
+        def pin(a):
+            t = torch.empty(a.shape, dtype=torch.float64 if a.dtype == np.float64 else torch.int64, pin_memory=True)
+            v = t.numpy()
+            v[...] = a
+            return v, t
+        keep = []
+        out = []
+        for a in (r, t3, t2, states, mods):
+            v, t = pin(np.ascontiguousarray(a))
+            keep.append(t)
+            out.append(v)
+        r, t3, t2, states, mods = out
+        make_inputs._keep = keep
+    grid = dict(x_width=W, nx=nx, y_width=W, ny=nx, z_width=W, nz=nx, confine_type="Spherical",
+                confine_length=Rc, vf_limit=0.5)
+    return r, t3, t2, states, mods, grid
+
+
+def bond_params(N: int, spacing=16.5, lp=53.0):
+    """SSWLC._find_parameters (polymers.pyx:1545-1601) for uniform spacing."""
+    import numpy as np
+    from chromo_b200.util import dss_params as tab
+    d = spacing / lp
+    vals = dict(eps_bend=np.interp(d, tab[:, 0], tab[:, 1]) / d,
+                gamma=np.interp(d, tab[:, 0], tab[:, 2]) * d * lp,
+                eps_par=np.interp(d, tab[:, 0], tab[:, 3]) / (d * lp ** 2),
+                eps_perp=np.interp(d, tab[:, 0], tab[:, 4]) / (d * lp ** 2),
+                eta=np.interp(d, tab[:, 0], tab[:, 5]) / lp)
+    return {k: np.full(N - 1, v) for k, v in vals.items()}
+
+
+# ------------------------------------------------------------- clock sampling
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------- CPU baseline
+def _ref_worker(args):
+    """One host core: the reference's Cython mc_sim on one replica of the workload."""
+    rank, N, warm, sweeps, kind = args
+    import numpy as np
+    sys.path.insert(0, str(ROOT / "oracle"))
+    sys.path.insert(0, str(ROOT))
+    r, t3, t2, states, mods, grid = make_inputs(1, N, 1000 + rank, pinned=False)
+    spec = dict(N=N, nb=1, r=r[0], t3=t3[0], t2=t2[0], states=states[0], mods=mods[0],
+                bead_length=np.full(N - 1, 16.5), lp=53.0, bead_rad=5.0, binders=[dict(HP1)], max_binders=-1,
+                field=dict(grid, chi=1.0))
+    import oracle as O
+    if kind == "reference":
+        poly, df, field, M = O.ref_objects(spec)
+        ctrl, mc, mcs, sh = M["mc_controller"], M["mc"], M["mc_sim"], M["shim"]
+        bb, mb = mc.get_amplitude_bounds([poly])
+        cs = ctrl.all_moves("/tmp/chromo_bench", bb.bounds, mb.bounds, ctrl.SimpleControl)
+        sh.c_srand(rank + 1)
+        with np.errstate(over="ignore"):
+            mcs.mc_sim([poly], df, warm, cs, field, 1.0, rank)
+            t0 = time.perf_counter()
+            mcs.mc_sim([poly], df, sweeps, cs, field, 1.0, rank + 7)
+            dt = time.perf_counter() - t0
+    else:
+        o = O.OracleSim(spec, srand_seed=rank + 1)
+        mv = O.make_moves(N, 16.5)
+        o.mc_sim(mv, warm, rank)
+        t0 = time.perf_counter()
+        o.mc_sim(mv, sweeps, rank + 7)
+        dt = time.perf_counter() - t0
+    return sweeps * ATTEMPTS_PER_SWEEP, dt
+
+
+def cpu_reference_sample(N: int, sweeps: int, warm: int, cores: int | None = None):
+    """Σ attempts over processes / max wall time, one process per host core."""
+    import multiprocessing as mp
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle as O
+    kind = "reference" if O.ref_available() else "port"
+    if kind == "port":
+        O.build_lib()
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_ref_worker, [(i, N, warm, sweeps, kind) for i in range(cores)], chunksize=1)
+    attempts = sum(a for a, _ in res)
+    tmax = max(t for _, t in res)
+    return dict(value=attempts / tmax, unit=UNIT, cores=cores, kind=kind,
+                sample=f"{cores} processes x {sweeps} MC sweeps ({sweeps * ATTEMPTS_PER_SWEEP} attempts each) of one "
+                       f"N={N} HP1 replica after {warm} warm-up sweeps; wall time of mc_sim only",
+                single_core=max(a / t for a, t in res)), tmax
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N = args.beads
+    vals, times = [], []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb, tmax = cpu_reference_sample(N, args.ref_sweeps, 2)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+            times.append(tmax)
+    v = sum(vals) / len(vals)
+    cb["value"] = v
+    line = dict(metric=METRIC, value=v, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * sum(times) / len(times), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=workload_config(args, 0), cpu_baseline=cb,
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def workload_config(args, cap):
+    Rc, nx, W = workload_params(args.beads)
+    return dict(workload=f"C2: chromatin {args.beads} beads, HP1 on H3K9me3 (synthetic marks), chi=1, mu=-1.2, "
+                         f"{args.replicas} replicas per GPU, {nx}^3 voxels, spherical confinement R={Rc:.1f} nm",
+                replicas_per_gpu=args.replicas, beads=args.beads, grid=nx, sweeps_per_step=args.sweeps,
+                attempts_per_sweep=ATTEMPTS_PER_SWEEP, rng="philox4x32-10", table_slots=cap,
+                l2="working set (state 737 MB + field 152 MB per GPU at C2) exceeds the 126 MB L2; no flush needed",
+                parallelism=f"replica-sharded x{args.gpus}")
+
+
+# --------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    from chromo_b200.ensemble import ReplicaEnsemble, default_moves
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: chromo_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    R, N, S, K, Wm = args.replicas, args.beads, args.sweeps, args.steps, max(args.warmup, 3)
+
+    r, t3, t2, states, mods, grid = make_inputs(R, N, 1234 + rank, pinned=True)
+    ens = ReplicaEnsemble(r, t3, t2, states, mods, binders=[dict(HP1)], bond_params=bond_params(N), grid=grid,
+                          bead_vol=(4 / 3) * math.pi * 5.0 ** 3, chi=1.0, mu=[-1.2],
+                          moves=default_moves(R, N, 16.5), device=local)
+    eng = ens.engine
+    cap = eng.set_table_capacity(args.table_slots)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=local)
+
+    def barrier():
+        torch.cuda.synchronize()
+        eng.sync()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput --------------------------------------
+    for w in range(Wm):
+        ens.mc_sim(S, 1.0, 100 + w, sync_host=False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ev[0].record(stream)
+    for k in range(K):
+        ens.mc_sim(S, 1.0, 1000 + k, sync_host=False)
+        ev[k + 1].record(stream)
+    eng.sync()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev[0].elapsed_time(ev[K])
+    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
+    attempts_last = eng.last_attempts()
+    algo_bytes_last = eng.last_algo_bytes()
+    ens.sync()
+    acc = ens.acceptance()
+    barrier()
+
+    # ---- end to end through the host-facing call --------------------------
+    h2d = 3 * R * N * 24 + 2 * R * N * 1 * 8
+    d2h = 3 * R * N * 24 + R * N * 1 * 8
+    Ke = max(1, min(K, args.e2e_steps))
+    ens.mc_sim(S, 1.0, 5000, sync_host=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for k in range(Ke):
+        ens.mc_sim(S, 1.0, 6000 + k, sync_host=True)
+    e1.record(stream)
+    eng.sync()
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+    barrier()
+
+    # ---- reduce over ranks --------------------------------------------------
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    attempts_step = R * S * ATTEMPTS_PER_SWEEP * world
+    value = attempts_step * K / (ms_total * 1e-3)
+    e2e = attempts_step * Ke / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks, peak_src = 6650.0, "fallback"
+        try:
+            mp = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+            peaks, peak_src = float(mp["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        achieved = algo_bytes_last / (kernel_ms[-1] * 1e-3) / 1e9
+        traffic = None
+        try:
+            tr = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+            traffic = tr.get("mc_sim_kernel", {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=Wm,
+            ms_per_step=ms_total / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+            data="synthetic", config=workload_config(args, cap),
+            e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=Ke),
+            gpu_launches=K + 4 * Ke,
+            clocks=clocks,
+            roofline=dict(bound="hbm", achieved=achieved, peak=peaks, unit="GB/s", frac=achieved / peaks,
+                          traffic=traffic, peak_source=peak_src, kernel="mc_sim_kernel<PhiloxRng,1>",
+                          kernel_ms=k_ms, algorithmic_bytes_per_launch=algo_bytes_last,
+                          bytes_per_attempt=algo_bytes_last / max(1, attempts_last),
+                          note="latency-bound (serial moves per replica, one warp each); see DESIGN.md"),
+            acceptance={k: round(float(v), 4) for k, v in acc.items()},
+            hbm_bytes=eng.bytes(),
+        )
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cb, _ = cpu_reference_sample(N, args.ref_sweeps, 2)
+                line["cpu_baseline"] = cb
+            except Exception as e:  # never lose the GPU number to a baseline hiccup
+                line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=str(e)[:200])
+        print(json.dumps(line))
+    ens.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--replicas", type=int, default=1024, help="replicas per GPU")
+    ap.add_argument("--beads", type=int, default=10000)
+    ap.add_argument("--sweeps", type=int, default=10, help="MC sweeps (161 attempts each) per bench step")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-sweeps", type=int, default=100, help="MC sweeps per process in the CPU reference sample")
+    ap.add_argument("--table-slots", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

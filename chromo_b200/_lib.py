@@ -64,7 +64,7 @@ SYMBOLS = [
     "chromo_upload_state", "chromo_download_state", "chromo_download_density",
     "chromo_upload_density", "chromo_field_recompute", "chromo_field_energy",
     "chromo_elastic_energy", "chromo_chi_observable", "chromo_srand", "chromo_numpy_seed",
-    "chromo_mc_sim", "chromo_get_moves", "chromo_set_moves", "chromo_last_attempts",
+    "chromo_mc_sim", "chromo_get_moves", "chromo_set_moves", "chromo_last_attempts", "chromo_last_algo_bytes",
     "chromo_mc_step",
 ]
 
@@ -98,6 +98,8 @@ def _declare(L):
     L.chromo_set_moves.argtypes = [_vp, _vp]
     L.chromo_last_attempts.argtypes = [_vp]
     L.chromo_last_attempts.restype = C.c_int64
+    L.chromo_last_algo_bytes.argtypes = [_vp]
+    L.chromo_last_algo_bytes.restype = C.c_int64
     L.chromo_mc_step.argtypes = [_vp, C.c_int64, C.c_int, C.c_double, C.c_int64, C.c_double, C.c_int,
                                  C.c_uint64, C.c_int, C.POINTER(StepReport), _pl, C.c_int64, _pd,
                                  C.c_int64, _pl, _pd, C.c_int64]

@@ -170,6 +170,7 @@ extern "C" int chromo_ctx_create(chromo_ctx **out, int device, const chromo_shap
     if ((rc = dev_alloc(c, &d.sel_bits, (size_t)d.R * ((d.N + 31) / 32)))) return rc;
     if ((rc = dev_alloc(c, &d.st_new, RN))) return rc;
     if ((rc = dev_alloc(c, &d.attempts, (size_t)d.R))) return rc;
+    if ((rc = dev_alloc(c, &d.algo_bytes, (size_t)d.R))) return rc;
     if ((rc = dev_alloc(c, &c->d_chi, (size_t)d.R))) return rc;
     if ((rc = dev_alloc(c, &c->d_mu, (size_t)d.R * d.nb))) return rc;
     d.chi = c->d_chi;
@@ -614,6 +615,18 @@ extern "C" int64_t chromo_last_attempts(chromo_ctx *c) {
     cudaSetDevice(c->device);
     std::vector<unsigned long long> a(c->d.R);
     if (cudaMemcpyAsync(a.data(), c->d.attempts, a.size() * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+        return -1;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    int64_t t = 0;
+    for (auto v : a) t += (int64_t)v;
+    return t;
+}
+
+extern "C" int64_t chromo_last_algo_bytes(chromo_ctx *c) {
+    if (!c) return -1;
+    cudaSetDevice(c->device);
+    std::vector<unsigned long long> a(c->d.R);
+    if (cudaMemcpyAsync(a.data(), c->d.algo_bytes, a.size() * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
         return -1;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
     int64_t t = 0;

@@ -37,6 +37,8 @@ struct WarpSh {
     int ind0, indf, n, binder;
     int count;                    // occupied hash slots
     int overflow;
+    int last_U;                   // touched voxels of the last field dE (all passes)
+    unsigned long long algo_bytes; // SURVEY 8(d) algorithmic bytes, accumulated by lane 0
     uint32_t draws[64];           // per-bead axis draws of tangent rotation
     signed char newst[256];       // new binding states (small path)
 };
@@ -372,6 +374,7 @@ struct McWarp {
                     break;
                 }
                 table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross);
+                if (lane == 0) S.last_U = (p == 0 ? 0 : S.last_U) + S.count;
                 if (DEBUG) table_debug_dump(C, H, S, lane, dbg);
                 if (P > 1) table_clear(H, S, NCOL, lane);
             }
@@ -401,6 +404,32 @@ struct McWarp {
             }
         bb += warp_sum(F.chi);
         dE += bb;
+        return dE;
+    }
+
+    // NullField.compute_dE fields.pyx:300-318: only the confinement acts
+    __device__ double confinement_dE_segment(int kind, int ind0, int n) {
+        const double *Rr = R_();
+        int out_t = 0, out_c = 0;
+        for (int base = 0; base < n; base += 32) {
+            int i = base + lane;
+            if (i < n) {
+                double x[3], y[3];
+                load3(Rr + 3 * (long long)(ind0 + i), x);
+                if (kind == 0) apply_affine(S.M, x, y);
+                else
+                    for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
+                if (C.confine_type == CHROMO_CONFINE_SPHERICAL) {
+                    out_t += (sqrt(dot3(y, y)) > C.confine_length);
+                    out_c += (sqrt(dot3(x, x)) > C.confine_length);
+                } else {
+                    for (int j = 0; j < 3; j++) out_t += (fabs(y[j]) > C.confine_length / 2);
+                }
+            }
+        }
+        int nt = warp_sum_int(out_t), nc = warp_sum_int(out_c);
+        double dE = (double)nt * CB_E_HUGE_FIELD;
+        dE -= (double)nc * CB_E_HUGE_FIELD;
         return dE;
     }
 
@@ -567,11 +596,12 @@ struct McWarp {
         double dE_field = 0.0;
         int passes = 1;
         if (C.field_active) dE_field = field_dE_segment(kind, ind0, n, 0, nullptr, passes);
+        else if (C.confine_type != CHROMO_CONFINE_NONE) dE_field = confinement_dE_segment(kind, ind0, n);
         if (DEBUG) debug_report_segment(kind, ind0, n, dE_poly, dE_field, passes);
 
         double dE = 0.0;
         dE += dE_poly;
-        if (C.field_active) dE += dE_field;
+        if (C.field_active || C.confine_type != CHROMO_CONFINE_NONE) dE += dE_field;
         bool acc = metropolis(dE);
         if (acc) { // MCAdapter.accept moves.pyx:190-226
             if (C.field_active) field_commit_segment(kind, ind0, n, 0, nullptr, passes);
@@ -598,6 +628,11 @@ struct McWarp {
             }
         }
         if (C.field_active) table_clear(H, S, NCOL, lane);
+        if (lane == 0) { // B = 72(n+2) + 72 n a + nb n + 8(nb+1) U (1+2a) + 80   
+            unsigned long long U = C.field_active ? (unsigned long long)S.last_U : 0ull;
+            S.algo_bytes += 72ull * (n + 2) + (acc ? 72ull * n : 0ull) + (unsigned long long)NB * n +
+                            8ull * NCOL * U * (acc ? 3ull : 1ull) + 80ull;
+        }
         track(mtype, acc);
     }
 
@@ -750,6 +785,11 @@ struct McWarp {
             }
         }
         if (C.field_active) table_clear(H, S, NCOL, lane);
+        if (lane == 0) { // binding: 24 n (positions) + nb n (1+a) + 8(nb+1) U (1+2a)
+            unsigned long long U = C.field_active ? (unsigned long long)S.last_U : 0ull;
+            S.algo_bytes += 24ull * n + (unsigned long long)NB * n * (acc ? 2ull : 1ull) +
+                            8ull * NCOL * U * (acc ? 3ull : 1ull);
+        }
         track(CHROMO_CHANGE_BINDING_STATE, acc);
     }
 
@@ -946,6 +986,8 @@ struct McWarp {
                 if (lane == 0) rng.restore(after);
             }
         }
+        if (lane == 0) // tangent rotation: B = 48 n + 72*2n + 48 n a   
+            S.algo_bytes += 48ull * k + 144ull * k + (acc ? 48ull * k : 0ull);
         track(CHROMO_TANGENT_ROTATION, acc);
     }
 
@@ -1043,6 +1085,10 @@ __global__ void __launch_bounds__(32, 8) mc_sim_kernel(DevCtx C, long long num_m
     HashTable H = carve_table(dyn, cap, C.ncol);
     table_reset_all(H, S, C.ncol, lane);
     if (lane < CHROMO_NUM_MOVES) S.mv[lane] = C.moves[(long long)rep * CHROMO_NUM_MOVES + lane];
+    if (lane == 0) {
+        S.algo_bytes = 0;
+        S.last_U = 0;
+    }
     Rng rng;
     rng_load<Rng>(rng, C, S, rep, lane, seed);
     __syncwarp();
@@ -1059,7 +1105,10 @@ __global__ void __launch_bounds__(32, 8) mc_sim_kernel(DevCtx C, long long num_m
     __syncwarp();
     long long a1 = 0;
     for (int m = 0; m < CHROMO_NUM_MOVES; m++) a1 += S.mv[m].num_attempt;
-    if (lane == 0) C.attempts[rep] = (unsigned long long)(a1 - a0);
+    if (lane == 0) {
+        C.attempts[rep] = (unsigned long long)(a1 - a0);
+        C.algo_bytes[rep] = S.algo_bytes;
+    }
     if (lane < CHROMO_NUM_MOVES) C.moves[(long long)rep * CHROMO_NUM_MOVES + lane] = S.mv[lane];
     rng_store<Rng>(rng, C, S, rep, lane);
 }
@@ -1085,6 +1134,8 @@ __global__ void __launch_bounds__(32) mc_step_kernel(DevCtx C, int rep, int mtyp
         dbg->dE_poly = dbg->dE_field = 0.0;
         dbg->accepted = 0;
         dbg->passes = 0;
+        S.algo_bytes = 0;
+        S.last_U = 0;
     }
     Rng rng;
     rng_load<Rng>(rng, C, S, rep, lane, seed);

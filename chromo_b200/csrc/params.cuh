@@ -46,6 +46,7 @@ struct DevCtx {
     uint32_t *sel_bits;              // [R][ceil(N/32)]
     signed char *st_new;             // [R][N]   binding large path
     unsigned long long *attempts;    // [R]
+    unsigned long long *algo_bytes;  // [R]   algorithmic bytes of the last mc_sim (SURVEY 8d formula)
 };
 
 #define CB_GLIBC_WORDS 36 // r[31], f, b (+pad)

@@ -219,6 +219,9 @@ class Engine:
     def last_attempts(self) -> int:
         return int(self._L.chromo_last_attempts(self._h))
 
+    def last_algo_bytes(self) -> int:
+        return int(self._L.chromo_last_algo_bytes(self._h))
+
     def stream(self) -> int:
         return int(self._L.chromo_ctx_stream(self._h) or 0)
 

@@ -1,0 +1,178 @@
+"""ReplicaEnsemble: many independent replicas / parameter points of one problem
+shape, resident in the HBM of one B200 and advanced by ONE kernel launch per
+`mc_sim` call (one warp per replica).
+
+This is the batched form of `chromo_b200.mc.mc_sim`: the reference runs one
+simulation per process; chi / chemical-potential sweeps and
+replica-exchange ladders are many such simulations, which is exactly what a GPU
+wants.  Replicas shard across GPUs by `chromo_b200.parallel`.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import MOVE_DTYPE, MOVE_NAMES, NUM_MOVES, RNG_PHILOX, RNG_REPLAY
+from .engine import Engine
+
+
+def default_moves(n_replicas: int, num_beads: int, min_spacing: float, controller: int = 1,
+                  per_cycle: Sequence[int] = (30, 1, 60, 60, 10), move_on: Sequence[int] = (1, 1, 1, 1, 1)):
+    """[R,5] controller state as `all_moves(..., SimpleControl)` builds it from
+    `get_amplitude_bounds` (mc/__init__.py:295-332, mc_controller.py:216-266)."""
+    N = num_beads
+    bead = [(min(30, N), min(150, N)), (min(50, N / 4), min(150, int(N / 2))), (min(10, N), min(150, N)),
+            (1, N), (1, 1)]
+    move = [(0.1 * np.pi, 0.25 * np.pi), (0.2 * np.pi, 0.25 * np.pi), (0.2 * min_spacing, 0.3 * min_spacing),
+            (0.05 * np.pi, 0.2 * np.pi), (0, 0)]
+    a = np.zeros((n_replicas, NUM_MOVES), dtype=MOVE_DTYPE)
+    for i in range(NUM_MOVES):
+        a["amp_move"][:, i] = move[i][0]
+        a["move_amp_lo"][:, i], a["move_amp_hi"][:, i] = move[i]
+        a["bead_amp_lo"][:, i], a["bead_amp_hi"][:, i] = bead[i]
+        a["amp_bead"][:, i] = int(bead[i][0])
+        a["alpha"][:, i] = 2 / (20.0 + 1)
+        a["num_per_cycle"][:, i] = per_cycle[i]
+        a["move_on"][:, i] = move_on[i]
+        a["controller"][:, i] = controller
+    return a
+
+
+class ReplicaEnsemble:
+    """R replicas: positions / orientations / states / marks as [R,N,.] host
+    arrays, one grid description, per-replica chi and chemical potentials."""
+
+    def __init__(self, r, t3, t2, states, chemical_mods, *, binders: Sequence[dict], bond_params: dict,
+                 grid: Optional[dict], bead_vol: float, chi=1.0, mu=None, max_binders: int = -1,
+                 moves: Optional[np.ndarray] = None, min_spacing: Optional[float] = None,
+                 access_vol=None, device: int = 0, field_prefactors=None):
+        self.r = np.ascontiguousarray(r, dtype=np.float64)
+        self.R, self.N = self.r.shape[0], self.r.shape[1]
+        self.t3 = np.ascontiguousarray(t3, dtype=np.float64)
+        self.t2 = np.ascontiguousarray(t2, dtype=np.float64)
+        self.states = np.ascontiguousarray(states, dtype=np.int64).reshape(self.R, self.N, -1)
+        self.nb = self.states.shape[2]
+        self.chemical_mods = np.ascontiguousarray(chemical_mods, dtype=np.int64).reshape(self.R, self.N, self.nb)
+        self.binders = [dict(b) for b in binders]
+        self.grid = grid
+        self.engine = Engine(self.R, self.N, self.nb, grid=grid, bead_vol=bead_vol, max_binders=max_binders,
+                             device=device)
+        if field_prefactors is None:
+            field_prefactors = self.prefactors_from_binders(self.binders, grid)
+        self.engine.set_binders(self.binders, *field_prefactors)
+        self.engine.set_bond_params(bond_params["eps_bend"], bond_params["eps_par"], bond_params["eps_perp"],
+                                    bond_params["gamma"], bond_params["eta"])
+        if access_vol is not None:
+            self.engine.set_access_volumes(access_vol)
+        self.chi = np.ascontiguousarray(np.broadcast_to(np.asarray(chi, dtype=float), (self.R,)))
+        if mu is None:
+            mu = [b["chemical_potential"] for b in self.binders]
+        self.mu = np.ascontiguousarray(np.broadcast_to(np.asarray(mu, dtype=float), (self.R, self.nb)))
+        self.engine.set_replica_params(self.chi, self.mu)
+        if moves is None:
+            moves = default_moves(self.R, self.N, 16.5 if min_spacing is None else min_spacing)
+        self.moves = np.ascontiguousarray(moves, dtype=MOVE_DTYPE).reshape(self.R, NUM_MOVES)
+        self.engine.set_moves(self.moves)
+        self.push()
+        if grid is not None and grid.get("nx", 0):
+            self.engine.field_recompute(clamp=True)  # UniformDensityField.__init__ fields.pyx:532
+
+    @staticmethod
+    def prefactors_from_binders(binders, grid):
+        """init_field_energy_prefactors fields.pyx:687-712."""
+        nb = len(binders)
+        pref, e_intra, xpref = np.zeros(nb), np.zeros(nb), np.zeros((nb, nb))
+        if grid is None or not grid.get("nx", 0):
+            return pref, e_intra, xpref
+        vol_bin = grid["x_width"] * grid["y_width"] * grid["z_width"] / (grid["nx"] * grid["ny"] * grid["nz"])
+        for i, b in enumerate(binders):
+            v_int = (4.0 / 3.0) * np.pi * b["interaction_radius"] ** 3
+            pref[i] = 0.5 * b["interaction_energy"] * v_int * vol_bin
+            e_intra[i] = b["interaction_energy"] * (1 - v_int / vol_bin)
+            for j, nxt in enumerate(binders):
+                if nxt["name"] in b.get("cross_talk", {}):
+                    xpref[i, j] = b["cross_talk"][nxt["name"]] * v_int * vol_bin
+        return pref, e_intra, xpref
+
+    # ---- host <-> device -------------------------------------------------
+    def push(self):
+        """Upload the host arrays (user-visible state) to the device."""
+        self.engine.upload(self.r, self.t3, self.t2, self.states, self.chemical_mods)
+
+    def pull(self):
+        """Refresh the host arrays from the device."""
+        self.engine.download_into(self.r, self.t3, self.t2, self.states)
+
+    def set_params(self, chi=None, mu=None):
+        if chi is not None:
+            self.chi = np.ascontiguousarray(np.broadcast_to(np.asarray(chi, dtype=float), (self.R,)))
+        if mu is not None:
+            self.mu = np.ascontiguousarray(np.broadcast_to(np.asarray(mu, dtype=float), (self.R, self.nb)))
+        self.engine.set_replica_params(self.chi, self.mu)
+
+    # ---- the hot path -------------------------------------------------------
+    def mc_sim(self, num_mc_steps: int, mu_adjust_factor: float = 1.0, random_seed: int = 0,
+               rng: str = "philox", sync_host: bool = True, numpy_seeds=None):
+        """`mc_sim` (mc_sim.pyx:26-103) for every replica.  With sync_host the
+        call is host-in / host-out like the reference's; without it the state
+        stays in HBM and the call returns as soon as the kernel is queued."""
+        mode = {"philox": RNG_PHILOX, "replay": RNG_REPLAY}[rng]
+        if sync_host:
+            self.push()
+            self.engine.mc_sim(num_mc_steps, self.moves, mu_adjust_factor, random_seed, mode,
+                               numpy_seeds=(random_seed if numpy_seeds is None else numpy_seeds)
+                               if mode == RNG_REPLAY else None)
+            self.pull()
+        else:
+            self.engine.mc_sim(num_mc_steps, None, mu_adjust_factor, random_seed, mode,
+                               numpy_seeds=numpy_seeds if mode == RNG_REPLAY else None)
+
+    def sync(self):
+        self.engine.sync()
+        self.moves = self.engine.get_moves()
+
+    def density(self):
+        return self.engine.density()
+
+    def field_energy(self):
+        return self.engine.field_energy()[0]
+
+    def elastic_energy(self):
+        return self.engine.elastic_energy()
+
+    def acceptance(self):
+        m = self.moves
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return {n: m["num_success"][:, i].sum() / max(1, m["num_attempt"][:, i].sum())
+                    for i, n in enumerate(MOVE_NAMES)}
+
+    def close(self):
+        self.engine.close()
+
+    # ---- construction helpers ----------------------------------------------
+    @classmethod
+    def from_polymers(cls, polymers, fields, controllers=None, device: int = 0):
+        """Stack reference-style objects (one polymer + one field per replica)."""
+        from .fields import binder_dicts
+        from .mc.mc_sim import controllers_to_moves
+        p0, f0 = polymers[0], fields[0]
+        st = lambda name: np.stack([getattr(p, name) for p in polymers])
+        grid = f0._grid()
+        bd = binder_dicts(p0)
+        pre = f0._prefactors(p0.num_binders)
+        bond = {k: np.stack([getattr(p, k) for p in polymers]) for k in
+                ("eps_bend", "eps_par", "eps_perp", "gamma", "eta")}
+        if all(np.array_equal(bond["eps_bend"][0], b) for b in bond["eps_bend"]):
+            bond = {k: v[0] for k, v in bond.items()}
+        moves = None
+        if controllers is not None:
+            moves = np.stack([controllers_to_moves(c) for c in controllers])
+        mu = np.array([[b["chemical_potential"] for b in binder_dicts(p)] for p in polymers])
+        ens = cls(st("r"), st("t3"), st("t2"), st("states"), st("chemical_mods"), binders=bd, bond_params=bond,
+                  grid=grid, bead_vol=p0.beads[0].vol, chi=[getattr(f, "chi", 1.0) for f in fields], mu=mu,
+                  max_binders=p0.max_binders, moves=moves, min_spacing=float(np.min(p0.bead_length)),
+                  access_vol=None if getattr(f0, "assume_fully_accessible", 1) == 1 else f0.access_vols,
+                  device=device, field_prefactors=pre)
+        return ens

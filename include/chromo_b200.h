@@ -196,6 +196,11 @@ int chromo_get_moves(chromo_ctx *ctx, chromo_move_state *moves /* [R][5] */);
 int chromo_set_moves(chromo_ctx *ctx, const chromo_move_state *moves /* [R][5] */);
 /* attempts executed by the last chromo_mc_sim call, summed over replicas */
 int64_t chromo_last_attempts(chromo_ctx *ctx);
+/* algorithmic bytes those attempts needed (per attempt
+ * 72(n+2) + 72 n a + nb n + 8(nb+1) U (1+2a) + 80 for segment moves, n beads,
+ * U touched voxels, a = accepted), summed over replicas: the numerator of the
+ * roofline figure bench.py reports */
+int64_t chromo_last_algo_bytes(chromo_ctx *ctx);
 
 /* One mc_step (mc_sim.pyx:106-182) of ONE replica through the same device code
  * as chromo_mc_sim, with everything the reference exposes after a step
