@@ -336,7 +336,8 @@ def run_ours(args):
         traffic = None
         try:
             tr = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
-            traffic = tr.get("mc_sim_kernel", {}).get("dram_bytes_per_launch")
+            per_attempt = tr.get("mc_sim_kernel", {}).get("dram_bytes_per_attempt")
+            traffic = per_attempt * attempts_last if per_attempt else None  # ncu DRAM bytes, scaled to this launch
         except Exception:
             pass
         line = dict(
