@@ -3,6 +3,7 @@
 // built for generic x86-64 (no FMA contraction), and a contracted
 // `x/dx - ind` could flip the last ulp of a weight or a floor().
 #pragma once
+#include "launch.cuh"
 #include "params.cuh"
 
 // ---------------------------------------------------------------- binning
@@ -14,12 +15,26 @@
 // Bit-exact contract: `%` is Python-modulo on doubles (cdivision=False,
 // setup.py:89): fmod, then +W when the remainder is negative.  The weight uses
 // the UNPATCHED floor index even when it is -1 (fields.pyx:1451-1462).
+// exact fmod for w > 0: the remainder is exactly representable, so one
+// division, one trunc and one fma reproduce C's fmod bit for bit (a / w can only
+// round UP to the next integer, which shows as a remainder of the wrong sign).
+__device__ __forceinline__ double fmod_exact(double a, double w) {
+    double q = trunc(a / w);
+    double r = fma(-q, w, a);
+    if (a >= 0.0) {
+        if (r < 0.0) r += w;
+    } else if (r > 0.0) {
+        r -= w;
+    }
+    return r;
+}
+
 __device__ __forceinline__ void bin_axis(double x, double half_width, double width,
                                          double half_step, double d, int n, int &ind_lo,
                                          int &ind_hi, double &w_lo) {
     double a = x + half_width;
-    double m = fmod(a, width); // exact (fmod has no rounding error)
-    if (m != 0.0 && m < 0.0) m = m + width;
+    double m = fmod_exact(a, width);
+    if (m != 0.0 && m < 0.0) m = m + width; // Python modulo: result takes the divisor's sign
     double xs = m - half_step;
     double q = xs / d; // IEEE division
     double fl = floor(q);
@@ -27,6 +42,14 @@ __device__ __forceinline__ void bin_axis(double x, double half_width, double wid
     w_lo = 1.0 - (q - fl);
     ind_lo = (ind == -1) ? n - 1 : ind;
     ind_hi = (ind_lo + 1 >= n) ? ind_lo + 1 - n : ind_lo + 1;
+}
+
+// lower / upper voxel index and lower-voxel weight along each axis
+__device__ __forceinline__ void bin_axes(const DevCtx &C, const double p[3], int lo[3], int hi[3],
+                                         double wl[3]) {
+    bin_axis(p[0], C.half_width[0], C.width[0], C.half_step[0], C.dxyz[0], C.nx, lo[0], hi[0], wl[0]);
+    bin_axis(p[1], C.half_width[1], C.width[1], C.half_step[1], C.dxyz[1], C.ny, lo[1], hi[1], wl[1]);
+    bin_axis(p[2], C.half_width[2], C.width[2], C.half_step[2], C.dxyz[2], C.nz, lo[2], hi[2], wl[2]);
 }
 
 __device__ __forceinline__ void bin_point(const DevCtx &C, double x, double y, double z,
@@ -60,12 +83,21 @@ __device__ __forceinline__ void bin_point(const DevCtx &C, double x, double y, d
 }
 
 // ------------------------------------------------------------- transforms
+// libdevice's fp64 sincos / acos are ~100 instructions each when inlined; one
+// out-of-line copy keeps the kernel inside the instruction cache
+static __device__ CB_NOINLINE double2 sincos_ni(double x) {
+    double s, c;
+    sincos(x, &s, &c);
+    return make_double2(s, c);
+}
+static __device__ CB_NOINLINE double acos_ni(double x) { return acos(x); }
+
 // arbitrary_axis_rotation linalg.pyx:62-139.  M is 3x4 row-major (M[4*j+3] is
 // the translation column).
 __device__ __forceinline__ void rotation_matrix(const double ax[3], const double pt[3],
                                                 double ang, double M[12]) {
-    double sn, c;
-    sincos(ang, &sn, &c);
+    const double2 sc = sincos_ni(ang);
+    const double sn = sc.x, c = sc.y;
     double omc = 1.0 - c;
     M[0] = ax[0] * ax[0] + (ax[1] * ax[1] + ax[2] * ax[2]) * c;
     M[1] = ax[0] * ax[1] * omc - ax[2] * sn;
@@ -101,13 +133,11 @@ __device__ __forceinline__ void apply_affine(const double *M, const double v[3],
 // uniform_sample_unit_sphere linalg.pyx:23-59 from two rand() outputs
 __device__ __forceinline__ void sphere_from_draws(uint32_t d1, uint32_t d2, double v[3]) {
     double phi = (double)d1 / CB_RAND_MAX * (2.0 * 3.14159265358979323846);
-    double theta = acos(((double)d2 / CB_RAND_MAX) * 2.0 - 1.0);
-    double sp, cp, st, ct;
-    sincos(phi, &sp, &cp);
-    sincos(theta, &st, &ct);
-    v[0] = cp * st;
-    v[1] = sp * st;
-    v[2] = ct;
+    double theta = acos_ni(((double)d2 / CB_RAND_MAX) * 2.0 - 1.0);
+    const double2 p = sincos_ni(phi), t = sincos_ni(theta);
+    v[0] = p.y * t.x;
+    v[1] = p.x * t.x;
+    v[2] = t.y;
 }
 
 // ---------------------------------------------------------- SSWLC energy

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #define CB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define CB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define CB_NOINLINE __noinline__
 #endif
 #include "params.cuh"
 

@@ -2,7 +2,7 @@
 // field dE -> Metropolis -> commit, for one replica per warp.
 //
 // Why a warp per replica: moves inside a replica are strictly serial (each
-// reads the density the previous one wrote), a typical move touches 3-30 beads
+// reads the density the previous one wrote), a typical move touches 1-30 beads
 // (16 voxel contributions each), so the parallelism inside a move fits 32 lanes
 // and the parallelism across the GPU comes from replicas.  The replica's voxel
 // field stays in HBM/L2 (C2: 148 KB per replica, 1,024 replicas = 152 MB, most
@@ -19,6 +19,14 @@
 // Moves whose touched-voxel set does not fit the table are evaluated in P
 // hash-partition passes (voxels with bin % P == p per pass): the energy is a
 // sum over voxels, so the passes are independent.
+//
+// Work mapping inside a move (v1, after the first ncu profile: the kernel was
+// instruction-fetch bound at 2.8k warp-instructions per attempt and 5 active
+// lanes): the 16 voxel contributions of a bead are spread over up to 16 lanes
+// (G lanes per bead, G = 16/8/4/2/1 by segment length), the four bond energies
+// of an elastic dE are evaluated by four lanes at once, and every heavy routine
+// has ONE call site or is CB_NOINLINE, which keeps the SASS small enough for
+// the instruction cache.
 #pragma once
 #include "geometry.cuh"
 #include "launch.cuh"
@@ -34,14 +42,18 @@ struct WarpSh {
     uint32_t grs[CB_GLIBC_WORDS]; // ReplayRng state
     uint32_t rng_save[CB_GLIBC_WORDS];
     double M[12];                 // affine map of the current move
+    double tan_new[32 * 6];       // tangent rotation: new t3 | t2 of the selected beads
+    int tinds[32];                // tangent rotation: selected beads (small path)
     int ind0, indf, n, binder;
     int count;                    // occupied hash slots
     int overflow;
     int last_U;                   // touched voxels of the last field dE (all passes)
+    int passes;
     unsigned long long algo_bytes; // SURVEY 8(d) algorithmic bytes, accumulated by lane 0
     uint32_t draws[64];           // per-bead axis draws of tangent rotation
     signed char newst[256];       // new binding states (small path)
 };
+static_assert(sizeof(WarpSh) <= 4096, "update kWarpShBytes in chromo_b200.cu");
 
 struct HashTable {
     int *keys;    // [cap]
@@ -72,7 +84,7 @@ __device__ __forceinline__ void table_reset_all(HashTable &H, WarpSh &S, int nco
     __syncwarp();
 }
 // clear only what the last move used
-__device__ __forceinline__ void table_clear(HashTable &H, WarpSh &S, int ncol, int lane) {
+static __device__ CB_NOINLINE void table_clear(HashTable &H, WarpSh &S, int ncol, int lane) {
     __syncwarp();
     int cnt = min(S.count, H.cap);
     for (int j = lane; j < cnt; j += 32) {
@@ -114,28 +126,87 @@ __device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin) {
     return -1;
 }
 
-// add one bead's 8-voxel stencil: sign * w[l] / V_access * {1, state_1..state_nb}
-// (fields.pyx:1476-1520; contributions with |x| <= 1e-18 are dropped, quirk 3)
+// ---------------------------------------------------------- scatter of a move
+// One pass of get_change_in_density (fields.pyx:1430-1520) for the segment
+// [ind0, ind0+n): every bead contributes -w/V*{1,state} at its current position
+// and +w/V*{1,state'} at its trial position to the 8 voxels around each.
+//   kind 0: trial = M r (crank-shaft, end-pivot)   kind 1: trial = r + t (slide)
+//   kind 2: trial position = current position, state' = newst (binding)
+// G lanes share a bead, each handling 16/G consecutive contributions
+// c = 8*k + l  (k: 0 current / 1 trial; l: voxel corner, bit0 x, bit1 y, bit2 z).
+// Returns the confinement counters of get_confinement_dE (fields.pyx:160-193):
+// x = # trial positions outside, y = # current positions outside (this lane's).
 template <int NB>
-__device__ __forceinline__ void table_scatter(const DevCtx &C, HashTable &H, WarpSh &S,
-                                              const int idx[8], const double w[8], double sign,
-                                              const signed char st[NB], int P, int p) {
+__device__ CB_NOINLINE int2 scatter_pass(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
+                                          int kind, int ind0, int n, int binder,
+                                          const signed char *newst, int P, int p) {
+    constexpr int NCOL = NB + 1;
+    const double *Rr = C.r + (long long)rep * C.N * 3;
+    const signed char *ST = C.states + (long long)rep * C.N * NB;
+    const int G = n <= 2 ? 16 : n <= 4 ? 8 : n <= 8 ? 4 : n <= 16 ? 2 : 1;
+    const int CPL = 16 / G, per_iter = 32 / G;
+    const int sub = lane % G;
+    int out_t = 0, out_c = 0;
+    for (int base = 0; base < n; base += per_iter) {
+        const int i = base + lane / G;
+        if (i >= n) continue;
+        const int bead = ind0 + i;
+        double x[3];
+        load3(Rr + 3 * bead, x);
+        signed char st[NB];
 #pragma unroll
-    for (int l = 0; l < 8; l++) {
-        int bin = idx[l];
-        if (P > 1 && (bin & (P - 1)) != p) continue;
-        int slot = table_claim(H, S, bin);
-        if (slot < 0) continue;
-        double V = C.access_vol ? C.access_vol[bin] : C.vol_bin;
-        double base = w[l] / V;
-        double t0 = sign * base;
-        if (fabs(t0) > 1E-18) atomicAdd(&H.vals[slot * (NB + 1)], t0);
+        for (int m = 0; m < NB; m++) st[m] = ST[bead * NB + m];
+        int cur_k = -1;
+        int lo[3], hi[3];
+        double wl[3], sign = 0.0;
+#pragma unroll 1
+        for (int c = sub * CPL; c < (sub + 1) * CPL; c++) {
+            const int k = c >> 3, l = c & 7;
+            if (k != cur_k) { // (re)bin for the current / the trial position
+                cur_k = k;
+                double y[3] = {x[0], x[1], x[2]};
+                if (k == 1) {
+                    if (kind == 0) apply_affine(S.M, x, y);
+                    else if (kind == 1)
+                        for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
+                    else {
 #pragma unroll
-        for (int m = 0; m < NB; m++) {
-            double t = sign * (base * (double)st[m]);
-            if (fabs(t) > 1E-18) atomicAdd(&H.vals[slot * (NB + 1) + 1 + m], t);
+                        for (int m = 0; m < NB; m++)
+                            if (m == binder) st[m] = newst[i];
+                    }
+                }
+                sign = k ? 1.0 : -1.0;
+                if (p == 0 && l == 0 && kind != 2) {
+                    if (C.confine_type == CHROMO_CONFINE_SPHERICAL) {
+                        int out = sqrt(dot3(y, y)) > C.confine_length;
+                        out_t += k ? out : 0;
+                        out_c += k ? 0 : out;
+                    } else if (C.confine_type == CHROMO_CONFINE_CUBICAL && k == 1) {
+                        // fields.pyx:178-193: the current configuration is never counted
+                        for (int j = 0; j < 3; j++) out_t += (fabs(y[j]) > C.confine_length / 2);
+                    }
+                }
+                bin_axes(C, y, lo, hi, wl);
+            }
+            // voxel corner l: index and weight (products in the reference's order (x*y)*z)
+            const int bx = l & 1, by = (l >> 1) & 1, bz = l >> 2;
+            const int bin = (bx ? hi[0] : lo[0]) + C.nx * ((by ? hi[1] : lo[1]) + C.ny * (bz ? hi[2] : lo[2]));
+            if (P > 1 && (bin & (P - 1)) != p) continue;
+            const double w = (bx ? 1.0 - wl[0] : wl[0]) * (by ? 1.0 - wl[1] : wl[1]) * (bz ? 1.0 - wl[2] : wl[2]);
+            const int slot = table_claim(H, S, bin);
+            if (slot < 0) continue;
+            const double V = C.access_vol ? C.access_vol[bin] : C.vol_bin;
+            const double dens = w / V;
+            const double t0 = sign * dens; // |x| <= 1e-18 contributions are dropped (quirk 3)
+            if (fabs(t0) > 1E-18) atomicAdd(&H.vals[slot * NCOL], t0);
+#pragma unroll
+            for (int m = 0; m < NB; m++) {
+                const double t = sign * (dens * (double)st[m]);
+                if (fabs(t) > 1E-18) atomicAdd(&H.vals[slot * NCOL + 1 + m], t);
+            }
         }
     }
+    return make_int2(out_t, out_c);
 }
 
 // Partial sums of get_dE_binders_and_beads / nonspecific_interact_dE over the
@@ -201,8 +272,8 @@ __device__ __forceinline__ void table_commit(const DevCtx &C, const HashTable &H
         for (int c = 0; c < C.ncol; c++) row[c] += H.vals[slot * C.ncol + c];
     }
 }
-__device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTable &H,
-                                                 const WarpSh &S, int lane, DebugOut *dbg) {
+static __device__ CB_NOINLINE void table_debug_dump(const DevCtx &C, const HashTable &H, const WarpSh &S,
+                                              int lane, DebugOut *dbg) {
     int cnt = S.count;
     long long base = dbg->n_touched;
     for (int j = lane; j < cnt; j += 32) {
@@ -218,28 +289,166 @@ __device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTabl
     __syncwarp();
 }
 
+// Field dE of a continuous segment: compute_dE fields.pyx:1149-1233 =
+// confinement + get_change_in_density + get_dE_binders_and_beads.  Returns dE
+// on all lanes; S.passes = number of partition passes; with one pass the
+// table still holds the delta-rho rows afterwards (used by the commit).
+// ddbl[a] = change in the number of doubly-bound beads (count_doubly_bound).
+template <int NB, bool DEBUG>
+__device__ CB_NOINLINE double field_dE_segment(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
+                                                int kind, int ind0, int n, int binder,
+                                                const signed char *newst, const int *ddbl, DebugOut *dbg) {
+    constexpr int NCOL = NB + 1;
+    const double chi = C.chi[rep];
+    int P = 1;
+    FieldSums<NB> F;
+    int2 conf = make_int2(0, 0);
+    bool want_cross = false;
+    for (int a = 0; a < NB * NB; a++) want_cross |= (C.xpref[a] != 0.0);
+    while (true) {
+#pragma unroll
+        for (int a = 0; a < NB; a++) F.sq[a] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NB * NB; a++) F.cross[a] = 0.0;
+        F.chi = 0.0;
+        if (DEBUG && lane == 0) dbg->n_touched = 0;
+        bool failed = false;
+        for (int p = 0; p < P; p++) {
+            int2 c = scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, P, p);
+            if (p == 0) conf = c;
+            __syncwarp();
+            if (S.overflow) {
+                failed = true;
+                break;
+            }
+            table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross);
+            if (lane == 0) S.last_U = (p == 0 ? 0 : S.last_U) + S.count;
+            if (DEBUG) table_debug_dump(C, H, S, lane, dbg);
+            if (P > 1) table_clear(H, S, NCOL, lane);
+        }
+        if (!failed) break;
+        table_clear(H, S, NCOL, lane);
+        P *= 2;
+    }
+    if (lane == 0) S.passes = P;
+    // ---- reduce and assemble in the reference's order ----
+    double dE = 0.0;
+    if (kind != 2) { // compute_dE fields.pyx:1209-1211
+        int nt = warp_sum_int(conf.x), nc = warp_sum_int(conf.y);
+        dE += (double)nt * CB_E_HUGE_FIELD;
+        dE -= (double)nc * CB_E_HUGE_FIELD;
+    }
+    double bb = 0.0; // get_dE_binders_and_beads fields.pyx:1760-1790
+#pragma unroll
+    for (int a = 0; a < NB; a++) {
+        double tot = warp_sum(F.sq[a]);
+        bb += C.pref[a] * tot;
+        bb += C.e_intra[a] * (double)(ddbl ? ddbl[a] : 0);
+    }
+#pragma unroll
+    for (int a = 0; a < NB; a++)
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            double tot = want_cross ? warp_sum(F.cross[a * NB + b]) : 0.0;
+            bb += C.xpref[a * NB + b] * tot;
+        }
+    bb += warp_sum(F.chi);
+    dE += bb;
+    __syncwarp();
+    return dE;
+}
+
+// apply the accepted move's density change (update_affected_densities)
+template <int NB>
+__device__ CB_NOINLINE void field_commit_segment(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
+                                                  int kind, int ind0, int n, int binder,
+                                                  const signed char *newst) {
+    const int passes = S.passes;
+    if (passes == 1) {
+        table_commit(C, H, S, rep, lane);
+        return;
+    }
+    for (int p = 0; p < passes; p++) {
+        table_clear(H, S, NB + 1, lane);
+        (void)scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, passes, p);
+        __syncwarp();
+        table_commit(C, H, S, rep, lane);
+    }
+}
+
+// NullField.compute_dE fields.pyx:300-318: only the confinement acts
+static __device__ CB_NOINLINE double confinement_dE_segment(const DevCtx &C, const WarpSh &S, int rep, int lane,
+                                                      int kind, int ind0, int n) {
+    const double *Rr = C.r + (long long)rep * C.N * 3;
+    int out_t = 0, out_c = 0;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane;
+        if (i < n) {
+            double x[3], y[3];
+            load3(Rr + 3 * (ind0 + i), x);
+            if (kind == 0) apply_affine(S.M, x, y);
+            else
+                for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
+            if (C.confine_type == CHROMO_CONFINE_SPHERICAL) {
+                out_t += (sqrt(dot3(y, y)) > C.confine_length);
+                out_c += (sqrt(dot3(x, x)) > C.confine_length);
+            } else {
+                for (int j = 0; j < 3; j++) out_t += (fabs(y[j]) > C.confine_length / 2);
+            }
+        }
+    }
+    int nt = warp_sum_int(out_t), nc = warp_sum_int(out_c);
+    double dE = (double)nt * CB_E_HUGE_FIELD;
+    dE -= (double)nc * CB_E_HUGE_FIELD;
+    return dE;
+}
+
+// ------------------------------------------------------------- elastic pairs
+// Energy of bond `bond` (beads bond, bond+1) with the (r, t3) of one of its
+// beads optionally replaced by trial values: moved = 0 none, 1 first bead,
+// 2 second bead.  E_pair with dr / dr_par / dr_perp / bend built as in
+// bead_pair_dE_poly_forward / _reverse (polymers.pyx:1148-1175, 1253-1346).
+static __device__ CB_NOINLINE double pair_energy(const DevCtx &C, int rep, int bond, int moved, double3 rn,
+                                           double3 tn) {
+    const double *Rr = C.r + (long long)rep * C.N * 3 + 3 * bond;
+    const double *T3 = C.t3 + (long long)rep * C.N * 3 + 3 * bond;
+    double r0[3], r1[3], t0[3], t1[3];
+    load3(Rr, r0);
+    load3(Rr + 3, r1);
+    load3(T3, t0);
+    load3(T3 + 3, t1);
+    if (moved == 1) {
+        r0[0] = rn.x, r0[1] = rn.y, r0[2] = rn.z;
+        t0[0] = tn.x, t0[1] = tn.y, t0[2] = tn.z;
+    } else if (moved == 2) {
+        r1[0] = rn.x, r1[1] = rn.y, r1[2] = rn.z;
+        t1[0] = tn.x, t1[1] = tn.y, t1[2] = tn.z;
+    }
+    Bond B = load_bond(C, rep, bond);
+    return bond_energy(B, r0, r1, t0, t1);
+}
+
 // ------------------------------------------------------- bead selection (lane 0)
+static __device__ CB_NOINLINE double u01(uint32_t x) { return (double)x / CB_RAND_MAX; }
+static __device__ CB_NOINLINE double log10_ni(double x) { return log10(x); }
+
 // capped_exponential bead_selection.pyx:19-67
 template <class Rng>
-__device__ int capped_exponential(Rng &g, int window, int cap) {
+__device__ __forceinline__ int capped_exponential(Rng &g, int window, int cap) {
     long long r;
     do {
-        r = (long long)(-log10(g.uniform() + 0.00001) * (double)window * 0.45 + 1.0001);
+        r = (long long)(-log10_ni(u01(g.next31()) + 0.00001) * (double)window * 0.45 + 1.0001);
     } while (r > cap);
     return (int)r;
 }
 // from_point bead_selection.pyx:115-154 (from_left 69-90, from_right 93-112)
 template <class Rng>
-__device__ int from_point(Rng &g, int window, int N, int ind0) {
+__device__ __forceinline__ int from_point(Rng &g, int window, int N, int ind0) {
     if (window < 1) return ind0;
     int side = (int)(g.next31() % 2u);
-    if (side == 0) {
-        int ws = max(min(window, ind0), 1);
-        int ub = max(ind0, 1);
-        return ub - capped_exponential(g, ws, ws);
-    }
-    int ws = max(min(window, N - ind0), 1);
-    return capped_exponential(g, ws, ws) + ind0;
+    int ws = side == 0 ? max(min(window, ind0), 1) : max(min(window, N - ind0), 1);
+    int ce = capped_exponential(g, ws, ws);
+    return side == 0 ? max(ind0, 1) - ce : ce + ind0;
 }
 // check_bead_bounds bead_selection.pyx:157-192
 __device__ __forceinline__ void check_bead_bounds(int b0, int b1, int N, int &ind0, int &indf) {
@@ -277,216 +486,62 @@ struct McWarp {
     __device__ double *T2_() const { return C.t2 + (long long)rep * C.N * 3; }
     __device__ signed char *ST_() const { return C.states + (long long)rep * C.N * NB; }
     __device__ const signed char *MOD_() const { return C.mods + (long long)rep * C.N * NB; }
+    __device__ bool has_field() const { return C.field_active || C.confine_type != CHROMO_CONFINE_NONE; }
 
-    // Metropolis test mc_sim.pyx:163-171 (lane 0 draws; result broadcast)
-    __device__ bool metropolis(double dE) {
+    // Metropolis test mc_sim.pyx:163-171 (lane 0 draws; result broadcast) and
+    // AcceptanceTracker.update_acceptance_rate mc_stat.py:190-207 + counters
+    __device__ CB_NOINLINE bool metropolis(int mtype, double dE) {
         int acc = 0;
-        double u = __longlong_as_double(0x7ff8000000000000LL);
         if (lane == 0) {
+            double u = __longlong_as_double(0x7ff8000000000000LL);
             if (DEBUG && force_accept >= 0) {
                 acc = force_accept;
             } else {
                 double e = exp(-dE);
-                u = rng.uniform();
+                u = u01(rng.next31());
                 acc = (u < e) ? 1 : 0;
             }
             if (DEBUG) {
                 dbg->u = u;
                 dbg->accepted = acc;
             }
-        }
-        return __shfl_sync(FULL_MASK, acc, 0) != 0;
-    }
-    // AcceptanceTracker.update_acceptance_rate mc_stat.py:190-207 + counters
-    __device__ void track(int mtype, bool acc) {
-        if (lane == 0) {
             chromo_move_state &mv = S.mv[mtype];
             if (acc) mv.num_success += 1;
             mv.acceptance_rate = (mv.alpha * (acc ? 1.0 : 0.0)) + (1.0 - mv.alpha) * mv.acceptance_rate;
         }
+        return __shfl_sync(FULL_MASK, acc, 0) != 0;
     }
 
-    // ---- field dE of a continuous segment under the affine map S.M -------
-    // kind: 0 = rotation (crank / pivot), 1 = translation (slide),
-    //       2 = state change (binding; positions unchanged)
-    // Returns dE_field (valid on all lanes).  Leaves the table holding the
-    // delta-rho rows when passes == 1.
-    __device__ double field_dE_segment(int kind, int ind0, int n, int binder, const signed char *newst,
-                                       int &passes_out) {
-        const double *Rr = R_();
-        const signed char *ST = ST_();
-        double chi = C.chi[rep];
-        int P = 1;
-        FieldSums<NB> F;
-        int out_t = 0, out_c = 0, dbl_t[NB], dbl_c[NB];
-        bool want_cross = false;
-        for (int a = 0; a < NB * NB; a++) want_cross |= (C.xpref[a] != 0.0);
-        while (true) {
-            for (int a = 0; a < NB; a++) {
-                F.sq[a] = 0.0;
-                dbl_t[a] = dbl_c[a] = 0;
+    // trial (r, t3) of a bead of the moving segment
+    __device__ __forceinline__ void trial_rt(int kind, const double r[3], const double t[3], double rn[3],
+                                             double tn[3]) const {
+        if (kind == 0) {
+            apply_affine(S.M, r, rn);
+            apply_rot(S.M, t, tn);
+        } else {
+            for (int j = 0; j < 3; j++) {
+                rn[j] = r[j] + S.M[4 * j + 3];
+                tn[j] = t[j];
             }
-            for (int a = 0; a < NB * NB; a++) F.cross[a] = 0.0;
-            F.chi = 0.0;
-            out_t = out_c = 0;
-            if (DEBUG && lane == 0) dbg->n_touched = 0;
-            bool failed = false;
-            for (int p = 0; p < P && !failed; p++) {
-                for (int base = 0; base < n; base += 32) {
-                    int i = base + lane;
-                    if (i < n) {
-                        int bead = ind0 + i;
-                        double x[3], y[3];
-                        load3(Rr + 3 * (long long)bead, x);
-                        signed char sc[NB], sn[NB];
-                        for (int m = 0; m < NB; m++) sn[m] = sc[m] = ST[(long long)bead * NB + m];
-                        int idx[8];
-                        double w[8];
-                        bin_point(C, x[0], x[1], x[2], idx, w);
-                        table_scatter<NB>(C, H, S, idx, w, -1.0, sc, P, p);
-                        if (kind == 2) {
-                            sn[binder] = newst[i];
-                            if (p == 0)
-                                for (int m = 0; m < NB; m++) {
-                                    dbl_c[m] += (sc[m] == 2);
-                                    dbl_t[m] += (sn[m] == 2);
-                                }
-                        } else {
-                            if (kind == 0) apply_affine(S.M, x, y);
-                            else
-                                for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
-                            if (p == 0 && C.confine_type == CHROMO_CONFINE_SPHERICAL) {
-                                // get_confinement_dE fields.pyx:160-175
-                                out_t += (sqrt(dot3(y, y)) > C.confine_length);
-                                out_c += (sqrt(dot3(x, x)) > C.confine_length);
-                            } else if (p == 0 && C.confine_type == CHROMO_CONFINE_CUBICAL) {
-                                // fields.pyx:178-193: the current configuration is never counted
-                                for (int j = 0; j < 3; j++) out_t += (fabs(y[j]) > C.confine_length / 2);
-                            }
-                            bin_point(C, y[0], y[1], y[2], idx, w);
-                        }
-                        table_scatter<NB>(C, H, S, idx, w, 1.0, sn, P, p);
-                    }
-                }
-                __syncwarp();
-                if (S.overflow) {
-                    failed = true;
-                    break;
-                }
-                table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross);
-                if (lane == 0) S.last_U = (p == 0 ? 0 : S.last_U) + S.count;
-                if (DEBUG) table_debug_dump(C, H, S, lane, dbg);
-                if (P > 1) table_clear(H, S, NCOL, lane);
-            }
-            if (!failed) break;
-            table_clear(H, S, NCOL, lane);
-            P *= 2;
-        }
-        passes_out = P;
-        // ---- reduce and assemble in the reference's order ----
-        double dE = 0.0;
-        if (kind != 2) { // compute_dE fields.pyx:1209-1211
-            int nt = warp_sum_int(out_t), nc = warp_sum_int(out_c);
-            dE += (double)nt * CB_E_HUGE_FIELD;
-            dE -= (double)nc * CB_E_HUGE_FIELD;
-        }
-        double bb = 0.0; // get_dE_binders_and_beads fields.pyx:1760-1790
-        for (int a = 0; a < NB; a++) {
-            double tot = warp_sum(F.sq[a]);
-            bb += C.pref[a] * tot;
-            int dd = (kind == 2) ? warp_sum_int(dbl_t[a] - dbl_c[a]) : 0;
-            bb += C.e_intra[a] * (double)dd;
-        }
-        for (int a = 0; a < NB; a++)
-            for (int b = 0; b < NB; b++) {
-                double tot = want_cross ? warp_sum(F.cross[a * NB + b]) : 0.0;
-                bb += C.xpref[a * NB + b] * tot;
-            }
-        bb += warp_sum(F.chi);
-        dE += bb;
-        return dE;
-    }
-
-    // NullField.compute_dE fields.pyx:300-318: only the confinement acts
-    __device__ double confinement_dE_segment(int kind, int ind0, int n) {
-        const double *Rr = R_();
-        int out_t = 0, out_c = 0;
-        for (int base = 0; base < n; base += 32) {
-            int i = base + lane;
-            if (i < n) {
-                double x[3], y[3];
-                load3(Rr + 3 * (long long)(ind0 + i), x);
-                if (kind == 0) apply_affine(S.M, x, y);
-                else
-                    for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
-                if (C.confine_type == CHROMO_CONFINE_SPHERICAL) {
-                    out_t += (sqrt(dot3(y, y)) > C.confine_length);
-                    out_c += (sqrt(dot3(x, x)) > C.confine_length);
-                } else {
-                    for (int j = 0; j < 3; j++) out_t += (fabs(y[j]) > C.confine_length / 2);
-                }
-            }
-        }
-        int nt = warp_sum_int(out_t), nc = warp_sum_int(out_c);
-        double dE = (double)nt * CB_E_HUGE_FIELD;
-        dE -= (double)nc * CB_E_HUGE_FIELD;
-        return dE;
-    }
-
-    // apply the accepted move's density change (update_affected_densities)
-    __device__ void field_commit_segment(int kind, int ind0, int n, int binder, const signed char *newst,
-                                         int passes) {
-        if (passes == 1) {
-            table_commit(C, H, S, rep, lane);
-            return;
-        }
-        const double *Rr = R_();
-        const signed char *ST = ST_();
-        for (int p = 0; p < passes; p++) {
-            table_clear(H, S, NCOL, lane);
-            for (int base = 0; base < n; base += 32) {
-                int i = base + lane;
-                if (i < n) {
-                    int bead = ind0 + i;
-                    double x[3], y[3];
-                    load3(Rr + 3 * (long long)bead, x);
-                    signed char sc[NB], sn[NB];
-                    for (int m = 0; m < NB; m++) sn[m] = sc[m] = ST[(long long)bead * NB + m];
-                    int idx[8];
-                    double w[8];
-                    bin_point(C, x[0], x[1], x[2], idx, w);
-                    table_scatter<NB>(C, H, S, idx, w, -1.0, sc, passes, p);
-                    if (kind == 2) sn[binder] = newst[i];
-                    else {
-                        if (kind == 0) apply_affine(S.M, x, y);
-                        else
-                            for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
-                        bin_point(C, y[0], y[1], y[2], idx, w);
-                    }
-                    table_scatter<NB>(C, H, S, idx, w, 1.0, sn, passes, p);
-                }
-            }
-            __syncwarp();
-            table_commit(C, H, S, rep, lane);
         }
     }
 
     // ---- crank-shaft / end-pivot / slide ---------------------------------
     __device__ void segment_move(int mtype) {
-        chromo_move_state &mv = S.mv[mtype];
         const int N = C.N;
         double *Rr = R_(), *T3 = T3_(), *T2 = T2_();
         if (lane == 0) {
+            chromo_move_state &mv = S.mv[mtype];
             mv.num_attempt += 1; // MCAdapter.propose moves.pyx:151
-            int ind0 = 0, indf = 0;
-            double ang = 0.0;
+            int ind0 = 0, indf = 0, ful = 0, rot = 0;
+            double ang = 0.0, axis[3] = {0.0, 0.0, 0.0};
             if (mtype == CHROMO_CRANK_SHAFT) { // move_funcs.pyx:80-99
-                ang = mv.amp_move * (rng.uniform() - 0.5);
-                int b0 = (int)(rng.uniform() * (double)N);
+                ang = mv.amp_move * (u01(rng.next31()) - 0.5);
+                int b0 = (int)(u01(rng.next31()) * (double)N);
                 int b1 = max(from_point(rng, mv.amp_bead, N, b0), 1);
                 check_bead_bounds(b0, b1, N, ind0, indf);
                 if (indf > ind0) {
-                    int a, b, ful; // get_crank_shaft_axis move_funcs.pyx:157-234
+                    int a, b; // get_crank_shaft_axis move_funcs.pyx:157-234
                     if (ind0 == indf - 1 && ind0 == 0) { a = indf; b = ind0; }
                     else if (ind0 == indf - 1 && ind0 == N - 1) { a = ind0; b = ind0 - 1; }
                     else if (ind0 == 0 && indf == N) { a = indf - 1; b = ind0; }
@@ -498,50 +553,50 @@ struct McWarp {
                     else if (ind0 != 0 && indf == N) ful = ind0 - 1;
                     else if (ind0 == 0 && indf == N) ful = ind0;
                     else ful = ind0 - 1;
-                    double ra[3], rb[3], pt[3], dir[3];
-                    load3(Rr + 3 * (long long)a, ra);
-                    load3(Rr + 3 * (long long)b, rb);
-                    load3(Rr + 3 * (long long)ful, pt);
-                    for (int j = 0; j < 3; j++) dir[j] = ra[j] - rb[j];
-                    double mag = sqrt((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
+                    for (int j = 0; j < 3; j++) axis[j] = Rr[3 * a + j] - Rr[3 * b + j];
+                    double mag = sqrt((axis[0] * axis[0] + axis[1] * axis[1]) + axis[2] * axis[2]);
                     if (mag < 1E-5) {
-                        uint32_t d1 = rng.next31(), d2 = rng.next31();
-                        sphere_from_draws(d1, d2, dir);
+                        rot = 2; // axis from the unit sphere (two more draws)
                     } else {
                         double sc = 1.0 / mag;
-                        for (int j = 0; j < 3; j++) dir[j] = dir[j] * sc;
+                        for (int j = 0; j < 3; j++) axis[j] = axis[j] * sc;
+                        rot = 1;
                     }
-                    rotation_matrix(dir, pt, ang, S.M);
                 }
             } else if (mtype == CHROMO_END_PIVOT) { // move_funcs.pyx:325-344
-                ang = mv.amp_move * (rng.uniform() - 0.5);
+                ang = mv.amp_move * (u01(rng.next31()) - 0.5);
                 int lhs = (int)(rng.next31() % 2u);
+                int ce = capped_exponential(rng, mv.amp_bead, mv.amp_bead);
                 if (lhs == 1) {
                     ind0 = 0;
-                    indf = capped_exponential(rng, mv.amp_bead, mv.amp_bead) + 1;
+                    indf = ce + 1;
                 } else {
-                    ind0 = N - capped_exponential(rng, mv.amp_bead, mv.amp_bead);
+                    ind0 = N - ce;
                     indf = N;
                 }
-                uint32_t d1 = rng.next31(), d2 = rng.next31();
-                double axis[3], pt[3];
-                sphere_from_draws(d1, d2, axis);
-                int ful; // get_end_pivot_fulcrum move_funcs.pyx:349-398
+                // get_end_pivot_fulcrum move_funcs.pyx:349-398
                 if (ind0 == 0 && indf != N) ful = indf;
                 else if (ind0 != 0 && indf == N) ful = ind0 - 1;
                 else if (ind0 == 0 && indf == N && lhs == 1) ful = indf - 1;
                 else ful = ind0;
-                load3(Rr + 3 * (long long)ful, pt);
-                rotation_matrix(axis, pt, ang, S.M);
+                rot = 2;
             } else { // slide move_funcs.pyx:441-463
-                double amp = mv.amp_move * rng.uniform();
+                ang = mv.amp_move * u01(rng.next31());
+                rot = 3;
+            }
+            if (rot >= 2) { // uniform_sample_unit_sphere linalg.pyx:23-59
                 uint32_t d1 = rng.next31(), d2 = rng.next31();
-                double dir[3];
-                sphere_from_draws(d1, d2, dir);
-                for (int j = 0; j < 3; j++) S.M[4 * j + 3] = dir[j] * amp;
+                sphere_from_draws(d1, d2, axis);
+            }
+            if (rot == 3) {
+                for (int j = 0; j < 3; j++) S.M[4 * j + 3] = axis[j] * ang;
                 int b0 = (int)(rng.next31() % (uint32_t)N);
                 int b1 = from_point(rng, mv.amp_bead, N, b0);
                 check_bead_bounds(b0, b1, N, ind0, indf);
+            } else if (rot != 0) {
+                double pt[3];
+                load3(Rr + 3 * ful, pt);
+                rotation_matrix(axis, pt, ang, S.M);
             }
             S.ind0 = ind0;
             S.indf = indf;
@@ -553,62 +608,46 @@ struct McWarp {
         const int kind = (mtype == CHROMO_SLIDE) ? 1 : 0;
 
         // ---- elastic dE: continuous_dE_poly polymers.pyx:1084-1146 -------
-        // lane 0: bond left of ind0 ("forward"), lane 1: bond right of indf-1 ("reverse")
-        double de = 0.0;
-        if (lane == 0 && ind0 != 0) {
-            double r0[3], r1[3], t0[3], t1[3], r1n[3], t1n[3];
-            load3(Rr + 3 * (long long)(ind0 - 1), r0);
-            load3(Rr + 3 * (long long)ind0, r1);
-            load3(T3 + 3 * (long long)(ind0 - 1), t0);
-            load3(T3 + 3 * (long long)ind0, t1);
-            if (kind == 0) {
-                apply_affine(S.M, r1, r1n);
-                apply_rot(S.M, t1, t1n);
-            } else {
-                for (int j = 0; j < 3; j++) {
-                    r1n[j] = r1[j] + S.M[4 * j + 3];
-                    t1n[j] = t1[j];
-                }
+        // four lanes, one bond energy each: 0 = left bond with the trial bead,
+        // 1 = left bond as is, 2 = right bond with the trial bead, 3 = as is
+        double e = 0.0;
+        if (lane < 4) {
+            const bool left = lane < 2;
+            const bool present = left ? (ind0 != 0) : (indf != N);
+            if (present) {
+                const int bond = left ? ind0 - 1 : indf - 1;
+                const int mbead = left ? ind0 : indf - 1;
+                double r[3], t[3], rn[3], tn[3];
+                load3(Rr + 3 * mbead, r);
+                load3(T3 + 3 * mbead, t);
+                trial_rt(kind, r, t, rn, tn);
+                const int moved = (lane & 1) ? 0 : (left ? 2 : 1);
+                e = pair_energy(C, rep, bond, moved, make_double3(rn[0], rn[1], rn[2]),
+                                make_double3(tn[0], tn[1], tn[2]));
             }
-            Bond B = load_bond(C, rep, ind0 - 1);
-            de = bond_energy(B, r0, r1n, t0, t1n) - bond_energy(B, r0, r1, t0, t1);
-        } else if (lane == 1 && indf != N) {
-            double r0[3], r1[3], t0[3], t1[3], r0n[3], t0n[3];
-            load3(Rr + 3 * (long long)(indf - 1), r0);
-            load3(Rr + 3 * (long long)indf, r1);
-            load3(T3 + 3 * (long long)(indf - 1), t0);
-            load3(T3 + 3 * (long long)indf, t1);
-            if (kind == 0) {
-                apply_affine(S.M, r0, r0n);
-                apply_rot(S.M, t0, t0n);
-            } else {
-                for (int j = 0; j < 3; j++) {
-                    r0n[j] = r0[j] + S.M[4 * j + 3];
-                    t0n[j] = t0[j];
-                }
-            }
-            Bond B = load_bond(C, rep, indf - 1);
-            de = bond_energy(B, r0n, r1, t0n, t1) - bond_energy(B, r0, r1, t0, t1);
         }
-        double dE_poly = __shfl_sync(FULL_MASK, de, 0) + __shfl_sync(FULL_MASK, de, 1);
+        const double e0 = __shfl_sync(FULL_MASK, e, 0), e1 = __shfl_sync(FULL_MASK, e, 1);
+        const double e2 = __shfl_sync(FULL_MASK, e, 2), e3 = __shfl_sync(FULL_MASK, e, 3);
+        const double dE_poly = (e0 - e1) + (e2 - e3);
 
         // ---- field dE ----------------------------------------------------
         double dE_field = 0.0;
-        int passes = 1;
-        if (C.field_active) dE_field = field_dE_segment(kind, ind0, n, 0, nullptr, passes);
-        else if (C.confine_type != CHROMO_CONFINE_NONE) dE_field = confinement_dE_segment(kind, ind0, n);
-        if (DEBUG) debug_report_segment(kind, ind0, n, dE_poly, dE_field, passes);
+        if (C.field_active)
+            dE_field = field_dE_segment<NB, DEBUG>(C, H, S, rep, lane, kind, ind0, n, 0, nullptr, nullptr, dbg);
+        else if (C.confine_type != CHROMO_CONFINE_NONE)
+            dE_field = confinement_dE_segment(C, S, rep, lane, kind, ind0, n);
+        if (DEBUG) debug_report(kind, ind0, n, 0, nullptr, dE_poly, dE_field);
 
         double dE = 0.0;
         dE += dE_poly;
-        if (C.field_active || C.confine_type != CHROMO_CONFINE_NONE) dE += dE_field;
-        bool acc = metropolis(dE);
+        if (has_field()) dE += dE_field;
+        const bool acc = metropolis(mtype, dE);
         if (acc) { // MCAdapter.accept moves.pyx:190-226
-            if (C.field_active) field_commit_segment(kind, ind0, n, 0, nullptr, passes);
+            if (C.field_active) field_commit_segment<NB>(C, H, S, rep, lane, kind, ind0, n, 0, nullptr);
             for (int base = 0; base < n; base += 32) {
                 int i = base + lane;
                 if (i < n) {
-                    long long o = 3 * (long long)(ind0 + i);
+                    const int o = 3 * (ind0 + i);
                     double x[3], y[3];
                     load3(Rr + o, x);
                     if (kind == 0) {
@@ -633,38 +672,40 @@ struct McWarp {
             S.algo_bytes += 72ull * (n + 2) + (acc ? 72ull * n : 0ull) + (unsigned long long)NB * n +
                             8ull * NCOL * U * (acc ? 3ull : 1ull) + 80ull;
         }
-        track(mtype, acc);
     }
 
-    __device__ void debug_report_segment(int kind, int ind0, int n, double dE_poly, double dE_field,
-                                         int passes) {
+    // instrumentation of the single-step kernel: moved beads + their trial rows
+    __device__ CB_NOINLINE void debug_report(int kind, int ind0, int n, int binder, const signed char *newst,
+                                              double dE_poly, double dE_field) {
         const double *Rr = R_(), *T3 = T3_(), *T2 = T2_();
         const signed char *ST = ST_();
-        int W = 9 + NB;
+        const int W = 9 + NB;
         for (int base = 0; base < n; base += 32) {
             int i = base + lane;
             if (i < n) {
                 if (i < dbg->inds_cap) dbg->inds[i] = ind0 + i;
                 if (i < dbg->rows_cap) {
-                    long long o = 3 * (long long)(ind0 + i);
-                    double x[3], y[3];
+                    const int o = 3 * (ind0 + i);
+                    double x[3], t[3], y[3], tn[3];
                     double *row = dbg->rows + (long long)i * W;
                     load3(Rr + o, x);
-                    if (kind == 0) apply_affine(S.M, x, y);
+                    load3(T3 + o, t);
+                    if (kind == 2) {
+                        store3(row, x);
+                        store3(row + 3, t);
+                    } else {
+                        trial_rt(kind, x, t, y, tn);
+                        store3(row, y);
+                        store3(row + 3, tn);
+                    }
+                    load3(T2 + o, t);
+                    if (kind == 0) apply_rot(S.M, t, tn);
                     else
-                        for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
-                    store3(row, y);
-                    load3(T3 + o, x);
-                    if (kind == 0) apply_rot(S.M, x, y);
-                    else
-                        for (int j = 0; j < 3; j++) y[j] = x[j];
-                    store3(row + 3, y);
-                    load3(T2 + o, x);
-                    if (kind == 0) apply_rot(S.M, x, y);
-                    else
-                        for (int j = 0; j < 3; j++) y[j] = x[j];
-                    store3(row + 6, y);
-                    for (int m = 0; m < NB; m++) row[9 + m] = (double)ST[(long long)(ind0 + i) * NB + m];
+                        for (int j = 0; j < 3; j++) tn[j] = t[j];
+                    store3(row + 6, tn);
+                    for (int m = 0; m < NB; m++)
+                        row[9 + m] = (kind == 2 && m == binder) ? (double)newst[i]
+                                                                : (double)ST[(ind0 + i) * NB + m];
                 }
             }
         }
@@ -672,18 +713,18 @@ struct McWarp {
             dbg->n_inds = n;
             dbg->dE_poly = dE_poly;
             dbg->dE_field = dE_field;
-            dbg->passes = passes;
+            dbg->passes = C.field_active ? S.passes : 0;
         }
         __syncwarp();
     }
 
     // ---- change_binding_state move_funcs.pyx:717-820 ----------------------
     __device__ void binding_move() {
-        chromo_move_state &mv = S.mv[CHROMO_CHANGE_BINDING_STATE];
         const int N = C.N;
         signed char *ST = ST_();
         const signed char *MOD = MOD_();
         if (lane == 0) {
+            chromo_move_state &mv = S.mv[CHROMO_CHANGE_BINDING_STATE];
             mv.num_attempt += 1;
             int binder = (int)(rng.next31() % (uint32_t)NB);
             int b0 = (int)(rng.next31() % (uint32_t)N);
@@ -705,25 +746,35 @@ struct McWarp {
 
         // ---- binding_dE / bead_binding_dE polymers.pyx:1383-1538 ----------
         double de = 0.0;
+        int ddbl[NB]; // count_doubly_bound fields.pyx:1877-1937: trial minus current
+#pragma unroll
+        for (int m = 0; m < NB; m++) ddbl[m] = 0;
         for (int base = 0; base < n; base += 32) {
             int i = base + lane;
             if (i < n) {
                 int bead = ind0 + i;
                 double d = 0.0;
                 int sc[NB], sn[NB];
-                for (int m = 0; m < NB; m++) sn[m] = sc[m] = ST[(long long)bead * NB + m];
-                sn[binder] = newst[i];
+#pragma unroll
+                for (int m = 0; m < NB; m++) {
+                    sc[m] = ST[bead * NB + m];
+                    sn[m] = (m == binder) ? (int)newst[i] : sc[m];
+                    ddbl[m] += (sn[m] == 2) - (sc[m] == 2);
+                }
                 if (C.max_binders != -1) {
                     long long tot = 0;
+#pragma unroll
                     for (int m = 0; m < NB; m++) tot += sn[m];
                     if (tot > C.max_binders) d += CB_E_HUGE_POLY * (double)(tot - C.max_binders);
                     tot = 0;
+#pragma unroll
                     for (int m = 0; m < NB; m++) tot += sc[m];
                     if (tot > C.max_binders) d -= CB_E_HUGE_POLY * (double)(tot - C.max_binders);
                 }
+#pragma unroll
                 for (int m = 0; m < NB; m++) {
-                    int Nm = MOD[(long long)bead * NB + m];
-                    const double *Ft = C.bindF + ((long long)m * C.S1 + Nm) * C.S1;
+                    int Nm = MOD[bead * NB + m];
+                    const double *Ft = C.bindF + (m * C.S1 + Nm) * C.S1;
                     double mu = C.mu[(long long)rep * NB + m];
                     d += Ft[sn[m]];
                     d -= Ft[sc[m]];
@@ -740,48 +791,23 @@ struct McWarp {
         }
         double dE_poly = warp_sum(de);
         if (n == 1) dE_poly = __shfl_sync(FULL_MASK, de, 0); // exact for the default amp_bead = 1
+#pragma unroll
+        for (int m = 0; m < NB; m++) ddbl[m] = warp_sum_int(ddbl[m]);
 
         double dE_field = 0.0;
-        int passes = 1;
-        if (C.field_active) dE_field = field_dE_segment(2, ind0, n, binder, newst, passes);
-        if (DEBUG) {
-            int W = 9 + NB;
-            for (int base = 0; base < n; base += 32) {
-                int i = base + lane;
-                if (i < n) {
-                    if (i < dbg->inds_cap) dbg->inds[i] = ind0 + i;
-                    if (i < dbg->rows_cap) {
-                        long long o = 3 * (long long)(ind0 + i);
-                        double *row = dbg->rows + (long long)i * W;
-                        for (int j = 0; j < 3; j++) {
-                            row[j] = R_()[o + j];
-                            row[3 + j] = T3_()[o + j];
-                            row[6 + j] = T2_()[o + j];
-                        }
-                        for (int m = 0; m < NB; m++)
-                            row[9 + m] = (m == binder) ? (double)newst[i]
-                                                       : (double)ST[(long long)(ind0 + i) * NB + m];
-                    }
-                }
-            }
-            if (lane == 0) {
-                dbg->n_inds = n;
-                dbg->dE_poly = dE_poly;
-                dbg->dE_field = dE_field;
-                dbg->passes = passes;
-            }
-            __syncwarp();
-        }
+        if (C.field_active)
+            dE_field = field_dE_segment<NB, DEBUG>(C, H, S, rep, lane, 2, ind0, n, binder, newst, ddbl, dbg);
+        if (DEBUG) debug_report(2, ind0, n, binder, newst, dE_poly, dE_field);
         double dE = 0.0;
         dE += dE_poly;
-        if (C.field_active) dE += dE_field;
-        bool acc = metropolis(dE);
+        if (has_field()) dE += dE_field;
+        const bool acc = metropolis(CHROMO_CHANGE_BINDING_STATE, dE);
         if (acc) {
-            if (C.field_active) field_commit_segment(2, ind0, n, binder, newst, passes);
+            if (C.field_active) field_commit_segment<NB>(C, H, S, rep, lane, 2, ind0, n, binder, newst);
             __syncwarp();
             for (int base = 0; base < n; base += 32) {
                 int i = base + lane;
-                if (i < n) ST[(long long)(ind0 + i) * NB + binder] = newst[i];
+                if (i < n) ST[(ind0 + i) * NB + binder] = newst[i];
             }
         }
         if (C.field_active) table_clear(H, S, NCOL, lane);
@@ -790,62 +816,86 @@ struct McWarp {
             S.algo_bytes += 24ull * n + (unsigned long long)NB * n * (acc ? 2ull : 1ull) +
                             8ull * NCOL * U * (acc ? 3ull : 1ull);
         }
-        track(CHROMO_CHANGE_BINDING_STATE, acc);
     }
 
     // ---- tangent_rotation move_funcs.pyx:470-582 --------------------------
     // per selected bead: own random axis, rotate t3/t2, both adjacent bonds
     // against the CURRENT neighbours (polymers.pyx:1075-1080; quirk 8); never
     // touches the field (mc_sim.pyx:145).
-    __device__ double tangent_bead(int bead, uint32_t d1, uint32_t d2, double ang, double t3n[3],
-                                   double t2n[3]) {
-        const double *Rr = R_(), *T3 = T3_(), *T2 = T2_();
+    // A chunk of up to 8 beads is evaluated by 4 lanes per bead (one bond energy
+    // each: left bond trial / as is, right bond trial / as is); the new tangents
+    // of chunk bead j go to out[6j..6j+5] (shared) when `out` is given, or
+    // straight to global memory when `store` is set.  Returns this chunk's dE on
+    // all lanes (ordered sum over beads).
+    __device__ CB_NOINLINE double tangent_chunk(const int *beads, int cnt, const uint32_t *draws, double ang,
+                                                 double *out, bool store, int dbg_base, double acc_in) {
+        const double *Rr = R_();
+        double *T3 = T3_(), *T2 = T2_();
         const int N = C.N;
-        double axis[3], M[12], t3c[3], t2c[3], rc[3];
-        const double origin[3] = {0.0, 0.0, 0.0};
-        sphere_from_draws(d1, d2, axis);
-        rotation_matrix(axis, origin, ang, M);
-        long long o = 3 * (long long)bead;
-        load3(T3 + o, t3c);
-        load3(T2 + o, t2c);
-        load3(Rr + o, rc);
-        apply_rot(M, t3c, t3n);
-        apply_rot(M, t2c, t2n);
-        double d = 0.0;
-        if (bead != 0) {
-            double r0[3], t0[3];
-            load3(Rr + o - 3, r0);
-            load3(T3 + o - 3, t0);
-            Bond B = load_bond(C, rep, bead - 1);
-            d += bond_energy(B, r0, rc, t0, t3n) - bond_energy(B, r0, rc, t0, t3c);
+        const int j = lane >> 2, which = lane & 3;
+        double e = 0.0;
+        if (j < cnt) {
+            const int bead = beads[j];
+            double axis[3], M[12], t3c[3], t2c[3], t3n[3], t2n[3], rc[3];
+            const double origin[3] = {0.0, 0.0, 0.0};
+            sphere_from_draws(draws[2 * j], draws[2 * j + 1], axis);
+            rotation_matrix(axis, origin, ang, M);
+            load3(T3 + 3 * bead, t3c);
+            load3(T2 + 3 * bead, t2c);
+            load3(Rr + 3 * bead, rc);
+            apply_rot(M, t3c, t3n);
+            apply_rot(M, t2c, t2n);
+            const bool left = which < 2;
+            const bool present = left ? (bead != 0) : (bead + 1 != N);
+            if (!store && present) {
+                const int moved = (which & 1) ? 0 : (left ? 2 : 1);
+                e = pair_energy(C, rep, left ? bead - 1 : bead, moved, make_double3(rc[0], rc[1], rc[2]),
+                                make_double3(t3n[0], t3n[1], t3n[2]));
+            }
+            if (which == 0) {
+                if (out) {
+                    store3(out + 6 * j, t3n);
+                    store3(out + 6 * j + 3, t2n);
+                }
+                if (store) {
+                    store3(T3 + 3 * bead, t3n);
+                    store3(T2 + 3 * bead, t2n);
+                }
+                if (DEBUG && !store && dbg_base + j < dbg->rows_cap) {
+                    double *row = dbg->rows + (long long)(dbg_base + j) * (9 + NB);
+                    store3(row, rc);
+                    store3(row + 3, t3n);
+                    store3(row + 6, t2n);
+                    for (int m = 0; m < NB; m++) row[9 + m] = (double)ST_()[bead * NB + m];
+                    if (dbg_base + j < dbg->inds_cap) dbg->inds[dbg_base + j] = bead;
+                }
+            }
         }
-        if (bead + 1 != N) {
-            double r1[3], t1[3];
-            load3(Rr + o + 3, r1);
-            load3(T3 + o + 3, t1);
-            Bond B = load_bond(C, rep, bead);
-            d += bond_energy(B, rc, r1, t3n, t1) - bond_energy(B, rc, r1, t3c, t1);
-        }
-        return d;
+        // per bead: (0 + (E_left' - E_left)) + (E_right' - E_right); then bead by bead
+        const double l0 = __shfl_down_sync(FULL_MASK, e, 1), r0 = __shfl_down_sync(FULL_MASK, e, 2),
+                     r1 = __shfl_down_sync(FULL_MASK, e, 3);
+        const double d = (e - l0) + (r0 - r1); // valid on which == 0 lanes
+        double tot = acc_in; // the reference accumulates bead by bead (polymers.pyx:1075-1080)
+        for (int b = 0; b < cnt; b++) tot += __shfl_sync(FULL_MASK, d, 4 * b);
+        return tot;
     }
 
     __device__ void tangent_move() {
-        chromo_move_state &mv = S.mv[CHROMO_TANGENT_ROTATION];
         const int N = C.N;
-        double *T3 = T3_(), *T2 = T2_();
         double ang = 0.0;
         int k = 0;
         if (lane == 0) {
+            chromo_move_state &mv = S.mv[CHROMO_TANGENT_ROTATION];
             mv.num_attempt += 1;
-            ang = mv.amp_move * (rng.uniform() - 0.5);
+            ang = mv.amp_move * (u01(rng.next31()) - 0.5);
             k = (int)(rng.next31() % (uint32_t)mv.amp_bead) + 1;
         }
         ang = __shfl_sync(FULL_MASK, ang, 0);
         k = __shfl_sync(FULL_MASK, k, 0);
-        double dE_poly = 0.0;
-        bool acc;
-        if (k <= 32) {
-            // get_inds move_funcs.pyx:552-582: k distinct draws, redraw on duplicates
+        const bool small = k <= 32;
+        int *inds = small ? S.tinds : C.tan_inds + (long long)rep * N;
+        // get_inds move_funcs.pyx:552-582: k distinct draws, redraw on duplicates
+        if (small) {
             int my = -1;
             for (int i = 0; i < k; i++) {
                 int c = 0;
@@ -857,51 +907,12 @@ struct McWarp {
                 } while (dup);
                 if (lane == i) my = c;
             }
-            if (lane == 0)
-                for (int i = 0; i < 2 * k; i++) S.draws[i] = rng.next31();
-            __syncwarp();
-            double t3n[3], t2n[3], d = 0.0;
-            if (lane < k) d = tangent_bead(my, S.draws[2 * lane], S.draws[2 * lane + 1], ang, t3n, t2n);
-            // ordered sum over beads (the reference accumulates bead by bead)
-            for (int i = 0; i < k; i++) dE_poly += __shfl_sync(FULL_MASK, d, i);
-            if (DEBUG) {
-                int W = 9 + NB;
-                if (lane < k) {
-                    if (lane < dbg->inds_cap) dbg->inds[lane] = my;
-                    if (lane < dbg->rows_cap) {
-                        double *row = dbg->rows + (long long)lane * W;
-                        for (int j = 0; j < 3; j++) {
-                            row[j] = R_()[3 * (long long)my + j];
-                            row[3 + j] = t3n[j];
-                            row[6 + j] = t2n[j];
-                        }
-                        for (int m = 0; m < NB; m++) row[9 + m] = (double)ST_()[(long long)my * NB + m];
-                    }
-                }
-                if (lane == 0) {
-                    dbg->n_inds = k;
-                    dbg->dE_poly = dE_poly;
-                    dbg->dE_field = 0.0;
-                    dbg->n_touched = 0;
-                    dbg->passes = 0;
-                }
-                __syncwarp();
-            }
-            double dE = 0.0;
-            dE += dE_poly;
-            acc = metropolis(dE);
-            if (acc && lane < k) {
-                store3(T3 + 3 * (long long)my, t3n);
-                store3(T2 + 3 * (long long)my, t2n);
-            }
+            if (lane < k) S.tinds[lane] = my;
         } else {
-            // large path: indices in HBM scratch, membership in a bitmap,
-            // per-bead draws regenerated on commit from a saved RNG state
-            int *inds = C.tan_inds + (long long)rep * N;
             uint32_t *bits = C.sel_bits + (long long)rep * ((N + 31) / 32);
             for (int i = lane; i < (N + 31) / 32; i += 32) bits[i] = 0u;
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0)
                 for (int i = 0; i < k; i++) {
                     int c;
                     do {
@@ -910,77 +921,54 @@ struct McWarp {
                     bits[c >> 5] |= 1u << (c & 31);
                     inds[i] = c;
                 }
-                rng.save(S.rng_save);
+        }
+        if (lane == 0 && !small) rng.save(S.rng_save);
+        __syncwarp();
+        // per-bead axis draws (phi, theta) in bead order, then the energies
+        double dE_poly = 0.0;
+        for (int base = 0; base < k; base += 8) {
+            const int cnt = min(8, k - base);
+            if (lane == 0)
+                for (int i = 0; i < 2 * cnt; i++) S.draws[i] = rng.next31();
+            __syncwarp();
+            dE_poly = tangent_chunk(inds + base, cnt, S.draws, ang, small ? S.tan_new + 6 * base : nullptr,
+                                    false, base, dE_poly);
+            __syncwarp();
+        }
+        if (DEBUG) {
+            if (lane == 0) {
+                dbg->n_inds = k;
+                dbg->dE_poly = dE_poly;
+                dbg->dE_field = 0.0;
+                dbg->n_touched = 0;
+                dbg->passes = 0;
             }
             __syncwarp();
-            double d = 0.0;
-            for (int base = 0; base < k; base += 32) {
-                int cnt = min(32, k - base);
-                if (lane == 0)
-                    for (int i = 0; i < 2 * cnt; i++) S.draws[i] = rng.next31();
-                __syncwarp();
-                if (lane < cnt) {
-                    double t3n[3], t2n[3];
-                    int bead = inds[base + lane];
-                    d += tangent_bead(bead, S.draws[2 * lane], S.draws[2 * lane + 1], ang, t3n, t2n);
-                    if (DEBUG && base + lane < dbg->rows_cap) {
-                        double *row = dbg->rows + (long long)(base + lane) * (9 + NB);
-                        for (int j = 0; j < 3; j++) {
-                            row[j] = R_()[3 * (long long)bead + j];
-                            row[3 + j] = t3n[j];
-                            row[6 + j] = t2n[j];
-                        }
-                        for (int m = 0; m < NB; m++) row[9 + m] = (double)ST_()[(long long)bead * NB + m];
-                    }
+        }
+        double dE = 0.0;
+        dE += dE_poly;
+        const bool acc = metropolis(CHROMO_TANGENT_ROTATION, dE);
+        if (acc) {
+            double *T3 = T3_(), *T2 = T2_();
+            if (small) {
+                if (lane < k) {
+                    store3(T3 + 3 * S.tinds[lane], S.tan_new + 6 * lane);
+                    store3(T2 + 3 * S.tinds[lane], S.tan_new + 6 * lane + 3);
                 }
-                __syncwarp();
-            }
-            dE_poly = warp_sum(d);
-            if (DEBUG) {
-                if (lane == 0) {
-                    dbg->n_inds = k;
-                    dbg->dE_poly = dE_poly;
-                    dbg->dE_field = 0.0;
-                    dbg->n_touched = 0;
-                    dbg->passes = 0;
-                }
-                for (int i = lane; i < k && i < dbg->inds_cap; i += 32) dbg->inds[i] = inds[i];
-                __syncwarp();
-            }
-            double dE = 0.0;
-            dE += dE_poly;
-            acc = metropolis(dE);
-            if (acc) {
-                // every selected bead is distinct and its energy used only the
-                // current neighbours, so all new tangents are computed from the
-                // pre-move state before any is stored
+            } else {
+                // regenerate the per-bead draws from the saved RNG state; a bead's new
+                // tangents depend on its own t3/t2 only, so storing chunk by chunk is safe
                 uint32_t after[CB_GLIBC_WORDS];
                 if (lane == 0) {
                     rng.save(after);
                     rng.restore(S.rng_save);
                 }
-                // pass 1: recompute and park the new tangents in registers per chunk,
-                // storing only after the whole chunk's loads are done; neighbours in
-                // other chunks may already be rotated, but tangents of a bead depend
-                // on its OWN t3/t2 only, so the stored values are unaffected.
-                for (int base = 0; base < k; base += 32) {
-                    int cnt = min(32, k - base);
+                for (int base = 0; base < k; base += 8) {
+                    const int cnt = min(8, k - base);
                     if (lane == 0)
                         for (int i = 0; i < 2 * cnt; i++) S.draws[i] = rng.next31();
                     __syncwarp();
-                    if (lane < cnt) {
-                        int bead = inds[base + lane];
-                        double axis[3], M[12], v[3], o3[3], o2[3];
-                        const double origin[3] = {0.0, 0.0, 0.0};
-                        sphere_from_draws(S.draws[2 * lane], S.draws[2 * lane + 1], axis);
-                        rotation_matrix(axis, origin, ang, M);
-                        load3(T3 + 3 * (long long)bead, v);
-                        apply_rot(M, v, o3);
-                        load3(T2 + 3 * (long long)bead, v);
-                        apply_rot(M, v, o2);
-                        store3(T3 + 3 * (long long)bead, o3);
-                        store3(T2 + 3 * (long long)bead, o2);
-                    }
+                    (void)tangent_chunk(inds + base, cnt, S.draws, ang, nullptr, true, base, 0.0);
                     __syncwarp();
                 }
                 if (lane == 0) rng.restore(after);
@@ -988,7 +976,6 @@ struct McWarp {
         }
         if (lane == 0) // tangent rotation: B = 48 n + 72*2n + 48 n a   
             S.algo_bytes += 48ull * k + 144ull * k + (acc ? 48ull * k : 0ull);
-        track(CHROMO_TANGENT_ROTATION, acc);
     }
 
     // SimpleControl.update_move_amplitude mc_controller.py:148-213 (lane 0)
@@ -1038,7 +1025,6 @@ __device__ __forceinline__ HashTable carve_table(unsigned char *dyn, int cap, in
     H.limit = cap - cap / 4 - 32;
     return H;
 }
-static_assert(sizeof(WarpSh) <= 2048, "update kWarpShBytes in chromo_b200.cu");
 
 template <class Rng>
 __device__ __forceinline__ void rng_load(Rng &rng, const DevCtx &C, WarpSh &S, int rep, int lane,
@@ -1077,7 +1063,7 @@ __device__ __forceinline__ void rng_store<PhiloxRng>(PhiloxRng &rng, const DevCt
 // mc_sim mc_sim.pyx:26-103 for every replica: grid = R blocks of one warp.
 template <class Rng, int NB>
 __global__ void __launch_bounds__(32, 8) mc_sim_kernel(DevCtx C, long long num_mc_steps, double mu_adjust,
-                                                    unsigned long long seed, int cap) {
+                                                       unsigned long long seed, int cap) {
     CB_DYN_SMEM(dyn);
     __shared__ WarpSh S;
     const int rep = blockIdx.x, lane = threadIdx.x;
@@ -1088,6 +1074,7 @@ __global__ void __launch_bounds__(32, 8) mc_sim_kernel(DevCtx C, long long num_m
     if (lane == 0) {
         S.algo_bytes = 0;
         S.last_U = 0;
+        S.passes = 1;
     }
     Rng rng;
     rng_load<Rng>(rng, C, S, rep, lane, seed);
@@ -1136,6 +1123,7 @@ __global__ void __launch_bounds__(32) mc_step_kernel(DevCtx C, int rep, int mtyp
         dbg->passes = 0;
         S.algo_bytes = 0;
         S.last_U = 0;
+        S.passes = 1;
     }
     Rng rng;
     rng_load<Rng>(rng, C, S, rep, lane, seed);

@@ -73,6 +73,11 @@ template <class T>
 static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, src); }
 template <class T>
 static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_exchange(v, (int)((threadIdx.x & 31) ^ (unsigned)m)); }
+template <class T>
+static inline T __shfl_down_sync(unsigned, T v, int d) {
+    int src = (int)(threadIdx.x & 31) + d;
+    return emu_exchange(v, src > 31 ? (int)(threadIdx.x & 31) : src);
+}
 static inline int __any_sync(unsigned, int pred) {
     unsigned base = threadIdx.x & ~31u;
     emu_blk->slots[threadIdx.x] = pred ? 1 : 0;
@@ -99,6 +104,13 @@ static inline double atomicAdd(double *a, double v) {
     return o;
 }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+struct double2 { double x, y; };
+struct double3 { double x, y, z; };
+struct int2 { int x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+static inline double3 make_double3(double x, double y, double z) { return double3{x, y, z}; }
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+#define CB_NOINLINE __attribute__((noinline))
 static inline double __longlong_as_double(long long v) {
     double d;
     memcpy(&d, &v, 8);
