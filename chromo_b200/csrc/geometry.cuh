@@ -92,12 +92,10 @@ static __device__ CB_NOINLINE double2 sincos_ni(double x) {
 }
 static __device__ CB_NOINLINE double acos_ni(double x) { return acos(x); }
 
-// arbitrary_axis_rotation linalg.pyx:62-139.  M is 3x4 row-major (M[4*j+3] is
-// the translation column).
-__device__ __forceinline__ void rotation_matrix(const double ax[3], const double pt[3],
-                                                double ang, double M[12]) {
-    const double2 sc = sincos_ni(ang);
-    const double sn = sc.x, c = sc.y;
+// arbitrary_axis_rotation linalg.pyx:62-139 given sin / cos of the angle.  M is
+// 3x4 row-major (M[4*j+3] is the translation column).
+__device__ __forceinline__ void rotation_matrix_sc(const double ax[3], const double pt[3],
+                                                   double sn, double c, double M[12]) {
     double omc = 1.0 - c;
     M[0] = ax[0] * ax[0] + (ax[1] * ax[1] + ax[2] * ax[2]) * c;
     M[1] = ax[0] * ax[1] * omc - ax[2] * sn;

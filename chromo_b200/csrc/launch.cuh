@@ -11,6 +11,7 @@
 #define CB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define CB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define CB_NOINLINE __noinline__
+#define CB_GRID_CONSTANT __grid_constant__
 #endif
 #include "params.cuh"
 

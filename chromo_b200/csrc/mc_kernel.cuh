@@ -43,6 +43,8 @@ struct WarpSh {
     uint32_t rng_save[CB_GLIBC_WORDS];
     double M[12];                 // affine map of the current move
     double tan_new[32 * 6];       // tangent rotation: new t3 | t2 of the selected beads
+    double tan_trig[9 * 32];      // tangent rotation: per-lane angles | sines | cosines
+    double trig[9];               // segment moves: angles | sines | cosines (lane 0)
     int tinds[32];                // tangent rotation: selected beads (small path)
     int ind0, indf, n, binder;
     int count;                    // occupied hash slots
@@ -53,7 +55,7 @@ struct WarpSh {
     uint32_t draws[64];           // per-bead axis draws of tangent rotation
     signed char newst[256];       // new binding states (small path)
 };
-static_assert(sizeof(WarpSh) <= 4096, "update kWarpShBytes in chromo_b200.cu");
+static_assert(sizeof(WarpSh) <= 6144, "update kWarpShBytes in chromo_b200.cu");
 
 struct HashTable {
     int *keys;    // [cap]
@@ -84,7 +86,7 @@ __device__ __forceinline__ void table_reset_all(HashTable &H, WarpSh &S, int nco
     __syncwarp();
 }
 // clear only what the last move used
-static __device__ CB_NOINLINE void table_clear(HashTable &H, WarpSh &S, int ncol, int lane) {
+__device__ __forceinline__ void table_clear(HashTable &H, WarpSh &S, int ncol, int lane) {
     __syncwarp();
     int cnt = min(S.count, H.cap);
     for (int j = lane; j < cnt; j += 32) {
@@ -137,7 +139,7 @@ __device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin) {
 // Returns the confinement counters of get_confinement_dE (fields.pyx:160-193):
 // x = # trial positions outside, y = # current positions outside (this lane's).
 template <int NB>
-__device__ CB_NOINLINE int2 scatter_pass(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
+__device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
                                           int kind, int ind0, int n, int binder,
                                           const signed char *newst, int P, int p) {
     constexpr int NCOL = NB + 1;
@@ -272,7 +274,7 @@ __device__ __forceinline__ void table_commit(const DevCtx &C, const HashTable &H
         for (int c = 0; c < C.ncol; c++) row[c] += H.vals[slot * C.ncol + c];
     }
 }
-static __device__ CB_NOINLINE void table_debug_dump(const DevCtx &C, const HashTable &H, const WarpSh &S,
+__device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTable &H, const WarpSh &S,
                                               int lane, DebugOut *dbg) {
     int cnt = S.count;
     long long base = dbg->n_touched;
@@ -295,7 +297,7 @@ static __device__ CB_NOINLINE void table_debug_dump(const DevCtx &C, const HashT
 // table still holds the delta-rho rows afterwards (used by the commit).
 // ddbl[a] = change in the number of doubly-bound beads (count_doubly_bound).
 template <int NB, bool DEBUG>
-__device__ CB_NOINLINE double field_dE_segment(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
+__device__ __forceinline__ double field_dE_segment(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
                                                 int kind, int ind0, int n, int binder,
                                                 const signed char *newst, const int *ddbl, DebugOut *dbg) {
     constexpr int NCOL = NB + 1;
@@ -358,16 +360,14 @@ __device__ CB_NOINLINE double field_dE_segment(const DevCtx &C, HashTable &H, Wa
     return dE;
 }
 
-// apply the accepted move's density change (update_affected_densities)
+// accepted move whose delta-rho needed several partition passes (rare): redo
+// each pass and apply it (update_affected_densities fields.pyx:1968-1975)
 template <int NB>
-__device__ CB_NOINLINE void field_commit_segment(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
-                                                  int kind, int ind0, int n, int binder,
-                                                  const signed char *newst) {
+__device__ CB_NOINLINE void field_commit_multipass(const DevCtx &C, HashTable H, WarpSh *Sp, int rep, int lane,
+                                                   int kind, int ind0, int n, int binder,
+                                                   const signed char *newst) {
+    WarpSh &S = *Sp;
     const int passes = S.passes;
-    if (passes == 1) {
-        table_commit(C, H, S, rep, lane);
-        return;
-    }
     for (int p = 0; p < passes; p++) {
         table_clear(H, S, NB + 1, lane);
         (void)scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, passes, p);
@@ -377,7 +377,7 @@ __device__ CB_NOINLINE void field_commit_segment(const DevCtx &C, HashTable &H, 
 }
 
 // NullField.compute_dE fields.pyx:300-318: only the confinement acts
-static __device__ CB_NOINLINE double confinement_dE_segment(const DevCtx &C, const WarpSh &S, int rep, int lane,
+__device__ __forceinline__ double confinement_dE_segment(const DevCtx &C, const WarpSh &S, int rep, int lane,
                                                       int kind, int ind0, int n) {
     const double *Rr = C.r + (long long)rep * C.N * 3;
     int out_t = 0, out_c = 0;
@@ -408,8 +408,8 @@ static __device__ CB_NOINLINE double confinement_dE_segment(const DevCtx &C, con
 // beads optionally replaced by trial values: moved = 0 none, 1 first bead,
 // 2 second bead.  E_pair with dr / dr_par / dr_perp / bend built as in
 // bead_pair_dE_poly_forward / _reverse (polymers.pyx:1148-1175, 1253-1346).
-static __device__ CB_NOINLINE double pair_energy(const DevCtx &C, int rep, int bond, int moved, double3 rn,
-                                           double3 tn) {
+__device__ __forceinline__ double pair_energy(const DevCtx &C, int rep, int bond, int moved,
+                                              const double rn[3], const double tn[3]) {
     const double *Rr = C.r + (long long)rep * C.N * 3 + 3 * bond;
     const double *T3 = C.t3 + (long long)rep * C.N * 3 + 3 * bond;
     double r0[3], r1[3], t0[3], t1[3];
@@ -417,38 +417,28 @@ static __device__ CB_NOINLINE double pair_energy(const DevCtx &C, int rep, int b
     load3(Rr + 3, r1);
     load3(T3, t0);
     load3(T3 + 3, t1);
-    if (moved == 1) {
-        r0[0] = rn.x, r0[1] = rn.y, r0[2] = rn.z;
-        t0[0] = tn.x, t0[1] = tn.y, t0[2] = tn.z;
-    } else if (moved == 2) {
-        r1[0] = rn.x, r1[1] = rn.y, r1[2] = rn.z;
-        t1[0] = tn.x, t1[1] = tn.y, t1[2] = tn.z;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        r0[j] = moved == 1 ? rn[j] : r0[j];
+        t0[j] = moved == 1 ? tn[j] : t0[j];
+        r1[j] = moved == 2 ? rn[j] : r1[j];
+        t1[j] = moved == 2 ? tn[j] : t1[j];
     }
     Bond B = load_bond(C, rep, bond);
     return bond_energy(B, r0, r1, t0, t1);
 }
 
 // ------------------------------------------------------- bead selection (lane 0)
-static __device__ CB_NOINLINE double u01(uint32_t x) { return (double)x / CB_RAND_MAX; }
-static __device__ CB_NOINLINE double log10_ni(double x) { return log10(x); }
+__device__ __forceinline__ double u01(uint32_t x) { return (double)x / CB_RAND_MAX; }
 
 // capped_exponential bead_selection.pyx:19-67
 template <class Rng>
 __device__ __forceinline__ int capped_exponential(Rng &g, int window, int cap) {
     long long r;
     do {
-        r = (long long)(-log10_ni(u01(g.next31()) + 0.00001) * (double)window * 0.45 + 1.0001);
+        r = (long long)(-log10(u01(g.next31()) + 0.00001) * (double)window * 0.45 + 1.0001);
     } while (r > cap);
     return (int)r;
-}
-// from_point bead_selection.pyx:115-154 (from_left 69-90, from_right 93-112)
-template <class Rng>
-__device__ __forceinline__ int from_point(Rng &g, int window, int N, int ind0) {
-    if (window < 1) return ind0;
-    int side = (int)(g.next31() % 2u);
-    int ws = side == 0 ? max(min(window, ind0), 1) : max(min(window, N - ind0), 1);
-    int ce = capped_exponential(g, ws, ws);
-    return side == 0 ? max(ind0, 1) - ce : ce + ind0;
 }
 // check_bead_bounds bead_selection.pyx:157-192
 __device__ __forceinline__ void check_bead_bounds(int b0, int b1, int N, int &ind0, int &indf) {
@@ -469,6 +459,11 @@ __device__ __forceinline__ void check_bead_bounds(int b0, int b1, int N, int &in
 }
 
 // =================================================================== moves
+// Every heavy routine below has exactly ONE call site in the kernel (so it is
+// inlined once: no ABI spills, shared-memory address spaces stay visible to the
+// compiler) -- the crank-shaft / end-pivot / slide / binding moves share one
+// code path (`segment_*`), tangent rotation has its own (`tangent_*`), and both
+// meet again in a single Metropolis test.
 template <class Rng, bool DEBUG, int NB>
 struct McWarp {
     static constexpr int NCOL = NB + 1;
@@ -481,35 +476,13 @@ struct McWarp {
     int force_accept; // DEBUG only: -1 Metropolis, 0/1 forced
     DebugOut *dbg;
 
-    __device__ double *R_() const { return C.r + (long long)rep * C.N * 3; }
-    __device__ double *T3_() const { return C.t3 + (long long)rep * C.N * 3; }
-    __device__ double *T2_() const { return C.t2 + (long long)rep * C.N * 3; }
-    __device__ signed char *ST_() const { return C.states + (long long)rep * C.N * NB; }
-    __device__ const signed char *MOD_() const { return C.mods + (long long)rep * C.N * NB; }
-    __device__ bool has_field() const { return C.field_active || C.confine_type != CHROMO_CONFINE_NONE; }
-
-    // Metropolis test mc_sim.pyx:163-171 (lane 0 draws; result broadcast) and
-    // AcceptanceTracker.update_acceptance_rate mc_stat.py:190-207 + counters
-    __device__ CB_NOINLINE bool metropolis(int mtype, double dE) {
-        int acc = 0;
-        if (lane == 0) {
-            double u = __longlong_as_double(0x7ff8000000000000LL);
-            if (DEBUG && force_accept >= 0) {
-                acc = force_accept;
-            } else {
-                double e = exp(-dE);
-                u = u01(rng.next31());
-                acc = (u < e) ? 1 : 0;
-            }
-            if (DEBUG) {
-                dbg->u = u;
-                dbg->accepted = acc;
-            }
-            chromo_move_state &mv = S.mv[mtype];
-            if (acc) mv.num_success += 1;
-            mv.acceptance_rate = (mv.alpha * (acc ? 1.0 : 0.0)) + (1.0 - mv.alpha) * mv.acceptance_rate;
-        }
-        return __shfl_sync(FULL_MASK, acc, 0) != 0;
+    __device__ __forceinline__ double *R_() const { return C.r + (long long)rep * C.N * 3; }
+    __device__ __forceinline__ double *T3_() const { return C.t3 + (long long)rep * C.N * 3; }
+    __device__ __forceinline__ double *T2_() const { return C.t2 + (long long)rep * C.N * 3; }
+    __device__ __forceinline__ signed char *ST_() const { return C.states + (long long)rep * C.N * NB; }
+    __device__ __forceinline__ const signed char *MOD_() const { return C.mods + (long long)rep * C.N * NB; }
+    __device__ __forceinline__ bool has_field() const {
+        return C.field_active || C.confine_type != CHROMO_CONFINE_NONE;
     }
 
     // trial (r, t3) of a bead of the moving segment
@@ -519,6 +492,7 @@ struct McWarp {
             apply_affine(S.M, r, rn);
             apply_rot(S.M, t, tn);
         } else {
+#pragma unroll
             for (int j = 0; j < 3; j++) {
                 rn[j] = r[j] + S.M[4 * j + 3];
                 tn[j] = t[j];
@@ -526,157 +500,264 @@ struct McWarp {
         }
     }
 
-    // ---- crank-shaft / end-pivot / slide ---------------------------------
-    __device__ void segment_move(int mtype) {
+    // ---- proposal of crank-shaft / end-pivot / slide / binding (lane 0) -----
+    // Draw order follows the reference exactly; the
+    // transcendental work on the drawn integers is done afterwards in one place.
+    __device__ __forceinline__ void segment_propose_lane0(int mtype) {
         const int N = C.N;
-        double *Rr = R_(), *T3 = T3_(), *T2 = T2_();
-        if (lane == 0) {
-            chromo_move_state &mv = S.mv[mtype];
-            mv.num_attempt += 1; // MCAdapter.propose moves.pyx:151
-            int ind0 = 0, indf = 0, ful = 0, rot = 0;
-            double ang = 0.0, axis[3] = {0.0, 0.0, 0.0};
-            if (mtype == CHROMO_CRANK_SHAFT) { // move_funcs.pyx:80-99
-                ang = mv.amp_move * (u01(rng.next31()) - 0.5);
-                int b0 = (int)(u01(rng.next31()) * (double)N);
-                int b1 = max(from_point(rng, mv.amp_bead, N, b0), 1);
-                check_bead_bounds(b0, b1, N, ind0, indf);
-                if (indf > ind0) {
-                    int a, b; // get_crank_shaft_axis move_funcs.pyx:157-234
-                    if (ind0 == indf - 1 && ind0 == 0) { a = indf; b = ind0; }
-                    else if (ind0 == indf - 1 && ind0 == N - 1) { a = ind0; b = ind0 - 1; }
-                    else if (ind0 == 0 && indf == N) { a = indf - 1; b = ind0; }
-                    else if (ind0 == 0) { a = indf; b = ind0; }
-                    else if (indf == N) { a = indf - 1; b = ind0 - 1; }
-                    else { a = indf; b = ind0 - 1; }
-                    // get_crank_shaft_fulcrum move_funcs.pyx:237-280
-                    if (ind0 == 0 && indf != N) ful = indf;
-                    else if (ind0 != 0 && indf == N) ful = ind0 - 1;
-                    else if (ind0 == 0 && indf == N) ful = ind0;
-                    else ful = ind0 - 1;
-                    for (int j = 0; j < 3; j++) axis[j] = Rr[3 * a + j] - Rr[3 * b + j];
-                    double mag = sqrt((axis[0] * axis[0] + axis[1] * axis[1]) + axis[2] * axis[2]);
-                    if (mag < 1E-5) {
-                        rot = 2; // axis from the unit sphere (two more draws)
+        const double *Rr = R_();
+        chromo_move_state &mv = S.mv[mtype];
+        mv.num_attempt += 1; // MCAdapter.propose moves.pyx:151
+        const bool crank = mtype == CHROMO_CRANK_SHAFT, pivot = mtype == CHROMO_END_PIVOT;
+        const bool slide = mtype == CHROMO_SLIDE, bind = mtype == CHROMO_CHANGE_BINDING_STATE;
+        double amp = 0.0;
+        uint32_t d1 = 0, d2 = 0;
+        int b0 = 0, lhs = 0, binder = 0;
+        bool sphere = pivot || slide;
+        if (crank) { // move_funcs.pyx:80-84
+            amp = mv.amp_move * (u01(rng.next31()) - 0.5);
+            b0 = (int)(u01(rng.next31()) * (double)N);
+        } else if (pivot) { // move_funcs.pyx:325-326
+            amp = mv.amp_move * (u01(rng.next31()) - 0.5);
+            lhs = (int)(rng.next31() % 2u);
+        } else if (slide) { // move_funcs.pyx:441-445
+            amp = mv.amp_move * u01(rng.next31());
+            d1 = rng.next31();
+            d2 = rng.next31();
+            b0 = (int)(rng.next31() % (uint32_t)N);
+        } else { // move_funcs.pyx:763-766
+            binder = (int)(rng.next31() % (uint32_t)NB);
+            b0 = (int)(rng.next31() % (uint32_t)N);
+        }
+        // exponential window: from_left / from_right / from_point (bead_selection.pyx:69-154)
+        int side = 0, ws = mv.amp_bead, ce = 0;
+        bool do_ce = true;
+        if (!pivot) {
+            if (mv.amp_bead < 1) do_ce = false;
+            else {
+                side = (int)(rng.next31() % 2u);
+                ws = side == 0 ? max(min(mv.amp_bead, b0), 1) : max(min(mv.amp_bead, N - b0), 1);
+            }
+        }
+        if (do_ce) ce = capped_exponential(rng, ws, ws);
+        int ind0, indf;
+        if (pivot) {
+            if (lhs == 1) {
+                ind0 = 0;
+                indf = ce + 1;
+            } else {
+                ind0 = N - ce;
+                indf = N;
+            }
+        } else {
+            int b1 = !do_ce ? b0 : (side == 0 ? max(b0, 1) - ce : ce + b0);
+            if (crank) b1 = max(b1, 1);
+            check_bead_bounds(b0, b1, N, ind0, indf);
+        }
+        const int n = indf - ind0;
+        S.ind0 = ind0;
+        S.indf = indf;
+        S.n = n;
+        S.binder = binder;
+        if (n <= 0) return;
+        if (bind) { // conduct_change_binding_states move_funcs.pyx:778-820
+            signed char *dst = (n <= 256) ? S.newst : (C.st_new + (long long)rep * N);
+            for (int i = 0; i < n; i++) dst[i] = (signed char)rng.randint(C.sites[binder] + 1);
+            return;
+        }
+        double axis[3] = {0.0, 0.0, 0.0};
+        int ful = 0;
+        if (crank) {
+            int a, b; // get_crank_shaft_axis move_funcs.pyx:157-234
+            if (ind0 == indf - 1 && ind0 == 0) { a = indf; b = ind0; }
+            else if (ind0 == indf - 1 && ind0 == N - 1) { a = ind0; b = ind0 - 1; }
+            else if (ind0 == 0 && indf == N) { a = indf - 1; b = ind0; }
+            else if (ind0 == 0) { a = indf; b = ind0; }
+            else if (indf == N) { a = indf - 1; b = ind0 - 1; }
+            else { a = indf; b = ind0 - 1; }
+            // get_crank_shaft_fulcrum move_funcs.pyx:237-280
+            if (ind0 == 0 && indf != N) ful = indf;
+            else if (ind0 != 0 && indf == N) ful = ind0 - 1;
+            else if (ind0 == 0 && indf == N) ful = ind0;
+            else ful = ind0 - 1;
+#pragma unroll
+            for (int j = 0; j < 3; j++) axis[j] = Rr[3 * a + j] - Rr[3 * b + j];
+            double mag = sqrt((axis[0] * axis[0] + axis[1] * axis[1]) + axis[2] * axis[2]);
+            if (mag < 1E-5) sphere = true; // axis from the unit sphere (two more draws)
+            else {
+                double sc = 1.0 / mag;
+#pragma unroll
+                for (int j = 0; j < 3; j++) axis[j] = axis[j] * sc;
+            }
+        } else if (pivot) { // get_end_pivot_fulcrum move_funcs.pyx:349-398
+            if (ind0 == 0 && indf != N) ful = indf;
+            else if (ind0 != 0 && indf == N) ful = ind0 - 1;
+            else if (ind0 == 0 && indf == N && lhs == 1) ful = indf - 1;
+            else ful = ind0;
+        }
+        if (sphere && !slide) {
+            d1 = rng.next31();
+            d2 = rng.next31();
+        }
+        // ---- one place for the trigonometry: angles in, (sin, cos) out ----
+        // uniform_sample_unit_sphere linalg.pyx:23-59, arbitrary_axis_rotation 62-139
+        double ang3[3], sn3[3], cs3[3];
+        ang3[0] = amp;
+        ang3[1] = u01(d1) * (2.0 * 3.14159265358979323846);
+        ang3[2] = sphere ? acos(u01(d2) * 2.0 - 1.0) : 0.0;
+#pragma unroll
+        for (int t = 0; t < 3; t++) { S.trig[t] = ang3[t]; }
+#pragma unroll 1
+        for (int t = slide ? 1 : 0; t < (sphere ? 3 : 1); t++) {
+            double s_, c_;
+            sincos(S.trig[t], &s_, &c_);
+            S.trig[3 + t] = s_;
+            S.trig[6 + t] = c_;
+        }
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            sn3[t] = S.trig[3 + t];
+            cs3[t] = S.trig[6 + t];
+        }
+        if (sphere) {
+            axis[0] = cs3[1] * sn3[2];
+            axis[1] = sn3[1] * sn3[2];
+            axis[2] = cs3[2];
+        }
+        if (slide) { // generate_translation_mat linalg.pyx:172-199
+#pragma unroll
+            for (int j = 0; j < 3; j++) S.M[4 * j + 3] = axis[j] * amp;
+        } else {
+            double pt[3];
+            load3(Rr + 3 * ful, pt);
+            rotation_matrix_sc(axis, pt, sn3[0], cs3[0], S.M);
+        }
+    }
+
+    // ---- elastic / binding part of dE for the segment moves -----------------
+    __device__ __forceinline__ double segment_dE_poly(int mtype, int kind, int ind0, int indf, int n,
+                                                      int binder, const signed char *newst, int ddbl[NB]) {
+        const int N = C.N;
+        if (kind != 2) {
+            // continuous_dE_poly polymers.pyx:1084-1146: four lanes, one bond energy each:
+            // 0 = left bond with the trial bead, 1 = left bond as is, 2 / 3 = right bond
+            const double *Rr = R_(), *T3 = T3_();
+            double e = 0.0;
+            if (lane < 4) {
+                const bool left = lane < 2;
+                const bool present = left ? (ind0 != 0) : (indf != N);
+                if (present) {
+                    const int bond = left ? ind0 - 1 : indf - 1;
+                    const int mbead = left ? ind0 : indf - 1;
+                    double r[3], t[3], rn[3], tn[3];
+                    load3(Rr + 3 * mbead, r);
+                    load3(T3 + 3 * mbead, t);
+                    trial_rt(kind, r, t, rn, tn);
+                    const int moved = (lane & 1) ? 0 : (left ? 2 : 1);
+                    e = pair_energy(C, rep, bond, moved, rn, tn);
+                }
+            }
+            const double e1 = __shfl_down_sync(FULL_MASK, e, 1);
+            const double d01 = e - e1; // lanes 0 and 2 hold (trial - current) of their bond
+            return __shfl_sync(FULL_MASK, d01, 0) + __shfl_sync(FULL_MASK, d01, 2);
+        }
+        // binding_dE / bead_binding_dE polymers.pyx:1383-1538
+        const signed char *ST = ST_();
+        const signed char *MOD = MOD_();
+        double de = 0.0;
+#pragma unroll
+        for (int m = 0; m < NB; m++) ddbl[m] = 0;
+        for (int base = 0; base < n; base += 32) {
+            int i = base + lane;
+            if (i < n) {
+                int bead = ind0 + i;
+                double d = 0.0;
+                int sc[NB], sn[NB];
+#pragma unroll
+                for (int m = 0; m < NB; m++) {
+                    sc[m] = ST[bead * NB + m];
+                    sn[m] = (m == binder) ? (int)newst[i] : sc[m];
+                    ddbl[m] += (sn[m] == 2) - (sc[m] == 2); // count_doubly_bound fields.pyx:1877-1937
+                }
+                if (C.max_binders != -1) {
+                    long long tot = 0;
+#pragma unroll
+                    for (int m = 0; m < NB; m++) tot += sn[m];
+                    if (tot > C.max_binders) d += CB_E_HUGE_POLY * (double)(tot - C.max_binders);
+                    tot = 0;
+#pragma unroll
+                    for (int m = 0; m < NB; m++) tot += sc[m];
+                    if (tot > C.max_binders) d -= CB_E_HUGE_POLY * (double)(tot - C.max_binders);
+                }
+#pragma unroll
+                for (int m = 0; m < NB; m++) {
+                    int Nm = MOD[bead * NB + m];
+                    const double *Ft = C.bindF + (m * C.S1 + Nm) * C.S1;
+                    double mu = C.mu[(long long)rep * NB + m];
+                    d += Ft[sn[m]];
+                    d -= Ft[sc[m]];
+                    if (mu > 0) {
+                        d -= (double)sn[m] * (mu * (-mu_adjust + 2.0));
+                        d += (double)sc[m] * (mu * (-mu_adjust + 2.0));
                     } else {
-                        double sc = 1.0 / mag;
-                        for (int j = 0; j < 3; j++) axis[j] = axis[j] * sc;
-                        rot = 1;
+                        d -= (double)sn[m] * mu * mu_adjust;
+                        d += (double)sc[m] * mu * mu_adjust;
                     }
                 }
-            } else if (mtype == CHROMO_END_PIVOT) { // move_funcs.pyx:325-344
-                ang = mv.amp_move * (u01(rng.next31()) - 0.5);
-                int lhs = (int)(rng.next31() % 2u);
-                int ce = capped_exponential(rng, mv.amp_bead, mv.amp_bead);
-                if (lhs == 1) {
-                    ind0 = 0;
-                    indf = ce + 1;
-                } else {
-                    ind0 = N - ce;
-                    indf = N;
-                }
-                // get_end_pivot_fulcrum move_funcs.pyx:349-398
-                if (ind0 == 0 && indf != N) ful = indf;
-                else if (ind0 != 0 && indf == N) ful = ind0 - 1;
-                else if (ind0 == 0 && indf == N && lhs == 1) ful = indf - 1;
-                else ful = ind0;
-                rot = 2;
-            } else { // slide move_funcs.pyx:441-463
-                ang = mv.amp_move * u01(rng.next31());
-                rot = 3;
-            }
-            if (rot >= 2) { // uniform_sample_unit_sphere linalg.pyx:23-59
-                uint32_t d1 = rng.next31(), d2 = rng.next31();
-                sphere_from_draws(d1, d2, axis);
-            }
-            if (rot == 3) {
-                for (int j = 0; j < 3; j++) S.M[4 * j + 3] = axis[j] * ang;
-                int b0 = (int)(rng.next31() % (uint32_t)N);
-                int b1 = from_point(rng, mv.amp_bead, N, b0);
-                check_bead_bounds(b0, b1, N, ind0, indf);
-            } else if (rot != 0) {
-                double pt[3];
-                load3(Rr + 3 * ful, pt);
-                rotation_matrix(axis, pt, ang, S.M);
-            }
-            S.ind0 = ind0;
-            S.indf = indf;
-            S.n = indf - ind0;
-        }
-        __syncwarp();
-        const int ind0 = S.ind0, indf = S.indf, n = S.n;
-        if (n <= 0) return; // mc_sim.pyx:151-152
-        const int kind = (mtype == CHROMO_SLIDE) ? 1 : 0;
-
-        // ---- elastic dE: continuous_dE_poly polymers.pyx:1084-1146 -------
-        // four lanes, one bond energy each: 0 = left bond with the trial bead,
-        // 1 = left bond as is, 2 = right bond with the trial bead, 3 = as is
-        double e = 0.0;
-        if (lane < 4) {
-            const bool left = lane < 2;
-            const bool present = left ? (ind0 != 0) : (indf != N);
-            if (present) {
-                const int bond = left ? ind0 - 1 : indf - 1;
-                const int mbead = left ? ind0 : indf - 1;
-                double r[3], t[3], rn[3], tn[3];
-                load3(Rr + 3 * mbead, r);
-                load3(T3 + 3 * mbead, t);
-                trial_rt(kind, r, t, rn, tn);
-                const int moved = (lane & 1) ? 0 : (left ? 2 : 1);
-                e = pair_energy(C, rep, bond, moved, make_double3(rn[0], rn[1], rn[2]),
-                                make_double3(tn[0], tn[1], tn[2]));
+                de += d;
             }
         }
-        const double e0 = __shfl_sync(FULL_MASK, e, 0), e1 = __shfl_sync(FULL_MASK, e, 1);
-        const double e2 = __shfl_sync(FULL_MASK, e, 2), e3 = __shfl_sync(FULL_MASK, e, 3);
-        const double dE_poly = (e0 - e1) + (e2 - e3);
+        double dE_poly = warp_sum(de);
+        if (n == 1) dE_poly = __shfl_sync(FULL_MASK, de, 0); // exact for the default amp_bead = 1
+#pragma unroll
+        for (int m = 0; m < NB; m++) ddbl[m] = warp_sum_int(ddbl[m]);
+        return dE_poly;
+    }
 
-        // ---- field dE ----------------------------------------------------
-        double dE_field = 0.0;
-        if (C.field_active)
-            dE_field = field_dE_segment<NB, DEBUG>(C, H, S, rep, lane, kind, ind0, n, 0, nullptr, nullptr, dbg);
-        else if (C.confine_type != CHROMO_CONFINE_NONE)
-            dE_field = confinement_dE_segment(C, S, rep, lane, kind, ind0, n);
-        if (DEBUG) debug_report(kind, ind0, n, 0, nullptr, dE_poly, dE_field);
-
-        double dE = 0.0;
-        dE += dE_poly;
-        if (has_field()) dE += dE_field;
-        const bool acc = metropolis(mtype, dE);
-        if (acc) { // MCAdapter.accept moves.pyx:190-226
-            if (C.field_active) field_commit_segment<NB>(C, H, S, rep, lane, kind, ind0, n, 0, nullptr);
+    // MCAdapter.accept moves.pyx:190-226 for the segment moves
+    __device__ __forceinline__ void segment_commit(int kind, int ind0, int n, int binder,
+                                                   const signed char *newst) {
+        if (C.field_active) {
+            if (S.passes == 1) table_commit(C, H, S, rep, lane);
+            else field_commit_multipass<NB>(C, H, &S, rep, lane, kind, ind0, n, binder, newst);
+        }
+        if (kind == 2) {
+            __syncwarp();
+            signed char *ST = ST_();
             for (int base = 0; base < n; base += 32) {
                 int i = base + lane;
-                if (i < n) {
-                    const int o = 3 * (ind0 + i);
-                    double x[3], y[3];
-                    load3(Rr + o, x);
-                    if (kind == 0) {
-                        apply_affine(S.M, x, y);
-                        store3(Rr + o, y);
-                        load3(T3 + o, x);
-                        apply_rot(S.M, x, y);
-                        store3(T3 + o, y);
-                        load3(T2 + o, x);
-                        apply_rot(S.M, x, y);
-                        store3(T2 + o, y);
-                    } else {
-                        for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
-                        store3(Rr + o, y);
-                    }
+                if (i < n) ST[(ind0 + i) * NB + binder] = newst[i];
+            }
+            return;
+        }
+        double *Rr = R_(), *T3 = T3_(), *T2 = T2_();
+        for (int base = 0; base < n; base += 32) {
+            int i = base + lane;
+            if (i < n) {
+                const int o = 3 * (ind0 + i);
+                double x[3], y[3];
+                load3(Rr + o, x);
+                if (kind == 0) {
+                    apply_affine(S.M, x, y);
+                    store3(Rr + o, y);
+                    load3(T3 + o, x);
+                    apply_rot(S.M, x, y);
+                    store3(T3 + o, y);
+                    load3(T2 + o, x);
+                    apply_rot(S.M, x, y);
+                    store3(T2 + o, y);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
+                    store3(Rr + o, y);
                 }
             }
-        }
-        if (C.field_active) table_clear(H, S, NCOL, lane);
-        if (lane == 0) { // B = 72(n+2) + 72 n a + nb n + 8(nb+1) U (1+2a) + 80   
-            unsigned long long U = C.field_active ? (unsigned long long)S.last_U : 0ull;
-            S.algo_bytes += 72ull * (n + 2) + (acc ? 72ull * n : 0ull) + (unsigned long long)NB * n +
-                            8ull * NCOL * U * (acc ? 3ull : 1ull) + 80ull;
         }
     }
 
     // instrumentation of the single-step kernel: moved beads + their trial rows
-    __device__ CB_NOINLINE void debug_report(int kind, int ind0, int n, int binder, const signed char *newst,
-                                              double dE_poly, double dE_field) {
+    __device__ __forceinline__ void debug_report(int kind, int ind0, int n, int binder, const signed char *newst,
+                                             double dE_poly, double dE_field) {
         const double *Rr = R_(), *T3 = T3_(), *T2 = T2_();
         const signed char *ST = ST_();
         const int W = 9 + NB;
@@ -718,106 +799,6 @@ struct McWarp {
         __syncwarp();
     }
 
-    // ---- change_binding_state move_funcs.pyx:717-820 ----------------------
-    __device__ void binding_move() {
-        const int N = C.N;
-        signed char *ST = ST_();
-        const signed char *MOD = MOD_();
-        if (lane == 0) {
-            chromo_move_state &mv = S.mv[CHROMO_CHANGE_BINDING_STATE];
-            mv.num_attempt += 1;
-            int binder = (int)(rng.next31() % (uint32_t)NB);
-            int b0 = (int)(rng.next31() % (uint32_t)N);
-            int b1 = from_point(rng, mv.amp_bead, N, b0);
-            int ind0, indf;
-            check_bead_bounds(b0, b1, N, ind0, indf);
-            S.ind0 = ind0;
-            S.indf = indf;
-            S.n = indf - ind0;
-            S.binder = binder;
-            int n = indf - ind0;
-            signed char *dst = (n <= 256) ? S.newst : (C.st_new + (long long)rep * N);
-            for (int i = 0; i < n; i++) dst[i] = (signed char)rng.randint(C.sites[binder] + 1);
-        }
-        __syncwarp();
-        const int ind0 = S.ind0, n = S.n, binder = S.binder;
-        if (n <= 0) return;
-        const signed char *newst = (n <= 256) ? S.newst : (C.st_new + (long long)rep * N);
-
-        // ---- binding_dE / bead_binding_dE polymers.pyx:1383-1538 ----------
-        double de = 0.0;
-        int ddbl[NB]; // count_doubly_bound fields.pyx:1877-1937: trial minus current
-#pragma unroll
-        for (int m = 0; m < NB; m++) ddbl[m] = 0;
-        for (int base = 0; base < n; base += 32) {
-            int i = base + lane;
-            if (i < n) {
-                int bead = ind0 + i;
-                double d = 0.0;
-                int sc[NB], sn[NB];
-#pragma unroll
-                for (int m = 0; m < NB; m++) {
-                    sc[m] = ST[bead * NB + m];
-                    sn[m] = (m == binder) ? (int)newst[i] : sc[m];
-                    ddbl[m] += (sn[m] == 2) - (sc[m] == 2);
-                }
-                if (C.max_binders != -1) {
-                    long long tot = 0;
-#pragma unroll
-                    for (int m = 0; m < NB; m++) tot += sn[m];
-                    if (tot > C.max_binders) d += CB_E_HUGE_POLY * (double)(tot - C.max_binders);
-                    tot = 0;
-#pragma unroll
-                    for (int m = 0; m < NB; m++) tot += sc[m];
-                    if (tot > C.max_binders) d -= CB_E_HUGE_POLY * (double)(tot - C.max_binders);
-                }
-#pragma unroll
-                for (int m = 0; m < NB; m++) {
-                    int Nm = MOD[bead * NB + m];
-                    const double *Ft = C.bindF + (m * C.S1 + Nm) * C.S1;
-                    double mu = C.mu[(long long)rep * NB + m];
-                    d += Ft[sn[m]];
-                    d -= Ft[sc[m]];
-                    if (mu > 0) {
-                        d -= (double)sn[m] * (mu * (-mu_adjust + 2.0));
-                        d += (double)sc[m] * (mu * (-mu_adjust + 2.0));
-                    } else {
-                        d -= (double)sn[m] * mu * mu_adjust;
-                        d += (double)sc[m] * mu * mu_adjust;
-                    }
-                }
-                de += d;
-            }
-        }
-        double dE_poly = warp_sum(de);
-        if (n == 1) dE_poly = __shfl_sync(FULL_MASK, de, 0); // exact for the default amp_bead = 1
-#pragma unroll
-        for (int m = 0; m < NB; m++) ddbl[m] = warp_sum_int(ddbl[m]);
-
-        double dE_field = 0.0;
-        if (C.field_active)
-            dE_field = field_dE_segment<NB, DEBUG>(C, H, S, rep, lane, 2, ind0, n, binder, newst, ddbl, dbg);
-        if (DEBUG) debug_report(2, ind0, n, binder, newst, dE_poly, dE_field);
-        double dE = 0.0;
-        dE += dE_poly;
-        if (has_field()) dE += dE_field;
-        const bool acc = metropolis(CHROMO_CHANGE_BINDING_STATE, dE);
-        if (acc) {
-            if (C.field_active) field_commit_segment<NB>(C, H, S, rep, lane, 2, ind0, n, binder, newst);
-            __syncwarp();
-            for (int base = 0; base < n; base += 32) {
-                int i = base + lane;
-                if (i < n) ST[(ind0 + i) * NB + binder] = newst[i];
-            }
-        }
-        if (C.field_active) table_clear(H, S, NCOL, lane);
-        if (lane == 0) { // binding: 24 n (positions) + nb n (1+a) + 8(nb+1) U (1+2a)
-            unsigned long long U = C.field_active ? (unsigned long long)S.last_U : 0ull;
-            S.algo_bytes += 24ull * n + (unsigned long long)NB * n * (acc ? 2ull : 1ull) +
-                            8ull * NCOL * U * (acc ? 3ull : 1ull);
-        }
-    }
-
     // ---- tangent_rotation move_funcs.pyx:470-582 --------------------------
     // per selected bead: own random axis, rotate t3/t2, both adjacent bonds
     // against the CURRENT neighbours (polymers.pyx:1075-1080; quirk 8); never
@@ -825,10 +806,11 @@ struct McWarp {
     // A chunk of up to 8 beads is evaluated by 4 lanes per bead (one bond energy
     // each: left bond trial / as is, right bond trial / as is); the new tangents
     // of chunk bead j go to out[6j..6j+5] (shared) when `out` is given, or
-    // straight to global memory when `store` is set.  Returns this chunk's dE on
-    // all lanes (ordered sum over beads).
-    __device__ CB_NOINLINE double tangent_chunk(const int *beads, int cnt, const uint32_t *draws, double ang,
-                                                 double *out, bool store, int dbg_base, double acc_in) {
+    // straight to global memory when `store` is set.  Returns acc_in + this
+    // chunk's dE on all lanes (bead-by-bead sum, as the reference accumulates).
+    __device__ __forceinline__ double tangent_chunk(const int *beads, int cnt, const uint32_t *draws,
+                                                    double ang, double *out, bool store, int dbg_base,
+                                                    double acc_in) {
         const double *Rr = R_();
         double *T3 = T3_(), *T2 = T2_();
         const int N = C.N;
@@ -836,10 +818,24 @@ struct McWarp {
         double e = 0.0;
         if (j < cnt) {
             const int bead = beads[j];
+            // trigonometry in one place: angle, phi, theta per lane
+            double *tr = S.tan_trig + lane;
+            tr[0] = ang;
+            tr[32] = u01(draws[2 * j]) * (2.0 * 3.14159265358979323846);
+            tr[64] = acos(u01(draws[2 * j + 1]) * 2.0 - 1.0);
+#pragma unroll 1
+            for (int t = 0; t < 3; t++) {
+                double s_, c_;
+                sincos(tr[32 * t], &s_, &c_);
+                tr[96 + 32 * t] = s_;
+                tr[192 + 32 * t] = c_;
+            }
             double axis[3], M[12], t3c[3], t2c[3], t3n[3], t2n[3], rc[3];
             const double origin[3] = {0.0, 0.0, 0.0};
-            sphere_from_draws(draws[2 * j], draws[2 * j + 1], axis);
-            rotation_matrix(axis, origin, ang, M);
+            axis[0] = tr[192 + 32] * tr[96 + 64];
+            axis[1] = tr[96 + 32] * tr[96 + 64];
+            axis[2] = tr[192 + 64];
+            rotation_matrix_sc(axis, origin, tr[96], tr[192], M);
             load3(T3 + 3 * bead, t3c);
             load3(T2 + 3 * bead, t2c);
             load3(Rr + 3 * bead, rc);
@@ -849,8 +845,7 @@ struct McWarp {
             const bool present = left ? (bead != 0) : (bead + 1 != N);
             if (!store && present) {
                 const int moved = (which & 1) ? 0 : (left ? 2 : 1);
-                e = pair_energy(C, rep, left ? bead - 1 : bead, moved, make_double3(rc[0], rc[1], rc[2]),
-                                make_double3(t3n[0], t3n[1], t3n[2]));
+                e = pair_energy(C, rep, left ? bead - 1 : bead, moved, rc, t3n);
             }
             if (which == 0) {
                 if (out) {
@@ -875,111 +870,29 @@ struct McWarp {
         const double l0 = __shfl_down_sync(FULL_MASK, e, 1), r0 = __shfl_down_sync(FULL_MASK, e, 2),
                      r1 = __shfl_down_sync(FULL_MASK, e, 3);
         const double d = (e - l0) + (r0 - r1); // valid on which == 0 lanes
-        double tot = acc_in; // the reference accumulates bead by bead (polymers.pyx:1075-1080)
+        double tot = acc_in;
         for (int b = 0; b < cnt; b++) tot += __shfl_sync(FULL_MASK, d, 4 * b);
         return tot;
     }
 
-    __device__ void tangent_move() {
-        const int N = C.N;
-        double ang = 0.0;
-        int k = 0;
-        if (lane == 0) {
-            chromo_move_state &mv = S.mv[CHROMO_TANGENT_ROTATION];
-            mv.num_attempt += 1;
-            ang = mv.amp_move * (u01(rng.next31()) - 0.5);
-            k = (int)(rng.next31() % (uint32_t)mv.amp_bead) + 1;
-        }
-        ang = __shfl_sync(FULL_MASK, ang, 0);
-        k = __shfl_sync(FULL_MASK, k, 0);
-        const bool small = k <= 32;
-        int *inds = small ? S.tinds : C.tan_inds + (long long)rep * N;
-        // get_inds move_funcs.pyx:552-582: k distinct draws, redraw on duplicates
-        if (small) {
-            int my = -1;
-            for (int i = 0; i < k; i++) {
-                int c = 0;
-                bool dup;
-                do {
-                    if (lane == 0) c = (int)(rng.next31() % (uint32_t)N);
-                    c = __shfl_sync(FULL_MASK, c, 0);
-                    dup = __any_sync(FULL_MASK, lane < i && my == c);
-                } while (dup);
-                if (lane == i) my = c;
-            }
-            if (lane < k) S.tinds[lane] = my;
-        } else {
-            uint32_t *bits = C.sel_bits + (long long)rep * ((N + 31) / 32);
-            for (int i = lane; i < (N + 31) / 32; i += 32) bits[i] = 0u;
-            __syncwarp();
-            if (lane == 0)
-                for (int i = 0; i < k; i++) {
-                    int c;
-                    do {
-                        c = (int)(rng.next31() % (uint32_t)N);
-                    } while ((bits[c >> 5] >> (c & 31)) & 1u);
-                    bits[c >> 5] |= 1u << (c & 31);
-                    inds[i] = c;
-                }
-        }
-        if (lane == 0 && !small) rng.save(S.rng_save);
-        __syncwarp();
-        // per-bead axis draws (phi, theta) in bead order, then the energies
+    // draws + energies of a tangent-rotation proposal; `pass` 0 = evaluate,
+    // 1 = re-run the per-bead draws and store (large path commit)
+    __device__ __forceinline__ double tangent_eval(const int *inds, int k, double ang, bool small, bool store) {
         double dE_poly = 0.0;
         for (int base = 0; base < k; base += 8) {
             const int cnt = min(8, k - base);
             if (lane == 0)
                 for (int i = 0; i < 2 * cnt; i++) S.draws[i] = rng.next31();
             __syncwarp();
-            dE_poly = tangent_chunk(inds + base, cnt, S.draws, ang, small ? S.tan_new + 6 * base : nullptr,
-                                    false, base, dE_poly);
+            dE_poly = tangent_chunk(inds + base, cnt, S.draws, ang,
+                                    (small && !store) ? S.tan_new + 6 * base : nullptr, store, base, dE_poly);
             __syncwarp();
         }
-        if (DEBUG) {
-            if (lane == 0) {
-                dbg->n_inds = k;
-                dbg->dE_poly = dE_poly;
-                dbg->dE_field = 0.0;
-                dbg->n_touched = 0;
-                dbg->passes = 0;
-            }
-            __syncwarp();
-        }
-        double dE = 0.0;
-        dE += dE_poly;
-        const bool acc = metropolis(CHROMO_TANGENT_ROTATION, dE);
-        if (acc) {
-            double *T3 = T3_(), *T2 = T2_();
-            if (small) {
-                if (lane < k) {
-                    store3(T3 + 3 * S.tinds[lane], S.tan_new + 6 * lane);
-                    store3(T2 + 3 * S.tinds[lane], S.tan_new + 6 * lane + 3);
-                }
-            } else {
-                // regenerate the per-bead draws from the saved RNG state; a bead's new
-                // tangents depend on its own t3/t2 only, so storing chunk by chunk is safe
-                uint32_t after[CB_GLIBC_WORDS];
-                if (lane == 0) {
-                    rng.save(after);
-                    rng.restore(S.rng_save);
-                }
-                for (int base = 0; base < k; base += 8) {
-                    const int cnt = min(8, k - base);
-                    if (lane == 0)
-                        for (int i = 0; i < 2 * cnt; i++) S.draws[i] = rng.next31();
-                    __syncwarp();
-                    (void)tangent_chunk(inds + base, cnt, S.draws, ang, nullptr, true, base, 0.0);
-                    __syncwarp();
-                }
-                if (lane == 0) rng.restore(after);
-            }
-        }
-        if (lane == 0) // tangent rotation: B = 48 n + 72*2n + 48 n a   
-            S.algo_bytes += 48ull * k + 144ull * k + (acc ? 48ull * k : 0ull);
+        return dE_poly;
     }
 
     // SimpleControl.update_move_amplitude mc_controller.py:148-213 (lane 0)
-    __device__ void update_amplitudes(int mtype) {
+    __device__ __forceinline__ void update_amplitudes(int mtype) {
         if (lane != 0) return;
         chromo_move_state &mv = S.mv[mtype];
         if (mv.controller != 1) return;
@@ -1004,11 +917,157 @@ struct McWarp {
         }
     }
 
-    __device__ void step(int mtype) {
-        if (mtype == CHROMO_TANGENT_ROTATION) tangent_move();
-        else if (mtype == CHROMO_CHANGE_BINDING_STATE) binding_move();
-        else segment_move(mtype);
+    // ---- one mc_step (mc_sim.pyx:106-182) -----------------------------------
+    __device__ __forceinline__ void step(int mtype) {
+        const int N = C.N;
+        const bool tangent = mtype == CHROMO_TANGENT_ROTATION;
+        double dE_poly = 0.0, dE_field = 0.0, ang = 0.0;
+        int kind = 0, ind0 = 0, n = 0, binder = 0, k = 0;
+        const signed char *newst = nullptr;
+        const int *tinds = S.tinds;
+        bool small = true;
+        // ================= proposal + energies =================
+        if (!tangent) {
+            if (lane == 0) segment_propose_lane0(mtype);
+            __syncwarp();
+            ind0 = S.ind0;
+            n = S.n;
+            binder = S.binder;
+            if (n <= 0) return; // mc_sim.pyx:151-152
+            kind = mtype == CHROMO_SLIDE ? 1 : (mtype == CHROMO_CHANGE_BINDING_STATE ? 2 : 0);
+            if (kind == 2) newst = (n <= 256) ? S.newst : (C.st_new + (long long)rep * N);
+            int ddbl[NB];
+#pragma unroll
+            for (int m = 0; m < NB; m++) ddbl[m] = 0;
+            dE_poly = segment_dE_poly(mtype, kind, ind0, S.indf, n, binder, newst, ddbl);
+            if (C.field_active)
+                dE_field = field_dE_segment<NB, DEBUG>(C, H, S, rep, lane, kind, ind0, n, binder, newst, ddbl, dbg);
+            else if (kind != 2 && C.confine_type != CHROMO_CONFINE_NONE)
+                dE_field = confinement_dE_segment(C, S, rep, lane, kind, ind0, n);
+            if (DEBUG) debug_report(kind, ind0, n, binder, newst, dE_poly, dE_field);
+        } else {
+            if (lane == 0) {
+                chromo_move_state &mv = S.mv[CHROMO_TANGENT_ROTATION];
+                mv.num_attempt += 1;
+                ang = mv.amp_move * (u01(rng.next31()) - 0.5);
+                k = (int)(rng.next31() % (uint32_t)mv.amp_bead) + 1;
+            }
+            ang = __shfl_sync(FULL_MASK, ang, 0);
+            k = __shfl_sync(FULL_MASK, k, 0);
+            small = k <= 32;
+            if (small) { // get_inds move_funcs.pyx:552-582: k distinct draws, redraw duplicates
+                int my = -1;
+                for (int i = 0; i < k; i++) {
+                    int c = 0;
+                    bool dup;
+                    do {
+                        if (lane == 0) c = (int)(rng.next31() % (uint32_t)N);
+                        c = __shfl_sync(FULL_MASK, c, 0);
+                        dup = __any_sync(FULL_MASK, lane < i && my == c);
+                    } while (dup);
+                    if (lane == i) my = c;
+                }
+                if (lane < k) S.tinds[lane] = my;
+            } else {
+                tinds = tangent_select_large(k);
+            }
+            __syncwarp();
+            dE_poly = tangent_eval(tinds, k, ang, small, false);
+            if (DEBUG) {
+                if (lane == 0) {
+                    dbg->n_inds = k;
+                    dbg->dE_poly = dE_poly;
+                    dbg->dE_field = 0.0;
+                    dbg->n_touched = 0;
+                    dbg->passes = 0;
+                }
+                __syncwarp();
+            }
+        }
+        // ================= Metropolis (mc_sim.pyx:163-171) =================
+        double dE = 0.0;
+        dE += dE_poly;
+        if (!tangent && has_field()) dE += dE_field;
+        int acc = 0;
+        if (lane == 0) {
+            double u = __longlong_as_double(0x7ff8000000000000LL);
+            if (DEBUG && force_accept >= 0) {
+                acc = force_accept;
+            } else {
+                double e = exp(-dE);
+                u = u01(rng.next31());
+                acc = (u < e) ? 1 : 0;
+            }
+            if (DEBUG) {
+                dbg->u = u;
+                dbg->accepted = acc;
+            }
+            // counters + AcceptanceTracker.update_acceptance_rate mc_stat.py:190-207
+            chromo_move_state &mv = S.mv[mtype];
+            if (acc) mv.num_success += 1;
+            mv.acceptance_rate = (mv.alpha * (acc ? 1.0 : 0.0)) + (1.0 - mv.alpha) * mv.acceptance_rate;
+            // algorithmic bytes of this attempt
+            if (tangent) {
+                S.algo_bytes += 48ull * k + 144ull * k + (acc ? 48ull * k : 0ull);
+            } else {
+                unsigned long long U = C.field_active ? (unsigned long long)S.last_U : 0ull;
+                if (kind == 2)
+                    S.algo_bytes += 24ull * n + (unsigned long long)NB * n * (acc ? 2ull : 1ull) +
+                                    8ull * NCOL * U * (acc ? 3ull : 1ull);
+                else
+                    S.algo_bytes += 72ull * (n + 2) + (acc ? 72ull * n : 0ull) + (unsigned long long)NB * n +
+                                    8ull * NCOL * U * (acc ? 3ull : 1ull) + 80ull;
+            }
+        }
+        acc = __shfl_sync(FULL_MASK, acc, 0);
+        // ================= accept (moves.pyx:156-239) =================
+        if (acc) {
+            if (!tangent) segment_commit(kind, ind0, n, binder, newst);
+            else if (small) {
+                if (lane < k) {
+                    store3(T3_() + 3 * S.tinds[lane], S.tan_new + 6 * lane);
+                    store3(T2_() + 3 * S.tinds[lane], S.tan_new + 6 * lane + 3);
+                }
+            } else {
+                tangent_commit_large(tinds, k, ang);
+            }
+        }
+        if (!tangent && C.field_active) table_clear(H, S, NCOL, lane);
         __syncwarp();
+    }
+
+    // tangent rotation of more than 32 beads (rare): indices in HBM scratch,
+    // membership in a bitmap, per-bead draws regenerated on commit
+    __device__ __forceinline__ const int *tangent_select_large(int k) {
+        const int N = C.N;
+        int *inds = C.tan_inds + (long long)rep * N;
+        uint32_t *bits = C.sel_bits + (long long)rep * ((N + 31) / 32);
+        for (int i = lane; i < (N + 31) / 32; i += 32) bits[i] = 0u;
+        __syncwarp();
+        if (lane == 0) {
+            for (int i = 0; i < k; i++) {
+                int c;
+                do {
+                    c = (int)(rng.next31() % (uint32_t)N);
+                } while ((bits[c >> 5] >> (c & 31)) & 1u);
+                bits[c >> 5] |= 1u << (c & 31);
+                inds[i] = c;
+            }
+            rng.save(S.rng_save);
+        }
+        __syncwarp();
+        return inds;
+    }
+    __device__ __forceinline__ void tangent_commit_large(const int *inds, int k, double ang) {
+        // a bead's new tangents depend on its own t3/t2 only, so regenerating the
+        // per-bead draws from the saved RNG state and storing chunk by chunk is safe
+        uint32_t after[CB_GLIBC_WORDS];
+        if (lane == 0) {
+            rng.save(after);
+            rng.restore(S.rng_save);
+        }
+        (void)tangent_eval(inds, k, ang, false, true);
+        if (lane == 0) rng.restore(after);
     }
 };
 
@@ -1062,7 +1121,7 @@ __device__ __forceinline__ void rng_store<PhiloxRng>(PhiloxRng &rng, const DevCt
 
 // mc_sim mc_sim.pyx:26-103 for every replica: grid = R blocks of one warp.
 template <class Rng, int NB>
-__global__ void __launch_bounds__(32, 8) mc_sim_kernel(DevCtx C, long long num_mc_steps, double mu_adjust,
+__global__ void __launch_bounds__(32, 8) mc_sim_kernel(const CB_GRID_CONSTANT DevCtx C, long long num_mc_steps, double mu_adjust,
                                                        unsigned long long seed, int cap) {
     CB_DYN_SMEM(dyn);
     __shared__ WarpSh S;
@@ -1102,7 +1161,7 @@ __global__ void __launch_bounds__(32, 8) mc_sim_kernel(DevCtx C, long long num_m
 
 // one instrumented mc_step of one replica (chromo_mc_step)
 template <class Rng, int NB>
-__global__ void __launch_bounds__(32) mc_step_kernel(DevCtx C, int rep, int mtype, double amp_move,
+__global__ void __launch_bounds__(32) mc_step_kernel(const CB_GRID_CONSTANT DevCtx C, int rep, int mtype, double amp_move,
                                                      int amp_bead, double mu_adjust,
                                                      unsigned long long seed, int force_accept,
                                                      DebugOut *dbg, int cap) {

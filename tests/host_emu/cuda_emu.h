@@ -111,6 +111,7 @@ static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline double3 make_double3(double x, double y, double z) { return double3{x, y, z}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 #define CB_NOINLINE __attribute__((noinline))
+#define CB_GRID_CONSTANT
 static inline double __longlong_as_double(long long v) {
     double d;
     memcpy(&d, &v, 8);
