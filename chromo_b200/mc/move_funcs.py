@@ -20,9 +20,9 @@ def _propose(name, polymer, amp_move, amp_bead):
         field = NullField([polymer])
         polymer._field = field
     e = field._push(polymer)
-    from . import mc_sim as _ms
+    from .mc_sim import _seed_for, rng_mode
     out = e.mc_step(0, MOVE_ID[name], amp_move, amp_bead, float(polymer.mu_adjust_factor),
-                    _ms.rng_mode(), _ms._seed_for(polymer), force_accept=0)
+                    rng_mode(), _seed_for(polymer), force_accept=0)
     inds = out["inds"]
     rows = out["rows"]
     polymer.r_trial[inds] = rows[:, 0:3]

@@ -1,0 +1,230 @@
+"""The reference-facing Python API (chromo_b200.polymers / binders / fields /
+mc) driven exactly like a chromo script, on both backends, against golden
+vectors from the reference and -- where oracle/_ref is built -- against the
+live reference."""
+import numpy as np
+import pytest
+
+import oracle as O
+from common import close, load_golden
+
+
+def build(spec, lazy=False):
+    import chromo_b200.binders as bnd
+    import chromo_b200.fields as fld
+    import chromo_b200.polymers as ply
+    objs = []
+    for b in spec["binders"]:
+        o = bnd.get_by_name(b["name"])
+        for k in ("sites_per_bead", "bind_energy_mod", "bind_energy_no_mod", "interaction_energy",
+                  "chemical_potential", "interaction_radius"):
+            setattr(o, k, b[k])
+        o.interaction_volume = (4.0 / 3.0) * np.pi * b["interaction_radius"] ** 3
+        o.cross_talk_interaction_energy = dict(b["cross_talk"])
+        o.cross_talk_field_energy_prefactor = {}
+        objs.append(o)
+    binders = bnd.make_binder_collection(objs)
+    N, nb = spec["N"], spec["nb"]
+    p = ply.Chromatin("c", spec["r"].copy(), bead_length=spec["bead_length"], t3=spec["t3"].copy(),
+                      t2=spec["t2"].copy(), states=spec["states"].reshape(N, nb).copy(),
+                      binder_names=np.array([b["name"] for b in spec["binders"]]),
+                      chemical_mods=spec["mods"].reshape(N, nb).copy(),
+                      chemical_mod_names=np.array([f"m{j}" for j in range(nb)]))
+    f = spec["field"]
+    field = fld.UniformDensityField([p], binders, f["x_width"], f["nx"], f["y_width"], f["ny"], f["z_width"],
+                                    f["nz"], confine_type=f["confine_type"], confine_length=f["confine_length"],
+                                    chi=f["chi"], vf_limit=f["vf_limit"])
+    return p, binders, field
+
+
+@pytest.mark.parametrize("name", ["static_c2", "static_c3"])
+def test_construction_and_energies(backend, name):
+    spec, g = load_golden(name)
+    p, binders, field = build(spec)
+    for k in ("eps_bend", "eps_par", "eps_perp", "gamma", "eta"):
+        assert np.array_equal(getattr(p, k), g[k]), k
+    assert np.allclose(field.density, g["density"], rtol=1e-12, atol=0)
+    assert np.array_equal(field.density != 0, g["density"] != 0)
+    assert field.vol_bin == float(g["vol_bin"]) and p.beads[0].vol == float(g["bead_vol"])
+    bd = field.binder_dict
+    assert np.array_equal([b["field_energy_prefactor"] for b in bd], g["field_pref"])
+    assert np.array_equal([b["interaction_energy_intranucleosome"] for b in bd], g["e_intra"])
+    assert close(field.compute_E(p), float(g["E_field"]))
+    assert close(p.compute_E(), float(g["E_poly"]))
+
+
+@pytest.mark.parametrize("name", ["mcsim_c2", "mcsim_c3"])
+def test_mc_sim_drop_in(backend, name):
+    """all_moves + SimpleControl + mc_sim, replaying the reference's RNG streams."""
+    from chromo_b200.mc import get_amplitude_bounds, mc_controller as ctrl, set_rng_mode
+    from chromo_b200.mc.mc_sim import mc_sim
+    spec, g = load_golden(name)
+    p, binders, field = build(spec)
+    bb, mb = get_amplitude_bounds([p])
+    cs = ctrl.all_moves("/tmp/chromo_b200_test", bb.bounds, mb.bounds, ctrl.SimpleControl)
+    for c, k in zip(cs, g["per_cycle"]):
+        c.move.num_per_cycle = int(k)
+    set_rng_mode("replay")
+    try:
+        field._engine_for(p).srand(int(g["srand_seed"]))
+        mc_sim([p], binders, int(g["steps"]), cs, field, float(g["mu_adjust"]), int(g["np_seed"]))
+    finally:
+        set_rng_mode("philox")
+    tol = 0 if backend == "emu" else 1e-7
+    assert np.allclose(p.r, g["final_r"], rtol=0, atol=tol)
+    assert np.allclose(p.t3, g["final_t3"], rtol=0, atol=tol)
+    assert np.array_equal(p.states, g["final_states"])
+    assert np.array_equal(p.r, p.r_trial) and np.array_equal(p.states, p.states_trial)
+    assert [c.move.num_attempt for c in cs] == list(g["num_attempt"])
+    assert [c.move.num_success for c in cs] == list(g["num_success"])
+    assert [c.move.amp_bead for c in cs] == list(g["amp_bead"])
+    assert np.array_equal([c.move.amp_move for c in cs], g["amp_move"])
+    assert np.array_equal([c.move.acceptance_tracker.acceptance_rate for c in cs], g["acceptance_rate"])
+    vol_bin = field.vol_bin
+    assert np.allclose(field.density, g["final_density"], rtol=1e-9, atol=1e-9 / vol_bin)
+
+
+def test_null_field_confinement_and_polymer_in_field(backend):
+    """Tutorial-2 style: SSWLC homopolymer, NullField with a spherical confinement,
+    physical moves only, production RNG, snapshot driver."""
+    import chromo_b200.binders as bnd
+    import chromo_b200.fields as fld
+    import chromo_b200.polymers as ply
+    from chromo_b200.mc import get_amplitude_bounds, mc_controller as ctrl, polymer_in_field
+    from chromo_b200.util import mu_schedules
+    rng = np.random.default_rng(5)
+    N, Rc = 120, 60.0
+    r = O.confined_walk(N, 5.0, Rc, rng)
+    t3, t2 = O.tangents_from_coords(r, rng)
+    p = ply.SSWLC("homopolymer", r, bead_length=np.full(N - 1, 5.0), lp=10.0, t3=t3, t2=t2)
+    assert p.num_binders == 1 and p.binder_names[0] == "null_reader"
+    binders = bnd.make_binder_collection([bnd.get_by_name("null_reader")])
+    field = fld.NullField([p], confine_type="Spherical", confine_length=Rc)
+    bb, mb = get_amplitude_bounds([p])
+    cs = ctrl.all_moves_except_binding_state("/tmp/chromo_b200_test", bb.bounds, mb.bounds, ctrl.SimpleControl)
+    E0 = p.compute_E()
+    snaps = []
+    polymer_in_field([p], binders, field, 5, 3, bb, mb, mc_move_controllers=cs, random_seed=3,
+                     mu_schedule=mu_schedules.Schedule(mu_schedules.linear_step_for_negative_cp),
+                     save_snapshot=lambda i, polys, f, c: snaps.append(polys[0].r.copy()))
+    assert len(snaps) == 3 and not np.array_equal(snaps[0], snaps[2])
+    assert [c.move.num_attempt for c in cs] == [75, 75, 75, 75]
+    assert np.all(np.linalg.norm(p.r, axis=1) <= Rc + 1e-9)          # the confinement held
+    assert np.allclose(np.linalg.norm(p.t3, axis=1), 1.0, atol=1e-9)  # rotations are orthogonal
+    assert p.compute_E() != E0
+    # the same run again is identical (Philox keyed by the seeds)
+    p2 = ply.SSWLC("homopolymer", r, bead_length=np.full(N - 1, 5.0), lp=10.0, t3=t3, t2=t2)
+    f2 = fld.NullField([p2], confine_type="Spherical", confine_length=Rc)
+    cs2 = ctrl.all_moves_except_binding_state("/tmp/chromo_b200_test", bb.bounds, mb.bounds, ctrl.SimpleControl)
+    polymer_in_field([p2], binders, f2, 5, 3, bb, mb, mc_move_controllers=cs2, random_seed=3,
+                     mu_schedule=mu_schedules.Schedule(mu_schedules.linear_step_for_negative_cp))
+    assert np.array_equal(p.r, p2.r)
+
+
+def test_move_functions_and_mc_step(backend):
+    """Proposals through the move functions leave the trial state in the polymer,
+    like the reference's cpdef move functions; mc_step runs one attempt."""
+    from chromo_b200.mc import mc_controller as ctrl, get_amplitude_bounds, move_funcs as mf
+    from chromo_b200.mc.mc_sim import mc_step
+    spec, g = load_golden("static_c2")
+    p, binders, field = build(spec)
+    inds = mf.slide(p, 2.0, 10)
+    assert len(inds) >= 1 and np.array_equal(np.diff(inds), np.ones(len(inds) - 1))
+    d = p.r_trial[inds] - p.r[inds]
+    assert np.allclose(d, d[0]) and 0 < np.linalg.norm(d[0]) <= 2.0 + 1e-12   # one rigid translation
+    assert np.array_equal(p.t3_trial[inds], p.t3[inds])
+    inds = mf.crank_shaft(p, 0.3, 30)
+    a = np.linalg.norm(p.r_trial[inds][1:] - p.r_trial[inds][:-1], axis=1) if len(inds) > 1 else np.zeros(0)
+    b = np.linalg.norm(p.r[inds][1:] - p.r[inds][:-1], axis=1) if len(inds) > 1 else np.zeros(0)
+    assert np.allclose(a, b)                                                   # a rigid rotation
+    bb, mb = get_amplitude_bounds([p])
+    cs = ctrl.all_moves("/tmp/chromo_b200_test", bb.bounds, mb.bounds, ctrl.SimpleControl)
+    r0 = p.r.copy()
+    for _ in range(6):
+        mc_step(cs[2].move, p, binders, field, True, False)
+    assert cs[2].move.num_attempt == 6 and 0 <= cs[2].move.num_success <= 6
+    assert (cs[2].move.num_success > 0) == (not np.array_equal(p.r, r0))
+
+
+def test_argument_validation(backend):
+    import chromo_b200.binders as bnd
+    import chromo_b200.fields as fld
+    import chromo_b200.polymers as ply
+    spec, g = load_golden("static_c2")
+    N = spec["N"]
+    with pytest.raises(ValueError, match="chemical state must be given a name"):
+        ply.Chromatin("c", spec["r"], bead_length=spec["bead_length"], t3=spec["t3"], t2=spec["t2"],
+                      states=np.zeros((N, 2), dtype=np.int64), binder_names=np.array(["HP1"]),
+                      chemical_mods=np.zeros((N, 2), dtype=np.int64), chemical_mod_names=np.array(["a", "b"]))
+    with pytest.raises(TypeError):
+        ply.Chromatin("c", spec["r"].tolist(), bead_length=spec["bead_length"])
+    with pytest.raises(ValueError, match="No binders found"):
+        bnd.get_by_name("HP2")
+    p, binders, field = build(spec)
+    with pytest.raises(NotImplementedError, match="same binders"):
+        fld.UniformDensityField([p], bnd.make_binder_collection([bnd.hp1, bnd.prc1]), 10, 2, 10, 2, 10, 2)
+    with pytest.raises(ValueError, match="Confinement type"):
+        f = spec["field"]
+        fld.UniformDensityField([p], binders, f["x_width"], f["nx"], f["y_width"], f["ny"], f["z_width"],
+                                f["nz"], confine_type="Ellipsoid", confine_length=1.0)
+
+
+def test_field_csv_round_trip(backend, tmp_path):
+    """tests/test_fields.py:12-59 of the reference: to_file / from_file."""
+    import chromo_b200.fields as fld
+    spec, g = load_golden("static_c2")
+    p, binders, field = build(spec)
+    path = tmp_path / "UniformDensityField"
+    field.to_file(path)
+    f2 = fld.UniformDensityField.from_file(path, [p], binders)
+    assert f2 == field and np.allclose(f2.density, field.density, rtol=1e-12)
+    with pytest.raises(ValueError, match="polymers, but"):
+        fld.UniformDensityField.from_file(path, [p, p], binders)
+
+
+def test_accessible_volumes(backend):
+    """assume_fully_accessible=0: voxels cut by the sphere get a reduced volume
+    (fields.pyx:714-951) and the kernels divide by it."""
+    import chromo_b200.fields as fld
+    spec, g = load_golden("static_c2")
+    p, binders, _ = build(spec)
+    f = spec["field"]
+    field = fld.UniformDensityField([p], binders, f["x_width"], f["nx"], f["y_width"], f["ny"], f["z_width"],
+                                    f["nz"], confine_type="Spherical", confine_length=f["confine_length"],
+                                    chi=f["chi"], assume_fully_accessible=0)
+    av = field.access_vols
+    assert av.min() < field.vol_bin and av.max() == field.vol_bin
+    # mass conservation with per-voxel volumes: sum rho * V_access = N
+    assert abs((field.density[:, 0] * av).sum() - spec["N"]) < 1e-9 * spec["N"]
+
+
+@pytest.mark.ref
+def test_against_live_reference(backend):
+    """Random problems beyond the goldens: the same script on the reference's
+    own Cython build (oracle/_ref) and on chromo_b200, replayed RNG."""
+    if not O.ref_available():
+        pytest.skip("oracle/_ref not built on this box")
+    from chromo_b200.mc import get_amplitude_bounds, mc_controller as ctrl, set_rng_mode
+    from chromo_b200.mc.mc_sim import mc_sim
+    for seed, nb in ((21, 1), (22, 2)):
+        spec = O.make_spec(N=180, nb=nb, seed=seed, cross_talk=-0.8 if nb == 2 else 0.0)
+        rp, rdf, rfield, M = O.ref_objects(spec)
+        rbb, rmb = M["mc"].get_amplitude_bounds([rp])
+        rcs = M["mc_controller"].all_moves("/tmp/x", rbb.bounds, rmb.bounds, M["mc_controller"].SimpleControl)
+        M["shim"].c_srand(seed)
+        with np.errstate(over="ignore"):
+            M["mc_sim"].mc_sim([rp], rdf, 6, rcs, rfield, 0.9, seed + 1)
+        p, binders, field = build(spec)
+        bb, mb = get_amplitude_bounds([p])
+        cs = ctrl.all_moves("/tmp/x", bb.bounds, mb.bounds, ctrl.SimpleControl)
+        set_rng_mode("replay")
+        try:
+            field._engine_for(p).srand(seed)
+            mc_sim([p], binders, 6, cs, field, 0.9, seed + 1)
+        finally:
+            set_rng_mode("philox")
+        assert [c.move.num_success for c in cs] == [c.move.num_success for c in rcs]
+        tol = 0 if backend == "emu" else 1e-7
+        assert np.allclose(p.r, np.asarray(rp.r), rtol=0, atol=tol)
+        assert np.array_equal(p.states, np.asarray(rp.states))
+        assert close(field.compute_E(p), rfield.compute_E(rp), 1e-9 if backend == "emu" else 1e-7)

@@ -1,0 +1,154 @@
+"""BASELINE.json's full sizes on the GPU, checked through size-independent
+properties (the oracle cannot run these sizes in seconds):
+  * mass conservation  sum(rho * V) = N  (validate_density_calculation.ipynb)
+  * the incrementally updated density equals a full recompute
+  * the oracle agrees on a sampled replica's total energies and bin sets
+  * states stay in [0, sites], beads stay inside the confinement, |t3| = 1
+  * idempotence: recompute twice -> same field
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle as O
+from common import close
+
+pytestmark = pytest.mark.gpu
+
+
+def _ensemble(R, N, nb=1, seed=0, grid=None, chi=1.0, mu=None, cross_talk=0.0):
+    import bench
+    from chromo_b200.ensemble import ReplicaEnsemble, default_moves
+    from chromo_b200.util import poly_paths as paths
+    rng = np.random.default_rng(seed)
+    Rc, nx, W = bench.workload_params(N)
+    nx = grid or nx
+    r = paths.confined_gaussian_walk(N, np.full(N - 1, 16.5), "Spherical", Rc, rng, replicas=R)
+    t3, t2 = paths.estimate_tangents_from_coordinates(r)
+    mods = paths.synthetic_marks(N, nb, rng, replicas=R)
+    states = np.zeros((R, N, nb), dtype=np.int64)
+    binders = [dict(O.HP1), dict(O.PRC1)][:nb]
+    for b in binders:
+        b["chemical_potential"] = -1.2
+    if nb == 2:
+        binders[0]["cross_talk"] = {"PRC1": cross_talk}
+    g = dict(x_width=W, nx=nx, y_width=W, ny=nx, z_width=W, nz=nx, confine_type="Spherical",
+             confine_length=Rc, vf_limit=0.5)
+    ens = ReplicaEnsemble(r, t3, t2, states, mods, binders=binders, bond_params=bench.bond_params(N), grid=g,
+                          bead_vol=(4 / 3) * math.pi * 125.0, chi=chi, mu=mu, moves=default_moves(R, N, 16.5))
+    return ens, g, binders, Rc
+
+
+def _spec_of(ens, g, binders, rep, chi=1.0):
+    N = ens.N
+    return dict(N=N, nb=ens.nb, r=ens.r[rep], t3=ens.t3[rep], t2=ens.t2[rep], states=ens.states[rep],
+                mods=ens.chemical_mods[rep], bead_length=np.full(N - 1, 16.5), lp=53.0, bead_rad=5.0,
+                binders=binders, max_binders=-1, field=dict(g, chi=chi))
+
+
+def _invariants(ens, g, Rc, sites=2):
+    dens = ens.density()
+    vol_bin = g["x_width"] ** 3 / g["nx"] ** 3
+    assert np.allclose(dens[..., 0].sum(axis=1) * vol_bin, ens.N, rtol=1e-9)
+    ens.engine.field_recompute(clamp=False)
+    d2 = ens.density()
+    assert np.allclose(dens, d2, rtol=1e-9, atol=1e-12 * d2.max())
+    ens.engine.field_recompute(clamp=False)
+    assert np.allclose(ens.density(), d2, rtol=1e-13, atol=0)
+    ens.pull()
+    assert ens.states.min() >= 0 and ens.states.max() <= sites
+    assert np.all(np.linalg.norm(ens.r, axis=2) <= Rc + 1e-9)
+    assert np.allclose(np.linalg.norm(ens.t3, axis=2), 1.0, atol=1e-9)
+    assert np.allclose(np.linalg.norm(ens.t2, axis=2), 1.0, atol=1e-9)
+    # per column: density of bound proteins = sum over beads of state * weights -> total = sum(states)/V
+    for b in range(ens.nb):
+        assert np.allclose(dens[..., 1 + b].sum(axis=1) * vol_bin, ens.states[..., b].sum(axis=1), rtol=1e-9)
+
+
+def test_c2_full_size(cuda_backend):
+    """C2: chromatin 10,000 beads, HP1, chi = 1 (64 replicas here; the bench runs 1,024)."""
+    ens, g, binders, Rc = _ensemble(64, 10_000, nb=1, seed=1)
+    ens.mc_sim(4, 1.0, 17, sync_host=False)
+    ens.sync()
+    assert ens.engine.last_attempts() == 64 * 4 * 161
+    _invariants(ens, g, Rc)
+    # one replica against the oracle: total energies + occupied-bin set of its final state
+    ens.pull()
+    spec = _spec_of(ens, g, binders, 5)
+    o = O.OracleSim(spec)
+    d = ens.density()[5]
+    assert np.array_equal(d != 0, o.density != 0)
+    assert np.allclose(d, o.density, rtol=1e-9, atol=0)
+    assert close(ens.field_energy()[5], o.field_E())
+    assert close(ens.elastic_energy()[5], o.poly_E())
+    acc = ens.acceptance()
+    assert all(0.05 < a < 0.99 for a in acc.values()), acc
+    ens.close()
+
+
+def test_c3_two_binders_with_sweep(cuda_backend):
+    """C3: HP1 + PRC1 with cross-talk and a chemical-potential sweep across replicas."""
+    R = 32
+    mu = np.stack([np.linspace(-2.0, 0.0, R), np.linspace(0.0, -2.0, R)], axis=1)
+    ens, g, binders, Rc = _ensemble(R, 10_000, nb=2, seed=2, mu=mu, cross_talk=-1.0)
+    ens.mc_sim(6, 1.0, 23, sync_host=False)
+    ens.sync()
+    _invariants(ens, g, Rc)
+    ens.pull()
+    bound = ens.states.sum(axis=1)  # [R, 2] proteins bound per replica
+    # more favourable chemical potential -> more binding (monotone trend across the sweep)
+    assert bound[-1, 0] > bound[0, 0] and bound[0, 1] > bound[-1, 1]
+    spec = _spec_of(ens, g, binders, 7)
+    for b, m in zip(spec["binders"], mu[7]):
+        b["chemical_potential"] = float(m)
+    o = O.OracleSim(spec)
+    assert close(ens.field_energy()[7], o.field_E())
+    ens.close()
+
+
+def test_c4_chromosome_scale(cuda_backend):
+    """C4: 400,000 beads, 65^3 grid (2 replicas): HBM-resident field, same invariants."""
+    ens, g, binders, Rc = _ensemble(2, 400_000, nb=1, seed=3, grid=65)
+    ens.mc_sim(2, 1.0, 29, sync_host=False)
+    ens.sync()
+    _invariants(ens, g, Rc)
+    ens.pull()
+    o = O.OracleSim(_spec_of(ens, g, binders, 1))
+    assert np.array_equal(ens.density()[1] != 0, o.density != 0)
+    assert close(ens.elastic_energy()[1], o.poly_E())
+    ens.close()
+
+
+def test_replay_matches_oracle_at_c2_size(cuda_backend):
+    """A replayed mc_sim at N = 10,000 reproduces the oracle's accept/reject
+    counts and final configuration (the oracle needs ~0.2 s per 1,000 attempts here)."""
+    ens, g, binders, Rc = _ensemble(2, 10_000, nb=1, seed=4)
+    spec = _spec_of(ens, g, binders, 1)
+    o = O.OracleSim(spec)
+    mv = O.make_moves(10_000, 16.5)
+    o.srand(9)
+    o.mc_sim(mv, 5, 77)
+    ens.engine.srand(9)
+    ens.mc_sim(5, 1.0, 77, rng="replay", sync_host=True)
+    assert [int(x) for x in ens.moves["num_success"][1]] == [m.num_success for m in mv]
+    assert np.allclose(ens.r[1], o.r, rtol=0, atol=1e-7)
+    assert np.array_equal(ens.states[1], o.states)
+    assert np.array_equal([float(x) for x in ens.moves["amp_move"][1]], [m.amp_move for m in mv])
+    ens.close()
+
+
+def test_replica_exchange_single_rank(cuda_backend):
+    """C5 on one rank: chi ladder, labels move, configurations do not."""
+    from chromo_b200.parallel import ReplicaExchange
+    R = 16
+    ens, g, binders, Rc = _ensemble(R, 2_000, nb=1, seed=5)
+    ladder = np.geomspace(0.25, 4.0, R)
+    ex = ReplicaExchange(ens, ladder, seed=3)
+    swaps = 0
+    for rnd in range(6):
+        ens.mc_sim(2, 1.0, 100 + rnd, sync_host=False)
+        swaps += ex.step()
+    assert np.array_equal(np.sort(ex.chi), ladder) and swaps > 0
+    _invariants(ens, g, Rc)
+    ens.close()
