@@ -299,8 +299,8 @@ def run_ours(args):
     barrier()
 
     # ---- end to end through the host-facing call --------------------------
-    h2d = 3 * R * N * 24 + 2 * R * N * 1 * 8
-    d2h = 3 * R * N * 24 + R * N * 1 * 8
+    h2d = (3 * R * N * 24 + 2 * R * N * 1 * 8) * world  # r, t3, t2 + states, chemical_mods (int64), all ranks
+    d2h = (3 * R * N * 24 + R * N * 1 * 8) * world      # r, t3, t2 + states, all ranks
     Ke = max(1, min(K, args.e2e_steps))
     ens.mc_sim(S, 1.0, 5000, sync_host=True)
     barrier()
