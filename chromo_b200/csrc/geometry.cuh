@@ -117,6 +117,47 @@ __device__ __forceinline__ void rotation_matrix_sc(const double ax[3], const dou
     M[11] = r2;
 }
 
+// the same matrix in two parts: 3x3 rotation (state-independent) ...
+__device__ __forceinline__ void rotation_3x3(const double ax[3], double sn, double c, double R[9]) {
+    double omc = 1.0 - c;
+    R[0] = ax[0] * ax[0] + (ax[1] * ax[1] + ax[2] * ax[2]) * c;
+    R[1] = ax[0] * ax[1] * omc - ax[2] * sn;
+    R[2] = ax[0] * ax[2] * omc + ax[1] * sn;
+    R[3] = ax[0] * ax[1] * omc + ax[2] * sn;
+    R[4] = ax[1] * ax[1] + (ax[0] * ax[0] + ax[2] * ax[2]) * c;
+    R[5] = ax[1] * ax[2] * omc - ax[0] * sn;
+    R[6] = ax[0] * ax[2] * omc - ax[1] * sn;
+    R[7] = ax[1] * ax[2] * omc + ax[0] * sn;
+    R[8] = ax[2] * ax[2] + (ax[0] * ax[0] + ax[1] * ax[1]) * c;
+}
+// ... and the translation column, which needs the fulcrum (linalg.pyx:115-139)
+__device__ __forceinline__ void rotation_translation(const double ax[3], const double pt[3], double sn,
+                                                     double c, double tv[3]) {
+    double omc = 1.0 - c;
+    double r0 = (pt[1] * ax[2] - pt[2] * ax[1]) * sn;
+    double r1 = (pt[2] * ax[0] - pt[0] * ax[2]) * sn;
+    double r2 = (pt[0] * ax[1] - pt[1] * ax[0]) * sn;
+    r0 += (pt[0] * (1.0 - ax[0] * ax[0]) - ax[0] * (pt[1] * ax[1] + pt[2] * ax[2])) * omc;
+    r1 += (pt[1] * (1.0 - ax[1] * ax[1]) - ax[1] * (pt[0] * ax[0] + pt[2] * ax[2])) * omc;
+    r2 += (pt[2] * (1.0 - ax[2] * ax[2]) - ax[2] * (pt[0] * ax[0] + pt[1] * ax[1])) * omc;
+    tv[0] = r0;
+    tv[1] = r1;
+    tv[2] = r2;
+}
+__device__ __forceinline__ void apply_rot3(const double *R, const double v[3], double o[3]) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) o[j] = (R[3 * j] * v[0] + R[3 * j + 1] * v[1]) + R[3 * j + 2] * v[2];
+}
+// axis of a degenerate crank-shaft (end beads coincide): rare, kept out of line
+static __device__ CB_NOINLINE void degenerate_axis(uint32_t d1, uint32_t d2, double *axis) {
+    double phi = (double)d1 / CB_RAND_MAX * (2.0 * 3.14159265358979323846);
+    double theta = acos_ni(((double)d2 / CB_RAND_MAX) * 2.0 - 1.0);
+    const double2 p = sincos_ni(phi), t = sincos_ni(theta);
+    axis[0] = p.y * t.x;
+    axis[1] = p.x * t.x;
+    axis[2] = t.y;
+}
+
 // transform_r_t3_t2 move_funcs.pyx:121-154: ((m0 x + m1 y) + m2 z) (+ t)
 __device__ __forceinline__ void apply_rot(const double *M, const double v[3], double o[3]) {
 #pragma unroll

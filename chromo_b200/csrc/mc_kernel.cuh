@@ -36,8 +36,23 @@
 #define FULL_MASK 0xffffffffu
 #define HASH_EMPTY (-1)
 
+// one prepared attempt (see McWarp::prepare)
+struct Prop {
+    double R[9];  // rotation part of the affine map (end-pivot; single-bead tangent rotation)
+    double ax[3]; // rotation axis (end-pivot) or translation vector (slide)
+    double sn, cs; // sin / cos of the rotation angle
+    double u;     // Metropolis uniform (batched mode)
+    int ind0, indf, n, binder;
+    int lhs, bead, newst0;
+    uint32_t used; // draws of the attempt's stream consumed by prepare (batched mode)
+};
+
 // per-warp shared state
 struct WarpSh {
+    Prop prop[32];                // prepared attempts of the current batch
+    unsigned long long attempt_base; // Philox: index of the batch's first attempt in the replica's stream
+    uint32_t rng_after[CB_GLIBC_WORDS];
+    int cur;                      // slot being executed
     chromo_move_state mv[CHROMO_NUM_MOVES];
     uint32_t grs[CB_GLIBC_WORDS]; // ReplayRng state
     uint32_t rng_save[CB_GLIBC_WORDS];
@@ -55,7 +70,7 @@ struct WarpSh {
     uint32_t draws[64];           // per-bead axis draws of tangent rotation
     signed char newst[256];       // new binding states (small path)
 };
-static_assert(sizeof(WarpSh) <= 6144, "update kWarpShBytes in chromo_b200.cu");
+static_assert(sizeof(WarpSh) <= 12288, "update kWarpShBytes in chromo_b200.cu");
 
 struct HashTable {
     int *keys;    // [cap]
@@ -459,14 +474,27 @@ __device__ __forceinline__ void check_bead_bounds(int b0, int b1, int N, int &in
 }
 
 // =================================================================== moves
-// Every heavy routine below has exactly ONE call site in the kernel (so it is
-// inlined once: no ABI spills, shared-memory address spaces stay visible to the
-// compiler) -- the crank-shaft / end-pivot / slide / binding moves share one
-// code path (`segment_*`), tangent rotation has its own (`tangent_*`), and both
-// meet again in a single Metropolis test.
+// An attempt is split into
+//   prepare : everything that does NOT depend on the replica's state -- RNG
+//             draws, exponential window (log10), all trigonometry, the rotation
+//             part of the affine map -- written to a `Prop` record in shared
+//             memory.  With the counter-based Philox generator attempt t has its
+//             own stream, so a batch of up to 32 attempts of one move type is
+//             prepared by 32 lanes AT ONCE (same code, different data): the
+//             scalar proposal work that dominated the instruction count of the
+//             serial version is amortised over the batch.  With the replayed
+//             reference streams (sequential by nature) the batch size is 1 and
+//             lane 0 prepares, in the reference's draw order.
+//   execute : the state-dependent rest, one attempt after the other: axis /
+//             fulcrum from current positions, elastic dE (4 lanes), field dE
+//             (scatter into the shared-memory table + reduction), Metropolis,
+//             commit.
+// Every heavy routine has exactly ONE call site (inlined once: no ABI spills,
+// shared-memory address spaces stay visible to the compiler).
 template <class Rng, bool DEBUG, int NB>
 struct McWarp {
     static constexpr int NCOL = NB + 1;
+    static constexpr bool BATCH = Rng::kBatched;
     const DevCtx &C;
     WarpSh &S;
     HashTable &H;
@@ -500,20 +528,25 @@ struct McWarp {
         }
     }
 
-    // ---- proposal of crank-shaft / end-pivot / slide / binding (lane 0) -----
-    // Draw order follows the reference exactly; the
-    // transcendental work on the drawn integers is done afterwards in one place.
-    __device__ __forceinline__ void segment_propose_lane0(int mtype) {
+    // ======================================================== prepare
+    // lanes [0, cnt) each prepare one attempt of move type `mtype`
+    __device__ __forceinline__ void prepare(int mtype, int cnt) {
+        if (lane >= cnt) return;
         const int N = C.N;
-        const double *Rr = R_();
-        chromo_move_state &mv = S.mv[mtype];
-        mv.num_attempt += 1; // MCAdapter.propose moves.pyx:151
+        Prop &P = S.prop[lane];
+        const chromo_move_state &mv = S.mv[mtype];
+        if (BATCH) {
+            rng.seek_attempt(S.attempt_base + (unsigned long long)lane);
+            P.u = u01(rng.next31()); // Metropolis uniform: draw 0 of the attempt's own stream
+        }
         const bool crank = mtype == CHROMO_CRANK_SHAFT, pivot = mtype == CHROMO_END_PIVOT;
         const bool slide = mtype == CHROMO_SLIDE, bind = mtype == CHROMO_CHANGE_BINDING_STATE;
+        const bool tangent = mtype == CHROMO_TANGENT_ROTATION;
         double amp = 0.0;
         uint32_t d1 = 0, d2 = 0;
-        int b0 = 0, lhs = 0, binder = 0;
+        int b0 = 0, lhs = 0, binder = 0, ind0 = 0, indf = 0, k = 0, bead = 0;
         bool sphere = pivot || slide;
+        // ---- integer draws, in the reference's order ----
         if (crank) { // move_funcs.pyx:80-84
             amp = mv.amp_move * (u01(rng.next31()) - 0.5);
             b0 = (int)(u01(rng.next31()) * (double)N);
@@ -525,49 +558,111 @@ struct McWarp {
             d1 = rng.next31();
             d2 = rng.next31();
             b0 = (int)(rng.next31() % (uint32_t)N);
-        } else { // move_funcs.pyx:763-766
+        } else if (bind) { // move_funcs.pyx:763-766
             binder = (int)(rng.next31() % (uint32_t)NB);
             b0 = (int)(rng.next31() % (uint32_t)N);
-        }
-        // exponential window: from_left / from_right / from_point (bead_selection.pyx:69-154)
-        int side = 0, ws = mv.amp_bead, ce = 0;
-        bool do_ce = true;
-        if (!pivot) {
-            if (mv.amp_bead < 1) do_ce = false;
-            else {
-                side = (int)(rng.next31() % 2u);
-                ws = side == 0 ? max(min(mv.amp_bead, b0), 1) : max(min(mv.amp_bead, N - b0), 1);
+        } else { // tangent_rotation move_funcs.pyx:503-504
+            amp = mv.amp_move * (u01(rng.next31()) - 0.5);
+            k = (int)(rng.next31() % (uint32_t)mv.amp_bead) + 1;
+            if (k == 1) { // one bead: index, then its axis (get_inds 552-582, rotate_select_beads 517-549)
+                bead = (int)(rng.next31() % (uint32_t)N);
+                d1 = rng.next31();
+                d2 = rng.next31();
+                sphere = true;
             }
         }
-        if (do_ce) ce = capped_exponential(rng, ws, ws);
-        int ind0, indf;
-        if (pivot) {
-            if (lhs == 1) {
-                ind0 = 0;
-                indf = ce + 1;
+        if (!tangent) {
+            // exponential window: from_left / from_right / from_point (bead_selection.pyx:69-154)
+            int side = 0, ws = mv.amp_bead, ce = 0;
+            bool do_ce = true;
+            if (!pivot) {
+                if (mv.amp_bead < 1) do_ce = false;
+                else {
+                    side = (int)(rng.next31() % 2u);
+                    ws = side == 0 ? max(min(mv.amp_bead, b0), 1) : max(min(mv.amp_bead, N - b0), 1);
+                }
+            }
+            if (do_ce) ce = capped_exponential(rng, ws, ws);
+            if (pivot) {
+                if (lhs == 1) {
+                    ind0 = 0;
+                    indf = ce + 1;
+                } else {
+                    ind0 = N - ce;
+                    indf = N;
+                }
+                d1 = rng.next31(); // la.uniform_sample_unit_sphere() move_funcs.pyx:336
+                d2 = rng.next31();
             } else {
-                ind0 = N - ce;
-                indf = N;
+                int b1 = !do_ce ? b0 : (side == 0 ? max(b0, 1) - ce : ce + b0);
+                if (crank) b1 = max(b1, 1);
+                check_bead_bounds(b0, b1, N, ind0, indf);
             }
-        } else {
-            int b1 = !do_ce ? b0 : (side == 0 ? max(b0, 1) - ce : ce + b0);
-            if (crank) b1 = max(b1, 1);
-            check_bead_bounds(b0, b1, N, ind0, indf);
         }
-        const int n = indf - ind0;
-        S.ind0 = ind0;
-        S.indf = indf;
-        S.n = n;
-        S.binder = binder;
-        if (n <= 0) return;
-        if (bind) { // conduct_change_binding_states move_funcs.pyx:778-820
-            signed char *dst = (n <= 256) ? S.newst : (C.st_new + (long long)rep * N);
-            for (int i = 0; i < n; i++) dst[i] = (signed char)rng.randint(C.sites[binder] + 1);
+        const int n = tangent ? k : indf - ind0;
+        P.ind0 = ind0;
+        P.indf = indf;
+        P.n = n;
+        P.binder = binder;
+        P.lhs = lhs;
+        P.bead = bead;
+        P.newst0 = 0;
+        if (bind && n >= 1) { // conduct_change_binding_states move_funcs.pyx:778-820
+            if (!BATCH) { // lane 0, sequential stream: draw all n states now, as the reference does
+                signed char *dst = (n <= 256) ? S.newst : (C.st_new + (long long)rep * N);
+                for (int i = 0; i < n; i++) dst[i] = (signed char)rng.randint(C.sites[binder] + 1);
+            } else if (n == 1) {
+                P.newst0 = rng.randint(C.sites[binder] + 1);
+            } // n > 1 in a batch: drawn at execute time from this attempt's stream
+        }
+        // ---- all the trigonometry in one place: angles in, (sin, cos) out ----
+        // uniform_sample_unit_sphere linalg.pyx:23-59, arbitrary_axis_rotation 62-139
+        double *tr = S.tan_trig + lane; // [9][32]: angle, phi, theta | sines | cosines
+        tr[0] = amp;
+        tr[32] = u01(d1) * (2.0 * 3.14159265358979323846);
+        tr[64] = sphere ? acos(u01(d2) * 2.0 - 1.0) : 0.0;
+        const int t_lo = (slide || bind) ? 1 : 0, t_hi = bind ? 1 : (sphere ? 3 : 1);
+#pragma unroll 1
+        for (int t = t_lo; t < t_hi; t++) {
+            double s_, c_;
+            sincos(tr[32 * t], &s_, &c_);
+            tr[96 + 32 * t] = s_;
+            tr[192 + 32 * t] = c_;
+        }
+        const double sn = tr[96], cs = tr[192];
+        double axis[3] = {0.0, 0.0, 0.0};
+        if (sphere) {
+            axis[0] = tr[192 + 32] * tr[96 + 64];
+            axis[1] = tr[96 + 32] * tr[96 + 64];
+            axis[2] = tr[192 + 64];
+        }
+        P.sn = sn;
+        P.cs = cs;
+        if (slide) { // generate_translation_mat linalg.pyx:172-199
+#pragma unroll
+            for (int j = 0; j < 3; j++) P.ax[j] = axis[j] * amp;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 3; j++) P.ax[j] = axis[j];
+            if (pivot || (tangent && k == 1)) rotation_3x3(axis, sn, cs, P.R);
+        }
+        if (BATCH) P.used = rng.position();
+    }
+
+    // ======================================================== execute
+    // lane 0: finish the affine map of attempt `P` from the current positions
+    __device__ __forceinline__ void finalize_segment_lane0(int mtype, const Prop &P) {
+        const int N = C.N;
+        const double *Rr = R_();
+        const int ind0 = P.ind0, indf = P.indf;
+        if (mtype == CHROMO_SLIDE) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) S.M[4 * j + 3] = P.ax[j];
             return;
         }
-        double axis[3] = {0.0, 0.0, 0.0};
-        int ful = 0;
-        if (crank) {
+        int ful;
+        double axis[3], Rm[9], pt[3];
+        if (mtype == CHROMO_CRANK_SHAFT) {
             int a, b; // get_crank_shaft_axis move_funcs.pyx:157-234
             if (ind0 == indf - 1 && ind0 == 0) { a = indf; b = ind0; }
             else if (ind0 == indf - 1 && ind0 == N - 1) { a = ind0; b = ind0 - 1; }
@@ -580,63 +675,45 @@ struct McWarp {
             else if (ind0 != 0 && indf == N) ful = ind0 - 1;
             else if (ind0 == 0 && indf == N) ful = ind0;
             else ful = ind0 - 1;
+            load3(Rr + 3 * ful, pt);
 #pragma unroll
             for (int j = 0; j < 3; j++) axis[j] = Rr[3 * a + j] - Rr[3 * b + j];
             double mag = sqrt((axis[0] * axis[0] + axis[1] * axis[1]) + axis[2] * axis[2]);
-            if (mag < 1E-5) sphere = true; // axis from the unit sphere (two more draws)
-            else {
+            if (mag < 1E-5) { // axis from the unit sphere: two more draws (move_funcs.pyx:229-230)
+                if (BATCH) rng.seek_attempt(S.attempt_base + (unsigned long long)S.cur, P.used);
+                uint32_t d1 = rng.next31(), d2 = rng.next31();
+                degenerate_axis(d1, d2, axis);
+            } else {
                 double sc = 1.0 / mag;
 #pragma unroll
                 for (int j = 0; j < 3; j++) axis[j] = axis[j] * sc;
             }
-        } else if (pivot) { // get_end_pivot_fulcrum move_funcs.pyx:349-398
+            rotation_3x3(axis, P.sn, P.cs, Rm);
+        } else { // end pivot: get_end_pivot_fulcrum move_funcs.pyx:349-398
             if (ind0 == 0 && indf != N) ful = indf;
             else if (ind0 != 0 && indf == N) ful = ind0 - 1;
-            else if (ind0 == 0 && indf == N && lhs == 1) ful = indf - 1;
+            else if (ind0 == 0 && indf == N && P.lhs == 1) ful = indf - 1;
             else ful = ind0;
-        }
-        if (sphere && !slide) {
-            d1 = rng.next31();
-            d2 = rng.next31();
-        }
-        // ---- one place for the trigonometry: angles in, (sin, cos) out ----
-        // uniform_sample_unit_sphere linalg.pyx:23-59, arbitrary_axis_rotation 62-139
-        double ang3[3], sn3[3], cs3[3];
-        ang3[0] = amp;
-        ang3[1] = u01(d1) * (2.0 * 3.14159265358979323846);
-        ang3[2] = sphere ? acos(u01(d2) * 2.0 - 1.0) : 0.0;
-#pragma unroll
-        for (int t = 0; t < 3; t++) { S.trig[t] = ang3[t]; }
-#pragma unroll 1
-        for (int t = slide ? 1 : 0; t < (sphere ? 3 : 1); t++) {
-            double s_, c_;
-            sincos(S.trig[t], &s_, &c_);
-            S.trig[3 + t] = s_;
-            S.trig[6 + t] = c_;
-        }
-#pragma unroll
-        for (int t = 0; t < 3; t++) {
-            sn3[t] = S.trig[3 + t];
-            cs3[t] = S.trig[6 + t];
-        }
-        if (sphere) {
-            axis[0] = cs3[1] * sn3[2];
-            axis[1] = sn3[1] * sn3[2];
-            axis[2] = cs3[2];
-        }
-        if (slide) { // generate_translation_mat linalg.pyx:172-199
-#pragma unroll
-            for (int j = 0; j < 3; j++) S.M[4 * j + 3] = axis[j] * amp;
-        } else {
-            double pt[3];
             load3(Rr + 3 * ful, pt);
-            rotation_matrix_sc(axis, pt, sn3[0], cs3[0], S.M);
+#pragma unroll
+            for (int j = 0; j < 3; j++) axis[j] = P.ax[j];
+#pragma unroll
+            for (int j = 0; j < 9; j++) Rm[j] = P.R[j];
+        }
+        double tv[3];
+        rotation_translation(axis, pt, P.sn, P.cs, tv);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            S.M[4 * j] = Rm[3 * j];
+            S.M[4 * j + 1] = Rm[3 * j + 1];
+            S.M[4 * j + 2] = Rm[3 * j + 2];
+            S.M[4 * j + 3] = tv[j];
         }
     }
 
     // ---- elastic / binding part of dE for the segment moves -----------------
-    __device__ __forceinline__ double segment_dE_poly(int mtype, int kind, int ind0, int indf, int n,
-                                                      int binder, const signed char *newst, int ddbl[NB]) {
+    __device__ __forceinline__ double segment_dE_poly(int kind, int ind0, int indf, int n, int binder,
+                                                      const signed char *newst, int ddbl[NB]) {
         const int N = C.N;
         if (kind != 2) {
             // continuous_dE_poly polymers.pyx:1084-1146: four lanes, one bond energy each:
@@ -756,8 +833,8 @@ struct McWarp {
     }
 
     // instrumentation of the single-step kernel: moved beads + their trial rows
-    __device__ __forceinline__ void debug_report(int kind, int ind0, int n, int binder, const signed char *newst,
-                                             double dE_poly, double dE_field) {
+    __device__ __forceinline__ void debug_report(int kind, int ind0, int n, int binder,
+                                                 const signed char *newst, double dE_poly, double dE_field) {
         const double *Rr = R_(), *T3 = T3_(), *T2 = T2_();
         const signed char *ST = ST_();
         const int W = 9 + NB;
@@ -803,14 +880,15 @@ struct McWarp {
     // per selected bead: own random axis, rotate t3/t2, both adjacent bonds
     // against the CURRENT neighbours (polymers.pyx:1075-1080; quirk 8); never
     // touches the field (mc_sim.pyx:145).
-    // A chunk of up to 8 beads is evaluated by 4 lanes per bead (one bond energy
-    // each: left bond trial / as is, right bond trial / as is); the new tangents
-    // of chunk bead j go to out[6j..6j+5] (shared) when `out` is given, or
-    // straight to global memory when `store` is set.  Returns acc_in + this
-    // chunk's dE on all lanes (bead-by-bead sum, as the reference accumulates).
+    // One bead is evaluated by 4 lanes (one bond energy each: left bond trial /
+    // as is, right bond trial / as is), up to 8 beads per call.  Rotations come
+    // either from the prepared record (`Rfix`, the common single-bead case) or
+    // from per-bead draws.  New tangents of chunk bead j go to out[6j..6j+5]
+    // (shared) when `out` is given, or straight to global memory when `store`.
+    // Returns acc_in + the chunk's dE on all lanes (bead-by-bead sum).
     __device__ __forceinline__ double tangent_chunk(const int *beads, int cnt, const uint32_t *draws,
-                                                    double ang, double *out, bool store, int dbg_base,
-                                                    double acc_in) {
+                                                    const double *Rfix, double sn, double cs, double *out,
+                                                    bool store, int dbg_base, double acc_in) {
         const double *Rr = R_();
         double *T3 = T3_(), *T2 = T2_();
         const int N = C.N;
@@ -818,29 +896,31 @@ struct McWarp {
         double e = 0.0;
         if (j < cnt) {
             const int bead = beads[j];
-            // trigonometry in one place: angle, phi, theta per lane
-            double *tr = S.tan_trig + lane;
-            tr[0] = ang;
-            tr[32] = u01(draws[2 * j]) * (2.0 * 3.14159265358979323846);
-            tr[64] = acos(u01(draws[2 * j + 1]) * 2.0 - 1.0);
+            double Rm[9], t3c[3], t2c[3], t3n[3], t2n[3], rc[3];
+            if (Rfix) {
+#pragma unroll
+                for (int q = 0; q < 9; q++) Rm[q] = Rfix[q];
+            } else {
+                double *tr = S.tan_trig + lane;
+                tr[32] = u01(draws[2 * j]) * (2.0 * 3.14159265358979323846);
+                tr[64] = acos_ni(u01(draws[2 * j + 1]) * 2.0 - 1.0);
 #pragma unroll 1
-            for (int t = 0; t < 3; t++) {
-                double s_, c_;
-                sincos(tr[32 * t], &s_, &c_);
-                tr[96 + 32 * t] = s_;
-                tr[192 + 32 * t] = c_;
+                for (int t = 1; t < 3; t++) {
+                    const double2 sc = sincos_ni(tr[32 * t]);
+                    tr[96 + 32 * t] = sc.x;
+                    tr[192 + 32 * t] = sc.y;
+                }
+                double axis[3];
+                axis[0] = tr[192 + 32] * tr[96 + 64];
+                axis[1] = tr[96 + 32] * tr[96 + 64];
+                axis[2] = tr[192 + 64];
+                rotation_3x3(axis, sn, cs, Rm);
             }
-            double axis[3], M[12], t3c[3], t2c[3], t3n[3], t2n[3], rc[3];
-            const double origin[3] = {0.0, 0.0, 0.0};
-            axis[0] = tr[192 + 32] * tr[96 + 64];
-            axis[1] = tr[96 + 32] * tr[96 + 64];
-            axis[2] = tr[192 + 64];
-            rotation_matrix_sc(axis, origin, tr[96], tr[192], M);
             load3(T3 + 3 * bead, t3c);
             load3(T2 + 3 * bead, t2c);
             load3(Rr + 3 * bead, rc);
-            apply_rot(M, t3c, t3n);
-            apply_rot(M, t2c, t2n);
+            apply_rot3(Rm, t3c, t3n);
+            apply_rot3(Rm, t2c, t2n);
             const bool left = which < 2;
             const bool present = left ? (bead != 0) : (bead + 1 != N);
             if (!store && present) {
@@ -875,16 +955,16 @@ struct McWarp {
         return tot;
     }
 
-    // draws + energies of a tangent-rotation proposal; `pass` 0 = evaluate,
-    // 1 = re-run the per-bead draws and store (large path commit)
-    __device__ __forceinline__ double tangent_eval(const int *inds, int k, double ang, bool small, bool store) {
+    // k > 1 beads: per-bead draws by lane 0 (8 beads per chunk), energies or stores
+    __device__ __forceinline__ double tangent_eval_multi(const int *inds, int k, double sn, double cs,
+                                                         bool small, bool store) {
         double dE_poly = 0.0;
         for (int base = 0; base < k; base += 8) {
             const int cnt = min(8, k - base);
             if (lane == 0)
                 for (int i = 0; i < 2 * cnt; i++) S.draws[i] = rng.next31();
             __syncwarp();
-            dE_poly = tangent_chunk(inds + base, cnt, S.draws, ang,
+            dE_poly = tangent_chunk(inds + base, cnt, S.draws, nullptr, sn, cs,
                                     (small && !store) ? S.tan_new + 6 * base : nullptr, store, base, dE_poly);
             __syncwarp();
         }
@@ -917,62 +997,74 @@ struct McWarp {
         }
     }
 
-    // ---- one mc_step (mc_sim.pyx:106-182) -----------------------------------
-    __device__ __forceinline__ void step(int mtype) {
+    // ---- execute prepared attempt `slot` (mc_step, mc_sim.pyx:106-182) -------
+    __device__ __forceinline__ void execute(int mtype, int slot) {
         const int N = C.N;
+        const Prop &P = S.prop[slot];
         const bool tangent = mtype == CHROMO_TANGENT_ROTATION;
-        double dE_poly = 0.0, dE_field = 0.0, ang = 0.0;
-        int kind = 0, ind0 = 0, n = 0, binder = 0, k = 0;
+        double dE_poly = 0.0, dE_field = 0.0;
+        const int ind0 = P.ind0, n = P.n, binder = P.binder;
+        int kind = 0;
         const signed char *newst = nullptr;
         const int *tinds = S.tinds;
-        bool small = true;
-        // ================= proposal + energies =================
+        const bool small = n <= 32;
+        if (lane == 0) {
+            S.mv[mtype].num_attempt += 1; // MCAdapter.propose moves.pyx:151
+            S.cur = slot;
+        }
+        if (n <= 0) return; // mc_sim.pyx:151-152
+        // ================= energies =================
         if (!tangent) {
-            if (lane == 0) segment_propose_lane0(mtype);
-            __syncwarp();
-            ind0 = S.ind0;
-            n = S.n;
-            binder = S.binder;
-            if (n <= 0) return; // mc_sim.pyx:151-152
             kind = mtype == CHROMO_SLIDE ? 1 : (mtype == CHROMO_CHANGE_BINDING_STATE ? 2 : 0);
+            if (lane == 0) {
+                if (kind != 2) finalize_segment_lane0(mtype, P);
+                else if (BATCH) { // new states of this attempt (sequential mode drew them in prepare)
+                    signed char *dst = (n <= 256) ? S.newst : (C.st_new + (long long)rep * N);
+                    if (n == 1) dst[0] = (signed char)P.newst0;
+                    else {
+                        rng.seek_attempt(S.attempt_base + (unsigned long long)slot, P.used);
+                        for (int i = 0; i < n; i++) dst[i] = (signed char)rng.randint(C.sites[binder] + 1);
+                    }
+                }
+            }
+            __syncwarp();
             if (kind == 2) newst = (n <= 256) ? S.newst : (C.st_new + (long long)rep * N);
             int ddbl[NB];
 #pragma unroll
             for (int m = 0; m < NB; m++) ddbl[m] = 0;
-            dE_poly = segment_dE_poly(mtype, kind, ind0, S.indf, n, binder, newst, ddbl);
+            dE_poly = segment_dE_poly(kind, ind0, P.indf, n, binder, newst, ddbl);
             if (C.field_active)
                 dE_field = field_dE_segment<NB, DEBUG>(C, H, S, rep, lane, kind, ind0, n, binder, newst, ddbl, dbg);
             else if (kind != 2 && C.confine_type != CHROMO_CONFINE_NONE)
                 dE_field = confinement_dE_segment(C, S, rep, lane, kind, ind0, n);
             if (DEBUG) debug_report(kind, ind0, n, binder, newst, dE_poly, dE_field);
         } else {
-            if (lane == 0) {
-                chromo_move_state &mv = S.mv[CHROMO_TANGENT_ROTATION];
-                mv.num_attempt += 1;
-                ang = mv.amp_move * (u01(rng.next31()) - 0.5);
-                k = (int)(rng.next31() % (uint32_t)mv.amp_bead) + 1;
-            }
-            ang = __shfl_sync(FULL_MASK, ang, 0);
-            k = __shfl_sync(FULL_MASK, k, 0);
-            small = k <= 32;
-            if (small) { // get_inds move_funcs.pyx:552-582: k distinct draws, redraw duplicates
-                int my = -1;
-                for (int i = 0; i < k; i++) {
-                    int c = 0;
-                    bool dup;
-                    do {
-                        if (lane == 0) c = (int)(rng.next31() % (uint32_t)N);
-                        c = __shfl_sync(FULL_MASK, c, 0);
-                        dup = __any_sync(FULL_MASK, lane < i && my == c);
-                    } while (dup);
-                    if (lane == i) my = c;
-                }
-                if (lane < k) S.tinds[lane] = my;
+            const int k = n;
+            if (k == 1) {
+                if (lane == 0) S.tinds[0] = P.bead;
+                __syncwarp();
+                dE_poly = tangent_chunk(S.tinds, 1, nullptr, P.R, P.sn, P.cs, S.tan_new, false, 0, 0.0);
             } else {
-                tinds = tangent_select_large(k);
+                if (BATCH && lane == 0) rng.seek_attempt(S.attempt_base + (unsigned long long)slot, P.used);
+                if (small) { // get_inds move_funcs.pyx:552-582: k distinct draws, redraw duplicates
+                    int my = -1;
+                    for (int i = 0; i < k; i++) {
+                        int c = 0;
+                        bool dup;
+                        do {
+                            if (lane == 0) c = (int)(rng.next31() % (uint32_t)N);
+                            c = __shfl_sync(FULL_MASK, c, 0);
+                            dup = __any_sync(FULL_MASK, lane < i && my == c);
+                        } while (dup);
+                        if (lane == i) my = c;
+                    }
+                    if (lane < k) S.tinds[lane] = my;
+                } else {
+                    tinds = tangent_select_large(k);
+                }
+                __syncwarp();
+                dE_poly = tangent_eval_multi(tinds, k, P.sn, P.cs, small, false);
             }
-            __syncwarp();
-            dE_poly = tangent_eval(tinds, k, ang, small, false);
             if (DEBUG) {
                 if (lane == 0) {
                     dbg->n_inds = k;
@@ -995,7 +1087,7 @@ struct McWarp {
                 acc = force_accept;
             } else {
                 double e = exp(-dE);
-                u = u01(rng.next31());
+                u = BATCH ? P.u : u01(rng.next31());
                 acc = (u < e) ? 1 : 0;
             }
             if (DEBUG) {
@@ -1008,7 +1100,7 @@ struct McWarp {
             mv.acceptance_rate = (mv.alpha * (acc ? 1.0 : 0.0)) + (1.0 - mv.alpha) * mv.acceptance_rate;
             // algorithmic bytes of this attempt
             if (tangent) {
-                S.algo_bytes += 48ull * k + 144ull * k + (acc ? 48ull * k : 0ull);
+                S.algo_bytes += 48ull * n + 144ull * n + (acc ? 48ull * n : 0ull);
             } else {
                 unsigned long long U = C.field_active ? (unsigned long long)S.last_U : 0ull;
                 if (kind == 2)
@@ -1024,15 +1116,25 @@ struct McWarp {
         if (acc) {
             if (!tangent) segment_commit(kind, ind0, n, binder, newst);
             else if (small) {
-                if (lane < k) {
+                if (lane < n) {
                     store3(T3_() + 3 * S.tinds[lane], S.tan_new + 6 * lane);
                     store3(T2_() + 3 * S.tinds[lane], S.tan_new + 6 * lane + 3);
                 }
             } else {
-                tangent_commit_large(tinds, k, ang);
+                tangent_commit_large(tinds, n, P.sn, P.cs);
             }
         }
         if (!tangent && C.field_active) table_clear(H, S, NCOL, lane);
+        __syncwarp();
+    }
+
+    // a batch of `cnt` attempts of one move type: prepare (parallel), then execute
+    __device__ __forceinline__ void run(int mtype, int cnt) {
+        prepare(mtype, cnt);
+        __syncwarp();
+#pragma unroll 1
+        for (int j = 0; j < cnt; j++) execute(mtype, j);
+        if (lane == 0) S.attempt_base += (unsigned long long)cnt;
         __syncwarp();
     }
 
@@ -1058,16 +1160,15 @@ struct McWarp {
         __syncwarp();
         return inds;
     }
-    __device__ __forceinline__ void tangent_commit_large(const int *inds, int k, double ang) {
+    __device__ __forceinline__ void tangent_commit_large(const int *inds, int k, double sn, double cs) {
         // a bead's new tangents depend on its own t3/t2 only, so regenerating the
         // per-bead draws from the saved RNG state and storing chunk by chunk is safe
-        uint32_t after[CB_GLIBC_WORDS];
         if (lane == 0) {
-            rng.save(after);
+            rng.save(S.rng_after);
             rng.restore(S.rng_save);
         }
-        (void)tangent_eval(inds, k, ang, false, true);
-        if (lane == 0) rng.restore(after);
+        (void)tangent_eval_multi(inds, k, sn, cs, false, true);
+        if (lane == 0) rng.restore(S.rng_after);
     }
 };
 
@@ -1094,16 +1195,18 @@ __device__ __forceinline__ void rng_load<ReplayRng>(ReplayRng &rng, const DevCtx
     for (int i = lane; i < CB_GLIBC_WORDS; i += 32) S.grs[i] = C.glibc[(long long)rep * CB_GLIBC_WORDS + i];
     rng.st = S.grs;
     rng.mt = C.mt + (long long)rep * CB_MT_WORDS;
+    if (lane == 0) S.attempt_base = 0;
     __syncwarp();
 }
 template <>
-__device__ __forceinline__ void rng_load<PhiloxRng>(PhiloxRng &rng, const DevCtx &C, WarpSh &, int rep, int,
-                                                    unsigned long long seed) {
+__device__ __forceinline__ void rng_load<PhiloxRng>(PhiloxRng &rng, const DevCtx &C, WarpSh &S, int rep,
+                                                    int lane, unsigned long long seed) {
     rng.k0 = (uint32_t)seed;
     rng.k1 = (uint32_t)(seed >> 32);
     rng.rep = (uint32_t)rep;
-    rng.ctr = C.philox_ctr[rep];
-    rng.have = 0;
+    rng.seek_attempt(C.philox_ctr[rep]);
+    if (lane == 0) S.attempt_base = C.philox_ctr[rep]; // attempts this replica has ever made
+    __syncwarp();
 }
 template <class Rng>
 __device__ __forceinline__ void rng_store(Rng &rng, const DevCtx &C, WarpSh &S, int rep, int lane);
@@ -1114,15 +1217,16 @@ __device__ __forceinline__ void rng_store<ReplayRng>(ReplayRng &, const DevCtx &
     for (int i = lane; i < CB_GLIBC_WORDS; i += 32) C.glibc[(long long)rep * CB_GLIBC_WORDS + i] = S.grs[i];
 }
 template <>
-__device__ __forceinline__ void rng_store<PhiloxRng>(PhiloxRng &rng, const DevCtx &C, WarpSh &, int rep,
+__device__ __forceinline__ void rng_store<PhiloxRng>(PhiloxRng &, const DevCtx &C, WarpSh &S, int rep,
                                                      int lane) {
-    if (lane == 0) C.philox_ctr[rep] = rng.ctr;
+    __syncwarp();
+    if (lane == 0) C.philox_ctr[rep] = S.attempt_base;
 }
 
 // mc_sim mc_sim.pyx:26-103 for every replica: grid = R blocks of one warp.
 template <class Rng, int NB>
-__global__ void __launch_bounds__(32, 8) mc_sim_kernel(const CB_GRID_CONSTANT DevCtx C, long long num_mc_steps, double mu_adjust,
-                                                       unsigned long long seed, int cap) {
+__global__ void __launch_bounds__(32, 8) mc_sim_kernel(const CB_GRID_CONSTANT DevCtx C, long long num_mc_steps,
+                                                       double mu_adjust, unsigned long long seed, int cap) {
     CB_DYN_SMEM(dyn);
     __shared__ WarpSh S;
     const int rep = blockIdx.x, lane = threadIdx.x;
@@ -1134,17 +1238,22 @@ __global__ void __launch_bounds__(32, 8) mc_sim_kernel(const CB_GRID_CONSTANT De
         S.algo_bytes = 0;
         S.last_U = 0;
         S.passes = 1;
+        S.cur = 0;
     }
     Rng rng;
     rng_load<Rng>(rng, C, S, rep, lane, seed);
     __syncwarp();
     McWarp<Rng, false, NB> W{C, S, H, rng, rep, lane, mu_adjust, -1, nullptr};
+    constexpr int B = Rng::kBatched ? 32 : 1;
     long long a0 = 0;
     for (int m = 0; m < CHROMO_NUM_MOVES; m++) a0 += S.mv[m].num_attempt;
     for (long long k = 0; k < num_mc_steps; k++)
         for (int m = 0; m < CHROMO_NUM_MOVES; m++) {
-            if (S.mv[m].move_on == 1)
-                for (int j = 0; j < S.mv[m].num_per_cycle; j++) W.step(m);
+            if (S.mv[m].move_on == 1) {
+                const int npc = S.mv[m].num_per_cycle;
+#pragma unroll 1
+                for (int j0 = 0; j0 < npc; j0 += B) W.run(m, min(B, npc - j0));
+            }
             W.update_amplitudes(m); // also for moves that are off (mc_sim.pyx:103)
             __syncwarp();
         }
@@ -1161,8 +1270,8 @@ __global__ void __launch_bounds__(32, 8) mc_sim_kernel(const CB_GRID_CONSTANT De
 
 // one instrumented mc_step of one replica (chromo_mc_step)
 template <class Rng, int NB>
-__global__ void __launch_bounds__(32) mc_step_kernel(const CB_GRID_CONSTANT DevCtx C, int rep, int mtype, double amp_move,
-                                                     int amp_bead, double mu_adjust,
+__global__ void __launch_bounds__(32) mc_step_kernel(const CB_GRID_CONSTANT DevCtx C, int rep, int mtype,
+                                                     double amp_move, int amp_bead, double mu_adjust,
                                                      unsigned long long seed, int force_accept,
                                                      DebugOut *dbg, int cap) {
     CB_DYN_SMEM(dyn);
@@ -1183,12 +1292,13 @@ __global__ void __launch_bounds__(32) mc_step_kernel(const CB_GRID_CONSTANT DevC
         S.algo_bytes = 0;
         S.last_U = 0;
         S.passes = 1;
+        S.cur = 0;
     }
     Rng rng;
     rng_load<Rng>(rng, C, S, rep, lane, seed);
     __syncwarp();
     McWarp<Rng, true, NB> W{C, S, H, rng, rep, lane, mu_adjust, force_accept, dbg};
-    W.step(mtype);
+    W.run(mtype, 1);
     __syncwarp();
     rng_store<Rng>(rng, C, S, rep, lane);
 }

@@ -19,8 +19,11 @@
 #include "params.cuh"
 
 struct ReplayRng {
+    static constexpr bool kBatched = false; // one sequential stream: attempts are prepared one at a time
     uint32_t *st; // shared: r[0..30], f at [31], b at [32]
     uint32_t *mt; // global: mt[0..623], pos at [624]
+    __device__ __forceinline__ void seek_attempt(unsigned long long, uint32_t = 0) {}
+    __device__ __forceinline__ uint32_t position() const { return 0; }
 
     __device__ __forceinline__ uint32_t next31() {
         uint32_t f = st[31], b = st[32];
@@ -96,29 +99,40 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[3] = c3;
 }
 
+// Counter-based: draw i of attempt t of replica r is word (i & 3) of
+// Philox4x32-10(counter = (t_lo, t_hi, i >> 2, r), key = seed).  Any lane can
+// therefore produce any attempt's stream, which is what lets a batch of
+// proposals be prepared by 32 lanes at once.
 struct PhiloxRng {
+    static constexpr bool kBatched = true;
     uint32_t k0, k1, rep;
-    unsigned long long ctr;
-    uint32_t b0, b1, b2, b3; // current block; scalars so they stay in registers
-    int have;
+    unsigned long long attempt;
+    uint32_t pos;            // next draw index within the attempt's stream
+    uint32_t b0, b1, b2, b3; // block pos >> 2 (valid when (pos & 3) != 0)
 
+    __device__ __forceinline__ void refill() {
+        uint32_t o[4];
+        philox4x32_10((uint32_t)attempt, (uint32_t)(attempt >> 32), pos >> 2, rep, k0, k1, o);
+        b0 = o[0];
+        b1 = o[1];
+        b2 = o[2];
+        b3 = o[3];
+    }
+    __device__ __forceinline__ void seek_attempt(unsigned long long t, uint32_t p = 0) {
+        attempt = t;
+        pos = p;
+        if (p & 3u) refill();
+    }
+    __device__ __forceinline__ uint32_t position() const { return pos; }
     __device__ __forceinline__ uint32_t next32() {
-        if (have == 0) {
-            uint32_t o[4];
-            philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), rep, 0x43484D4Fu, k0, k1, o);
-            b0 = o[0];
-            b1 = o[1];
-            b2 = o[2];
-            b3 = o[3];
-            ctr++;
-            have = 4;
-        }
-        --have;
-        return have == 3 ? b0 : have == 2 ? b1 : have == 1 ? b2 : b3;
+        const uint32_t w = pos & 3u;
+        if (w == 0) refill();
+        ++pos;
+        return w == 0 ? b0 : w == 1 ? b1 : w == 2 ? b2 : b3;
     }
     __device__ __forceinline__ uint32_t next31() { return next32() >> 1; }
     __device__ __forceinline__ double uniform() { return (double)next31() / CB_RAND_MAX; }
-    __device__ int randint(int high) {
+    __device__ __forceinline__ int randint(int high) {
         uint32_t rng = (uint32_t)(high - 1);
         if (rng == 0) return 0;
         uint32_t mask = rng;
@@ -133,22 +147,13 @@ struct PhiloxRng {
         } while (v > rng);
         return (int)v;
     }
-    __device__ void save(uint32_t *dst) const {
-        dst[0] = (uint32_t)ctr;
-        dst[1] = (uint32_t)(ctr >> 32);
-        dst[2] = (uint32_t)have;
-        dst[3] = b0;
-        dst[4] = b1;
-        dst[5] = b2;
-        dst[6] = b3;
+    __device__ __forceinline__ void save(uint32_t *dst) const {
+        dst[0] = (uint32_t)attempt;
+        dst[1] = (uint32_t)(attempt >> 32);
+        dst[2] = pos;
     }
-    __device__ void restore(const uint32_t *src) {
-        ctr = (unsigned long long)src[0] | ((unsigned long long)src[1] << 32);
-        have = (int)src[2];
-        b0 = src[3];
-        b1 = src[4];
-        b2 = src[5];
-        b3 = src[6];
+    __device__ __forceinline__ void restore(const uint32_t *src) {
+        seek_attempt((unsigned long long)src[0] | ((unsigned long long)src[1] << 32), src[2]);
     }
 };
 
