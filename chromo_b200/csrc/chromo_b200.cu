@@ -147,8 +147,11 @@ extern "C" int chromo_ctx_create(chromo_ctx **out, int device, const chromo_shap
             d.dxyz[j] = s->width[j] / n3[j];
             d.half_width[j] = 0.5 * s->width[j];
             d.half_step[j] = 0.5 * d.dxyz[j];
+            d.inv_width[j] = 1.0 / d.width[j];
+            d.inv_dxyz[j] = 1.0 / d.dxyz[j];
         }
         d.vol_bin = s->width[0] * s->width[1] * s->width[2] / (double)d.n_bins;
+        d.inv_vol_bin = 1.0 / d.vol_bin;
         // smallest hundredth K with double(K/100) > vf_limit (see round2_exceeds)
         double K = 0.0;
         while (K / 100.0 <= d.vf_limit && K < 1e7) K += 1.0;

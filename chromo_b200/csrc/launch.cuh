@@ -12,6 +12,7 @@
 #define CB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define CB_NOINLINE __noinline__
 #define CB_GRID_CONSTANT __grid_constant__
+__device__ __forceinline__ void cb_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #endif
 #include "params.cuh"
 

@@ -160,6 +160,7 @@ __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, Warp
     constexpr int NCOL = NB + 1;
     const double *Rr = C.r + (long long)rep * C.N * 3;
     const signed char *ST = C.states + (long long)rep * C.N * NB;
+    const double *dens_rows = C.density + (long long)rep * C.n_bins * NCOL;
     const int G = n <= 2 ? 16 : n <= 4 ? 8 : n <= 8 ? 4 : n <= 16 ? 2 : 1;
     const int CPL = 16 / G, per_iter = 32 / G;
     const int sub = lane % G;
@@ -212,8 +213,9 @@ __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, Warp
             const double w = (bx ? 1.0 - wl[0] : wl[0]) * (by ? 1.0 - wl[1] : wl[1]) * (bz ? 1.0 - wl[2] : wl[2]);
             const int slot = table_claim(H, S, bin);
             if (slot < 0) continue;
-            const double V = C.access_vol ? C.access_vol[bin] : C.vol_bin;
-            const double dens = w / V;
+            // w / V_access: exact division by the constant voxel volume, or by the per-voxel one
+            const double dens = C.access_vol ? w / C.access_vol[bin] : div_const(w, C.vol_bin, C.inv_vol_bin);
+            cb_prefetch(dens_rows + (long long)bin * NCOL); // the density row is needed by table_energy
             const double t0 = sign * dens; // |x| <= 1e-18 contributions are dropped (quirk 3)
             if (fabs(t0) > 1E-18) atomicAdd(&H.vals[slot * NCOL], t0);
 #pragma unroll
@@ -444,7 +446,10 @@ __device__ __forceinline__ double pair_energy(const DevCtx &C, int rep, int bond
 }
 
 // ------------------------------------------------------- bead selection (lane 0)
-__device__ __forceinline__ double u01(uint32_t x) { return (double)x / CB_RAND_MAX; }
+// (double)rand() / RAND_MAX, exactly (div_const)
+__device__ __forceinline__ double u01(uint32_t x) {
+    return div_const((double)x, CB_RAND_MAX, 1.0 / CB_RAND_MAX);
+}
 
 // capped_exponential bead_selection.pyx:19-67
 template <class Rng>
@@ -1128,12 +1133,41 @@ struct McWarp {
         __syncwarp();
     }
 
+    // pull the rows the NEXT attempt will read towards the SM while this one runs
+    __device__ __forceinline__ void prefetch_attempt(int mtype, const Prop &P) {
+        const int N = C.N;
+        int first, count;
+        if (mtype == CHROMO_TANGENT_ROTATION) {
+            if (P.n != 1) return;
+            first = max(P.bead - 1, 0);
+            count = min(P.bead + 1, N - 1) - first + 1;
+        } else {
+            if (P.n <= 0) return;
+            first = max(P.ind0 - 1, 0);
+            count = min(P.indf, N - 1) - first + 1;
+        }
+        // 24 bytes per bead and array: one prefetch per 128-byte line
+        const int lines = (count * 24 + 127) / 128 + 1;
+        if (lane < min(lines, 32)) {
+            const long long off = (long long)first * 3 + (long long)lane * 16;
+            if (off < (long long)N * 3) {
+                cb_prefetch(R_() + off);
+                if (mtype != CHROMO_CHANGE_BINDING_STATE) cb_prefetch(T3_() + off);
+                if (mtype == CHROMO_TANGENT_ROTATION || mtype == CHROMO_CRANK_SHAFT || mtype == CHROMO_END_PIVOT)
+                    cb_prefetch(T2_() + off);
+            }
+        }
+    }
+
     // a batch of `cnt` attempts of one move type: prepare (parallel), then execute
     __device__ __forceinline__ void run(int mtype, int cnt) {
         prepare(mtype, cnt);
         __syncwarp();
 #pragma unroll 1
-        for (int j = 0; j < cnt; j++) execute(mtype, j);
+        for (int j = 0; j < cnt; j++) {
+            if (j + 1 < cnt) prefetch_attempt(mtype, S.prop[j + 1]);
+            execute(mtype, j);
+        }
         if (lane == 0) S.attempt_base += (unsigned long long)cnt;
         __syncwarp();
     }

@@ -24,7 +24,8 @@ struct DevCtx {
     int nx, ny, nz, n_bins;
     int field_active, confine_type;
     double width[3], dxyz[3], half_width[3], half_step[3];
-    double vol_bin, bead_vol, confine_length, vf_limit;
+    double inv_width[3], inv_dxyz[3]; // correctly rounded reciprocals, for div_const
+    double vol_bin, inv_vol_bin, bead_vol, confine_length, vf_limit;
     long long max_binders;
     double *r, *t3, *t2;
     signed char *states, *mods;

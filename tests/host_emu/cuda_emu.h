@@ -112,6 +112,7 @@ static inline double3 make_double3(double x, double y, double z) { return double
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 #define CB_NOINLINE __attribute__((noinline))
 #define CB_GRID_CONSTANT
+static inline void cb_prefetch(const void *) {}
 static inline double __longlong_as_double(long long v) {
     double d;
     memcpy(&d, &v, 8);
