@@ -9,8 +9,9 @@ per replica, HP1 on synthetic H3K9me3 marks, chi = 1, mu = -1.2, spherical
 confinement, 21^3 voxel grid, canonical 161-attempt sweep (30 crank-shaft, 1
 end-pivot, 60 slide, 60 tangent-rotation, 10 binding) with SimpleControl, and
 1,024 replicas PER GPU (weak scaling: replicas shard across ranks, no data-path
-collective).  One bench "step" = one `mc_sim` call of --sweeps MC sweeps over
-every replica = R * sweeps * 161 move attempts.
+collective).  One bench "step" = one `mc_sim` call of --sweeps MC sweeps
+(default 50; the reference's own scripts call mc_sim with 1,000-6,000 sweeps per
+snapshot) over every replica = R * sweeps * 161 move attempts.
 
 value : attempts/s with the state resident in HBM (CUDA events on the kernel's
         stream around K back-to-back mc_sim launches, max over ranks).
@@ -159,8 +160,10 @@ class ClockSampler:
 
 # ---------------------------------------------------------------- CPU baseline
 def _ref_worker(args):
-    """One host core: the reference's Cython mc_sim on one replica of the workload."""
-    rank, N, warm, sweeps, kind = args
+    """One host core: the reference's Cython mc_sim on one replica of the workload.
+    Warm-up sweeps let SimpleControl bring the amplitudes to their working point
+    (segments grow from ~7 to ~30 beads), as they are in the GPU arm's timed region."""
+    rank, N, warm, sweeps, reps, kind = args
     import numpy as np
     sys.path.insert(0, str(ROOT / "oracle"))
     sys.path.insert(0, str(ROOT))
@@ -169,6 +172,7 @@ def _ref_worker(args):
                 bead_length=np.full(N - 1, 16.5), lp=53.0, bead_rad=5.0, binders=[dict(HP1)], max_binders=-1,
                 field=dict(grid, chi=1.0))
     import oracle as O
+    times = []
     if kind == "reference":
         poly, df, field, M = O.ref_objects(spec)
         ctrl, mc, mcs, sh = M["mc_controller"], M["mc"], M["mc_sim"], M["shim"]
@@ -177,21 +181,25 @@ def _ref_worker(args):
         sh.c_srand(rank + 1)
         with np.errstate(over="ignore"):
             mcs.mc_sim([poly], df, warm, cs, field, 1.0, rank)
-            t0 = time.perf_counter()
-            mcs.mc_sim([poly], df, sweeps, cs, field, 1.0, rank + 7)
-            dt = time.perf_counter() - t0
+            for k in range(reps):
+                t0 = time.perf_counter()
+                mcs.mc_sim([poly], df, sweeps, cs, field, 1.0, rank + 7 + k)
+                times.append(time.perf_counter() - t0)
+        amp = [c.move.amp_bead for c in cs]
     else:
         o = O.OracleSim(spec, srand_seed=rank + 1)
         mv = O.make_moves(N, 16.5)
         o.mc_sim(mv, warm, rank)
-        t0 = time.perf_counter()
-        o.mc_sim(mv, sweeps, rank + 7)
-        dt = time.perf_counter() - t0
-    return sweeps * ATTEMPTS_PER_SWEEP, dt
+        for k in range(reps):
+            t0 = time.perf_counter()
+            o.mc_sim(mv, sweeps, rank + 7 + k)
+            times.append(time.perf_counter() - t0)
+        amp = [m.amp_bead for m in mv]
+    return sweeps * ATTEMPTS_PER_SWEEP, times, amp
 
 
-def cpu_reference_sample(N: int, sweeps: int, warm: int, cores: int | None = None):
-    """Σ attempts over processes / max wall time, one process per host core."""
+def cpu_reference_sample(N: int, sweeps: int, warm: int, reps: int = 1, cores: int | None = None):
+    """One process per host core; per repetition: sum of attempts / max wall time."""
     import multiprocessing as mp
     sys.path.insert(0, str(ROOT / "oracle"))
     import oracle as O
@@ -201,13 +209,20 @@ def cpu_reference_sample(N: int, sweeps: int, warm: int, cores: int | None = Non
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_ref_worker, [(i, N, warm, sweeps, kind) for i in range(cores)], chunksize=1)
-    attempts = sum(a for a, _ in res)
-    tmax = max(t for _, t in res)
-    return dict(value=attempts / tmax, unit=UNIT, cores=cores, kind=kind,
-                sample=f"{cores} processes x {sweeps} MC sweeps ({sweeps * ATTEMPTS_PER_SWEEP} attempts each) of one "
-                       f"N={N} HP1 replica after {warm} warm-up sweeps; wall time of mc_sim only",
-                single_core=max(a / t for a, t in res)), tmax
+        res = pool.map(_ref_worker, [(i, N, warm, sweeps, reps, kind) for i in range(cores)], chunksize=1)
+    per_rep = []
+    for k in range(reps):
+        attempts = sum(a for a, _, _ in res)
+        tmax = max(t[k] for _, t, _ in res)
+        per_rep.append((attempts / tmax, tmax))
+    value = sum(v for v, _ in per_rep) / reps
+    amp = [sum(a[i] for _, _, a in res) / len(res) for i in range(5)]
+    cb = dict(value=value, unit=UNIT, cores=cores, kind=kind,
+              sample=f"{cores} processes (one per host core) x {sweeps} MC sweeps ({sweeps * ATTEMPTS_PER_SWEEP} attempts "
+                     f"each) of one N={N} HP1 replica, after {warm} warm-up sweeps that bring SimpleControl to its "
+                     f"working point; wall time of mc_sim only",
+              single_core=max(a / min(t) for a, t, _ in res), amp_bead_mean=[round(x, 2) for x in amp])
+    return cb, per_rep
 
 
 def run_reference(args):
@@ -215,17 +230,12 @@ def run_reference(args):
     if rank != 0:
         return
     N = args.beads
-    vals, times = [], []
-    cb = None
-    for i in range(args.warmup + args.steps):
-        cb, tmax = cpu_reference_sample(N, args.ref_sweeps, 2)
-        if i >= args.warmup:
-            vals.append(cb["value"])
-            times.append(tmax)
-    v = sum(vals) / len(vals)
+    cb, per_rep = cpu_reference_sample(N, args.ref_sweeps, args.ref_warm, reps=args.warmup + args.steps)
+    timed = per_rep[args.warmup:]
+    v = sum(x for x, _ in timed) / len(timed)
     cb["value"] = v
     line = dict(metric=METRIC, value=v, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1e3 * sum(times) / len(times), higher_is_better=True,
+                warmup=args.warmup, ms_per_step=1e3 * sum(t for _, t in timed) / len(timed), higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=workload_config(args, 0), cpu_baseline=cb,
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -276,6 +286,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput --------------------------------------
+    # untimed: let SimpleControl bring the amplitudes to their working point (same for the CPU arm)
+    ens.mc_sim(args.ref_warm, 1.0, 99, sync_host=False)
     for w in range(Wm):
         ens.mc_sim(S, 1.0, 100 + w, sync_host=False)
     barrier()
@@ -296,6 +308,7 @@ def run_ours(args):
     algo_bytes_last = eng.last_algo_bytes()
     ens.sync()
     acc = ens.acceptance()
+    amp_bead_mean = [float(x) for x in ens.moves["amp_bead"].mean(axis=0)]
     barrier()
 
     # ---- end to end through the host-facing call --------------------------
@@ -353,11 +366,12 @@ def run_ours(args):
                           bytes_per_attempt=algo_bytes_last / max(1, attempts_last),
                           note="latency-bound (serial moves per replica, one warp each); see DESIGN.md"),
             acceptance={k: round(float(v), 4) for k, v in acc.items()},
+            amp_bead_mean=[round(x, 2) for x in amp_bead_mean],
             hbm_bytes=eng.bytes(),
         )
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cb, _ = cpu_reference_sample(N, args.ref_sweeps, 2)
+                cb, _ = cpu_reference_sample(N, args.ref_sweeps, args.ref_warm)
                 line["cpu_baseline"] = cb
             except Exception as e:  # never lose the GPU number to a baseline hiccup
                 line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=str(e)[:200])
@@ -375,9 +389,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicas", type=int, default=1024, help="replicas per GPU")
     ap.add_argument("--beads", type=int, default=10000)
-    ap.add_argument("--sweeps", type=int, default=10, help="MC sweeps (161 attempts each) per bench step")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--sweeps", type=int, default=50, help="MC sweeps (161 attempts each) per bench step")
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-sweeps", type=int, default=100, help="MC sweeps per process in the CPU reference sample")
+    ap.add_argument("--ref-warm", type=int, default=400, help="warm-up sweeps of the CPU reference (controller settles)")
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -273,6 +273,8 @@ extern "C" int chromo_set_binders(chromo_ctx *c, const int64_t *sites, const dou
         d.e_intra[a] = e_intra[a];
         for (int b = 0; b < d.nb; b++) d.xpref[a * d.nb + b] = xpref[a * d.nb + b];
     }
+    d.any_cross = 0;
+    for (int a = 0; a < d.nb * d.nb; a++) d.any_cross |= (d.xpref[a] != 0.0);
     d.S1 = (int)S + 1;
     if (c->d_bindF) return fail(CHROMO_ERR_STATE, "binders already set for this context");
     int rc = replace_buf(c, &c->d_bindF, bind_F, (size_t)d.nb * d.S1 * d.S1);

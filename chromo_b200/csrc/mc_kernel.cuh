@@ -322,8 +322,7 @@ __device__ __forceinline__ double field_dE_segment(const DevCtx &C, HashTable &H
     int P = 1;
     FieldSums<NB> F;
     int2 conf = make_int2(0, 0);
-    bool want_cross = false;
-    for (int a = 0; a < NB * NB; a++) want_cross |= (C.xpref[a] != 0.0);
+    const bool want_cross = C.any_cross != 0;
     while (true) {
 #pragma unroll
         for (int a = 0; a < NB; a++) F.sq[a] = 0.0;

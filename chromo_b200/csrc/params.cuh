@@ -37,6 +37,7 @@ struct DevCtx {
     const double *mu;      // [R][nb]
     double pref[CB_MAXNB], e_intra[CB_MAXNB], xpref[CB_MAXNB * CB_MAXNB];
     int sites[CB_MAXNB];
+    int any_cross; // some cross-talk prefactor is non-zero
     const double *bindF; // [nb][S1][S1]
     int S1;
     chromo_move_state *moves;        // [R][5]
