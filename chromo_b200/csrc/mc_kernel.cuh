@@ -178,8 +178,11 @@ __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, Warp
         int lo[3], hi[3];
         double wl[3], sign = 0.0;
 #pragma unroll 1
+        // lanes walk the 8 corners in a lane-rotated order so that neighbouring beads (which
+        // mostly share a cell) do not hit the same voxel's slot in the same instruction
+        const int rot = CPL >= 8 ? (lane / G) & 7 : 0;
         for (int c = sub * CPL; c < (sub + 1) * CPL; c++) {
-            const int k = c >> 3, l = c & 7;
+            const int k = c >> 3, l = ((c & 7) + rot) & 7;
             if (k != cur_k) { // (re)bin for the current / the trial position
                 cur_k = k;
                 double y[3] = {x[0], x[1], x[2]};
@@ -194,7 +197,7 @@ __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, Warp
                     }
                 }
                 sign = k ? 1.0 : -1.0;
-                if (p == 0 && l == 0 && kind != 2) {
+                if (p == 0 && (c & 7) == 0 && kind != 2) {
                     if (C.confine_type == CHROMO_CONFINE_SPHERICAL) {
                         int out = sqrt(dot3(y, y)) > C.confine_length;
                         out_t += k ? out : 0;
