@@ -85,7 +85,7 @@ static int dev_alloc(chromo_ctx *c, T **p, size_t n) {
 static inline size_t table_bytes(int cap, int ncol) {
     return (size_t)cap * (ncol * sizeof(double) + 2 * sizeof(int));
 }
-static const size_t kWarpShBytes = 12288; // >= sizeof(WarpSh), checked in mc_kernel.cuh
+static const size_t kWarpShBytes = 8704; // >= sizeof(WarpSh), checked in mc_kernel.cuh
 
 static int choose_table(chromo_ctx *c) {
     // Shared memory per replica-warp = static WarpSh + the delta-density hash.

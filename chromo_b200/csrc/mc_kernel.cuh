@@ -58,8 +58,6 @@ struct WarpSh {
     uint32_t rng_save[CB_GLIBC_WORDS];
     double M[12];                 // affine map of the current move
     double tan_new[32 * 6];       // tangent rotation: new t3 | t2 of the selected beads
-    double tan_trig[9 * 32];      // tangent rotation: per-lane angles | sines | cosines
-    double trig[9];               // segment moves: angles | sines | cosines (lane 0)
     int tinds[32];                // tangent rotation: selected beads (small path)
     int ind0, indf, n, binder;
     int count;                    // occupied hash slots
@@ -70,7 +68,7 @@ struct WarpSh {
     uint32_t draws[64];           // per-bead axis draws of tangent rotation
     signed char newst[256];       // new binding states (small path)
 };
-static_assert(sizeof(WarpSh) <= 12288, "update kWarpShBytes in chromo_b200.cu");
+static_assert(sizeof(WarpSh) <= 8704, "update kWarpShBytes in chromo_b200.cu");
 
 struct HashTable {
     int *keys;    // [cap]
@@ -622,26 +620,21 @@ struct McWarp {
                 P.newst0 = rng.randint(C.sites[binder] + 1);
             } // n > 1 in a batch: drawn at execute time from this attempt's stream
         }
-        // ---- all the trigonometry in one place: angles in, (sin, cos) out ----
+        // ---- the trigonometry (one out-of-line sincos / acos each, shared by all call sites) ----
         // uniform_sample_unit_sphere linalg.pyx:23-59, arbitrary_axis_rotation 62-139
-        double *tr = S.tan_trig + lane; // [9][32]: angle, phi, theta | sines | cosines
-        tr[0] = amp;
-        tr[32] = u01(d1) * (2.0 * 3.14159265358979323846);
-        tr[64] = sphere ? acos(u01(d2) * 2.0 - 1.0) : 0.0;
-        const int t_lo = (slide || bind) ? 1 : 0, t_hi = bind ? 1 : (sphere ? 3 : 1);
-#pragma unroll 1
-        for (int t = t_lo; t < t_hi; t++) {
-            double s_, c_;
-            sincos(tr[32 * t], &s_, &c_);
-            tr[96 + 32 * t] = s_;
-            tr[192 + 32 * t] = c_;
+        double sn = 0.0, cs = 1.0;
+        if (!(slide || bind)) {
+            const double2 sc = sincos_ni(amp);
+            sn = sc.x;
+            cs = sc.y;
         }
-        const double sn = tr[96], cs = tr[192];
         double axis[3] = {0.0, 0.0, 0.0};
         if (sphere) {
-            axis[0] = tr[192 + 32] * tr[96 + 64];
-            axis[1] = tr[96 + 32] * tr[96 + 64];
-            axis[2] = tr[192 + 64];
+            const double2 ph = sincos_ni(u01(d1) * (2.0 * 3.14159265358979323846));
+            const double2 th = sincos_ni(acos_ni(u01(d2) * 2.0 - 1.0));
+            axis[0] = ph.y * th.x;
+            axis[1] = ph.x * th.x;
+            axis[2] = th.y;
         }
         P.sn = sn;
         P.cs = cs;
@@ -908,19 +901,12 @@ struct McWarp {
 #pragma unroll
                 for (int q = 0; q < 9; q++) Rm[q] = Rfix[q];
             } else {
-                double *tr = S.tan_trig + lane;
-                tr[32] = u01(draws[2 * j]) * (2.0 * 3.14159265358979323846);
-                tr[64] = acos_ni(u01(draws[2 * j + 1]) * 2.0 - 1.0);
-#pragma unroll 1
-                for (int t = 1; t < 3; t++) {
-                    const double2 sc = sincos_ni(tr[32 * t]);
-                    tr[96 + 32 * t] = sc.x;
-                    tr[192 + 32 * t] = sc.y;
-                }
+                const double2 ph = sincos_ni(u01(draws[2 * j]) * (2.0 * 3.14159265358979323846));
+                const double2 th = sincos_ni(acos_ni(u01(draws[2 * j + 1]) * 2.0 - 1.0));
                 double axis[3];
-                axis[0] = tr[192 + 32] * tr[96 + 64];
-                axis[1] = tr[96 + 32] * tr[96 + 64];
-                axis[2] = tr[192 + 64];
+                axis[0] = ph.y * th.x;
+                axis[1] = ph.x * th.x;
+                axis[2] = th.y;
                 rotation_3x3(axis, sn, cs, Rm);
             }
             load3(T3 + 3 * bead, t3c);

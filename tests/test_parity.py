@@ -161,7 +161,9 @@ def test_large_moves_take_partition_passes(backend, oracle_mod):
             a = out["dtrial"][np.argsort(out["touched"])]
             b = o.density_trial[np.sort(touched)]
             assert np.allclose(a, b, rtol=1e-9, atol=1e-9 / o.s.vol_bin)
-            assert close_dE(out["dE_field"], dEf)
+            # voxels above vf_limit contribute +-1e99*phi terms that cancel to ~1e-16 of themselves
+            sc = huge_scale(o.density, o.density_trial, np.sort(touched), o.s.bead_vol, spec["field"]["vf_limit"])
+            assert close_dE(out["dE_field"], dEf, sc)
         ip = inds.ctypes.data_as(O._pl)
         if acc:
             O.lib().oc_accept(C.byref(o.s), C.byref(mvs[m]), m, ip, len(inds))
