@@ -59,11 +59,22 @@ struct chromo_ctx {
     int cap = 0;           // hash-table capacity (slots) of the MC kernel
     size_t smem_bytes = 0;
     double roundK = 0.0;
+    double min_access_vol = 0.0; // smallest positive per-voxel volume (0: uniform voxels)
     bool have_binders = false, have_bonds = false, have_state = false;
     int64_t last_attempts = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
 };
+
+// exponent base of the MC kernel's fixed-point delta-density cells (mc_kernel.cuh, fx_exponent):
+// floor(log2(2^61 * V_min / max_state))
+static void refresh_fx_base(chromo_ctx *c) {
+    DevCtx &d = c->d;
+    double vmin = (d.access_vol && c->min_access_vol > 0.0) ? c->min_access_vol : d.vol_bin;
+    int smax = 1;
+    for (int a = 0; a < d.nb; a++) smax = std::max(smax, d.sites[a]);
+    d.fx_base = (vmin > 0.0) ? 61 + (int)ilogb(vmin / (double)smax) : 61;
+}
 
 extern "C" const char *chromo_last_error(void) { return g_err.c_str(); }
 extern "C" int chromo_version(void) { return 100; }
@@ -212,6 +223,7 @@ extern "C" int chromo_ctx_create(chromo_ctx **out, int device, const chromo_shap
         CK(cudaStreamSynchronize(c->stream));
     }
     choose_table(c);
+    refresh_fx_base(c);
     *out = c;
     return CHROMO_OK;
 }
@@ -281,6 +293,7 @@ extern "C" int chromo_set_binders(chromo_ctx *c, const int64_t *sites, const dou
     if (rc) return rc;
     d.bindF = c->d_bindF;
     c->have_binders = true;
+    refresh_fx_base(c);
     return CHROMO_OK;
 }
 
@@ -324,12 +337,18 @@ extern "C" int chromo_set_access_volumes(chromo_ctx *c, const double *access_vol
     CK(cudaSetDevice(c->device));
     if (!access_vol) {
         c->d.access_vol = nullptr;
+        refresh_fx_base(c);
         return CHROMO_OK;
     }
     if (!c->d.field_active) return fail(CHROMO_ERR_STATE, "context has no field");
     int rc = replace_buf(c, &c->d_access, access_vol, (size_t)c->d.n_bins);
     if (rc) return rc;
     c->d.access_vol = c->d_access;
+    c->min_access_vol = 0.0;
+    for (int i = 0; i < c->d.n_bins; i++)
+        if (access_vol[i] > 0.0 && (c->min_access_vol == 0.0 || access_vol[i] < c->min_access_vol))
+            c->min_access_vol = access_vol[i];
+    refresh_fx_base(c);
     return CHROMO_OK;
 }
 

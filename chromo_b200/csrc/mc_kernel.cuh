@@ -71,9 +71,9 @@ struct WarpSh {
 static_assert(sizeof(WarpSh) <= 8704, "update kWarpShBytes in chromo_b200.cu");
 
 struct HashTable {
-    int *keys;    // [cap]
-    int *list;    // [cap]   occupied slots, in claim order
-    double *vals; // [cap][ncol]
+    int *keys;      // [cap]
+    int *list;      // [cap]   occupied slots, in claim order
+    uint32_t *vals; // [cap][ncol][2]  delta-rho in 64-bit fixed point (low word, high word)
     int cap, shift, limit;
 };
 
@@ -88,10 +88,40 @@ __device__ __forceinline__ int warp_sum_int(int v) {
     return v;
 }
 
+// ------------------------------------------------- fixed-point delta-rho cells
+// Shared memory has no native 64-bit or floating-point atomic add on sm_100a
+// (both compile to ATOMS.CAST.SPIN loops, three dependent shared-memory round
+// trips per try -- the top stall of the v3-v6 profiles).  The delta-rho of a move
+// is therefore accumulated as a 64-bit integer in units of 2^-E through TWO
+// native 32-bit ATOMS.ADD: the low word's returned old value gives the carry,
+// the high-word add is fire-and-forget.  E is chosen per move from the segment
+// length so that the sum cannot overflow (fx_exponent); at n = 16 beads the
+// quantum is 2^-70 nm^-3, finer than the fp64 ulp of a single w/V term, and
+// the result no longer depends on the order in which lanes arrive
+// (bit-reproducible runs).
+__device__ __forceinline__ void fx_add(uint32_t *cell, long long v) {
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)((unsigned long long)v >> 32);
+    const uint32_t old = atomicAdd(&cell[0], lo);
+    const uint32_t carry = (uint32_t)(old + lo) < lo ? 1u : 0u;
+    atomicAdd(&cell[1], hi + carry);
+}
+__device__ __forceinline__ double fx_read(const uint32_t *cell, double inv_scale) {
+    const long long v = (long long)(((unsigned long long)cell[1] << 32) | (unsigned long long)cell[0]);
+    return (double)v * inv_scale;
+}
+// 2^e as a double
+__device__ __forceinline__ double pow2_double(int e) { return __hiloint2double((1023 + e) << 20, 0); }
+// every voxel receives at most 2n terms of magnitude <= max_state / V_min per
+// move; C.fx_base = floor(log2(2^61 * V_min / max_state)) (host), so with
+// E = fx_base - ceil(log2(n)) the sum stays below 2^62 in magnitude.
+__device__ __forceinline__ int fx_exponent(const DevCtx &C, int n) {
+    return C.fx_base - (n > 1 ? 32 - __clz(n - 1) : 0);
+}
+
 // ---------------------------------------------------------------- hash table
 __device__ __forceinline__ void table_reset_all(HashTable &H, WarpSh &S, int ncol, int lane) {
     for (int i = lane; i < H.cap; i += 32) H.keys[i] = HASH_EMPTY;
-    for (int i = lane; i < H.cap * ncol; i += 32) H.vals[i] = 0.0;
+    for (int i = lane; i < H.cap * ncol * 2; i += 32) H.vals[i] = 0u;
     if (lane == 0) {
         S.count = 0;
         S.overflow = 0;
@@ -105,7 +135,7 @@ __device__ __forceinline__ void table_clear(HashTable &H, WarpSh &S, int ncol, i
     for (int j = lane; j < cnt; j += 32) {
         int slot = H.list[j];
         H.keys[slot] = HASH_EMPTY;
-        for (int c = 0; c < ncol; c++) H.vals[slot * ncol + c] = 0.0;
+        for (int c = 0; c < ncol; c++) *(unsigned long long *)&H.vals[(slot * ncol + c) * 2] = 0ull;
     }
     __syncwarp();
     if (lane == 0) {
@@ -114,31 +144,25 @@ __device__ __forceinline__ void table_clear(HashTable &H, WarpSh &S, int ncol, i
     }
     __syncwarp();
 }
-// claim (or find) the slot of `bin`; -1 on overflow.  Claims stop once `limit`
-// slots are taken (at most 32 more can be in flight), so the list never
-// overruns and every claimed slot is listed (table_clear relies on that).
-__device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin) {
+// claim (or find) the slot of `bin`: one ATOMS.CAS on the key in the common
+// case.  `checked` (moves that could overflow the table: 16 n > limit): -1 once
+// the overflow flag is up; the flag rises when `limit` slots are taken, at most
+// 32 more claims can be in flight, so the table never fills and every claimed
+// slot is listed (table_clear relies on that).
+__device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin, bool checked) {
     uint32_t slot = ((uint32_t)bin * 2654435761u) >> H.shift;
-    for (int probe = 0; probe < H.cap; probe++) {
-        int cur = *(volatile int *)&H.keys[slot];
-        if (cur == bin) return (int)slot;
-        if (cur == HASH_EMPTY) {
-            if (*(volatile int *)&S.count >= H.limit) {
-                S.overflow = 1;
-                return -1;
-            }
-            int prev = atomicCAS(&H.keys[slot], HASH_EMPTY, bin);
-            if (prev == bin) return (int)slot;
-            if (prev == HASH_EMPTY) {
-                int pos = atomicAdd(&S.count, 1);
-                H.list[pos] = (int)slot;
-                return (int)slot;
-            }
+    if (checked && *(volatile int *)&S.overflow) return -1;
+    while (true) {
+        const int prev = atomicCAS(&H.keys[slot], HASH_EMPTY, bin);
+        if (prev == bin) return (int)slot;
+        if (prev == HASH_EMPTY) {
+            const int pos = atomicAdd(&S.count, 1);
+            H.list[pos] = (int)slot;
+            if (checked && pos + 1 >= H.limit) S.overflow = 1;
+            return (int)slot;
         }
         slot = (slot + 1) & (uint32_t)(H.cap - 1);
     }
-    S.overflow = 1;
-    return -1;
 }
 
 // ---------------------------------------------------------- scatter of a move
@@ -147,21 +171,25 @@ __device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin) {
 // and +w/V*{1,state'} at its trial position to the 8 voxels around each.
 //   kind 0: trial = M r (crank-shaft, end-pivot)   kind 1: trial = r + t (slide)
 //   kind 2: trial position = current position, state' = newst (binding)
-// G lanes share a bead, each handling 16/G consecutive contributions
-// c = 8*k + l  (k: 0 current / 1 trial; l: voxel corner, bit0 x, bit1 y, bit2 z).
+// G lanes share a bead (G = 16/8/4/2/1 by segment length).  A bead whose current
+// and trial positions fall in the same cell (most slides and small rotations,
+// every binding move) has 8 merged units -- one per voxel corner l (bit0 x,
+// bit1 y, bit2 z), trial minus current -- otherwise 16 units (k = 0 current /
+// 1 trial, corner l); the lanes of the bead split the units evenly.
 // Returns the confinement counters of get_confinement_dE (fields.pyx:160-193):
 // x = # trial positions outside, y = # current positions outside (this lane's).
 template <int NB>
 __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
                                           int kind, int ind0, int n, int binder,
-                                          const signed char *newst, int P, int p) {
+                                          const signed char *newst, int P, int p, double scale) {
     constexpr int NCOL = NB + 1;
     const double *Rr = C.r + (long long)rep * C.N * 3;
     const signed char *ST = C.states + (long long)rep * C.N * NB;
     const double *dens_rows = C.density + (long long)rep * C.n_bins * NCOL;
     const int G = n <= 2 ? 16 : n <= 4 ? 8 : n <= 8 ? 4 : n <= 16 ? 2 : 1;
-    const int CPL = 16 / G, per_iter = 32 / G;
-    const int sub = lane % G;
+    const int per_iter = 32 / G;
+    const int sub = lane & (G - 1);
+    const bool checked = P > 1 || 16 * n > H.limit;
     int out_t = 0, out_c = 0;
     for (int base = 0; base < n; base += per_iter) {
         const int i = base + lane / G;
@@ -169,61 +197,88 @@ __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, Warp
         const int bead = ind0 + i;
         double x[3];
         load3(Rr + 3 * bead, x);
-        signed char st[NB];
+        int mult[NB]; // column m+1 receives (column-0 term) * mult[m]
 #pragma unroll
-        for (int m = 0; m < NB; m++) st[m] = ST[bead * NB + m];
-        int cur_k = -1;
-        int lo[3], hi[3];
-        double wl[3], sign = 0.0;
+        for (int m = 0; m < NB; m++) mult[m] = ST[bead * NB + m];
+        int loc[3], hic[3], lot[3], hit[3];
+        double wc[3], wt[3];
+        bin_axes(C, x, loc, hic, wc);
+        bool same = true;
+        if (kind == 2) {
+            // state change only: the bead column cancels exactly (quirk 4), the
+            // binder's column gets w/V * (s' - s)
+#pragma unroll
+            for (int m = 0; m < NB; m++) mult[m] = (m == binder) ? (int)newst[i] - mult[m] : 0;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                lot[j] = loc[j];
+                hit[j] = hic[j];
+                wt[j] = wc[j];
+            }
+        } else {
+            double y[3];
+            if (kind == 0) apply_affine(S.M, x, y);
+            else
+                for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
+            if (p == 0 && sub == 0) {
+                if (C.confine_type == CHROMO_CONFINE_SPHERICAL) {
+                    out_t += sqrt(dot3(y, y)) > C.confine_length;
+                    out_c += sqrt(dot3(x, x)) > C.confine_length;
+                } else if (C.confine_type == CHROMO_CONFINE_CUBICAL) {
+                    // fields.pyx:178-193: the current configuration is never counted
+                    for (int j = 0; j < 3; j++) out_t += (fabs(y[j]) > C.confine_length / 2);
+                }
+            }
+            bin_axes(C, y, lot, hit, wt);
+            same = loc[0] == lot[0] && loc[1] == lot[1] && loc[2] == lot[2];
+        }
+        const int nunits = same ? 8 : 16;
+        const int cpl = max(nunits / G, 1);
+        const int u0 = sub * cpl, u1 = min(u0 + cpl, nunits);
+        // a lane that walks all 8 corners starts at a lane-dependent corner, so that
+        // neighbouring beads (which mostly share a cell) do not hit one slot together
+        const int rot = cpl >= 8 ? (lane / G) & 7 : 0;
 #pragma unroll 1
-        // lanes walk the 8 corners in a lane-rotated order so that neighbouring beads (which
-        // mostly share a cell) do not hit the same voxel's slot in the same instruction
-        const int rot = CPL >= 8 ? (lane / G) & 7 : 0;
-        for (int c = sub * CPL; c < (sub + 1) * CPL; c++) {
-            const int k = c >> 3, l = ((c & 7) + rot) & 7;
-            if (k != cur_k) { // (re)bin for the current / the trial position
-                cur_k = k;
-                double y[3] = {x[0], x[1], x[2]};
-                if (k == 1) {
-                    if (kind == 0) apply_affine(S.M, x, y);
-                    else if (kind == 1)
-                        for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
-                    else {
-#pragma unroll
-                        for (int m = 0; m < NB; m++)
-                            if (m == binder) st[m] = newst[i];
-                    }
-                }
-                sign = k ? 1.0 : -1.0;
-                if (p == 0 && (c & 7) == 0 && kind != 2) {
-                    if (C.confine_type == CHROMO_CONFINE_SPHERICAL) {
-                        int out = sqrt(dot3(y, y)) > C.confine_length;
-                        out_t += k ? out : 0;
-                        out_c += k ? 0 : out;
-                    } else if (C.confine_type == CHROMO_CONFINE_CUBICAL && k == 1) {
-                        // fields.pyx:178-193: the current configuration is never counted
-                        for (int j = 0; j < 3; j++) out_t += (fabs(y[j]) > C.confine_length / 2);
-                    }
-                }
-                bin_axes(C, y, lo, hi, wl);
-            }
-            // voxel corner l: index and weight (products in the reference's order (x*y)*z)
+        for (int u = u0; u < u1; u++) {
+            const int k = u >> 3, l = ((u & 7) + rot) & 7;
             const int bx = l & 1, by = (l >> 1) & 1, bz = l >> 2;
-            const int bin = (bx ? hi[0] : lo[0]) + C.nx * ((by ? hi[1] : lo[1]) + C.ny * (bz ? hi[2] : lo[2]));
+            // voxel index and weights (products in the reference's order (x*y)*z)
+            const int ix = k ? (bx ? hit[0] : lot[0]) : (bx ? hic[0] : loc[0]);
+            const int iy = k ? (by ? hit[1] : lot[1]) : (by ? hic[1] : loc[1]);
+            const int iz = k ? (bz ? hit[2] : lot[2]) : (bz ? hic[2] : loc[2]);
+            const int bin = ix + C.nx * (iy + C.ny * iz);
             if (P > 1 && (bin & (P - 1)) != p) continue;
-            const double w = (bx ? 1.0 - wl[0] : wl[0]) * (by ? 1.0 - wl[1] : wl[1]) * (bz ? 1.0 - wl[2] : wl[2]);
-            const int slot = table_claim(H, S, bin);
+            const int slot = table_claim(H, S, bin, checked);
             if (slot < 0) continue;
-            // w / V_access: exact division by the constant voxel volume, or by the per-voxel one
-            const double dens = C.access_vol ? w / C.access_vol[bin] : div_const(w, C.vol_bin, C.inv_vol_bin);
             cb_prefetch(dens_rows + (long long)bin * NCOL); // the density row is needed by table_energy
-            const double t0 = sign * dens; // |x| <= 1e-18 contributions are dropped (quirk 3)
-            if (fabs(t0) > 1E-18) atomicAdd(&H.vals[slot * NCOL], t0);
-#pragma unroll
-            for (int m = 0; m < NB; m++) {
-                const double t = sign * (dens * (double)st[m]);
-                if (fabs(t) > 1E-18) atomicAdd(&H.vals[slot * NCOL + 1 + m], t);
+            const double w_c = (bx ? 1.0 - wc[0] : wc[0]) * (by ? 1.0 - wc[1] : wc[1]) * (bz ? 1.0 - wc[2] : wc[2]);
+            const double w_t = (bx ? 1.0 - wt[0] : wt[0]) * (by ? 1.0 - wt[1] : wt[1]) * (bz ? 1.0 - wt[2] : wt[2]);
+            // w / V_access: exact division by the constant voxel volume, or by the per-voxel one;
+            // |x| <= 1e-18 terms are dropped (quirk 3)
+            double d_c, d_t;
+            if (C.access_vol) {
+                const double V = C.access_vol[bin];
+                d_c = w_c / V;
+                d_t = w_t / V;
+            } else {
+                d_c = div_const(w_c, C.vol_bin, C.inv_vol_bin);
+                d_t = div_const(w_t, C.vol_bin, C.inv_vol_bin);
             }
+            const long long f_c = fabs(d_c) > 1E-18 ? __double2ll_rn(d_c * scale) : 0ll;
+            const long long f_t = fabs(d_t) > 1E-18 ? __double2ll_rn(d_t * scale) : 0ll;
+            long long v0, vs; // bead column; base of the binder columns
+            if (kind == 2) {
+                v0 = 0;
+                vs = f_c;
+            } else {
+                v0 = same ? f_t - f_c : (k ? f_t : -f_c);
+                vs = v0;
+            }
+            uint32_t *cell = H.vals + (size_t)slot * NCOL * 2;
+            if (v0 != 0) fx_add(cell, v0);
+#pragma unroll
+            for (int m = 0; m < NB; m++)
+                if (mult[m] != 0 && vs != 0) fx_add(cell + 2 * (1 + m), vs * (long long)mult[m]);
         }
     }
     return make_int2(out_t, out_c);
@@ -240,7 +295,7 @@ struct FieldSums {
 template <int NB>
 __device__ __forceinline__ void table_energy(const DevCtx &C, const HashTable &H, const WarpSh &S,
                                              int rep, double chi, int lane, FieldSums<NB> &F,
-                                             bool want_cross) {
+                                             bool want_cross, double inv_scale) {
     constexpr int NCOL = NB + 1;
     int cnt = S.count;
     const double *dens = C.density + (long long)rep * C.n_bins * NCOL;
@@ -248,11 +303,13 @@ __device__ __forceinline__ void table_energy(const DevCtx &C, const HashTable &H
         int slot = H.list[j];
         int bin = H.keys[slot];
         const double *row = dens + (long long)bin * NCOL;
-        double rho[NCOL], rn[NCOL];
+        double rho[NCOL], rn[NCOL], dr0 = 0.0;
 #pragma unroll
         for (int c = 0; c < NCOL; c++) {
             rho[c] = row[c];
-            rn[c] = rho[c] + H.vals[slot * NCOL + c];
+            const double dr = fx_read(H.vals + ((size_t)slot * NCOL + c) * 2, inv_scale);
+            if (c == 0) dr0 = dr;
+            rn[c] = rho[c] + dr;
         }
 #pragma unroll
         for (int a = 0; a < NB; a++) {
@@ -272,7 +329,7 @@ __device__ __forceinline__ void table_energy(const DevCtx &C, const HashTable &H
         }
         double V = C.access_vol ? C.access_vol[bin] : C.vol_bin;
         double vf0 = rho[0] * C.bead_vol;
-        double vf1 = vf0 + (H.vals[slot * NCOL] * C.bead_vol);
+        double vf1 = vf0 + (dr0 * C.bead_vol);
         double e = 0.0;
         if (vf1 > C.vf_limit) e += CB_E_HUGE_FIELD * vf1;
         else e += chi * (V / C.bead_vol) * (vf1 * vf1);
@@ -283,17 +340,17 @@ __device__ __forceinline__ void table_energy(const DevCtx &C, const HashTable &H
 }
 // update_affected_densities fields.pyx:1968-1975 for the voxels in the table
 __device__ __forceinline__ void table_commit(const DevCtx &C, const HashTable &H, const WarpSh &S,
-                                             int rep, int lane) {
+                                             int rep, int lane, double inv_scale) {
     int cnt = S.count;
     double *dens = C.density + (long long)rep * C.n_bins * C.ncol;
     for (int j = lane; j < cnt; j += 32) {
         int slot = H.list[j];
         double *row = dens + (long long)H.keys[slot] * C.ncol;
-        for (int c = 0; c < C.ncol; c++) row[c] += H.vals[slot * C.ncol + c];
+        for (int c = 0; c < C.ncol; c++) row[c] += fx_read(H.vals + ((size_t)slot * C.ncol + c) * 2, inv_scale);
     }
 }
 __device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTable &H, const WarpSh &S,
-                                              int lane, DebugOut *dbg) {
+                                              int lane, DebugOut *dbg, double inv_scale) {
     int cnt = S.count;
     long long base = dbg->n_touched;
     for (int j = lane; j < cnt; j += 32) {
@@ -301,7 +358,8 @@ __device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTabl
         if (o < dbg->touched_cap) {
             int slot = H.list[j];
             dbg->touched[o] = H.keys[slot];
-            for (int c = 0; c < C.ncol; c++) dbg->dtrial[o * C.ncol + c] = H.vals[slot * C.ncol + c];
+            for (int c = 0; c < C.ncol; c++)
+                dbg->dtrial[o * C.ncol + c] = fx_read(H.vals + ((size_t)slot * C.ncol + c) * 2, inv_scale);
         }
     }
     __syncwarp();
@@ -320,6 +378,8 @@ __device__ __forceinline__ double field_dE_segment(const DevCtx &C, HashTable &H
                                                 const signed char *newst, const int *ddbl, DebugOut *dbg) {
     constexpr int NCOL = NB + 1;
     const double chi = C.chi[rep];
+    const int fxe = fx_exponent(C, n);
+    const double scale = pow2_double(fxe), inv_scale = pow2_double(-fxe);
     int P = 1;
     FieldSums<NB> F;
     int2 conf = make_int2(0, 0);
@@ -333,16 +393,16 @@ __device__ __forceinline__ double field_dE_segment(const DevCtx &C, HashTable &H
         if (DEBUG && lane == 0) dbg->n_touched = 0;
         bool failed = false;
         for (int p = 0; p < P; p++) {
-            int2 c = scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, P, p);
+            int2 c = scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, P, p, scale);
             if (p == 0) conf = c;
             __syncwarp();
             if (S.overflow) {
                 failed = true;
                 break;
             }
-            table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross);
+            table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross, inv_scale);
             if (lane == 0) S.last_U = (p == 0 ? 0 : S.last_U) + S.count;
-            if (DEBUG) table_debug_dump(C, H, S, lane, dbg);
+            if (DEBUG) table_debug_dump(C, H, S, lane, dbg, inv_scale);
             if (P > 1) table_clear(H, S, NCOL, lane);
         }
         if (!failed) break;
@@ -385,11 +445,13 @@ __device__ CB_NOINLINE void field_commit_multipass(const DevCtx &C, HashTable H,
                                                    const signed char *newst) {
     WarpSh &S = *Sp;
     const int passes = S.passes;
+    const int fxe = fx_exponent(C, n);
+    const double scale = pow2_double(fxe), inv_scale = pow2_double(-fxe);
     for (int p = 0; p < passes; p++) {
         table_clear(H, S, NB + 1, lane);
-        (void)scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, passes, p);
+        (void)scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, passes, p, scale);
         __syncwarp();
-        table_commit(C, H, S, rep, lane);
+        table_commit(C, H, S, rep, lane, inv_scale);
     }
 }
 
@@ -795,7 +857,7 @@ struct McWarp {
     __device__ __forceinline__ void segment_commit(int kind, int ind0, int n, int binder,
                                                    const signed char *newst) {
         if (C.field_active) {
-            if (S.passes == 1) table_commit(C, H, S, rep, lane);
+            if (S.passes == 1) table_commit(C, H, S, rep, lane, pow2_double(-fx_exponent(C, n)));
             else field_commit_multipass<NB>(C, H, &S, rep, lane, kind, ind0, n, binder, newst);
         }
         if (kind == 2) {
@@ -1197,7 +1259,7 @@ struct McWarp {
 // ------------------------------------------------------------------ kernels
 __device__ __forceinline__ HashTable carve_table(unsigned char *dyn, int cap, int ncol) {
     HashTable H;
-    H.vals = (double *)dyn;
+    H.vals = (uint32_t *)dyn;
     H.keys = (int *)(dyn + (size_t)cap * ncol * sizeof(double));
     H.list = H.keys + cap;
     H.cap = cap;

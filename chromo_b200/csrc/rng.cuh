@@ -16,6 +16,7 @@
 // Draws are consumed by lane 0 of the replica's warp (the reference's stream is
 // sequential with data-dependent draw counts).
 #pragma once
+#include "launch.cuh"
 #include "params.cuh"
 
 struct ReplayRng {
@@ -110,7 +111,8 @@ struct PhiloxRng {
     uint32_t pos;            // next draw index within the attempt's stream
     uint32_t b0, b1, b2, b3; // block pos >> 2 (valid when (pos & 3) != 0)
 
-    __device__ __forceinline__ void refill() {
+    // out of line: ~70 instructions that would otherwise be inlined at every draw site
+    __device__ CB_NOINLINE void refill() {
         uint32_t o[4];
         philox4x32_10((uint32_t)attempt, (uint32_t)(attempt >> 32), pos >> 2, rep, k0, k1, o);
         b0 = o[0];

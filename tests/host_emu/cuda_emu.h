@@ -103,6 +103,15 @@ static inline double atomicAdd(double *a, double v) {
     } while (!__atomic_compare_exchange_n(p, &old, nw, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
     return o;
 }
+static inline unsigned atomicAdd(unsigned *a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
+static inline long long __double2ll_rn(double x) { return llrint(x); } // default rounding mode: to nearest even
+static inline double __hiloint2double(int hi, int lo) {
+    uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 struct double2 { double x, y; };
 struct double3 { double x, y, z; };
