@@ -56,14 +56,17 @@ struct chromo_ctx {
     double *d_dbg_rows = nullptr, *d_dbg_dtrial = nullptr;
     int64_t dbg_inds_cap = 0, dbg_touched_cap = 0;
     int nblk_bins = 1, nblk_bonds = 1;
-    int cap = 0;           // hash-table capacity (slots) of the MC kernel
-    size_t smem_bytes = 0;
+    int cap = 0;           // slots of each warp's delta-density table in the MC kernel
+    int warps = CB_MAX_WARPS; // warps per replica of the production (Philox) MC kernel
+    int rpb = 1;              // replicas per thread block
+    int rpb_fixed = 0;        // > 0: set by chromo_ctx_set_replicas_per_block
     double roundK = 0.0;
     double min_access_vol = 0.0; // smallest positive per-voxel volume (0: uniform voxels)
     bool have_binders = false, have_bonds = false, have_state = false;
     int64_t last_attempts = 0;
     int sm_count = 148;
-    size_t smem_optin = 0;
+    size_t smem_optin = 227 * 1024; // largest block
+    size_t smem_sm = 228 * 1024;    // per SM
 };
 
 // exponent base of the MC kernel's fixed-point delta-density cells (mc_kernel.cuh, fx_exponent):
@@ -92,26 +95,20 @@ static int dev_alloc(chromo_ctx *c, T **p, size_t n) {
     return 0;
 }
 
-// shared-memory footprint of the MC kernel (must match mc_kernel.cuh)
-static inline size_t table_bytes(int cap, int ncol) {
-    return (size_t)cap * (ncol * sizeof(double) + 2 * sizeof(int));
-}
-static const size_t kWarpShBytes = 8704; // >= sizeof(WarpSh), checked in mc_kernel.cuh
-
 static int choose_table(chromo_ctx *c) {
-    // Shared memory per replica-warp = static WarpSh + the delta-density hash.
-    // Pick the largest power-of-two capacity (<= 2048 slots) that still lets
-    // every replica be resident at once (one wave); never below 128 slots.
+    // One thread block per SM holds `rpb` replicas (mc_kernel.cuh, mc_sim_kernel); all replicas
+    // are resident at once when R <= SMs x CB_MAX_RPB.  Pick the largest per-warp table (<= 2048
+    // slots, a multiple of 32, never below 128) that lets the block's replicas share the SM's
+    // shared memory.
     const int ncol = c->d.ncol;
-    const int R = c->d.R;
-    int want_per_sm = (R + c->sm_count - 1) / c->sm_count;
-    if (want_per_sm > 32) want_per_sm = 32; // resident-block limit per SM
-    size_t budget = c->smem_optin ? c->smem_optin : 227 * 1024;
-    size_t per_block = budget / (size_t)want_per_sm;
+    int rpb = (c->d.R + c->sm_count - 1) / c->sm_count;
+    rpb = std::max(1, std::min(rpb, CB_MAX_RPB));
+    if (c->rpb_fixed > 0) rpb = c->rpb_fixed;
+    const size_t per_replica = c->smem_optin / (size_t)rpb;
     int cap = 2048;
-    while (cap > 128 && table_bytes(cap, ncol) + kWarpShBytes + 1024 > per_block) cap >>= 1;
+    while (cap > 128 && cb_replica_smem(cap, ncol, c->warps) > per_replica) cap -= 32;
     c->cap = cap;
-    c->smem_bytes = table_bytes(cap, ncol);
+    c->rpb = rpb;
     return 0;
 }
 
@@ -133,6 +130,7 @@ extern "C" int chromo_ctx_create(chromo_ctx **out, int device, const chromo_shap
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->smem_sm = prop.sharedMemPerMultiprocessor;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     DevCtx &d = c->d;
     d.R = (int)s->n_replicas;
@@ -248,13 +246,32 @@ extern "C" int chromo_ctx_set_table_capacity(chromo_ctx *c, int64_t cap, int64_t
     if (cap == 0) {
         choose_table(c);
     } else {
-        if (cap < 128 || cap > 4096 || (cap & (cap - 1))) return fail(CHROMO_ERR_ARG, "capacity must be a power of two in [128, 4096]");
-        if (table_bytes((int)cap, c->d.ncol) + kWarpShBytes + 1024 > (c->smem_optin ? c->smem_optin : 227 * 1024))
+        if (cap < 128 || cap > 4096 || (cap % 32)) return fail(CHROMO_ERR_ARG, "capacity must be a multiple of 32 in [128, 4096]");
+        if ((size_t)c->rpb * cb_replica_smem((int)cap, c->d.ncol, c->warps) > c->smem_optin)
             return fail(CHROMO_ERR_ARG, "capacity does not fit in shared memory");
         c->cap = (int)cap;
-        c->smem_bytes = table_bytes((int)cap, c->d.ncol);
     }
     if (cap_out) *cap_out = c->cap;
+    return CHROMO_OK;
+}
+extern "C" int chromo_ctx_set_warps_per_replica(chromo_ctx *c, int64_t warps, int64_t *warps_out) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    if (warps != 0) {
+        if (warps < 1 || warps > CB_MAX_WARPS) return fail(CHROMO_ERR_ARG, "warps per replica must be in [1, %d]", CB_MAX_WARPS);
+        c->warps = (int)warps;
+        choose_table(c);
+    }
+    if (warps_out) *warps_out = c->warps;
+    return CHROMO_OK;
+}
+extern "C" int chromo_ctx_set_replicas_per_block(chromo_ctx *c, int64_t rpb, int64_t *rpb_out) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    if (rpb != 0) {
+        if (rpb < -1 || rpb > CB_MAX_RPB) return fail(CHROMO_ERR_ARG, "replicas per block must be in [1, %d] (-1 = automatic)", CB_MAX_RPB);
+        c->rpb_fixed = rpb < 0 ? 0 : (int)rpb;
+        choose_table(c);
+    }
+    if (rpb_out) *rpb_out = c->rpb;
     return CHROMO_OK;
 }
 extern "C" void *chromo_ctx_stream(chromo_ctx *c) { return c ? (void *)c->stream : nullptr; }
@@ -619,7 +636,7 @@ extern "C" int chromo_mc_sim(chromo_ctx *c, int64_t num_mc_steps, chromo_move_st
     DevCtx &d = c->d;
     if (moves && (rc = chromo_set_moves(c, moves))) return rc;
     if (rng_mode == CHROMO_RNG_REPLAY && numpy_seeds && (rc = chromo_numpy_seed(c, numpy_seeds))) return rc;
-    McSimArgs a{d, (long long)num_mc_steps, mu_adjust_factor, (unsigned long long)seed, c->cap, c->smem_bytes, c->stream};
+    McSimArgs a{d, (long long)num_mc_steps, mu_adjust_factor, (unsigned long long)seed, c->cap, c->warps, c->rpb, c->stream};
     int e;
     if (rng_mode == CHROMO_RNG_REPLAY) e = d.nb <= 2 ? cb_mc_sim_replay_12(a) : cb_mc_sim_replay_34(a);
     else if (rng_mode == CHROMO_RNG_PHILOX) e = d.nb <= 2 ? cb_mc_sim_philox_12(a) : cb_mc_sim_philox_34(a);
@@ -683,7 +700,7 @@ extern "C" int chromo_mc_step(chromo_ctx *c, int64_t replica, int move, double a
     h.dtrial = c->d_dbg_dtrial;
     CK(cudaMemcpyAsync(c->d_dbg, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
     McStepArgs a{d, (int)replica, move, amp_move, (int)amp_bead, mu_adjust_factor, (unsigned long long)seed,
-                 force_accept, c->d_dbg, c->cap, c->smem_bytes, c->stream};
+                 force_accept, c->d_dbg, c->cap, c->stream};
     int e;
     if (rng_mode == CHROMO_RNG_REPLAY) e = d.nb <= 2 ? cb_mc_step_replay_12(a) : cb_mc_step_replay_34(a);
     else if (rng_mode == CHROMO_RNG_PHILOX) e = d.nb <= 2 ? cb_mc_step_philox_12(a) : cb_mc_step_philox_34(a);

@@ -13,7 +13,29 @@
 #define CB_NOINLINE __noinline__
 #define CB_GRID_CONSTANT __grid_constant__
 __device__ __forceinline__ void cb_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cb_backoff() { __nanosleep(20); }
+// named barrier `id` (1..15) for `count` threads of the block
+__device__ __forceinline__ void cb_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 #endif
+#include <cstddef>
+// shared-memory bytes of one warp's delta-density table: cap x (ncol 64-bit cells + key + list entry)
+static inline __host__ __device__ size_t cb_table_bytes(int cap, int ncol) {
+    return (size_t)cap * ((size_t)ncol * 8 + 8);
+}
+// shared memory of the MC kernel per replica / per warp (>= sizeof(ReplicaSh), sizeof(WarpSh);
+// checked in mc_kernel.cuh) and the largest number of warps per replica that is instantiated
+#define CB_REPLICA_SH_BYTES 5632
+#define CB_WARP_SH_BYTES 1280
+#define CB_MAX_WARPS 2
+// shared memory of one replica: ReplicaSh | WarpSh x warps | table x warps
+static inline __host__ __device__ size_t cb_replica_smem(int cap, int ncol, int warps) {
+    return CB_REPLICA_SH_BYTES + (size_t)warps * (CB_WARP_SH_BYTES + cb_table_bytes(cap, ncol));
+}
+// replicas that share one thread block (one block per SM; their warps go through the move types
+// of a sweep together, see mc_sim_kernel)
+#define CB_MAX_RPB 7
 #include "params.cuh"
 
 struct McSimArgs {
@@ -21,8 +43,9 @@ struct McSimArgs {
     long long num_mc_steps;
     double mu_adjust;
     unsigned long long seed;
-    int cap;
-    size_t smem;
+    int cap;   // slots of each warp's table
+    int warps; // warps per replica (Philox kernels: 1 or 2; the replay kernels always run 1)
+    int rpb;   // replicas per block (1..CB_MAX_RPB)
     cudaStream_t stream;
 };
 struct McStepArgs {
@@ -35,7 +58,6 @@ struct McStepArgs {
     int force_accept;
     DebugOut *dbg;
     int cap;
-    size_t smem;
     cudaStream_t stream;
 };
 // each returns a cudaError_t as int; defined in mc_inst.cu

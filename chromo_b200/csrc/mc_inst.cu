@@ -22,20 +22,30 @@ constexpr int NB_A = 3, NB_B = 4;
 constexpr int NB_A = 1, NB_B = 2;
 #endif
 
+template <int NB, int NW>
+static int sim_launch(const McSimArgs &a) {
+    auto k = mc_sim_kernel<InstRng, NB, NW>;
+    const size_t smem = (size_t)a.rpb * cb_replica_smem(a.cap, a.d.ncol, NW);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    CB_LAUNCH(k, (a.d.R + a.rpb - 1) / a.rpb, 32 * NW * a.rpb, smem, a.stream, a.d, a.num_mc_steps, a.mu_adjust,
+              a.seed, a.cap, a.rpb);
+    return (int)cudaGetLastError();
+}
 template <int NB>
 static int sim_one(const McSimArgs &a) {
-    auto k = mc_sim_kernel<InstRng, NB>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
-    if (e != cudaSuccess) return (int)e;
-    CB_LAUNCH(k, a.d.R, 32, a.smem, a.stream, a.d, a.num_mc_steps, a.mu_adjust, a.seed, a.cap);
-    return (int)cudaGetLastError();
+#if !CB_INST_REPLAY
+    if (a.warps == 2) return sim_launch<NB, 2>(a);
+#endif
+    return sim_launch<NB, 1>(a);
 }
 template <int NB>
 static int step_one(const McStepArgs &a) {
     auto k = mc_step_kernel<InstRng, NB>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
+    const size_t smem = cb_table_bytes(a.cap, a.d.ncol);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    CB_LAUNCH(k, 1, 32, a.smem, a.stream, a.d, a.replica, a.move, a.amp_move, a.amp_bead, a.mu_adjust,
+    CB_LAUNCH(k, 1, 32, smem, a.stream, a.d, a.replica, a.move, a.amp_move, a.amp_bead, a.mu_adjust,
               a.seed, a.force_accept, a.dbg, a.cap);
     return (int)cudaGetLastError();
 }

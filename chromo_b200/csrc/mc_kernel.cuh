@@ -36,45 +36,55 @@
 #define FULL_MASK 0xffffffffu
 #define HASH_EMPTY (-1)
 
+#define CB_KSEL 16      // tangent rotation: bead sets up to this size are drawn in the batched prepare
+#define CB_TAN_SMALL 16 // tangent rotation: new tangents of up to this many beads are staged in shared memory
+#define CB_NEWST 128    // binding: new states of up to this many beads are staged in shared memory
+
 // one prepared attempt (see McWarp::prepare)
 struct Prop {
-    double R[9];  // rotation part of the affine map (end-pivot; single-bead tangent rotation)
-    double ax[3]; // rotation axis (end-pivot) or translation vector (slide)
+    double ax[3];  // rotation axis (end-pivot, single-bead tangent rotation) or translation vector (slide)
     double sn, cs; // sin / cos of the rotation angle
-    double u;     // Metropolis uniform (batched mode)
-    int ind0, indf, n, binder;
-    int lhs, bead, newst0;
+    double u;      // Metropolis uniform (batched mode)
+    int ind0, indf, n;
+    int aux;       // binder (binding) | left-hand side (end-pivot) | bead (single-bead tangent rotation)
+    int newst0;    // binding, n == 1: the new state
     uint32_t used; // draws of the attempt's stream consumed by prepare (batched mode)
 };
 
-// per-warp shared state
+// per-warp shared state (each warp of a replica's block works on its own attempt)
 struct WarpSh {
-    Prop prop[32];                // prepared attempts of the current batch
-    unsigned long long attempt_base; // Philox: index of the batch's first attempt in the replica's stream
-    uint32_t rng_after[CB_GLIBC_WORDS];
-    int cur;                      // slot being executed
-    chromo_move_state mv[CHROMO_NUM_MOVES];
-    uint32_t grs[CB_GLIBC_WORDS]; // ReplayRng state
-    uint32_t rng_save[CB_GLIBC_WORDS];
-    double M[12];                 // affine map of the current move
-    double tan_new[32 * 6];       // tangent rotation: new t3 | t2 of the selected beads
-    int tinds[32];                // tangent rotation: selected beads (small path)
-    int ind0, indf, n, binder;
-    int count;                    // occupied hash slots
+    double M[12];                    // affine map of the current move
+    double tan_new[CB_TAN_SMALL * 6]; // tangent rotation: new t3 | t2 of the selected beads
+    int tinds[CB_TAN_SMALL];         // tangent rotation: selected beads (sequential-stream path)
+    int count;                       // occupied hash slots
     int overflow;
-    int last_U;                   // touched voxels of the last field dE (all passes)
+    int last_U;                      // touched voxels of the last field dE (all passes)
     int passes;
-    unsigned long long algo_bytes; // SURVEY 8(d) algorithmic bytes, accumulated by lane 0
-    uint32_t draws[64];           // per-bead axis draws of tangent rotation
-    signed char newst[256];       // new binding states (small path)
+    uint32_t draws[16];              // per-bead axis draws of tangent rotation (8 beads per chunk)
+    signed char newst[CB_NEWST];     // new binding states (small path)
 };
-static_assert(sizeof(WarpSh) <= 8704, "update kWarpShBytes in chromo_b200.cu");
+
+// per-replica shared state
+struct ReplicaSh {
+    Prop prop[32];                   // prepared attempts of the current batch
+    chromo_move_state mv[CHROMO_NUM_MOVES];
+    unsigned long long attempt_base; // Philox: index of the batch's first attempt in the replica's stream
+    unsigned long long algo_bytes;   // SURVEY 8(d) algorithmic bytes, accumulated under the commit token
+    int token;                       // attempt of the batch whose turn it is to evaluate the field and commit
+    unsigned accepted;               // bit j: attempt j of the batch was accepted
+    int tsel[32][CB_KSEL];           // tangent rotation: bead sets drawn by the batched prepare
+    uint32_t grs[CB_GLIBC_WORDS];    // ReplayRng state
+    uint32_t rng_save[CB_GLIBC_WORDS];
+    uint32_t rng_after[CB_GLIBC_WORDS];
+};
+static_assert(sizeof(ReplicaSh) <= CB_REPLICA_SH_BYTES && sizeof(WarpSh) <= CB_WARP_SH_BYTES, "update launch.cuh");
+static_assert(CB_KSEL <= CB_TAN_SMALL, "prepared bead sets are staged in shared memory");
 
 struct HashTable {
     int *keys;      // [cap]
     int *list;      // [cap]   occupied slots, in claim order
     uint32_t *vals; // [cap][ncol][2]  delta-rho in 64-bit fixed point (low word, high word)
-    int cap, shift, limit;
+    int cap, limit; // cap: any size >= 128 (not necessarily a power of two)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -150,7 +160,7 @@ __device__ __forceinline__ void table_clear(HashTable &H, WarpSh &S, int ncol, i
 // 32 more claims can be in flight, so the table never fills and every claimed
 // slot is listed (table_clear relies on that).
 __device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin, bool checked) {
-    uint32_t slot = ((uint32_t)bin * 2654435761u) >> H.shift;
+    uint32_t slot = __umulhi((uint32_t)bin * 2654435761u, (uint32_t)H.cap);
     if (checked && *(volatile int *)&S.overflow) return -1;
     while (true) {
         const int prev = atomicCAS(&H.keys[slot], HASH_EMPTY, bin);
@@ -161,7 +171,7 @@ __device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin, boo
             if (checked && pos + 1 >= H.limit) S.overflow = 1;
             return (int)slot;
         }
-        slot = (slot + 1) & (uint32_t)(H.cap - 1);
+        slot = slot + 1 == (uint32_t)H.cap ? 0u : slot + 1;
     }
 }
 
@@ -368,46 +378,75 @@ __device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTabl
 }
 
 // Field dE of a continuous segment: compute_dE fields.pyx:1149-1233 =
-// confinement + get_change_in_density + get_dE_binders_and_beads.  Returns dE
-// on all lanes; S.passes = number of partition passes; with one pass the
-// table still holds the delta-rho rows afterwards (used by the commit).
+// confinement + get_change_in_density + get_dE_binders_and_beads, in two stages.
+//
+//   field_scatter (stage 1) depends only on the positions / states of the
+//       segment's own beads: it fills this warp's delta-rho table and counts the
+//       confinement violations.  It does NOT read the density.
+//   field_finish  (stage 2) gathers the touched voxels' density rows, forms the
+//       energy change and returns dE on all lanes.  It reads the density and so
+//       has to run after every earlier attempt of the replica has committed.
+//
+// The split is what lets the warps of a replica overlap: stage 1 of attempt
+// j+1 runs while attempt j is still in stage 2 (see McWarp::attempt).
+// S.passes = number of partition passes; with one pass the table still holds
+// the delta-rho rows afterwards (used by the commit).  Moves whose touched set
+// overflows the table are re-scattered in hash-partition passes inside stage 2.
 // ddbl[a] = change in the number of doubly-bound beads (count_doubly_bound).
+template <int NB>
+__device__ __forceinline__ int2 field_scatter(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
+                                              int kind, int ind0, int n, int binder, const signed char *newst) {
+    const double scale = pow2_double(fx_exponent(C, n));
+    const int2 conf = scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, 1, 0, scale);
+    __syncwarp();
+    return conf;
+}
 template <int NB, bool DEBUG>
-__device__ __forceinline__ double field_dE_segment(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
-                                                int kind, int ind0, int n, int binder,
-                                                const signed char *newst, const int *ddbl, DebugOut *dbg) {
+__device__ __forceinline__ double field_finish(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
+                                               int kind, int ind0, int n, int binder, const signed char *newst,
+                                               int2 conf, const int *ddbl, DebugOut *dbg) {
     constexpr int NCOL = NB + 1;
     const double chi = C.chi[rep];
     const int fxe = fx_exponent(C, n);
     const double scale = pow2_double(fxe), inv_scale = pow2_double(-fxe);
-    int P = 1;
     FieldSums<NB> F;
-    int2 conf = make_int2(0, 0);
     const bool want_cross = C.any_cross != 0;
-    while (true) {
 #pragma unroll
-        for (int a = 0; a < NB; a++) F.sq[a] = 0.0;
+    for (int a = 0; a < NB; a++) F.sq[a] = 0.0;
 #pragma unroll
-        for (int a = 0; a < NB * NB; a++) F.cross[a] = 0.0;
-        F.chi = 0.0;
-        if (DEBUG && lane == 0) dbg->n_touched = 0;
-        bool failed = false;
-        for (int p = 0; p < P; p++) {
-            int2 c = scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, P, p, scale);
-            if (p == 0) conf = c;
-            __syncwarp();
-            if (S.overflow) {
-                failed = true;
-                break;
+    for (int a = 0; a < NB * NB; a++) F.cross[a] = 0.0;
+    F.chi = 0.0;
+    if (DEBUG && lane == 0) dbg->n_touched = 0;
+    int P = 1;
+    if (!S.overflow) {
+        table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross, inv_scale);
+        if (lane == 0) S.last_U = S.count;
+        if (DEBUG) table_debug_dump(C, H, S, lane, dbg, inv_scale);
+    } else {
+        bool failed = true;
+        while (failed) { // rare: the touched set does not fit the table
+            P *= 2;
+#pragma unroll
+            for (int a = 0; a < NB; a++) F.sq[a] = 0.0;
+#pragma unroll
+            for (int a = 0; a < NB * NB; a++) F.cross[a] = 0.0;
+            F.chi = 0.0;
+            if (DEBUG && lane == 0) dbg->n_touched = 0;
+            failed = false;
+            for (int p = 0; p < P; p++) {
+                table_clear(H, S, NCOL, lane);
+                (void)scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, P, p, scale);
+                __syncwarp();
+                if (S.overflow) {
+                    failed = true;
+                    break;
+                }
+                table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross, inv_scale);
+                if (lane == 0) S.last_U = (p == 0 ? 0 : S.last_U) + S.count;
+                if (DEBUG) table_debug_dump(C, H, S, lane, dbg, inv_scale);
             }
-            table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross, inv_scale);
-            if (lane == 0) S.last_U = (p == 0 ? 0 : S.last_U) + S.count;
-            if (DEBUG) table_debug_dump(C, H, S, lane, dbg, inv_scale);
-            if (P > 1) table_clear(H, S, NCOL, lane);
         }
-        if (!failed) break;
         table_clear(H, S, NCOL, lane);
-        P *= 2;
     }
     if (lane == 0) S.passes = P;
     // ---- reduce and assemble in the reference's order ----
@@ -543,33 +582,44 @@ __device__ __forceinline__ void check_bead_bounds(int b0, int b1, int N, int &in
 // =================================================================== moves
 // An attempt is split into
 //   prepare : everything that does NOT depend on the replica's state -- RNG
-//             draws, exponential window (log10), all trigonometry, the rotation
-//             part of the affine map -- written to a `Prop` record in shared
+//             draws, exponential window (log10), the trigonometry, the bead set
+//             of a tangent rotation -- written to a `Prop` record in shared
 //             memory.  With the counter-based Philox generator attempt t has its
 //             own stream, so a batch of up to 32 attempts of one move type is
-//             prepared by 32 lanes AT ONCE (same code, different data): the
-//             scalar proposal work that dominated the instruction count of the
-//             serial version is amortised over the batch.  With the replayed
-//             reference streams (sequential by nature) the batch size is 1 and
-//             lane 0 prepares, in the reference's draw order.
-//   execute : the state-dependent rest, one attempt after the other: axis /
-//             fulcrum from current positions, elastic dE (4 lanes), field dE
-//             (scatter into the shared-memory table + reduction), Metropolis,
-//             commit.
+//             prepared by 32 lanes AT ONCE (same code, different data).  With
+//             the replayed reference streams (sequential by nature) the batch
+//             size is 1 and lane 0 prepares, in the reference's draw order.
+//   stage 1 : reads the replica's bead rows only: affine map from the current
+//             positions, elastic / binding dE, scatter of the delta-density
+//             into this warp's table (or the new tangents of a tangent
+//             rotation).
+//   stage 2 : reads the density: gather + energy reduction, Metropolis, commit.
+//
+// NW warps work on one replica.  Warp w takes attempts w, w+NW, ... of the
+// batch; stage 1 runs AHEAD of the attempt's turn, stage 2 runs when the
+// replica's commit token reaches the attempt, so stage 1 of attempt j+1
+// overlaps stage 2 of attempt j while the attempts still take effect strictly
+// in order.  If an attempt that committed in between was accepted and touched
+// beads this attempt reads (rare: segments of ~30 beads out of 10^4), stage 1 is
+// simply redone once the turn has come -- so the result is the sequential
+// one, bit for bit (tests/test_gpu_scale.py compares NW = 1 against NW = 2).
 // Every heavy routine has exactly ONE call site (inlined once: no ABI spills,
 // shared-memory address spaces stay visible to the compiler).
-template <class Rng, bool DEBUG, int NB>
+template <class Rng, bool DEBUG, int NB, int NW>
 struct McWarp {
     static constexpr int NCOL = NB + 1;
     static constexpr bool BATCH = Rng::kBatched;
+    static_assert(NW == 1 || Rng::kBatched, "several warps per replica need the counter-based generator");
     const DevCtx &C;
+    ReplicaSh &B;
     WarpSh &S;
     HashTable &H;
     Rng &rng;
-    int rep, lane;
+    int rep, lane, wid, local; // replica, lane, warp within the replica, replica within the block
     double mu_adjust;
     int force_accept; // DEBUG only: -1 Metropolis, 0/1 forced
     DebugOut *dbg;
+    unsigned long long abase; // Philox: index of the batch's first attempt in the replica's stream
 
     __device__ __forceinline__ double *R_() const { return C.r + (long long)rep * C.N * 3; }
     __device__ __forceinline__ double *T3_() const { return C.t3 + (long long)rep * C.N * 3; }
@@ -578,6 +628,60 @@ struct McWarp {
     __device__ __forceinline__ const signed char *MOD_() const { return C.mods + (long long)rep * C.N * NB; }
     __device__ __forceinline__ bool has_field() const {
         return C.field_active || C.confine_type != CHROMO_CONFINE_NONE;
+    }
+    __device__ __forceinline__ void block_sync() const {
+        if (NW > 1) cb_bar_sync(1 + local, 32 * NW); // the replica's own named barrier
+        else __syncwarp();
+    }
+
+    // ---- the replica's commit token -------------------------------------------
+    __device__ __forceinline__ void wait_turn(int slot) const {
+        if (NW > 1) {
+            if (lane == 0)
+                while (*(volatile int *)&B.token != slot) cb_backoff();
+            __syncwarp();
+            __threadfence_block();
+        }
+    }
+    __device__ __forceinline__ void pass_turn(int slot, int acc) const {
+        if (NW > 1) {
+            __threadfence_block(); // this lane's commit stores, before the token moves
+            __syncwarp();
+            if (lane == 0) {
+                if (acc) *(volatile unsigned *)&B.accepted = *(volatile unsigned *)&B.accepted | (1u << slot);
+                __threadfence_block();
+                *(volatile int *)&B.token = slot + 1;
+            }
+        }
+    }
+    // did an attempt that committed after this warp's previous turn change rows that stage 1 of
+    // attempt `slot` has read?  Writes of a segment move: beads [ind0, indf); reads: one more bead
+    // on either side.  Tangent rotation: the selected beads; reads: their neighbours as well.
+    __device__ __forceinline__ bool stale(int mtype, int slot) const {
+        if (NW == 1) return false;
+        const unsigned accepted = *(volatile unsigned *)&B.accepted;
+        const Prop &P = B.prop[slot];
+        bool hit = false;
+        for (int j = max(0, slot - NW + 1); j < slot; j++) {
+            if (!((accepted >> j) & 1u)) continue;
+            const Prop &Q = B.prop[j];
+            if (mtype != CHROMO_TANGENT_ROTATION) {
+                hit |= (Q.ind0 < P.indf + 1) && (P.ind0 - 1 < Q.indf);
+            } else if (Q.n > CB_KSEL) {
+                hit = true; // its bead set was drawn at execute time: assume the worst
+            } else {
+                // lanes: a = lane % 16 walks this attempt's beads, the halves split the other's
+                const int a = lane & 15;
+                if (a < P.n) {
+                    const int mine = P.n == 1 ? P.aux : B.tsel[slot][a];
+                    for (int q = lane >> 4; q < Q.n; q += 2) {
+                        const int other = Q.n == 1 ? Q.aux : B.tsel[j][q];
+                        hit |= (other - mine <= 1) && (mine - other <= 1);
+                    }
+                }
+            }
+        }
+        return __any_sync(FULL_MASK, hit);
     }
 
     // trial (r, t3) of a bead of the moving segment
@@ -596,14 +700,14 @@ struct McWarp {
     }
 
     // ======================================================== prepare
-    // lanes [0, cnt) each prepare one attempt of move type `mtype`
+    // lanes [0, cnt) of warp 0 each prepare one attempt of move type `mtype`
     __device__ __forceinline__ void prepare(int mtype, int cnt) {
         if (lane >= cnt) return;
         const int N = C.N;
-        Prop &P = S.prop[lane];
-        const chromo_move_state &mv = S.mv[mtype];
+        Prop &P = B.prop[lane];
+        const chromo_move_state &mv = B.mv[mtype];
         if (BATCH) {
-            rng.seek_attempt(S.attempt_base + (unsigned long long)lane);
+            rng.seek_attempt(abase + (unsigned long long)lane);
             P.u = u01(rng.next31()); // Metropolis uniform: draw 0 of the attempt's own stream
         }
         const bool crank = mtype == CHROMO_CRANK_SHAFT, pivot = mtype == CHROMO_END_PIVOT;
@@ -636,6 +740,20 @@ struct McWarp {
                 d1 = rng.next31();
                 d2 = rng.next31();
                 sphere = true;
+            } else if (BATCH && k <= CB_KSEL) {
+                // get_inds move_funcs.pyx:552-582: k distinct draws, duplicates redrawn; the per-bead
+                // axis draws follow in the attempt's stream and are made at execute time
+                int *sel = B.tsel[lane];
+                for (int i = 0; i < k; i++) {
+                    int c;
+                    bool dup;
+                    do {
+                        c = (int)(rng.next31() % (uint32_t)N);
+                        dup = false;
+                        for (int q = 0; q < i; q++) dup |= (sel[q] == c);
+                    } while (dup);
+                    sel[i] = c;
+                }
             }
         }
         if (!tangent) {
@@ -670,20 +788,18 @@ struct McWarp {
         P.ind0 = ind0;
         P.indf = indf;
         P.n = n;
-        P.binder = binder;
-        P.lhs = lhs;
-        P.bead = bead;
+        P.aux = bind ? binder : (pivot ? lhs : bead);
         P.newst0 = 0;
         if (bind && n >= 1) { // conduct_change_binding_states move_funcs.pyx:778-820
             if (!BATCH) { // lane 0, sequential stream: draw all n states now, as the reference does
-                signed char *dst = (n <= 256) ? S.newst : (C.st_new + (long long)rep * N);
+                signed char *dst = (n <= CB_NEWST) ? S.newst : (C.st_new + (long long)rep * N);
                 for (int i = 0; i < n; i++) dst[i] = (signed char)rng.randint(C.sites[binder] + 1);
             } else if (n == 1) {
                 P.newst0 = rng.randint(C.sites[binder] + 1);
             } // n > 1 in a batch: drawn at execute time from this attempt's stream
         }
         // ---- the trigonometry (one out-of-line sincos / acos each, shared by all call sites) ----
-        // uniform_sample_unit_sphere linalg.pyx:23-59, arbitrary_axis_rotation 62-139
+        // uniform_sample_unit_sphere linalg.pyx:23-59
         double sn = 0.0, cs = 1.0;
         if (!(slide || bind)) {
             const double2 sc = sincos_ni(amp);
@@ -700,20 +816,15 @@ struct McWarp {
         }
         P.sn = sn;
         P.cs = cs;
-        if (slide) { // generate_translation_mat linalg.pyx:172-199
 #pragma unroll
-            for (int j = 0; j < 3; j++) P.ax[j] = axis[j] * amp;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 3; j++) P.ax[j] = axis[j];
-            if (pivot || (tangent && k == 1)) rotation_3x3(axis, sn, cs, P.R);
-        }
+        for (int j = 0; j < 3; j++) P.ax[j] = slide ? axis[j] * amp : axis[j]; // generate_translation_mat linalg.pyx:172-199
         if (BATCH) P.used = rng.position();
     }
 
-    // ======================================================== execute
-    // lane 0: finish the affine map of attempt `P` from the current positions
-    __device__ __forceinline__ void finalize_segment_lane0(int mtype, const Prop &P) {
+    // ======================================================== stage 1
+    // lane 0: the affine map of attempt `P` from the current positions
+    // (arbitrary_axis_rotation linalg.pyx:62-139)
+    __device__ __forceinline__ void finalize_segment_lane0(int mtype, const Prop &P, int slot) {
         const int N = C.N;
         const double *Rr = R_();
         const int ind0 = P.ind0, indf = P.indf;
@@ -742,7 +853,7 @@ struct McWarp {
             for (int j = 0; j < 3; j++) axis[j] = Rr[3 * a + j] - Rr[3 * b + j];
             double mag = sqrt((axis[0] * axis[0] + axis[1] * axis[1]) + axis[2] * axis[2]);
             if (mag < 1E-5) { // axis from the unit sphere: two more draws (move_funcs.pyx:229-230)
-                if (BATCH) rng.seek_attempt(S.attempt_base + (unsigned long long)S.cur, P.used);
+                if (BATCH) rng.seek_attempt(abase + (unsigned long long)slot, P.used);
                 uint32_t d1 = rng.next31(), d2 = rng.next31();
                 degenerate_axis(d1, d2, axis);
             } else {
@@ -750,18 +861,16 @@ struct McWarp {
 #pragma unroll
                 for (int j = 0; j < 3; j++) axis[j] = axis[j] * sc;
             }
-            rotation_3x3(axis, P.sn, P.cs, Rm);
         } else { // end pivot: get_end_pivot_fulcrum move_funcs.pyx:349-398
             if (ind0 == 0 && indf != N) ful = indf;
             else if (ind0 != 0 && indf == N) ful = ind0 - 1;
-            else if (ind0 == 0 && indf == N && P.lhs == 1) ful = indf - 1;
+            else if (ind0 == 0 && indf == N && P.aux == 1) ful = indf - 1;
             else ful = ind0;
             load3(Rr + 3 * ful, pt);
 #pragma unroll
             for (int j = 0; j < 3; j++) axis[j] = P.ax[j];
-#pragma unroll
-            for (int j = 0; j < 9; j++) Rm[j] = P.R[j];
         }
+        rotation_3x3(axis, P.sn, P.cs, Rm);
         double tv[3];
         rotation_translation(axis, pt, P.sn, P.cs, tv);
 #pragma unroll
@@ -943,13 +1052,13 @@ struct McWarp {
     // against the CURRENT neighbours (polymers.pyx:1075-1080; quirk 8); never
     // touches the field (mc_sim.pyx:145).
     // One bead is evaluated by 4 lanes (one bond energy each: left bond trial /
-    // as is, right bond trial / as is), up to 8 beads per call.  Rotations come
-    // either from the prepared record (`Rfix`, the common single-bead case) or
+    // as is, right bond trial / as is), up to 8 beads per call.  The axis comes
+    // either from the prepared record (`axfix`, the common single-bead case) or
     // from per-bead draws.  New tangents of chunk bead j go to out[6j..6j+5]
     // (shared) when `out` is given, or straight to global memory when `store`.
     // Returns acc_in + the chunk's dE on all lanes (bead-by-bead sum).
     __device__ __forceinline__ double tangent_chunk(const int *beads, int cnt, const uint32_t *draws,
-                                                    const double *Rfix, double sn, double cs, double *out,
+                                                    const double *axfix, double sn, double cs, double *out,
                                                     bool store, int dbg_base, double acc_in) {
         const double *Rr = R_();
         double *T3 = T3_(), *T2 = T2_();
@@ -958,19 +1067,18 @@ struct McWarp {
         double e = 0.0;
         if (j < cnt) {
             const int bead = beads[j];
-            double Rm[9], t3c[3], t2c[3], t3n[3], t2n[3], rc[3];
-            if (Rfix) {
+            double Rm[9], t3c[3], t2c[3], t3n[3], t2n[3], rc[3], axis[3];
+            if (axfix) {
 #pragma unroll
-                for (int q = 0; q < 9; q++) Rm[q] = Rfix[q];
+                for (int q = 0; q < 3; q++) axis[q] = axfix[q];
             } else {
                 const double2 ph = sincos_ni(u01(draws[2 * j]) * (2.0 * 3.14159265358979323846));
                 const double2 th = sincos_ni(acos_ni(u01(draws[2 * j + 1]) * 2.0 - 1.0));
-                double axis[3];
                 axis[0] = ph.y * th.x;
                 axis[1] = ph.x * th.x;
                 axis[2] = th.y;
-                rotation_3x3(axis, sn, cs, Rm);
             }
+            rotation_3x3(axis, sn, cs, Rm);
             load3(T3 + 3 * bead, t3c);
             load3(T2 + 3 * bead, t2c);
             load3(Rr + 3 * bead, rc);
@@ -1010,14 +1118,25 @@ struct McWarp {
         return tot;
     }
 
-    // k > 1 beads: per-bead draws by lane 0 (8 beads per chunk), energies or stores
+    // k > 1 beads, 8 per chunk: energies or stores.  The two axis draws of bead b are draws
+    // `first + 2b`, `first + 2b + 1` of the attempt's stream: with the counter-based generator
+    // (`par`) every bead's lane fetches its own, otherwise lane 0 draws them in order.
     __device__ __forceinline__ double tangent_eval_multi(const int *inds, int k, double sn, double cs,
-                                                         bool small, bool store) {
+                                                         bool small, bool store, bool par,
+                                                         unsigned long long att, uint32_t first) {
         double dE_poly = 0.0;
         for (int base = 0; base < k; base += 8) {
             const int cnt = min(8, k - base);
-            if (lane == 0)
+            if (BATCH && par) {
+                if (lane < cnt) {
+                    Rng g = rng;
+                    g.seek_attempt(att, first + 2u * (uint32_t)(base + lane));
+                    S.draws[2 * lane] = g.next31();
+                    S.draws[2 * lane + 1] = g.next31();
+                }
+            } else if (lane == 0) {
                 for (int i = 0; i < 2 * cnt; i++) S.draws[i] = rng.next31();
+            }
             __syncwarp();
             dE_poly = tangent_chunk(inds + base, cnt, S.draws, nullptr, sn, cs,
                                     (small && !store) ? S.tan_new + 6 * base : nullptr, store, base, dE_poly);
@@ -1026,10 +1145,10 @@ struct McWarp {
         return dE_poly;
     }
 
-    // SimpleControl.update_move_amplitude mc_controller.py:148-213 (lane 0)
+    // SimpleControl.update_move_amplitude mc_controller.py:148-213 (one thread)
     __device__ __forceinline__ void update_amplitudes(int mtype) {
-        if (lane != 0) return;
-        chromo_move_state &mv = S.mv[mtype];
+        if (lane != 0 || wid != 0) return;
+        chromo_move_state &mv = B.mv[mtype];
         if (mv.controller != 1) return;
         const double setpoint = 0.5, factor = 0.95;
         double a = mv.acceptance_rate;
@@ -1052,58 +1171,66 @@ struct McWarp {
         }
     }
 
-    // ---- execute prepared attempt `slot` (mc_step, mc_sim.pyx:106-182) -------
-    __device__ __forceinline__ void execute(int mtype, int slot) {
+    // ---- attempt `slot` of the batch (mc_step, mc_sim.pyx:106-182) ------------
+    __device__ __forceinline__ void attempt(int mtype, int slot) {
         const int N = C.N;
-        const Prop &P = S.prop[slot];
+        const Prop &P = B.prop[slot];
         const bool tangent = mtype == CHROMO_TANGENT_ROTATION;
-        double dE_poly = 0.0, dE_field = 0.0;
-        const int ind0 = P.ind0, n = P.n, binder = P.binder;
-        int kind = 0;
+        const int ind0 = P.ind0, n = P.n;
+        const int binder = mtype == CHROMO_CHANGE_BINDING_STATE ? P.aux : 0;
+        const int kind = mtype == CHROMO_SLIDE ? 1 : (mtype == CHROMO_CHANGE_BINDING_STATE ? 2 : 0);
+        const unsigned long long att = abase + (unsigned long long)slot;
+        if (n <= 0) { // mc_sim.pyx:151-152: counted, nothing else happens
+            wait_turn(slot);
+            if (lane == 0) B.mv[mtype].num_attempt += 1; // MCAdapter.propose moves.pyx:151
+            pass_turn(slot, 0);
+            return;
+        }
         const signed char *newst = nullptr;
         const int *tinds = S.tinds;
-        const bool small = n <= 32;
-        if (lane == 0) {
-            S.mv[mtype].num_attempt += 1; // MCAdapter.propose moves.pyx:151
-            S.cur = slot;
-        }
-        if (n <= 0) return; // mc_sim.pyx:151-152
-        // ================= energies =================
-        if (!tangent) {
-            kind = mtype == CHROMO_SLIDE ? 1 : (mtype == CHROMO_CHANGE_BINDING_STATE ? 2 : 0);
-            if (lane == 0) {
-                if (kind != 2) finalize_segment_lane0(mtype, P);
-                else if (BATCH) { // new states of this attempt (sequential mode drew them in prepare)
-                    signed char *dst = (n <= 256) ? S.newst : (C.st_new + (long long)rep * N);
-                    if (n == 1) dst[0] = (signed char)P.newst0;
-                    else {
-                        rng.seek_attempt(S.attempt_base + (unsigned long long)slot, P.used);
-                        for (int i = 0; i < n; i++) dst[i] = (signed char)rng.randint(C.sites[binder] + 1);
-                    }
-                }
-            }
-            __syncwarp();
-            if (kind == 2) newst = (n <= 256) ? S.newst : (C.st_new + (long long)rep * N);
-            int ddbl[NB];
+        const bool small = n <= CB_TAN_SMALL;
+        const bool presel = BATCH && n <= CB_KSEL; // tangent rotation: bead set drawn in prepare
+        double dE_poly = 0.0, dE_field = 0.0;
+        int2 conf = make_int2(0, 0);
+        int ddbl[NB];
+        // stage 1 may run ahead of the attempt's turn unless it needs sequential draws or the
+        // replica-wide HBM scratch (large tangent / binding moves)
+        bool my_turn = !(NW > 1 && (tangent ? presel : (kind != 2 || n <= CB_NEWST)));
+        if (my_turn) wait_turn(slot);
+        while (true) {
+            // ================= stage 1: bead rows only =================
 #pragma unroll
             for (int m = 0; m < NB; m++) ddbl[m] = 0;
-            dE_poly = segment_dE_poly(kind, ind0, P.indf, n, binder, newst, ddbl);
-            if (C.field_active)
-                dE_field = field_dE_segment<NB, DEBUG>(C, H, S, rep, lane, kind, ind0, n, binder, newst, ddbl, dbg);
-            else if (kind != 2 && C.confine_type != CHROMO_CONFINE_NONE)
-                dE_field = confinement_dE_segment(C, S, rep, lane, kind, ind0, n);
-            if (DEBUG) debug_report(kind, ind0, n, binder, newst, dE_poly, dE_field);
-        } else {
-            const int k = n;
-            if (k == 1) {
-                if (lane == 0) S.tinds[0] = P.bead;
+            if (!tangent) {
+                if (lane == 0) {
+                    if (kind != 2) finalize_segment_lane0(mtype, P, slot);
+                    else if (BATCH) { // new states of this attempt (sequential mode drew them in prepare)
+                        signed char *dst = (n <= CB_NEWST) ? S.newst : (C.st_new + (long long)rep * N);
+                        if (n == 1) dst[0] = (signed char)P.newst0;
+                        else {
+                            rng.seek_attempt(att, P.used);
+                            for (int i = 0; i < n; i++) dst[i] = (signed char)rng.randint(C.sites[binder] + 1);
+                        }
+                    }
+                }
                 __syncwarp();
-                dE_poly = tangent_chunk(S.tinds, 1, nullptr, P.R, P.sn, P.cs, S.tan_new, false, 0, 0.0);
+                if (kind == 2) newst = (n <= CB_NEWST) ? S.newst : (C.st_new + (long long)rep * N);
+                dE_poly = segment_dE_poly(kind, ind0, P.indf, n, binder, newst, ddbl);
+                if (C.field_active) conf = field_scatter<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst);
+                else if (kind != 2 && C.confine_type != CHROMO_CONFINE_NONE)
+                    dE_field = confinement_dE_segment(C, S, rep, lane, kind, ind0, n);
+            } else if (n == 1) {
+                if (lane == 0) S.tinds[0] = P.aux;
+                __syncwarp();
+                dE_poly = tangent_chunk(S.tinds, 1, nullptr, P.ax, P.sn, P.cs, S.tan_new, false, 0, 0.0);
+            } else if (presel) {
+                tinds = B.tsel[slot];
+                dE_poly = tangent_eval_multi(tinds, n, P.sn, P.cs, true, false, true, att, P.used);
             } else {
-                if (BATCH && lane == 0) rng.seek_attempt(S.attempt_base + (unsigned long long)slot, P.used);
+                if (BATCH && lane == 0) rng.seek_attempt(att, P.used);
                 if (small) { // get_inds move_funcs.pyx:552-582: k distinct draws, redraw duplicates
                     int my = -1;
-                    for (int i = 0; i < k; i++) {
+                    for (int i = 0; i < n; i++) {
                         int c = 0;
                         bool dup;
                         do {
@@ -1113,25 +1240,35 @@ struct McWarp {
                         } while (dup);
                         if (lane == i) my = c;
                     }
-                    if (lane < k) S.tinds[lane] = my;
+                    if (lane < n) S.tinds[lane] = my;
                 } else {
-                    tinds = tangent_select_large(k);
+                    tinds = tangent_select_large(n);
                 }
                 __syncwarp();
-                dE_poly = tangent_eval_multi(tinds, k, P.sn, P.cs, small, false);
+                dE_poly = tangent_eval_multi(tinds, n, P.sn, P.cs, small, false, false, att, 0u);
             }
-            if (DEBUG) {
-                if (lane == 0) {
-                    dbg->n_inds = k;
-                    dbg->dE_poly = dE_poly;
-                    dbg->dE_field = 0.0;
-                    dbg->n_touched = 0;
-                    dbg->passes = 0;
-                }
-                __syncwarp();
-            }
+            if (my_turn) break;
+            wait_turn(slot);
+            my_turn = true;
+            if (!stale(mtype, slot)) break;
+            if (!tangent && C.field_active) table_clear(H, S, NCOL, lane); // rows changed under stage 1: redo it
         }
-        // ================= Metropolis (mc_sim.pyx:163-171) =================
+        // ================= stage 2: density, Metropolis, commit =================
+        if (!tangent) {
+            if (C.field_active)
+                dE_field = field_finish<NB, DEBUG>(C, H, S, rep, lane, kind, ind0, n, binder, newst, conf, ddbl, dbg);
+            if (DEBUG) debug_report(kind, ind0, n, binder, newst, dE_poly, dE_field);
+        } else if (DEBUG) {
+            if (lane == 0) {
+                dbg->n_inds = n;
+                dbg->dE_poly = dE_poly;
+                dbg->dE_field = 0.0;
+                dbg->n_touched = 0;
+                dbg->passes = 0;
+            }
+            __syncwarp();
+        }
+        // Metropolis (mc_sim.pyx:163-171)
         double dE = 0.0;
         dE += dE_poly;
         if (!tangent && has_field()) dE += dE_field;
@@ -1150,47 +1287,51 @@ struct McWarp {
                 dbg->accepted = acc;
             }
             // counters + AcceptanceTracker.update_acceptance_rate mc_stat.py:190-207
-            chromo_move_state &mv = S.mv[mtype];
+            chromo_move_state &mv = B.mv[mtype];
+            mv.num_attempt += 1; // MCAdapter.propose moves.pyx:151
             if (acc) mv.num_success += 1;
             mv.acceptance_rate = (mv.alpha * (acc ? 1.0 : 0.0)) + (1.0 - mv.alpha) * mv.acceptance_rate;
             // algorithmic bytes of this attempt
+            unsigned long long ab;
             if (tangent) {
-                S.algo_bytes += 48ull * n + 144ull * n + (acc ? 48ull * n : 0ull);
+                ab = 48ull * n + 144ull * n + (acc ? 48ull * n : 0ull);
             } else {
                 unsigned long long U = C.field_active ? (unsigned long long)S.last_U : 0ull;
                 if (kind == 2)
-                    S.algo_bytes += 24ull * n + (unsigned long long)NB * n * (acc ? 2ull : 1ull) +
-                                    8ull * NCOL * U * (acc ? 3ull : 1ull);
+                    ab = 24ull * n + (unsigned long long)NB * n * (acc ? 2ull : 1ull) +
+                         8ull * NCOL * U * (acc ? 3ull : 1ull);
                 else
-                    S.algo_bytes += 72ull * (n + 2) + (acc ? 72ull * n : 0ull) + (unsigned long long)NB * n +
-                                    8ull * NCOL * U * (acc ? 3ull : 1ull) + 80ull;
+                    ab = 72ull * (n + 2) + (acc ? 72ull * n : 0ull) + (unsigned long long)NB * n +
+                         8ull * NCOL * U * (acc ? 3ull : 1ull) + 80ull;
             }
+            B.algo_bytes += ab;
         }
         acc = __shfl_sync(FULL_MASK, acc, 0);
-        // ================= accept (moves.pyx:156-239) =================
+        // accept (moves.pyx:156-239)
         if (acc) {
             if (!tangent) segment_commit(kind, ind0, n, binder, newst);
             else if (small) {
                 if (lane < n) {
-                    store3(T3_() + 3 * S.tinds[lane], S.tan_new + 6 * lane);
-                    store3(T2_() + 3 * S.tinds[lane], S.tan_new + 6 * lane + 3);
+                    store3(T3_() + 3 * tinds[lane], S.tan_new + 6 * lane);
+                    store3(T2_() + 3 * tinds[lane], S.tan_new + 6 * lane + 3);
                 }
             } else {
                 tangent_commit_large(tinds, n, P.sn, P.cs);
             }
         }
+        pass_turn(slot, acc);
         if (!tangent && C.field_active) table_clear(H, S, NCOL, lane);
         __syncwarp();
     }
 
-    // pull the rows the NEXT attempt will read towards the SM while this one runs
+    // pull the rows a later attempt will read towards the SM while this one runs
     __device__ __forceinline__ void prefetch_attempt(int mtype, const Prop &P) {
         const int N = C.N;
         int first, count;
         if (mtype == CHROMO_TANGENT_ROTATION) {
             if (P.n != 1) return;
-            first = max(P.bead - 1, 0);
-            count = min(P.bead + 1, N - 1) - first + 1;
+            first = max(P.aux - 1, 0);
+            count = min(P.aux + 1, N - 1) - first + 1;
         } else {
             if (P.n <= 0) return;
             first = max(P.ind0 - 1, 0);
@@ -1209,20 +1350,27 @@ struct McWarp {
         }
     }
 
-    // a batch of `cnt` attempts of one move type: prepare (parallel), then execute
+    // a batch of `cnt` attempts of one move type: prepare (lanes of warp 0), then the warps take
+    // the attempts round-robin
     __device__ __forceinline__ void run(int mtype, int cnt) {
-        prepare(mtype, cnt);
-        __syncwarp();
-#pragma unroll 1
-        for (int j = 0; j < cnt; j++) {
-            if (j + 1 < cnt) prefetch_attempt(mtype, S.prop[j + 1]);
-            execute(mtype, j);
+        if (wid == 0) {
+            prepare(mtype, cnt);
+            if (lane == 0) {
+                *(volatile int *)&B.token = 0;
+                *(volatile unsigned *)&B.accepted = 0u;
+            }
         }
-        if (lane == 0) S.attempt_base += (unsigned long long)cnt;
-        __syncwarp();
+        block_sync();
+#pragma unroll 1
+        for (int j = wid; j < cnt; j += NW) {
+            if (j + NW < cnt) prefetch_attempt(mtype, B.prop[j + NW]);
+            attempt(mtype, j);
+        }
+        abase += (unsigned long long)cnt;
+        block_sync();
     }
 
-    // tangent rotation of more than 32 beads (rare): indices in HBM scratch,
+    // tangent rotation of more than CB_TAN_SMALL beads (rare): indices in HBM scratch,
     // membership in a bitmap, per-bead draws regenerated on commit
     __device__ __forceinline__ const int *tangent_select_large(int k) {
         const int N = C.N;
@@ -1239,7 +1387,7 @@ struct McWarp {
                 bits[c >> 5] |= 1u << (c & 31);
                 inds[i] = c;
             }
-            rng.save(S.rng_save);
+            rng.save(B.rng_save);
         }
         __syncwarp();
         return inds;
@@ -1248,11 +1396,11 @@ struct McWarp {
         // a bead's new tangents depend on its own t3/t2 only, so regenerating the
         // per-bead draws from the saved RNG state and storing chunk by chunk is safe
         if (lane == 0) {
-            rng.save(S.rng_after);
-            rng.restore(S.rng_save);
+            rng.save(B.rng_after);
+            rng.restore(B.rng_save);
         }
-        (void)tangent_eval_multi(inds, k, sn, cs, false, true);
-        if (lane == 0) rng.restore(S.rng_after);
+        (void)tangent_eval_multi(inds, k, sn, cs, false, true, false, 0ull, 0u);
+        if (lane == 0) rng.restore(B.rng_after);
     }
 };
 
@@ -1260,96 +1408,103 @@ struct McWarp {
 __device__ __forceinline__ HashTable carve_table(unsigned char *dyn, int cap, int ncol) {
     HashTable H;
     H.vals = (uint32_t *)dyn;
-    H.keys = (int *)(dyn + (size_t)cap * ncol * sizeof(double));
+    H.keys = (int *)(dyn + (size_t)cap * ncol * 8);
     H.list = H.keys + cap;
     H.cap = cap;
-    int lg = 0;
-    while ((1 << lg) < cap) lg++;
-    H.shift = 32 - lg;
     H.limit = cap - cap / 4 - 32;
     return H;
 }
 
 template <class Rng>
-__device__ __forceinline__ void rng_load(Rng &rng, const DevCtx &C, WarpSh &S, int rep, int lane,
-                                         unsigned long long seed);
+__device__ __forceinline__ unsigned long long rng_load(Rng &rng, const DevCtx &C, ReplicaSh &B, int rep, int tid,
+                                                       unsigned long long seed);
 template <>
-__device__ __forceinline__ void rng_load<ReplayRng>(ReplayRng &rng, const DevCtx &C, WarpSh &S, int rep,
-                                                    int lane, unsigned long long) {
-    for (int i = lane; i < CB_GLIBC_WORDS; i += 32) S.grs[i] = C.glibc[(long long)rep * CB_GLIBC_WORDS + i];
-    rng.st = S.grs;
+__device__ __forceinline__ unsigned long long rng_load<ReplayRng>(ReplayRng &rng, const DevCtx &C, ReplicaSh &B,
+                                                                  int rep, int tid, unsigned long long) {
+    for (int i = tid; i < CB_GLIBC_WORDS; i += 32) B.grs[i] = C.glibc[(long long)rep * CB_GLIBC_WORDS + i];
+    rng.st = B.grs;
     rng.mt = C.mt + (long long)rep * CB_MT_WORDS;
-    if (lane == 0) S.attempt_base = 0;
-    __syncwarp();
+    return 0ull;
 }
 template <>
-__device__ __forceinline__ void rng_load<PhiloxRng>(PhiloxRng &rng, const DevCtx &C, WarpSh &S, int rep,
-                                                    int lane, unsigned long long seed) {
+__device__ __forceinline__ unsigned long long rng_load<PhiloxRng>(PhiloxRng &rng, const DevCtx &C, ReplicaSh &,
+                                                                  int rep, int, unsigned long long seed) {
     rng.k0 = (uint32_t)seed;
     rng.k1 = (uint32_t)(seed >> 32);
     rng.rep = (uint32_t)rep;
     rng.seek_attempt(C.philox_ctr[rep]);
-    if (lane == 0) S.attempt_base = C.philox_ctr[rep]; // attempts this replica has ever made
-    __syncwarp();
+    return C.philox_ctr[rep]; // attempts this replica has ever made
 }
 template <class Rng>
-__device__ __forceinline__ void rng_store(Rng &rng, const DevCtx &C, WarpSh &S, int rep, int lane);
+__device__ __forceinline__ void rng_store(const DevCtx &C, ReplicaSh &B, int rep, int tid, unsigned long long abase);
 template <>
-__device__ __forceinline__ void rng_store<ReplayRng>(ReplayRng &, const DevCtx &C, WarpSh &S, int rep,
-                                                     int lane) {
-    __syncwarp();
-    for (int i = lane; i < CB_GLIBC_WORDS; i += 32) C.glibc[(long long)rep * CB_GLIBC_WORDS + i] = S.grs[i];
+__device__ __forceinline__ void rng_store<ReplayRng>(const DevCtx &C, ReplicaSh &B, int rep, int tid,
+                                                     unsigned long long) {
+    for (int i = tid; i < CB_GLIBC_WORDS; i += 32) C.glibc[(long long)rep * CB_GLIBC_WORDS + i] = B.grs[i];
 }
 template <>
-__device__ __forceinline__ void rng_store<PhiloxRng>(PhiloxRng &, const DevCtx &C, WarpSh &S, int rep,
-                                                     int lane) {
-    __syncwarp();
-    if (lane == 0) C.philox_ctr[rep] = S.attempt_base;
+__device__ __forceinline__ void rng_store<PhiloxRng>(const DevCtx &C, ReplicaSh &, int rep, int tid,
+                                                     unsigned long long abase) {
+    if (tid == 0) C.philox_ctr[rep] = abase;
 }
 
-// mc_sim mc_sim.pyx:26-103 for every replica: grid = R blocks of one warp.
-template <class Rng, int NB>
-__global__ void __launch_bounds__(32, 8) mc_sim_kernel(const CB_GRID_CONSTANT DevCtx C, long long num_mc_steps,
-                                                       double mu_adjust, unsigned long long seed, int cap) {
+// mc_sim mc_sim.pyx:26-103 for every replica.  One thread block per SM holds `rpb`
+// replicas (NW warps each); grid = ceil(R / rpb).  The replicas of a block are independent
+// simulations, but they go through the move types of a sweep TOGETHER (a block-wide barrier
+// after each move type): the kernel is bound by instruction fetch (140 KB of SASS against a
+// 32 KB L1.5 instruction cache), and warps that run the same move type share its code.
+template <class Rng, int NB, int NW>
+__global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, 1)
+    mc_sim_kernel(const CB_GRID_CONSTANT DevCtx C, long long num_mc_steps, double mu_adjust,
+                  unsigned long long seed, int cap, int rpb) {
     CB_DYN_SMEM(dyn);
-    __shared__ WarpSh S;
-    const int rep = blockIdx.x, lane = threadIdx.x;
-    if (rep >= C.R) return;
-    HashTable H = carve_table(dyn, cap, C.ncol);
-    table_reset_all(H, S, C.ncol, lane);
-    if (lane < CHROMO_NUM_MOVES) S.mv[lane] = C.moves[(long long)rep * CHROMO_NUM_MOVES + lane];
-    if (lane == 0) {
-        S.algo_bytes = 0;
-        S.last_U = 0;
-        S.passes = 1;
-        S.cur = 0;
-    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, local = warp / NW, wid = warp % NW;
+    const int rep = blockIdx.x * rpb + local, rtid = wid * 32 + lane; // thread index within the replica
+    const bool active = rep < C.R; // the last block may hold fewer replicas; its spare warps only keep the barriers
+    unsigned char *base = dyn + (size_t)local * cb_replica_smem(cap, C.ncol, NW);
+    ReplicaSh &B = *(ReplicaSh *)base;
+    WarpSh &S = *(WarpSh *)(base + CB_REPLICA_SH_BYTES + (size_t)wid * CB_WARP_SH_BYTES);
+    HashTable H = carve_table(base + CB_REPLICA_SH_BYTES + (size_t)NW * CB_WARP_SH_BYTES +
+                                  (size_t)wid * cb_table_bytes(cap, C.ncol), cap, C.ncol);
     Rng rng;
-    rng_load<Rng>(rng, C, S, rep, lane, seed);
-    __syncwarp();
-    McWarp<Rng, false, NB> W{C, S, H, rng, rep, lane, mu_adjust, -1, nullptr};
-    constexpr int B = Rng::kBatched ? 32 : 1;
+    unsigned long long abase0 = 0;
+    if (active) {
+        table_reset_all(H, S, C.ncol, lane);
+        if (rtid < CHROMO_NUM_MOVES) B.mv[rtid] = C.moves[(long long)rep * CHROMO_NUM_MOVES + rtid];
+        if (rtid == 0) B.algo_bytes = 0;
+        if (lane == 0) {
+            S.last_U = 0;
+            S.passes = 1;
+        }
+        abase0 = rng_load<Rng>(rng, C, B, rep, rtid, seed);
+    }
+    McWarp<Rng, false, NB, NW> W{C, B, S, H, rng, rep, lane, wid, local, mu_adjust, -1, nullptr, abase0};
+    __syncthreads();
     long long a0 = 0;
-    for (int m = 0; m < CHROMO_NUM_MOVES; m++) a0 += S.mv[m].num_attempt;
+    if (active)
+        for (int m = 0; m < CHROMO_NUM_MOVES; m++) a0 += B.mv[m].num_attempt;
+    constexpr int BS = Rng::kBatched ? 32 : 1;
     for (long long k = 0; k < num_mc_steps; k++)
         for (int m = 0; m < CHROMO_NUM_MOVES; m++) {
-            if (S.mv[m].move_on == 1) {
-                const int npc = S.mv[m].num_per_cycle;
+            if (active) {
+                if (B.mv[m].move_on == 1) {
+                    const int npc = B.mv[m].num_per_cycle;
 #pragma unroll 1
-                for (int j0 = 0; j0 < npc; j0 += B) W.run(m, min(B, npc - j0));
+                    for (int j0 = 0; j0 < npc; j0 += BS) W.run(m, min(BS, npc - j0));
+                }
+                W.update_amplitudes(m); // also for moves that are off (mc_sim.pyx:103)
             }
-            W.update_amplitudes(m); // also for moves that are off (mc_sim.pyx:103)
-            __syncwarp();
+            __syncthreads(); // the block's replicas enter the next move type together
         }
-    __syncwarp();
+    if (!active) return;
     long long a1 = 0;
-    for (int m = 0; m < CHROMO_NUM_MOVES; m++) a1 += S.mv[m].num_attempt;
-    if (lane == 0) {
+    for (int m = 0; m < CHROMO_NUM_MOVES; m++) a1 += B.mv[m].num_attempt;
+    if (rtid == 0) {
         C.attempts[rep] = (unsigned long long)(a1 - a0);
-        C.algo_bytes[rep] = S.algo_bytes;
+        C.algo_bytes[rep] = B.algo_bytes;
     }
-    if (lane < CHROMO_NUM_MOVES) C.moves[(long long)rep * CHROMO_NUM_MOVES + lane] = S.mv[lane];
-    rng_store<Rng>(rng, C, S, rep, lane);
+    if (rtid < CHROMO_NUM_MOVES) C.moves[(long long)rep * CHROMO_NUM_MOVES + rtid] = B.mv[rtid];
+    rng_store<Rng>(C, B, rep, rtid, W.abase);
 }
 
 // one instrumented mc_step of one replica (chromo_mc_step)
@@ -1359,30 +1514,30 @@ __global__ void __launch_bounds__(32) mc_step_kernel(const CB_GRID_CONSTANT DevC
                                                      unsigned long long seed, int force_accept,
                                                      DebugOut *dbg, int cap) {
     CB_DYN_SMEM(dyn);
+    __shared__ ReplicaSh B;
     __shared__ WarpSh S;
     const int lane = threadIdx.x;
     HashTable H = carve_table(dyn, cap, C.ncol);
     table_reset_all(H, S, C.ncol, lane);
-    if (lane < CHROMO_NUM_MOVES) S.mv[lane] = C.moves[(long long)rep * CHROMO_NUM_MOVES + lane];
+    if (lane < CHROMO_NUM_MOVES) B.mv[lane] = C.moves[(long long)rep * CHROMO_NUM_MOVES + lane];
     __syncwarp();
     if (lane == 0) {
-        S.mv[mtype].amp_move = amp_move;
-        S.mv[mtype].amp_bead = amp_bead;
+        B.mv[mtype].amp_move = amp_move;
+        B.mv[mtype].amp_bead = amp_bead;
         dbg->n_inds = 0;
         dbg->n_touched = 0;
         dbg->dE_poly = dbg->dE_field = 0.0;
         dbg->accepted = 0;
         dbg->passes = 0;
-        S.algo_bytes = 0;
+        B.algo_bytes = 0;
         S.last_U = 0;
         S.passes = 1;
-        S.cur = 0;
     }
     Rng rng;
-    rng_load<Rng>(rng, C, S, rep, lane, seed);
+    const unsigned long long abase0 = rng_load<Rng>(rng, C, B, rep, lane, seed);
     __syncwarp();
-    McWarp<Rng, true, NB> W{C, S, H, rng, rep, lane, mu_adjust, force_accept, dbg};
+    McWarp<Rng, true, NB, 1> W{C, B, S, H, rng, rep, lane, 0, 0, mu_adjust, force_accept, dbg, abase0};
     W.run(mtype, 1);
     __syncwarp();
-    rng_store<Rng>(rng, C, S, rep, lane);
+    rng_store<Rng>(C, B, rep, lane, W.abase);
 }

@@ -213,6 +213,18 @@ class Engine:
         check(self._L.chromo_ctx_set_table_capacity(self._h, int(cap), C.byref(out)))
         return int(out.value)
 
+    def set_warps_per_replica(self, warps: int = 0) -> int:
+        """Warps that work on one replica in the production MC kernel (1 or 2; 0 = query)."""
+        out = C.c_int64(0)
+        check(self._L.chromo_ctx_set_warps_per_replica(self._h, int(warps), C.byref(out)))
+        return int(out.value)
+
+    def set_replicas_per_block(self, rpb: int = 0) -> int:
+        """Replicas sharing one thread block of the MC kernel (1..7; -1 = automatic; 0 = query)."""
+        out = C.c_int64(0)
+        check(self._L.chromo_ctx_set_replicas_per_block(self._h, int(rpb), C.byref(out)))
+        return int(out.value)
+
     def sync(self):
         check(self._L.chromo_ctx_sync(self._h))
 

@@ -112,12 +112,26 @@ int chromo_ctx_sync(chromo_ctx *ctx);
 void *chromo_ctx_stream(chromo_ctx *ctx);
 /* bytes of HBM held by the context */
 int64_t chromo_ctx_bytes(chromo_ctx *ctx);
-/* Tuning knob: slots (power of two, 128..4096) of the per-replica shared-memory
+/* Tuning knob: slots (a multiple of 32, 128..4096) of the per-warp shared-memory
  * delta-density hash used by the MC kernel; 0 = choose from the replica count so
  * that all replicas are resident at once.  Moves that touch more voxels than fit
  * are evaluated in several hash-partition passes (same result).  Returns the
  * capacity in effect through *cap_out (may be NULL). */
 int chromo_ctx_set_table_capacity(chromo_ctx *ctx, int64_t cap, int64_t *cap_out);
+/* Tuning knob: warps that work on one replica in the production (Philox) MC
+ * kernel, 1 or 2 (default 2; 0 = leave unchanged).  With 2, the bead-row stage of
+ * attempt j+1 overlaps the density stage of attempt j; attempts still take
+ * effect strictly in order and the results are bit-identical to 1 warp.  The
+ * replayed-RNG kernels (sequential streams) always use 1.  Re-chooses the table
+ * capacity.  Returns the value in effect through *warps_out (may be NULL). */
+int chromo_ctx_set_warps_per_replica(chromo_ctx *ctx, int64_t warps, int64_t *warps_out);
+/* Tuning knob: replicas that share one thread block of the MC kernel, 1..7
+ * (-1 = automatic: ceil(replicas / SMs), at most 7; 0 = leave unchanged).  The
+ * replicas of a block stay independent simulations but enter each move type of
+ * a sweep together, so that their warps share instruction-cache lines.  Results
+ * do not depend on it.  Re-chooses the table capacity.  Returns the value in
+ * effect through *rpb_out (may be NULL). */
+int chromo_ctx_set_replicas_per_block(chromo_ctx *ctx, int64_t rpb, int64_t *rpb_out);
 
 /* ---- parameters -------------------------------------------------------- */
 /* Reader-protein tables.

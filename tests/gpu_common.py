@@ -16,9 +16,9 @@ def engine_from_spec(spec, R=1, device=0, chi=None, mu=None):
     f = spec["field"]
     bead_vol = (4 / 3) * np.pi * spec["bead_rad"] ** 3
     e = Engine(R, N, nb, grid=f, bead_vol=bead_vol, max_binders=spec.get("max_binders", -1), device=device)
-    if f is not None:
+    if f is not None and f["nx"] * f["ny"] * f["nz"] > 0:
         vol_bin = f["x_width"] * f["y_width"] * f["z_width"] / (f["nx"] * f["ny"] * f["nz"])
-    else:
+    else:  # NullField (nx = ny = nz = 0 keeps the confinement, fields.pyx:280-318)
         vol_bin = 1.0
     pref, e_intra, xpref = O.field_prefactors(spec["binders"], vol_bin)
     e.set_binders(spec["binders"], pref, e_intra, xpref)
@@ -28,7 +28,7 @@ def engine_from_spec(spec, R=1, device=0, chi=None, mu=None):
                          mu=[b["chemical_potential"] for b in spec["binders"]] if mu is None else mu)
     tile = lambda a: np.broadcast_to(np.asarray(a), (R,) + np.asarray(a).shape).copy()
     e.upload(tile(spec["r"]), tile(spec["t3"]), tile(spec["t2"]), tile(spec["states"]), tile(spec["mods"]))
-    if f is not None:
+    if f is not None and f["nx"] * f["ny"] * f["nz"] > 0:
         e.field_recompute(clamp=True)
     return e
 

@@ -12,6 +12,7 @@
 // full mask, which is what this model requires.
 #pragma once
 #include <pthread.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
@@ -47,6 +48,7 @@ struct EmuBlock {
     pthread_barrier_t block_bar;
     std::vector<pthread_barrier_t> warp_bar;
     std::vector<uint64_t> slots; // one per thread
+    std::atomic<int> nb_count[16], nb_gen[16]; // named barriers (bar.sync id, count)
     unsigned char *dyn = nullptr;
 };
 inline thread_local EmuBlock *emu_blk = nullptr;
@@ -54,6 +56,16 @@ inline thread_local EmuBlock *emu_blk = nullptr;
 static inline void emu_warp_wait() { pthread_barrier_wait(&emu_blk->warp_bar[threadIdx.x >> 5]); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_wait(); }
 static inline void __syncthreads() { pthread_barrier_wait(&emu_blk->block_bar); }
+static inline void cb_bar_sync(int id, int count) {
+    EmuBlock *b = emu_blk;
+    const int gen = b->nb_gen[id].load();
+    if (b->nb_count[id].fetch_add(1) + 1 == count) {
+        b->nb_count[id].store(0);
+        b->nb_gen[id].fetch_add(1);
+    } else {
+        while (b->nb_gen[id].load() == gen) sched_yield();
+    }
+}
 
 template <class T>
 static inline T emu_exchange(T v, int src_lane) {
@@ -122,6 +134,8 @@ static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 #define CB_NOINLINE __attribute__((noinline))
 #define CB_GRID_CONSTANT
 static inline void cb_prefetch(const void *) {}
+static inline void cb_backoff() { sched_yield(); }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline double __longlong_as_double(long long v) {
     double d;
     memcpy(&d, &v, 8);
@@ -140,6 +154,7 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 struct cudaDeviceProp {
     int multiProcessorCount;
     size_t sharedMemPerBlockOptin;
+    size_t sharedMemPerMultiprocessor;
 };
 static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
@@ -147,6 +162,7 @@ static inline cudaError_t cudaSetDevice(int) { return 0; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     p->multiProcessorCount = 148;
     p->sharedMemPerBlockOptin = 227 * 1024;
+    p->sharedMemPerMultiprocessor = 228 * 1024;
     return 0;
 }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, int) { *s = (void *)1; return 0; }
@@ -170,6 +186,10 @@ static void emu_launch(K kernel, dim3 grid, dim3 block, size_t smem, A... args) 
     const unsigned nw = (nt + 31) / 32;
     EmuBlock blk;
     blk.slots.assign(nw * 32, 0);
+    for (int i = 0; i < 16; i++) {
+        blk.nb_count[i].store(0);
+        blk.nb_gen[i].store(0);
+    }
     blk.warp_bar.resize(nw);
     std::vector<unsigned char> dyn(smem + 64);
     blk.dyn = (unsigned char *)(((uintptr_t)dyn.data() + 15) & ~(uintptr_t)15);

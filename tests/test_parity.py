@@ -227,11 +227,63 @@ def test_philox_is_deterministic_and_consistent(backend, oracle_mod):
             assert np.allclose(n3, 1.0, atol=1e-9)
         e.close()
     assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
-    # densities are accumulated with atomics: equal up to summation order
+    # the initial full recompute uses fp64 atomics at L2 (order-dependent in the last ulp); the MC
+    # kernel's own updates are order-independent (see test_two_warps_per_replica_match_one)
     assert np.allclose(runs[0][2], runs[1][2], rtol=1e-12, atol=1e-15 * runs[0][2].max())
     assert not np.array_equal(runs[0][0][0], runs[0][0][1])
     acc = runs[0][3]["num_success"].sum() / runs[0][3]["num_attempt"].sum()
     assert 0.2 < acc < 0.95
+
+
+@pytest.mark.parametrize("case", ["mixed", "dense", "no_field"])
+def test_two_warps_per_replica_match_one(backend, oracle_mod, case):
+    """The production kernel with two warps per replica (stage 1 of attempt j+1
+    overlapping stage 2 of attempt j, redone when an accepted attempt changed
+    rows it had read) gives the sequential result bit for bit.  "dense": a
+    short chain with wide windows, so nearly every look-ahead is stale;
+    "no_field": only confinement (NullField path)."""
+    O = oracle_mod
+    if case == "mixed":
+        spec = O.make_spec(N=400, nb=2, seed=21, cross_talk=-0.5, random_states=True)
+        sweeps, per_cycle = 6, (30, 1, 60, 60, 10)
+    elif case == "dense":
+        spec = O.make_spec(N=40, nb=1, seed=22, random_states=True)
+        sweeps, per_cycle = 8, (30, 5, 60, 60, 30)
+    else:
+        spec = O.make_spec(N=120, nb=1, seed=23, random_states=False)
+        spec["field"] = dict(spec["field"], nx=0, ny=0, nz=0)
+        sweeps, per_cycle = 6, (30, 1, 60, 60, 10)
+    R = 3
+    out = []
+    dens0 = None
+    for warps in (1, 2):
+        e = engine_from_spec(spec, R=R)
+        assert e.set_warps_per_replica(warps) == warps
+        # one replica per block vs. all three sharing a block (move types entered together)
+        assert e.set_replicas_per_block(1 if warps == 1 else R) == (1 if warps == 1 else R)
+        if case != "no_field":  # same starting density, bit for bit (the full recompute is atomics-ordered)
+            if dens0 is None:
+                dens0 = e.density()
+            e.upload_density(dens0)
+        mv = moves_array(spec, R, per_cycle)
+        if case == "dense":
+            mv["amp_bead"][:, 3] = 12  # tangent rotation: bead sets of up to 12 (prepared) ...
+            mv["bead_amp_hi"][:, 3] = 24  # ... growing past CB_KSEL = 16 (sequential path)
+            mv["amp_bead"][:, 4] = 5
+            mv["bead_amp_hi"][:, 4] = 5
+        e.mc_sim(sweeps, mv, 1.0, 4242, PHILOX)
+        r, t3, t2, st = e.download()
+        out.append((r, t3, t2, st, e.density() if case != "no_field" else None, mv.copy(), e.last_attempts()))
+        e.close()
+    a, b = out
+    for x, y in zip(a[:4], b[:4]):
+        assert np.array_equal(x, y)
+    if case != "no_field":
+        assert np.array_equal(a[4], b[4])
+    for f in ("num_attempt", "num_success", "amp_bead", "amp_move", "acceptance_rate"):
+        assert np.array_equal(a[5][f], b[5][f]), f
+    assert a[6] == b[6] == R * sweeps * sum(per_cycle)
+    assert a[5]["num_success"].sum() > 0
 
 
 def test_error_behaviour(backend, oracle_mod):

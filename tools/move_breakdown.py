@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--warm", type=int, default=400)
     ap.add_argument("--sweeps", type=int, default=20)
     ap.add_argument("--table-slots", type=int, default=0)
+    ap.add_argument("--warps", type=int, default=0, help="warps per replica (0 = library default)")
+    ap.add_argument("--rpb", type=int, default=0, help="replicas per block (0 = library default)")
     a = ap.parse_args()
     R, N = a.replicas, a.beads
     r, t3, t2, states, mods, grid = bench.make_inputs(R, N, 1234, pinned=False)
@@ -40,7 +42,9 @@ def main():
                           grid=grid, bead_vol=(4 / 3) * math.pi * 5.0 ** 3, chi=1.0, mu=[-1.2],
                           moves=default_moves(R, N, 16.5), device=0)
     eng = ens.engine
-    eng.set_table_capacity(a.table_slots)
+    warps = eng.set_warps_per_replica(a.warps)
+    rpb = eng.set_replicas_per_block(a.rpb)
+    cap = eng.set_table_capacity(a.table_slots)
     stream = torch.cuda.ExternalStream(eng.stream(), device=0)
 
     def timed(sweeps, seed):
@@ -57,7 +61,7 @@ def main():
     ens.sync()
     base = ens.moves.copy()
     per_cycle = base["num_per_cycle"][0].copy()
-    out = dict(amp_bead_mean=[round(float(x), 2) for x in base["amp_bead"].mean(axis=0)],
+    out = dict(warps=warps, rpb=rpb, table_slots=cap, amp_bead_mean=[round(float(x), 2) for x in base["amp_bead"].mean(axis=0)],
                amp_move_mean=[round(float(x), 4) for x in base["amp_move"].mean(axis=0)])
     timed(2, 5)
     ms_all = timed(a.sweeps, 7)
