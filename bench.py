@@ -275,6 +275,8 @@ def run_ours(args):
                           bead_vol=(4 / 3) * math.pi * 5.0 ** 3, chi=1.0, mu=[-1.2],
                           moves=default_moves(R, N, 16.5), device=local)
     eng = ens.engine
+    warps = eng.set_warps_per_replica(args.warps)
+    rpb = eng.set_replicas_per_block(args.rpb)
     cap = eng.set_table_capacity(args.table_slots)
     stream = torch.cuda.ExternalStream(eng.stream(), device=local)
 
@@ -356,7 +358,7 @@ def run_ours(args):
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=Wm,
             ms_per_step=ms_total / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-            data="synthetic", config=workload_config(args, cap),
+            data="synthetic", config=dict(workload_config(args, cap), warps_per_replica=warps, replicas_per_block=rpb),
             e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=Ke),
             gpu_launches=K + 4 * Ke,
             clocks=clocks,
@@ -394,6 +396,8 @@ def main():
     ap.add_argument("--ref-sweeps", type=int, default=100, help="MC sweeps per process in the CPU reference sample")
     ap.add_argument("--ref-warm", type=int, default=400, help="warm-up sweeps of the CPU reference (controller settles)")
     ap.add_argument("--table-slots", type=int, default=0)
+    ap.add_argument("--warps", type=int, default=0, help="warps per replica in the MC kernel (0 = library default)")
+    ap.add_argument("--rpb", type=int, default=0, help="replicas per thread block (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -57,7 +57,7 @@ struct chromo_ctx {
     int64_t dbg_inds_cap = 0, dbg_touched_cap = 0;
     int nblk_bins = 1, nblk_bonds = 1;
     int cap = 0;           // slots of each warp's delta-density table in the MC kernel
-    int warps = CB_MAX_WARPS; // warps per replica of the production (Philox) MC kernel
+    int warps = 1;            // warps per replica of the production (Philox) MC kernel (1 or 2)
     int rpb = 1;              // replicas per thread block
     int rpb_fixed = 0;        // > 0: set by chromo_ctx_set_replicas_per_block
     double roundK = 0.0;
@@ -97,15 +97,16 @@ static int dev_alloc(chromo_ctx *c, T **p, size_t n) {
 
 static int choose_table(chromo_ctx *c) {
     // One thread block per SM holds `rpb` replicas (mc_kernel.cuh, mc_sim_kernel); all replicas
-    // are resident at once when R <= SMs x CB_MAX_RPB.  Pick the largest per-warp table (<= 2048
-    // slots, a multiple of 32, never below 128) that lets the block's replicas share the SM's
-    // shared memory.
+    // are resident at once when R <= SMs x CB_MAX_RPB.  Pick the largest per-warp table (a multiple
+    // of 32 slots, never below 128) that lets the block's replicas share the SM's shared memory;
+    // at most 768 slots when replicas share a block (measured: beyond that the shared-memory
+    // carve-out only takes L1 away from the bead rows), 2048 otherwise.
     const int ncol = c->d.ncol;
     int rpb = (c->d.R + c->sm_count - 1) / c->sm_count;
     rpb = std::max(1, std::min(rpb, CB_MAX_RPB));
     if (c->rpb_fixed > 0) rpb = c->rpb_fixed;
     const size_t per_replica = c->smem_optin / (size_t)rpb;
-    int cap = 2048;
+    int cap = rpb > 1 ? 768 : 2048;
     while (cap > 128 && cb_replica_smem(cap, ncol, c->warps) > per_replica) cap -= 32;
     c->cap = cap;
     c->rpb = rpb;

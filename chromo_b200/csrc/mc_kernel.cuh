@@ -1325,11 +1325,21 @@ struct McWarp {
     }
 
     // pull the rows a later attempt will read towards the SM while this one runs
-    __device__ __forceinline__ void prefetch_attempt(int mtype, const Prop &P) {
+    __device__ __forceinline__ void prefetch_attempt(int mtype, const Prop &P, int slot) {
         const int N = C.N;
         int first, count;
         if (mtype == CHROMO_TANGENT_ROTATION) {
-            if (P.n != 1) return;
+            if (P.n != 1) {
+                if (BATCH && P.n <= CB_KSEL && lane < P.n) { // prepared bead set: the bead's line (+ neighbours)
+                    const long long o = 3ll * max(B.tsel[slot][lane] - 1, 0);
+                    cb_prefetch(R_() + o);
+                    cb_prefetch(T3_() + o);
+                    cb_prefetch(T2_() + o);
+                    cb_prefetch(T3_() + min(o + 6, 3ll * N - 1));
+                    cb_prefetch(R_() + min(o + 6, 3ll * N - 1));
+                }
+                return;
+            }
             first = max(P.aux - 1, 0);
             count = min(P.aux + 1, N - 1) - first + 1;
         } else {
@@ -1343,7 +1353,12 @@ struct McWarp {
             const long long off = (long long)first * 3 + (long long)lane * 16;
             if (off < (long long)N * 3) {
                 cb_prefetch(R_() + off);
-                if (mtype != CHROMO_CHANGE_BINDING_STATE) cb_prefetch(T3_() + off);
+                if (mtype == CHROMO_CHANGE_BINDING_STATE) {
+                    if (lane == 0) {
+                        cb_prefetch(ST_() + (long long)P.ind0 * NB);
+                        cb_prefetch(MOD_() + (long long)P.ind0 * NB);
+                    }
+                } else cb_prefetch(T3_() + off);
                 if (mtype == CHROMO_TANGENT_ROTATION || mtype == CHROMO_CRANK_SHAFT || mtype == CHROMO_END_PIVOT)
                     cb_prefetch(T2_() + off);
             }
@@ -1363,7 +1378,7 @@ struct McWarp {
         block_sync();
 #pragma unroll 1
         for (int j = wid; j < cnt; j += NW) {
-            if (j + NW < cnt) prefetch_attempt(mtype, B.prop[j + NW]);
+            if (j + NW < cnt) prefetch_attempt(mtype, B.prop[j + NW], j + NW);
             attempt(mtype, j);
         }
         abase += (unsigned long long)cnt;
@@ -1450,8 +1465,8 @@ __device__ __forceinline__ void rng_store<PhiloxRng>(const DevCtx &C, ReplicaSh 
 
 // mc_sim mc_sim.pyx:26-103 for every replica.  One thread block per SM holds `rpb`
 // replicas (NW warps each); grid = ceil(R / rpb).  The replicas of a block are independent
-// simulations, but they go through the move types of a sweep TOGETHER (a block-wide barrier
-// after each move type): the kernel is bound by instruction fetch (140 KB of SASS against a
+// simulations, but they go through the move types of a sweep TOGETHER (a block-wide
+// barrier after each): the kernel is bound by instruction fetch (140 KB of SASS against a
 // 32 KB L1.5 instruction cache), and warps that run the same move type share its code.
 template <class Rng, int NB, int NW>
 __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, 1)
@@ -1494,7 +1509,10 @@ __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, 1)
                 }
                 W.update_amplitudes(m); // also for moves that are off (mc_sim.pyx:103)
             }
-            __syncthreads(); // the block's replicas enter the next move type together
+            // The block's replicas enter the next move type together.  (Measured on B200: skipping
+            // the barrier before the short move types -- 1 end-pivot, 10 binding attempts -- costs
+            // more in lost instruction-cache sharing than the wait for the slowest replica does.)
+            __syncthreads();
         }
     if (!active) return;
     long long a1 = 0;

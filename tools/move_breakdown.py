@@ -35,15 +35,19 @@ def main():
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0, help="warps per replica (0 = library default)")
     ap.add_argument("--rpb", type=int, default=0, help="replicas per block (0 = library default)")
+    ap.add_argument("--lib", default=None, help="another build of the C-ABI library (tools/build_variant.sh), for A/B runs")
     a = ap.parse_args()
     R, N = a.replicas, a.beads
+    if a.lib:
+        from chromo_b200 import _lib
+        _lib.use_library(a.lib)
     r, t3, t2, states, mods, grid = bench.make_inputs(R, N, 1234, pinned=False)
     ens = ReplicaEnsemble(r, t3, t2, states, mods, binders=[dict(bench.HP1)], bond_params=bench.bond_params(N),
                           grid=grid, bead_vol=(4 / 3) * math.pi * 5.0 ** 3, chi=1.0, mu=[-1.2],
                           moves=default_moves(R, N, 16.5), device=0)
     eng = ens.engine
     warps = eng.set_warps_per_replica(a.warps)
-    rpb = eng.set_replicas_per_block(a.rpb)
+    rpb = eng.set_replicas_per_block(a.rpb) if hasattr(eng._L, "chromo_ctx_set_replicas_per_block") else 1
     cap = eng.set_table_capacity(a.table_slots)
     stream = torch.cuda.ExternalStream(eng.stream(), device=0)
 
