@@ -26,7 +26,7 @@ static inline __host__ __device__ size_t cb_table_bytes(int cap, int ncol) {
 }
 // shared memory of the MC kernel per replica / per warp (>= sizeof(ReplicaSh), sizeof(WarpSh);
 // checked in mc_kernel.cuh) and the largest number of warps per replica that is instantiated
-#define CB_REPLICA_SH_BYTES 5632
+#define CB_REPLICA_SH_BYTES 8576
 #define CB_WARP_SH_BYTES 1280
 #define CB_MAX_WARPS 2
 // shared memory of one replica: ReplicaSh | WarpSh x warps | table x warps

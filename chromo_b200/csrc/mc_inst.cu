@@ -52,3 +52,13 @@ static int step_one(const McStepArgs &a) {
 
 int NAME(sim)(const McSimArgs &a) { return a.d.nb == NB_A ? sim_one<NB_A>(a) : sim_one<NB_B>(a); }
 int NAME(step)(const McStepArgs &a) { return a.d.nb == NB_A ? step_one<NB_A>(a) : step_one<NB_B>(a); }
+
+#if defined(CB_PHASE_TIMERS) && !CB_INST_REPLAY && !CB_INST_HI
+// development only: read and reset the phase timers of the Philox nb<=2 kernels
+extern "C" int cb_phase_read(unsigned long long *out) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, cb_phase_acc, sizeof(unsigned long long) * CHROMO_NUM_MOVES * CB_NPHASE);
+    if (e != cudaSuccess) return (int)e;
+    static unsigned long long zero[CHROMO_NUM_MOVES * CB_NPHASE];
+    return (int)cudaMemcpyToSymbol(cb_phase_acc, zero, sizeof(zero));
+}
+#endif

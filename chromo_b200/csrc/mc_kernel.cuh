@@ -36,6 +36,27 @@
 #define FULL_MASK 0xffffffffu
 #define HASH_EMPTY (-1)
 
+// Development-only phase timers (tools/build_variant.sh WORK x.so -DCB_PHASE_TIMERS): cycles per phase
+// of an attempt, summed over warps, per move type.  Never defined in the product build.
+#ifdef CB_PHASE_TIMERS
+#define CB_NPHASE 16
+__device__ unsigned long long cb_phase_acc[CHROMO_NUM_MOVES][CB_NPHASE];
+#define CB_T0() long long cb_t_ = clock64()
+#define CB_LAP(ph)                                           \
+    do {                                                     \
+        const long long cb_n_ = clock64();                   \
+        tacc[ph] += (unsigned long long)(cb_n_ - cb_t_);     \
+        cb_t_ = cb_n_;                                       \
+    } while (0)
+#else
+#define CB_T0() do { } while (0)
+#define CB_LAP(ph) do { } while (0)
+#endif
+
+#ifndef CB_UNIT_UNROLL
+#define CB_UNIT_UNROLL 1 // voxel-contribution loop of scatter_pass (A/B knob)
+#endif
+constexpr int cb_unit_unroll = CB_UNIT_UNROLL;
 #define CB_KSEL 16      // tangent rotation: bead sets up to this size are drawn in the batched prepare
 #define CB_TAN_SMALL 16 // tangent rotation: new tangents of up to this many beads are staged in shared memory
 #define CB_NEWST 128    // binding: new states of up to this many beads are staged in shared memory
@@ -49,6 +70,10 @@ struct Prop {
     int aux;       // binder (binding) | left-hand side (end-pivot) | bead (single-bead tangent rotation)
     int newst0;    // binding, n == 1: the new state
     uint32_t used; // draws of the attempt's stream consumed by prepare (batched mode)
+    // segment moves: the state-DEPENDENT scalar half, from the rows as they were when it was computed
+    // (segment_rows_prepare); redone if an accepted attempt of the batch changed those rows since
+    double M[12];   // 3x4 affine map (slide: translation column only)
+    double dE_poly; // elastic energy change of the two bonds at the segment's ends
 };
 
 // per-warp shared state (each warp of a replica's block works on its own attempt)
@@ -248,7 +273,7 @@ __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, Warp
         // a lane that walks all 8 corners starts at a lane-dependent corner, so that
         // neighbouring beads (which mostly share a cell) do not hit one slot together
         const int rot = cpl >= 8 ? (lane / G) & 7 : 0;
-#pragma unroll 1
+#pragma unroll cb_unit_unroll
         for (int u = u0; u < u1; u++) {
             const int k = u >> 3, l = ((u & 7) + rot) & 7;
             const int bx = l & 1, by = (l >> 1) & 1, bz = l >> 2;
@@ -526,15 +551,22 @@ __device__ __forceinline__ double confinement_dE_segment(const DevCtx &C, const 
 // beads optionally replaced by trial values: moved = 0 none, 1 first bead,
 // 2 second bead.  E_pair with dr / dr_par / dr_perp / bend built as in
 // bead_pair_dE_poly_forward / _reverse (polymers.pyx:1148-1175, 1253-1346).
+__device__ __forceinline__ double pair_energy_p(const double *Rr, const double *T3, const double *bondp, int bond,
+                                                int moved, const double rn[3], const double tn[3]);
 __device__ __forceinline__ double pair_energy(const DevCtx &C, int rep, int bond, int moved,
                                               const double rn[3], const double tn[3]) {
-    const double *Rr = C.r + (long long)rep * C.N * 3 + 3 * bond;
-    const double *T3 = C.t3 + (long long)rep * C.N * 3 + 3 * bond;
+    return pair_energy_p(C.r + (long long)rep * C.N * 3, C.t3 + (long long)rep * C.N * 3,
+                         C.bond + (long long)rep * C.bond_stride, bond, moved, rn, tn);
+}
+
+// the same from explicit row pointers (`bondp` = the replica's bond-parameter rows)
+__device__ __forceinline__ double pair_energy_p(const double *Rr, const double *T3, const double *bondp, int bond,
+                                                int moved, const double rn[3], const double tn[3]) {
     double r0[3], r1[3], t0[3], t1[3];
-    load3(Rr, r0);
-    load3(Rr + 3, r1);
-    load3(T3, t0);
-    load3(T3 + 3, t1);
+    load3(Rr + 3 * bond, r0);
+    load3(Rr + 3 * bond + 3, r1);
+    load3(T3 + 3 * bond, t0);
+    load3(T3 + 3 * bond + 3, t1);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         r0[j] = moved == 1 ? rn[j] : r0[j];
@@ -542,8 +574,112 @@ __device__ __forceinline__ double pair_energy(const DevCtx &C, int rep, int bond
         r1[j] = moved == 2 ? rn[j] : r1[j];
         t1[j] = moved == 2 ? tn[j] : t1[j];
     }
-    Bond B = load_bond(C, rep, bond);
+    const double *p = bondp + (long long)bond * 5;
+    Bond B;
+    B.eps_bend = p[0];
+    B.eps_par = p[1];
+    B.eps_perp = p[2];
+    B.gamma = p[3];
+    B.eta = p[4];
     return bond_energy(B, r0, r1, t0, t1);
+}
+
+// The state-dependent scalar half of a segment move (crank-shaft, end-pivot, slide), ONE THREAD per
+// attempt: the 3x4 affine map from the current positions (arbitrary_axis_rotation linalg.pyx:62-139,
+// get_crank_shaft_axis / _fulcrum move_funcs.pyx:157-280, get_end_pivot_fulcrum 349-398) and the elastic
+// energy change of the two bonds at the segment's ends (continuous_dE_poly polymers.pyx:1084-1146:
+// (E_left' - E_left) + (E_right' - E_right)), written to P->M and P->dE_poly.
+// Out of line and on explicit pointers: the one copy serves the batched prepare (32 attempts on 32
+// lanes, off the per-attempt path) and the recompute of an attempt whose rows were changed by an
+// accepted attempt of the same batch.  Returns 1 without writing when the crank-shaft axis is
+// degenerate and `axis_in` is null: the caller draws one (move_funcs.pyx:229-230) and calls again.
+static __device__ CB_NOINLINE int segment_rows_prepare(const double *Rr, const double *T3, const double *bondp, int N,
+                                                       int mtype, Prop *P, const double *axis_in) {
+    const int ind0 = P->ind0, indf = P->indf;
+    double M[12];
+    if (mtype == CHROMO_SLIDE) {
+#pragma unroll
+        for (int j = 0; j < 12; j++) M[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) M[4 * j + 3] = P->ax[j]; // generate_translation_mat linalg.pyx:172-199
+    } else {
+        int ful;
+        double axis[3], pt[3];
+        if (mtype == CHROMO_CRANK_SHAFT) {
+            int a, b; // get_crank_shaft_axis move_funcs.pyx:157-234
+            if (ind0 == indf - 1 && ind0 == 0) { a = indf; b = ind0; }
+            else if (ind0 == indf - 1 && ind0 == N - 1) { a = ind0; b = ind0 - 1; }
+            else if (ind0 == 0 && indf == N) { a = indf - 1; b = ind0; }
+            else if (ind0 == 0) { a = indf; b = ind0; }
+            else if (indf == N) { a = indf - 1; b = ind0 - 1; }
+            else { a = indf; b = ind0 - 1; }
+            // get_crank_shaft_fulcrum move_funcs.pyx:237-280
+            if (ind0 == 0 && indf != N) ful = indf;
+            else if (ind0 != 0 && indf == N) ful = ind0 - 1;
+            else if (ind0 == 0 && indf == N) ful = ind0;
+            else ful = ind0 - 1;
+#pragma unroll
+            for (int j = 0; j < 3; j++) axis[j] = Rr[3 * a + j] - Rr[3 * b + j];
+            const double mag = sqrt((axis[0] * axis[0] + axis[1] * axis[1]) + axis[2] * axis[2]);
+            if (mag < 1E-5) {
+                if (!axis_in) return 1;
+#pragma unroll
+                for (int j = 0; j < 3; j++) axis[j] = axis_in[j];
+            } else {
+                const double sc = 1.0 / mag;
+#pragma unroll
+                for (int j = 0; j < 3; j++) axis[j] = axis[j] * sc;
+            }
+        } else { // end pivot: get_end_pivot_fulcrum move_funcs.pyx:349-398
+            if (ind0 == 0 && indf != N) ful = indf;
+            else if (ind0 != 0 && indf == N) ful = ind0 - 1;
+            else if (ind0 == 0 && indf == N && P->aux == 1) ful = indf - 1;
+            else ful = ind0;
+#pragma unroll
+            for (int j = 0; j < 3; j++) axis[j] = P->ax[j];
+        }
+        load3(Rr + 3 * ful, pt);
+        double Rm[9], tv[3];
+        rotation_3x3(axis, P->sn, P->cs, Rm);
+        rotation_translation(axis, pt, P->sn, P->cs, tv);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            M[4 * j] = Rm[3 * j];
+            M[4 * j + 1] = Rm[3 * j + 1];
+            M[4 * j + 2] = Rm[3 * j + 2];
+            M[4 * j + 3] = tv[j];
+        }
+    }
+    // the two end bonds: which = 0 left (bond ind0-1, its second bead moves), 1 right (bond indf-1, its
+    // first bead moves)
+    double d[2] = {0.0, 0.0};
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+        const bool present = which == 0 ? (ind0 != 0) : (indf != N);
+        if (!present) continue;
+        const int bond = which == 0 ? ind0 - 1 : indf - 1;
+        const int mbead = which == 0 ? ind0 : indf - 1;
+        double r[3], t[3], rn[3], tn[3];
+        load3(Rr + 3 * mbead, r);
+        load3(T3 + 3 * mbead, t);
+        if (mtype == CHROMO_SLIDE) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                rn[j] = r[j] + M[4 * j + 3];
+                tn[j] = t[j];
+            }
+        } else {
+            apply_affine(M, r, rn);
+            apply_rot(M, t, tn);
+        }
+        const double e_trial = pair_energy_p(Rr, T3, bondp, bond, which == 0 ? 2 : 1, rn, tn);
+        const double e_cur = pair_energy_p(Rr, T3, bondp, bond, 0, rn, tn);
+        d[which] = e_trial - e_cur;
+    }
+#pragma unroll
+    for (int j = 0; j < 12; j++) P->M[j] = M[j];
+    P->dE_poly = d[0] + d[1];
+    return 0;
 }
 
 // ------------------------------------------------------- bead selection (lane 0)
@@ -620,6 +756,14 @@ struct McWarp {
     int force_accept; // DEBUG only: -1 Metropolis, 0/1 forced
     DebugOut *dbg;
     unsigned long long abase; // Philox: index of the batch's first attempt in the replica's stream
+#ifdef CB_PHASE_TIMERS
+    unsigned long long tacc[CB_NPHASE] = {};
+    __device__ __forceinline__ void flush_timers(int mtype) {
+        if (lane == 0)
+            for (int i = 0; i < CB_NPHASE; i++) atomicAdd(&cb_phase_acc[mtype][i], tacc[i]);
+        for (int i = 0; i < CB_NPHASE; i++) tacc[i] = 0;
+    }
+#endif
 
     __device__ __forceinline__ double *R_() const { return C.r + (long long)rep * C.N * 3; }
     __device__ __forceinline__ double *T3_() const { return C.t3 + (long long)rep * C.N * 3; }
@@ -644,7 +788,9 @@ struct McWarp {
         }
     }
     __device__ __forceinline__ void pass_turn(int slot, int acc) const {
-        if (NW > 1) {
+        if (NW == 1) { // same warp: the next attempt reads the bit after the __syncwarp that ends this one
+            if (acc && lane == 0) B.accepted |= 1u << slot;
+        } else {
             __threadfence_block(); // this lane's commit stores, before the token moves
             __syncwarp();
             if (lane == 0) {
@@ -684,19 +830,36 @@ struct McWarp {
         return __any_sync(FULL_MASK, hit);
     }
 
-    // trial (r, t3) of a bead of the moving segment
-    __device__ __forceinline__ void trial_rt(int kind, const double r[3], const double t[3], double rn[3],
-                                             double tn[3]) const {
-        if (kind == 0) {
-            apply_affine(S.M, r, rn);
-            apply_rot(S.M, t, tn);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                rn[j] = r[j] + S.M[4 * j + 3];
-                tn[j] = t[j];
+    // ---- prepared affine map / elastic dE of a segment move (segment_rows_prepare) ----
+    __device__ __forceinline__ const double *bond_rows() const { return C.bond + (long long)rep * C.bond_stride; }
+    // accepted attempts of the batch before `slot` (bits only ever get set while a batch runs)
+    __device__ __forceinline__ unsigned accepted_before(int slot) const {
+        return *(volatile unsigned *)&B.accepted & ((1u << slot) - 1u);
+    }
+    // did one of the accepted attempts in `bits` write rows that attempt `slot` reads?  A segment move
+    // writes beads [ind0, indf) and reads one more bead on either side (batches hold ONE move type).
+    __device__ __forceinline__ bool rows_changed(unsigned bits, int slot) const {
+        const Prop &P = B.prop[slot];
+        bool hit = false;
+        if ((bits >> lane) & 1u) {
+            const Prop &Q = B.prop[lane];
+            hit = (Q.ind0 < P.indf + 1) && (P.ind0 - 1 < Q.indf);
+        }
+        return __any_sync(FULL_MASK, hit);
+    }
+    // one thread redoes the state-dependent half of attempt `slot` from the rows as they are now
+    __device__ __forceinline__ void rows_recompute(int mtype, int slot) {
+        if (lane == 0) {
+            Prop *Pp = &B.prop[slot];
+            if (segment_rows_prepare(R_(), T3_(), bond_rows(), C.N, mtype, Pp, nullptr)) {
+                if (BATCH) rng.seek_attempt(abase + (unsigned long long)slot, Pp->used);
+                double axis[3];
+                const uint32_t d1 = rng.next31(), d2 = rng.next31();
+                degenerate_axis(d1, d2, axis);
+                (void)segment_rows_prepare(R_(), T3_(), bond_rows(), C.N, mtype, Pp, axis);
             }
         }
+        __syncwarp();
     }
 
     // ======================================================== prepare
@@ -819,96 +982,23 @@ struct McWarp {
 #pragma unroll
         for (int j = 0; j < 3; j++) P.ax[j] = slide ? axis[j] * amp : axis[j]; // generate_translation_mat linalg.pyx:172-199
         if (BATCH) P.used = rng.position();
+        // ---- the state-dependent half of a segment move, from the rows as they are now ----
+        if ((crank || pivot || slide) && n > 0) {
+            if (segment_rows_prepare(R_(), T3_(), bond_rows(), N, mtype, &P, nullptr)) {
+                // degenerate crank-shaft axis: two more draws (move_funcs.pyx:229-230); in the batched
+                // mode they are draws `used`, `used + 1` of the attempt's own stream
+                double dax[3];
+                const uint32_t e1 = rng.next31(), e2 = rng.next31();
+                degenerate_axis(e1, e2, dax);
+                (void)segment_rows_prepare(R_(), T3_(), bond_rows(), N, mtype, &P, dax);
+            }
+        }
     }
 
     // ======================================================== stage 1
-    // lane 0: the affine map of attempt `P` from the current positions
-    // (arbitrary_axis_rotation linalg.pyx:62-139)
-    __device__ __forceinline__ void finalize_segment_lane0(int mtype, const Prop &P, int slot) {
-        const int N = C.N;
-        const double *Rr = R_();
-        const int ind0 = P.ind0, indf = P.indf;
-        if (mtype == CHROMO_SLIDE) {
-#pragma unroll
-            for (int j = 0; j < 3; j++) S.M[4 * j + 3] = P.ax[j];
-            return;
-        }
-        int ful;
-        double axis[3], Rm[9], pt[3];
-        if (mtype == CHROMO_CRANK_SHAFT) {
-            int a, b; // get_crank_shaft_axis move_funcs.pyx:157-234
-            if (ind0 == indf - 1 && ind0 == 0) { a = indf; b = ind0; }
-            else if (ind0 == indf - 1 && ind0 == N - 1) { a = ind0; b = ind0 - 1; }
-            else if (ind0 == 0 && indf == N) { a = indf - 1; b = ind0; }
-            else if (ind0 == 0) { a = indf; b = ind0; }
-            else if (indf == N) { a = indf - 1; b = ind0 - 1; }
-            else { a = indf; b = ind0 - 1; }
-            // get_crank_shaft_fulcrum move_funcs.pyx:237-280
-            if (ind0 == 0 && indf != N) ful = indf;
-            else if (ind0 != 0 && indf == N) ful = ind0 - 1;
-            else if (ind0 == 0 && indf == N) ful = ind0;
-            else ful = ind0 - 1;
-            load3(Rr + 3 * ful, pt);
-#pragma unroll
-            for (int j = 0; j < 3; j++) axis[j] = Rr[3 * a + j] - Rr[3 * b + j];
-            double mag = sqrt((axis[0] * axis[0] + axis[1] * axis[1]) + axis[2] * axis[2]);
-            if (mag < 1E-5) { // axis from the unit sphere: two more draws (move_funcs.pyx:229-230)
-                if (BATCH) rng.seek_attempt(abase + (unsigned long long)slot, P.used);
-                uint32_t d1 = rng.next31(), d2 = rng.next31();
-                degenerate_axis(d1, d2, axis);
-            } else {
-                double sc = 1.0 / mag;
-#pragma unroll
-                for (int j = 0; j < 3; j++) axis[j] = axis[j] * sc;
-            }
-        } else { // end pivot: get_end_pivot_fulcrum move_funcs.pyx:349-398
-            if (ind0 == 0 && indf != N) ful = indf;
-            else if (ind0 != 0 && indf == N) ful = ind0 - 1;
-            else if (ind0 == 0 && indf == N && P.aux == 1) ful = indf - 1;
-            else ful = ind0;
-            load3(Rr + 3 * ful, pt);
-#pragma unroll
-            for (int j = 0; j < 3; j++) axis[j] = P.ax[j];
-        }
-        rotation_3x3(axis, P.sn, P.cs, Rm);
-        double tv[3];
-        rotation_translation(axis, pt, P.sn, P.cs, tv);
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            S.M[4 * j] = Rm[3 * j];
-            S.M[4 * j + 1] = Rm[3 * j + 1];
-            S.M[4 * j + 2] = Rm[3 * j + 2];
-            S.M[4 * j + 3] = tv[j];
-        }
-    }
-
-    // ---- elastic / binding part of dE for the segment moves -----------------
-    __device__ __forceinline__ double segment_dE_poly(int kind, int ind0, int indf, int n, int binder,
-                                                      const signed char *newst, int ddbl[NB]) {
-        const int N = C.N;
-        if (kind != 2) {
-            // continuous_dE_poly polymers.pyx:1084-1146: four lanes, one bond energy each:
-            // 0 = left bond with the trial bead, 1 = left bond as is, 2 / 3 = right bond
-            const double *Rr = R_(), *T3 = T3_();
-            double e = 0.0;
-            if (lane < 4) {
-                const bool left = lane < 2;
-                const bool present = left ? (ind0 != 0) : (indf != N);
-                if (present) {
-                    const int bond = left ? ind0 - 1 : indf - 1;
-                    const int mbead = left ? ind0 : indf - 1;
-                    double r[3], t[3], rn[3], tn[3];
-                    load3(Rr + 3 * mbead, r);
-                    load3(T3 + 3 * mbead, t);
-                    trial_rt(kind, r, t, rn, tn);
-                    const int moved = (lane & 1) ? 0 : (left ? 2 : 1);
-                    e = pair_energy(C, rep, bond, moved, rn, tn);
-                }
-            }
-            const double e1 = __shfl_down_sync(FULL_MASK, e, 1);
-            const double d01 = e - e1; // lanes 0 and 2 hold (trial - current) of their bond
-            return __shfl_sync(FULL_MASK, d01, 0) + __shfl_sync(FULL_MASK, d01, 2);
-        }
+    // ---- binding part of dE (the elastic part of the other segment moves is prepared per batch) ----
+    __device__ __forceinline__ double binding_dE_poly(int ind0, int n, int binder, const signed char *newst,
+                                                      int ddbl[NB]) {
         // binding_dE / bead_binding_dE polymers.pyx:1383-1538
         const signed char *ST = ST_();
         const signed char *MOD = MOD_();
@@ -1023,7 +1113,15 @@ struct McWarp {
                         store3(row, x);
                         store3(row + 3, t);
                     } else {
-                        trial_rt(kind, x, t, y, tn);
+                        if (kind == 0) {
+                            apply_affine(S.M, x, y);
+                            apply_rot(S.M, t, tn);
+                        } else {
+                            for (int j = 0; j < 3; j++) {
+                                y[j] = x[j] + S.M[4 * j + 3];
+                                tn[j] = t[j];
+                            }
+                        }
                         store3(row, y);
                         store3(row + 3, tn);
                     }
@@ -1196,15 +1294,26 @@ struct McWarp {
         // stage 1 may run ahead of the attempt's turn unless it needs sequential draws or the
         // replica-wide HBM scratch (large tangent / binding moves)
         bool my_turn = !(NW > 1 && (tangent ? presel : (kind != 2 || n <= CB_NEWST)));
+        const bool segmove = !tangent && kind != 2;
+        unsigned seen = 0u; // accepted attempts of the batch whose writes the prepared map / elastic dE reflect
+        CB_T0();
         if (my_turn) wait_turn(slot);
+        CB_LAP(2);
         while (true) {
             // ================= stage 1: bead rows only =================
 #pragma unroll
             for (int m = 0; m < NB; m++) ddbl[m] = 0;
             if (!tangent) {
-                if (lane == 0) {
-                    if (kind != 2) finalize_segment_lane0(mtype, P, slot);
-                    else if (BATCH) { // new states of this attempt (sequential mode drew them in prepare)
+                if (segmove) {
+                    // the map and the elastic dE were prepared with the batch; redo them if an attempt
+                    // accepted since then wrote this segment's rows or its neighbours'
+                    const unsigned now = accepted_before(slot);
+                    if (rows_changed(now & ~seen, slot)) rows_recompute(mtype, slot);
+                    seen = now;
+                    if (lane < 12) S.M[lane] = P.M[lane];
+                    dE_poly = P.dE_poly;
+                } else if (lane == 0) {
+                    if (BATCH) { // new states of this attempt (sequential mode drew them in prepare)
                         signed char *dst = (n <= CB_NEWST) ? S.newst : (C.st_new + (long long)rep * N);
                         if (n == 1) dst[0] = (signed char)P.newst0;
                         else {
@@ -1214,10 +1323,14 @@ struct McWarp {
                     }
                 }
                 __syncwarp();
+                CB_LAP(12);
                 if (kind == 2) newst = (n <= CB_NEWST) ? S.newst : (C.st_new + (long long)rep * N);
-                dE_poly = segment_dE_poly(kind, ind0, P.indf, n, binder, newst, ddbl);
-                if (C.field_active) conf = field_scatter<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst);
-                else if (kind != 2 && C.confine_type != CHROMO_CONFINE_NONE)
+                if (kind == 2) dE_poly = binding_dE_poly(ind0, n, binder, newst, ddbl);
+                CB_LAP(13);
+                if (C.field_active) {
+                    conf = field_scatter<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst);
+                    CB_LAP(14);
+                } else if (kind != 2 && C.confine_type != CHROMO_CONFINE_NONE)
                     dE_field = confinement_dE_segment(C, S, rep, lane, kind, ind0, n);
             } else if (n == 1) {
                 if (lane == 0) S.tinds[0] = P.aux;
@@ -1247,12 +1360,16 @@ struct McWarp {
                 __syncwarp();
                 dE_poly = tangent_eval_multi(tinds, n, P.sn, P.cs, small, false, false, att, 0u);
             }
+            CB_LAP(1);
             if (my_turn) break;
             wait_turn(slot);
+            CB_LAP(2);
             my_turn = true;
-            if (!stale(mtype, slot)) break;
+            if (segmove ? !rows_changed(accepted_before(slot) & ~seen, slot) : !stale(mtype, slot)) break;
             if (!tangent && C.field_active) table_clear(H, S, NCOL, lane); // rows changed under stage 1: redo it
+            CB_LAP(3);
         }
+        CB_LAP(3);
         // ================= stage 2: density, Metropolis, commit =================
         if (!tangent) {
             if (C.field_active)
@@ -1268,6 +1385,7 @@ struct McWarp {
             }
             __syncwarp();
         }
+        CB_LAP(4);
         // Metropolis (mc_sim.pyx:163-171)
         double dE = 0.0;
         dE += dE_poly;
@@ -1307,6 +1425,7 @@ struct McWarp {
             B.algo_bytes += ab;
         }
         acc = __shfl_sync(FULL_MASK, acc, 0);
+        CB_LAP(5);
         // accept (moves.pyx:156-239)
         if (acc) {
             if (!tangent) segment_commit(kind, ind0, n, binder, newst);
@@ -1319,9 +1438,15 @@ struct McWarp {
                 tangent_commit_large(tinds, n, P.sn, P.cs);
             }
         }
+        CB_LAP(6);
         pass_turn(slot, acc);
         if (!tangent && C.field_active) table_clear(H, S, NCOL, lane);
         __syncwarp();
+        CB_LAP(7);
+#ifdef CB_PHASE_TIMERS
+        tacc[11] += 1;
+        tacc[15] += (unsigned long long)n;
+#endif
     }
 
     // pull the rows a later attempt will read towards the SM while this one runs
@@ -1368,6 +1493,7 @@ struct McWarp {
     // a batch of `cnt` attempts of one move type: prepare (lanes of warp 0), then the warps take
     // the attempts round-robin
     __device__ __forceinline__ void run(int mtype, int cnt) {
+        CB_T0();
         if (wid == 0) {
             prepare(mtype, cnt);
             if (lane == 0) {
@@ -1375,14 +1501,22 @@ struct McWarp {
                 *(volatile unsigned *)&B.accepted = 0u;
             }
         }
+        CB_LAP(8);
         block_sync();
+        CB_LAP(9);
 #pragma unroll 1
         for (int j = wid; j < cnt; j += NW) {
+            CB_T0();
             if (j + NW < cnt) prefetch_attempt(mtype, B.prop[j + NW], j + NW);
+            CB_LAP(0);
             attempt(mtype, j);
         }
         abase += (unsigned long long)cnt;
-        block_sync();
+        {
+            CB_T0();
+            block_sync();
+            CB_LAP(9);
+        }
     }
 
     // tangent rotation of more than CB_TAN_SMALL beads (rare): indices in HBM scratch,
@@ -1509,6 +1643,14 @@ __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, 1)
                 }
                 W.update_amplitudes(m); // also for moves that are off (mc_sim.pyx:103)
             }
+#ifdef CB_PHASE_TIMERS
+            {
+                long long t0_ = clock64();
+                __syncthreads();
+                W.tacc[10] += (unsigned long long)(clock64() - t0_);
+                if (active) W.flush_timers(m);
+            }
+#endif
             // The block's replicas enter the next move type together.  (Measured on B200: skipping
             // the barrier before the short move types -- 1 end-pivot, 10 binding attempts -- costs
             // more in lost instruction-cache sharing than the wait for the slowest replica does.)
