@@ -115,6 +115,109 @@ class PolymerBase(TransformedObject):
         if self.lp == 0:
             raise ValueError("Specify the persistence length in the subclass of Polymer")
 
+    # ---- snapshot I/O: the reference's CSV schema (polymers.pyx:575-792) ----
+    def to_dataframe(self):
+        """One row per bead under a two-level header: (r|t3|t2, x|y|z), (states, binder),
+        (chemical_mods, mark), then single-level columns bead_length (N-1 bond lengths and a
+        trailing 0), the other per-polymer arrays (`max_binders`, broadcast) and the scalars
+        (`name`, `lp`, ...: value in row 0, empty below).  Same columns, order and cell text as
+        PolymerBase.to_dataframe (polymers.pyx:575-668)."""
+        import pandas as pd
+        n = self.num_beads
+        cols, data = [], []
+        held = [str(a) for a in self._arrays if hasattr(self, str(a))]
+        for name in held:
+            if name in self._3d_arrays:
+                arr = np.asarray(getattr(self, name), dtype=np.float64)
+                for k, axis in enumerate("xyz"):
+                    cols.append((name, axis))
+                    data.append(arr[:, k])
+        if len(self.chemical_mod_names) > 0:
+            st = np.asarray(self.states)
+            for j, nm in enumerate(self.binder_names):
+                cols.append(("states", str(nm)))
+                data.append(st[:, j])
+            cm = np.asarray(self.chemical_mods)
+            for j, nm in enumerate(self.chemical_mod_names):
+                cols.append(("chemical_mods", str(nm)))
+                data.append(cm[:, j].astype(int))
+        cols.append(("bead_length", ""))
+        data.append(np.append(np.asarray(self.bead_length, dtype=np.float64), 0.0))
+        for name in held:
+            if name in self._3d_arrays or name in ("states", "chemical_mods", "bead_length"):
+                continue
+            cols.append((name, ""))
+            data.append(np.broadcast_to(np.asarray(getattr(self, name)), (n,)))
+        for name in self._single_values:
+            name = str(name)
+            if not hasattr(self, name):
+                continue
+            col = np.full(n, "", dtype=object)
+            val = getattr(self, name)
+            col[0] = str(float(val)) if name != "name" else str(val)
+            cols.append((name, ""))
+            data.append(col)
+        df = pd.DataFrame({i: d for i, d in enumerate(data)})
+        df.columns = pd.MultiIndex.from_tuples(cols)
+        return df
+
+    def to_csv(self, path):
+        """polymers.pyx:670-684."""
+        return self.to_dataframe().to_csv(path)
+
+    def to_file(self, path):
+        """Synonym of `to_csv` (polymers.pyx:686-693)."""
+        return self.to_csv(path)
+
+    @classmethod
+    def from_dataframe(cls, df, name=None, **kwargs):
+        """Inverse of `to_dataframe` (polymers.pyx:713-765): the top-level column names are
+        the constructor's keyword arguments."""
+        top = list(dict.fromkeys(df.columns.get_level_values(0)))
+        kw = {}
+        for key in top:
+            kw[key] = np.array(df[key].to_numpy(), order="C", copy=True)  # pandas hands out read-only views
+        if "states" in top:
+            kw["binder_names"] = df["states"].columns.to_numpy()
+            kw["states"] = np.array(kw["states"], dtype=np.int64, order="C")
+        if "chemical_mods" in top:
+            kw["chemical_mod_names"] = df["chemical_mods"].columns.to_numpy()
+            kw["chemical_mods"] = np.array(kw["chemical_mods"], dtype=np.int64, order="C")
+        for key in ("r", "t3", "t2"):
+            if key in kw:
+                kw[key] = np.array(kw[key], dtype=np.float64, order="C")
+        if "max_binders" in top:
+            kw["max_binders"] = int(np.ravel(kw["max_binders"])[0])
+        stored = np.ravel(kw.pop("name"))[0] if "name" in top else None
+        kw["name"] = name if name is not None else (stored if stored is not None else "unnamed")
+        for key in ("lp", "lt", "bp_wrap"):
+            if key in top:
+                kw[key] = float(np.ravel(kw[key])[0])
+        if "bead_length" in top:
+            kw["bead_length"] = np.ravel(kw["bead_length"])[:-1].astype(float)
+        kw.update(kwargs)
+        return cls(**kw)
+
+    @classmethod
+    def from_csv(cls, csv_file):
+        """polymers.pyx:695-710 (reads a file written by `to_csv`)."""
+        return cls.from_file(csv_file)
+
+    @classmethod
+    def from_file(cls, path, name=None, **kwargs):
+        """polymers.pyx:767-792: the polymer is named after the file unless `name` is given."""
+        import pandas as pd
+        if name is None:
+            name = str(path).split("/")[-1].split(".")[0]
+        # round-trip float parsing: a snapshot reloads bit for bit (the reference's default parser can be
+        # off by an ulp, which a resumed run would carry along)
+        df = pd.read_csv(path, header=[0, 1], index_col=0, float_precision="round_trip")
+        return cls.from_dataframe(df, name, **kwargs)
+
+    def update_log_path(self, log_path):
+        """polymers.pyx:794-802."""
+        self.log_path = log_path
+
     def get_num_binders(self):
         return self.states.shape[1]
 

@@ -6,11 +6,14 @@ TEST INFRASTRUCTURE ONLY.  Nothing in the product (chromo_b200/) imports this.
 What it does:
   1. copies /root/reference/chromo to a scratch dir under /tmp (the reference
      tree is read-only and must not be written to);
-  2. applies the two one-line *toolchain compatibility* patches that the
+  2. applies the three one-line *toolchain compatibility* patches that the
      container's Cython 3.3 / pandas 3 need (no arithmetic is touched):
        - chromo/mc/moves.pxd:41-43 + moves.pyx:345  `cpdef list move_list`
          (Cython 3: "Variables cannot be declared with cpdef")
        - chromo/binders.pyx:237  DataFrame.append -> pd.concat
+       - chromo/polymers.pyx:665  `df[name] = arr_temp` with an (N, 1) object
+         array (pandas 3: "Buffer has wrong number of dimensions") ->
+         `arr_temp[:, 0]`; only the CSV snapshot writer (to_dataframe) uses it
   3. adds `oracle_shim.pyx`, a thin `def` wrapper around the reference's
      `cdef` methods (compute_dE, propose, update_affected_densities) so tests
      can call them from Python;
@@ -114,6 +117,9 @@ def build(force: bool = False) -> bool:
         _patch(work / "chromo/binders.pyx",
                "df = df.append(binder.dict(), ignore_index=True)",
                "df = pd.concat([df, pd.DataFrame([binder.dict()])], ignore_index=True)")
+        # patch 3: pandas 3 refuses an (N, 1) object array as a column (snapshot writer only)
+        _patch(work / "chromo/polymers.pyx", "            df[name] = arr_temp\n",
+               "            df[name] = arr_temp[:, 0]\n")
         (work / "oracle_shim.pyx").write_text(SHIM)
         (work / "setup_ref.py").write_text(SETUP % (ncpu, ncpu))
         env = dict(os.environ)

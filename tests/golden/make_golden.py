@@ -145,7 +145,26 @@ def golden_mc_sim(name, spec, steps, srand_seed, np_seed, mu_adjust=1.0, per_cyc
     print(name, "success", out["num_success"], "E", out["E_field"], out["E_poly"])
 
 
+def golden_csv(name, spec, polymer_name):
+    """CSV snapshot of the spec's polymer written by the reference's own writer
+    (PolymerBase.to_csv, polymers.pyx:575-684)."""
+    import warnings
+    poly, _, _, _ = O.ref_objects(spec)
+    poly.name = polymer_name
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        poly.to_csv(str(OUT / f"{name}.csv"))
+    np.savez_compressed(OUT / f"{name}_spec.npz", **spec_to_npz(spec))
+
+
 if __name__ == "__main__":
+    only = sys.argv[1:]  # e.g. `make_golden.py csv`: just the snapshot CSVs
+    # snapshot CSVs: two-binder chromatin and a null_reader SSWLC (lp != 53 -> the SSWLC class)
+    golden_csv("snapshot_chromatin", O.make_spec(N=40, nb=2, seed=11, cross_talk=-1.5), "Chr-1")
+    golden_csv("snapshot_sswlc", O.make_spec(N=25, nb=1, seed=12, binders=[dict(O.NULL_READER)], confine="",
+                                             grid=4, random_states=False, lp=10.0), "homopolymer")
+    if only == ["csv"]:
+        sys.exit(0)
     # C1-like: homopolymer, null_reader, periodic box (confine_type="")
     c1 = O.make_spec(N=200, nb=1, seed=1, binders=[dict(O.NULL_READER)], confine="", grid=8,
                      random_states=False)
