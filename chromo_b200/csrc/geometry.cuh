@@ -102,6 +102,38 @@ static __device__ CB_NOINLINE double2 sincos_ni(double x) {
     return make_double2(s, c);
 }
 static __device__ CB_NOINLINE double acos_ni(double x) { return acos(x); }
+static __device__ CB_NOINLINE double2 sincospi_ni(double x) {
+    double s, c;
+    sincospi(x, &s, &c);
+    return make_double2(s, c);
+}
+
+// Point on the unit sphere from two uniforms u1, u2 in [0, 1]
+// (uniform_sample_unit_sphere linalg.pyx:23-59: phi = 2 pi u1, theta = acos(2 u2 - 1),
+// (cos phi sin theta, sin phi sin theta, cos theta)).
+//   EXACT = true : the reference's own sequence of libm calls (replay / parity mode: the same
+//                  draws give the same axis to the last bit under the same libm);
+//   EXACT = false: cos theta = x and sin theta = sqrt((1 - x)(1 + x)) for x = 2 u2 - 1, and
+//                  sincospi(2 u1): the same point to ~1 ulp at a third of the instructions and
+//                  without the out-of-line acos / sincos (production mode, whose counter-based
+//                  draws are not the reference's anyway).
+template <bool EXACT>
+__device__ __forceinline__ void unit_sphere_point(double u1, double u2, double v[3]) {
+    if (EXACT) {
+        const double2 ph = sincos_ni(u1 * (2.0 * 3.14159265358979323846));
+        const double2 th = sincos_ni(acos_ni(u2 * 2.0 - 1.0));
+        v[0] = ph.y * th.x;
+        v[1] = ph.x * th.x;
+        v[2] = th.y;
+    } else {
+        const double x = u2 * 2.0 - 1.0;
+        const double st = sqrt((1.0 - x) * (1.0 + x));
+        const double2 ph = sincospi_ni(u1 * 2.0);
+        v[0] = ph.y * st;
+        v[1] = ph.x * st;
+        v[2] = x;
+    }
+}
 
 // arbitrary_axis_rotation linalg.pyx:62-139 given sin / cos of the angle.  M is
 // 3x4 row-major (M[4*j+3] is the translation column).

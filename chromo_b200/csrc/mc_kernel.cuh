@@ -971,11 +971,7 @@ struct McWarp {
         }
         double axis[3] = {0.0, 0.0, 0.0};
         if (sphere) {
-            const double2 ph = sincos_ni(u01(d1) * (2.0 * 3.14159265358979323846));
-            const double2 th = sincos_ni(acos_ni(u01(d2) * 2.0 - 1.0));
-            axis[0] = ph.y * th.x;
-            axis[1] = ph.x * th.x;
-            axis[2] = th.y;
+            unit_sphere_point<!BATCH>(u01(d1), u01(d2), axis);
         }
         P.sn = sn;
         P.cs = cs;
@@ -1170,11 +1166,7 @@ struct McWarp {
 #pragma unroll
                 for (int q = 0; q < 3; q++) axis[q] = axfix[q];
             } else {
-                const double2 ph = sincos_ni(u01(draws[2 * j]) * (2.0 * 3.14159265358979323846));
-                const double2 th = sincos_ni(acos_ni(u01(draws[2 * j + 1]) * 2.0 - 1.0));
-                axis[0] = ph.y * th.x;
-                axis[1] = ph.x * th.x;
-                axis[2] = th.y;
+                unit_sphere_point<!BATCH>(u01(draws[2 * j]), u01(draws[2 * j + 1]), axis);
             }
             rotation_3x3(axis, sn, cs, Rm);
             load3(T3 + 3 * bead, t3c);

@@ -125,6 +125,11 @@ static inline double __hiloint2double(int hi, int lo) {
 }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+// CUDA's sincospi (production-mode sphere points); the emulator only has to agree to rounding
+static inline void sincospi(double x, double *s, double *c) {
+    *s = sin(3.14159265358979323846 * x);
+    *c = cos(3.14159265358979323846 * x);
+}
 struct double2 { double x, y; };
 struct double3 { double x, y, z; };
 struct int2 { int x, y; };
