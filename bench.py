@@ -16,9 +16,10 @@ snapshot) over every replica = R * sweeps * 161 move attempts.
 value : attempts/s with the state resident in HBM (CUDA events on the kernel's
         stream around K back-to-back mc_sim launches, max over ranks).
 e2e   : the same metric through the host-facing call (ReplicaEnsemble.mc_sim with
-        sync_host=True): per step the r/t3/t2/states arrays go pinned-host ->
-        device, the kernel runs, and they come back -- like handing the
-        reference its numpy arrays.
+        sync_host=True -> chromo_mc_sim_host): per step the r/t3/t2/states/marks
+        arrays go pinned-host -> device, the kernel runs, and r/t3/t2/states come
+        back -- like handing the reference its numpy arrays.  Copies and kernel are
+        pipelined over replica chunks inside the one call.
 roofline : dominant kernel = mc_sim_kernel; achieved = algorithmic bytes
         (counted in-kernel with SURVEY.md 8d's per-attempt formula) / kernel time.
 cpu_baseline : the reference's own Cython mc_sim (oracle/_ref, kind "reference";
@@ -317,6 +318,11 @@ def run_ours(args):
     h2d = (3 * R * N * 24 + 2 * R * N * 1 * 8) * world  # r, t3, t2 + states, chemical_mods (int64), all ranks
     d2h = (3 * R * N * 24 + R * N * 1 * 8) * world      # r, t3, t2 + states, all ranks
     Ke = max(1, min(K, args.e2e_steps))
+    # replica chunks of the pipelined host path (the library's automatic rule, include/chromo_b200.h)
+    nblk = -(-R // rpb)
+    e2e_chunks = 4
+    while e2e_chunks > 1 and e2e_chunks * -(-nblk // e2e_chunks) > torch.cuda.get_device_properties(local).multi_processor_count:
+        e2e_chunks -= 1
     ens.mc_sim(S, 1.0, 5000, sync_host=True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -359,8 +365,10 @@ def run_ours(args):
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=Wm,
             ms_per_step=ms_total / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
             data="synthetic", config=dict(workload_config(args, cap), warps_per_replica=warps, replicas_per_block=rpb),
-            e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=Ke),
-            gpu_launches=K + 4 * Ke,
+            e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=Ke,
+                     ms_per_step=e2e_ms / Ke, replica_chunks=e2e_chunks,
+                     path="chromo_mc_sim_host: pinned host arrays -> device -> kernel -> host, pipelined over replica chunks"),
+            gpu_launches=K + 4 * e2e_chunks * Ke,  # e2e: per replica chunk 2 narrowing kernels, the MC kernel, 1 widening
             clocks=clocks,
             roofline=dict(bound="hbm", achieved=achieved, peak=peaks, unit="GB/s", frac=achieved / peaks,
                           traffic=traffic, peak_source=peak_src, kernel="mc_sim_kernel<PhiloxRng,1>",

@@ -65,7 +65,7 @@ SYMBOLS = [
     "chromo_upload_state", "chromo_download_state", "chromo_download_density",
     "chromo_upload_density", "chromo_field_recompute", "chromo_field_energy",
     "chromo_elastic_energy", "chromo_chi_observable", "chromo_srand", "chromo_numpy_seed",
-    "chromo_mc_sim", "chromo_get_moves", "chromo_set_moves", "chromo_last_attempts", "chromo_last_algo_bytes",
+    "chromo_mc_sim", "chromo_mc_sim_host", "chromo_get_moves", "chromo_set_moves", "chromo_last_attempts", "chromo_last_algo_bytes",
     "chromo_mc_step",
 ]
 
@@ -97,6 +97,8 @@ def _declare(L):
     L.chromo_srand.argtypes = [_vp, _pu]
     L.chromo_numpy_seed.argtypes = [_vp, _pu]
     L.chromo_mc_sim.argtypes = [_vp, C.c_int64, _vp, C.c_double, C.c_uint64, C.c_int, _pu]
+    L.chromo_mc_sim_host.argtypes = [_vp, C.c_int64, _vp, C.c_double, C.c_uint64, C.c_int, _pu,
+                                     _pd, _pd, _pd, _pl, _pl, C.c_int64]
     L.chromo_get_moves.argtypes = [_vp, _vp]
     L.chromo_set_moves.argtypes = [_vp, _vp]
     L.chromo_last_attempts.argtypes = [_vp]

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/chromo_b200.h"
@@ -51,6 +52,11 @@ struct chromo_ctx {
     int *d_dcount = nullptr;
     long long *d_stage = nullptr;
     int64_t stage_elems = 0;
+    // host-array path (chromo_mc_sim_host): one stream + int64 staging buffer per replica chunk
+    std::vector<cudaStream_t> chunk_streams;
+    std::vector<cudaEvent_t> chunk_uploaded; // chunk k's upload is complete (chunk k+1's upload waits for it)
+    std::vector<long long *> chunk_stage;
+    int64_t chunk_stage_elems = 0;
     DebugOut *d_dbg = nullptr;
     long long *d_dbg_inds = nullptr, *d_dbg_touched = nullptr;
     double *d_dbg_rows = nullptr, *d_dbg_dtrial = nullptr;
@@ -231,6 +237,12 @@ extern "C" int chromo_ctx_destroy(chromo_ctx *c) {
     if (!c) return CHROMO_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (cudaStream_t st : c->chunk_streams) {
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+    }
+    for (cudaEvent_t e : c->chunk_uploaded) cudaEventDestroy(e);
+    for (long long *p : c->chunk_stage) cudaFree(p);
     for (void *p : c->allocs) cudaFree(p);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -644,6 +656,120 @@ extern "C" int chromo_mc_sim(chromo_ctx *c, int64_t num_mc_steps, chromo_move_st
     else return fail(CHROMO_ERR_ARG, "unknown rng_mode %d", rng_mode);
     if (e) return fail(CHROMO_ERR_CUDA, "mc_sim launch failed: %s", cudaGetErrorString((cudaError_t)e));
     CK(cudaGetLastError());
+    if (moves) {
+        CK(cudaMemcpyAsync(moves, d.moves, sizeof(chromo_move_state) * d.R * CHROMO_NUM_MOVES,
+                           cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return CHROMO_OK;
+}
+
+// mc_sim on host arrays, pipelined over replica chunks (see include/chromo_b200.h)
+extern "C" int chromo_mc_sim_host(chromo_ctx *c, int64_t num_mc_steps, chromo_move_state *moves,
+                                  double mu_adjust_factor, uint64_t seed, int rng_mode,
+                                  const uint32_t *numpy_seeds, double *r, double *t3, double *t2,
+                                  int64_t *states, const int64_t *mods, int64_t n_chunks) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    if (!r || !t3 || !t2 || !states || !mods) return fail(CHROMO_ERR_ARG, "null host array");
+    if (num_mc_steps < 0) return fail(CHROMO_ERR_ARG, "negative num_mc_steps");
+    if (rng_mode != CHROMO_RNG_REPLAY && rng_mode != CHROMO_RNG_PHILOX) return fail(CHROMO_ERR_ARG, "unknown rng_mode %d", rng_mode);
+    if (n_chunks < 0 || n_chunks > 64) return fail(CHROMO_ERR_ARG, "n_chunks must be in [0, 64]");
+    c->have_state = true; // the state arrives with this call
+    int rc = check_ready(c);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    DevCtx &d = c->d;
+    if (moves && (rc = chromo_set_moves(c, moves))) return rc;
+    if (rng_mode == CHROMO_RNG_REPLAY && numpy_seeds && (rc = chromo_numpy_seed(c, numpy_seeds))) return rc;
+    CK(cudaStreamSynchronize(c->stream)); // everything queued on the context's own stream comes first
+    // chunks are whole thread blocks; automatic = as many (<= 4) as keep every chunk's blocks resident at once
+    const int rpb = c->rpb, nblk = (d.R + rpb - 1) / rpb;
+    int chunks = (int)n_chunks;
+    if (chunks == 0) {
+        chunks = 4;
+        while (chunks > 1 && chunks * ((nblk + chunks - 1) / chunks) > c->sm_count) chunks--;
+    }
+    chunks = std::max(1, std::min(chunks, nblk));
+    const int blk_per_chunk = (nblk + chunks - 1) / chunks;
+    const int64_t rep_per_chunk = (int64_t)blk_per_chunk * rpb;
+    const int64_t stage_need = rep_per_chunk * d.N * d.nb;
+    if (stage_need > c->chunk_stage_elems) { // (re)size the staging buffers
+        for (long long *p : c->chunk_stage) cudaFree(p);
+        c->chunk_stage.clear();
+        c->chunk_stage_elems = stage_need;
+    }
+    while ((int)c->chunk_streams.size() < chunks) {
+        cudaStream_t st;
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        c->chunk_streams.push_back(st);
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->chunk_uploaded.push_back(e);
+    }
+    while ((int)c->chunk_stage.size() < chunks) {
+        void *q = nullptr;
+        CK(cudaMalloc(&q, (size_t)c->chunk_stage_elems * 8));
+        c->chunk_stage.push_back((long long *)q);
+    }
+#ifndef CHROMO_HOST_EMU
+    // development aid (CHROMO_TIMELINE=1): per chunk, ms from the start of the call to the end of its
+    // upload, its kernel and its download, printed to stderr
+    const bool timeline = getenv("CHROMO_TIMELINE") != nullptr;
+    std::vector<cudaEvent_t> evs;
+    if (timeline) {
+        evs.resize(1 + 3 * (size_t)chunks);
+        for (auto &e : evs) cudaEventCreate(&e);
+        cudaEventRecord(evs[0], c->chunk_streams[0]);
+    }
+#define CB_MARK(i) do { if (timeline) cudaEventRecord(evs[1 + 3 * k + (i)], st); } while (0)
+#else
+#define CB_MARK(i) do { } while (0)
+#endif
+    for (int k = 0; k < chunks; k++) {
+        const int64_t first = (int64_t)k * rep_per_chunk, n = std::min<int64_t>(rep_per_chunk, d.R - first);
+        if (n <= 0) break;
+        cudaStream_t st = c->chunk_streams[k];
+        long long *stage = c->chunk_stage[k];
+        const size_t off = (size_t)first * d.N, cnt = (size_t)n * d.N, cs = cnt * d.nb;
+        // uploads go over the link one chunk at a time, in order: left to itself the copy engine
+        // time-slices the streams and every chunk's data arrives at the end (measured on B200)
+        if (k > 0) CK(cudaStreamWaitEvent(st, c->chunk_uploaded[k - 1], 0));
+        CK(cudaMemcpyAsync(d.r + off * 3, r + off * 3, cnt * 24, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d.t3 + off * 3, t3 + off * 3, cnt * 24, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d.t2 + off * 3, t2 + off * 3, cnt * 24, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(stage, states + off * d.nb, cs * 8, cudaMemcpyHostToDevice, st));
+        CB_LAUNCH(narrow_i64_kernel, (unsigned)((cs + 255) / 256), 256, 0, st, (const long long *)stage, d.states + off * d.nb, (long long)cs);
+        CK(cudaMemcpyAsync(stage, mods + off * d.nb, cs * 8, cudaMemcpyHostToDevice, st));
+        CB_LAUNCH(narrow_i64_kernel, (unsigned)((cs + 255) / 256), 256, 0, st, (const long long *)stage, d.mods + off * d.nb, (long long)cs);
+        CK(cudaEventRecord(c->chunk_uploaded[k], st));
+        CB_MARK(0);
+        McSimArgs a{d, (long long)num_mc_steps, mu_adjust_factor, (unsigned long long)seed, c->cap, c->warps, c->rpb, st,
+                    (int)first, (int)n};
+        int e;
+        if (rng_mode == CHROMO_RNG_REPLAY) e = d.nb <= 2 ? cb_mc_sim_replay_12(a) : cb_mc_sim_replay_34(a);
+        else e = d.nb <= 2 ? cb_mc_sim_philox_12(a) : cb_mc_sim_philox_34(a);
+        if (e) return fail(CHROMO_ERR_CUDA, "mc_sim launch failed: %s", cudaGetErrorString((cudaError_t)e));
+        CB_MARK(1);
+        CK(cudaMemcpyAsync(r + off * 3, d.r + off * 3, cnt * 24, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(t3 + off * 3, d.t3 + off * 3, cnt * 24, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(t2 + off * 3, d.t2 + off * 3, cnt * 24, cudaMemcpyDeviceToHost, st));
+        CB_LAUNCH(widen_i8_kernel, (unsigned)((cs + 255) / 256), 256, 0, st, d.states + off * d.nb, stage, (long long)cs);
+        CK(cudaMemcpyAsync(states + off * d.nb, stage, cs * 8, cudaMemcpyDeviceToHost, st));
+        CB_MARK(2);
+        CK(cudaGetLastError());
+    }
+    for (int k = 0; k < chunks; k++) CK(cudaStreamSynchronize(c->chunk_streams[k]));
+#ifndef CHROMO_HOST_EMU
+    if (timeline) {
+        for (int k = 0; k < chunks; k++) {
+            float t[3] = {0, 0, 0};
+            for (int i = 0; i < 3; i++) cudaEventElapsedTime(&t[i], evs[0], evs[1 + 3 * k + i]);
+            fprintf(stderr, "[chromo timeline] chunk %d: uploaded %.2f ms, kernel done %.2f ms, downloaded %.2f ms\n", k, t[0], t[1], t[2]);
+        }
+        for (auto &e : evs) cudaEventDestroy(e);
+    }
+#endif
+#undef CB_MARK
     if (moves) {
         CK(cudaMemcpyAsync(moves, d.moves, sizeof(chromo_move_state) * d.R * CHROMO_NUM_MOVES,
                            cudaMemcpyDeviceToHost, c->stream));

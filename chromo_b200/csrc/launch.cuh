@@ -47,6 +47,7 @@ struct McSimArgs {
     int warps; // warps per replica (Philox kernels: 1 or 2; the replay kernels always run 1)
     int rpb;   // replicas per block (1..CB_MAX_RPB)
     cudaStream_t stream;
+    int rep0 = 0, nrep = -1; // replica sub-range [rep0, rep0 + nrep) (nrep < 0: all of the context's)
 };
 struct McStepArgs {
     DevCtx d;

@@ -28,8 +28,10 @@ static int sim_launch(const McSimArgs &a) {
     const size_t smem = (size_t)a.rpb * cb_replica_smem(a.cap, a.d.ncol, NW);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    CB_LAUNCH(k, (a.d.R + a.rpb - 1) / a.rpb, 32 * NW * a.rpb, smem, a.stream, a.d, a.num_mc_steps, a.mu_adjust,
-              a.seed, a.cap, a.rpb);
+    const int nrep = a.nrep < 0 ? a.d.R - a.rep0 : a.nrep;
+    if (nrep <= 0) return 0;
+    CB_LAUNCH(k, (nrep + a.rpb - 1) / a.rpb, 32 * NW * a.rpb, smem, a.stream, a.d, a.num_mc_steps, a.mu_adjust,
+              a.seed, a.cap, a.rpb, a.rep0, a.rep0 + nrep);
     return (int)cudaGetLastError();
 }
 template <int NB>

@@ -1597,11 +1597,12 @@ __device__ __forceinline__ void rng_store<PhiloxRng>(const DevCtx &C, ReplicaSh 
 template <class Rng, int NB, int NW>
 __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, 1)
     mc_sim_kernel(const CB_GRID_CONSTANT DevCtx C, long long num_mc_steps, double mu_adjust,
-                  unsigned long long seed, int cap, int rpb) {
+                  unsigned long long seed, int cap, int rpb, int rep0, int rep_end) {
     CB_DYN_SMEM(dyn);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, local = warp / NW, wid = warp % NW;
-    const int rep = blockIdx.x * rpb + local, rtid = wid * 32 + lane; // thread index within the replica
-    const bool active = rep < C.R; // the last block may hold fewer replicas; its spare warps only keep the barriers
+    // replicas [rep0, rep_end) of the context: the host-array path launches one grid per replica chunk
+    const int rep = rep0 + blockIdx.x * rpb + local, rtid = wid * 32 + lane; // thread index within the replica
+    const bool active = rep < rep_end; // the last block may hold fewer replicas; its spare warps only keep the barriers
     unsigned char *base = dyn + (size_t)local * cb_replica_smem(cap, C.ncol, NW);
     ReplicaSh &B = *(ReplicaSh *)base;
     WarpSh &S = *(WarpSh *)(base + CB_REPLICA_SH_BYTES + (size_t)wid * CB_WARP_SH_BYTES);

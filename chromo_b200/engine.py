@@ -207,6 +207,34 @@ class Engine:
         check(self._L.chromo_mc_sim(self._h, int(num_mc_steps), mp, float(mu_adjust_factor),
                                     int(seed) & 0xFFFFFFFFFFFFFFFF, int(rng_mode), _lib.uptr(ns)))
 
+    def mc_sim_host(self, num_mc_steps: int, r, t3, t2, states, mods, moves: Optional[np.ndarray] = None,
+                    mu_adjust_factor: float = 1.0, seed: int = 0, rng_mode: int = RNG_PHILOX, numpy_seeds=None,
+                    n_chunks: int = 0):
+        """mc_sim on HOST arrays in the reference's layouts, in place (r, t3, t2 [R,N,3] f64; states,
+        mods [R,N,nb] int64): upload, kernel and download pipelined over replica chunks
+        (chromo_mc_sim_host).  The arrays must be C-contiguous and of exactly these dtypes -- they are
+        written through their own memory, no copies are made."""
+        for name, a, dt in (("r", r, np.float64), ("t3", t3, np.float64), ("t2", t2, np.float64),
+                            ("states", states, np.int64), ("mods", mods, np.int64)):
+            want = self.R * self.N * (3 if dt is np.float64 else self.nb)
+            if not isinstance(a, np.ndarray) or a.dtype != dt or not a.flags.c_contiguous or a.size != want:
+                raise ValueError(f"`{name}` must be a C-contiguous {np.dtype(dt).name} array of {want} elements")
+        for name, a in (("r", r), ("t3", t3), ("t2", t2), ("states", states)):
+            if not a.flags.writeable:
+                raise ValueError(f"`{name}` is read-only: mc_sim writes its result into it")
+        mp = None
+        if moves is not None:
+            if moves.dtype != MOVE_DTYPE or not moves.flags.c_contiguous or moves.size != self.R * NUM_MOVES:
+                raise ValueError("moves must be a C-contiguous [R,5] array of MOVE_DTYPE")
+            mp = moves.ctypes.data_as(C.c_void_p)
+        ns = None
+        if numpy_seeds is not None:
+            ns = np.ascontiguousarray(np.broadcast_to(np.asarray(numpy_seeds, dtype=np.uint32), (self.R,)))
+        check(self._L.chromo_mc_sim_host(self._h, int(num_mc_steps), mp, float(mu_adjust_factor),
+                                         int(seed) & 0xFFFFFFFFFFFFFFFF, int(rng_mode), _lib.uptr(ns),
+                                         _lib.dptr(r), _lib.dptr(t3), _lib.dptr(t2), _lib.lptr(states),
+                                         _lib.lptr(mods), int(n_chunks)))
+
     def set_table_capacity(self, cap: int = 0) -> int:
         """Slots of the per-replica shared-memory delta-density hash (0 = auto)."""
         out = C.c_int64(0)

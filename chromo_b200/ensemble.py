@@ -114,16 +114,22 @@ class ReplicaEnsemble:
 
     # ---- the hot path -------------------------------------------------------
     def mc_sim(self, num_mc_steps: int, mu_adjust_factor: float = 1.0, random_seed: int = 0,
-               rng: str = "philox", sync_host: bool = True, numpy_seeds=None):
+               rng: str = "philox", sync_host: bool = True, numpy_seeds=None, n_chunks: int = 0):
         """`mc_sim` (mc_sim.pyx:26-103) for every replica.  With sync_host the
-        call is host-in / host-out like the reference's; without it the state
-        stays in HBM and the call returns as soon as the kernel is queued."""
+        call is host-in / host-out like the reference's: the host arrays go to the
+        device, the kernel runs and they come back, pipelined over `n_chunks` replica
+        chunks (0 = automatic; -1 = the unpipelined upload / run / download sequence).
+        Without it the state stays in HBM and the call returns as soon as the kernel is
+        queued."""
         mode = {"philox": RNG_PHILOX, "replay": RNG_REPLAY}[rng]
-        if sync_host:
+        ns = ((random_seed if numpy_seeds is None else numpy_seeds) if mode == RNG_REPLAY else None)
+        if sync_host and n_chunks >= 0:
+            self.engine.mc_sim_host(num_mc_steps, self.r, self.t3, self.t2, self.states, self.chemical_mods,
+                                    self.moves, mu_adjust_factor, random_seed, mode, numpy_seeds=ns,
+                                    n_chunks=n_chunks)
+        elif sync_host:
             self.push()
-            self.engine.mc_sim(num_mc_steps, self.moves, mu_adjust_factor, random_seed, mode,
-                               numpy_seeds=(random_seed if numpy_seeds is None else numpy_seeds)
-                               if mode == RNG_REPLAY else None)
+            self.engine.mc_sim(num_mc_steps, self.moves, mu_adjust_factor, random_seed, mode, numpy_seeds=ns)
             self.pull()
         else:
             self.engine.mc_sim(num_mc_steps, None, mu_adjust_factor, random_seed, mode,

@@ -210,6 +210,24 @@ int chromo_mc_sim(chromo_ctx *ctx, int64_t num_mc_steps, chromo_move_state *move
                   const uint32_t *numpy_seeds);
 int chromo_get_moves(chromo_ctx *ctx, chromo_move_state *moves /* [R][5] */);
 int chromo_set_moves(chromo_ctx *ctx, const chromo_move_state *moves /* [R][5] */);
+/* The same call on caller-owned HOST arrays, in and out -- what the reference's
+ * mc_sim does to the polymers' numpy arrays (mc_sim.pyx:26-103 mutates poly.r, t3, t2,
+ * states in place; moves.pyx:156-299).  r / t3 / t2: [R][N][3] f64, states / mods:
+ * [R][N][nb] int64, in the reference's layouts; states and the three coordinate
+ * arrays are overwritten with the result, mods is only read.  The replicas are
+ * processed in `n_chunks` chunks (0 = automatic: as many as keep every chunk's thread
+ * blocks resident at once, at most 4), each on its own stream: while chunk k runs,
+ * chunk k+1 is still arriving over PCIe and chunk k-1 is already on its way back.
+ * Pinned (page-locked) host arrays make the copies asynchronous; pageable ones work,
+ * serialised by the driver.  The voxel densities are the field's state, not the
+ * polymers' (fields.pxd:54): they stay on the device between calls, exactly as
+ * with chromo_upload_state + chromo_mc_sim + chromo_download_state, whose result
+ * this call reproduces bit for bit (each replica has its own RNG stream). */
+int chromo_mc_sim_host(chromo_ctx *ctx, int64_t num_mc_steps, chromo_move_state *moves,
+                       double mu_adjust_factor, uint64_t seed, int rng_mode,
+                       const uint32_t *numpy_seeds, double *r, double *t3, double *t2,
+                       int64_t *states, const int64_t *mods, int64_t n_chunks);
+
 /* attempts executed by the last chromo_mc_sim call, summed over replicas */
 int64_t chromo_last_attempts(chromo_ctx *ctx);
 /* algorithmic bytes those attempts needed (per attempt

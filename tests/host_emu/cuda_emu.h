@@ -173,6 +173,12 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, int) { *s = (void *)1; return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+typedef void *cudaEvent_t;
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, int) { *e = (void *)1; return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return 0; }
 static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n); return *p ? 0 : 2; }
 static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
 static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }

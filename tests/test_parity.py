@@ -305,3 +305,41 @@ def test_error_behaviour(backend, oracle_mod):
     with pytest.raises(_lib.ChromoError, match="set_binders"):
         e2.mc_sim(1, None, 1.0, 0, PHILOX)
     e.close(), e2.close()
+
+
+def test_host_array_path_matches_resident_path(backend, oracle_mod):
+    """chromo_mc_sim_host (host arrays in and out, pipelined over replica chunks) reproduces
+    upload + mc_sim + download bit for bit, for any chunking: replicas have their own streams."""
+    from chromo_b200.ensemble import ReplicaEnsemble, default_moves
+    O = oracle_mod
+    R, N = 9, 60
+    specs = [O.make_spec(N=N, nb=1, seed=50 + i) for i in range(R)]
+    st = lambda k: np.stack([s[k] for s in specs])
+    kw = dict(binders=specs[0]["binders"], bond_params=O.bond_params(specs[0]["bead_length"], 53.0),
+              grid=specs[0]["field"], bead_vol=(4 / 3) * np.pi * 5.0 ** 3, chi=1.0)
+    out = {}
+    for n_chunks in (-1, 0, 3):           # unpipelined; automatic; 3 ragged chunks (5 blocks of 2 replicas)
+        ens = ReplicaEnsemble(st("r"), st("t3"), st("t2"), st("states"), st("mods"),
+                              moves=default_moves(R, N, 16.5), **kw)
+        ens.engine.set_replicas_per_block(2)
+        for k in range(2):
+            ens.mc_sim(2, 1.0, 77 + k, n_chunks=n_chunks)
+        out[n_chunks] = (ens.r.copy(), ens.t3.copy(), ens.t2.copy(), ens.states.copy(), ens.moves.copy(),
+                         ens.density().copy())
+        assert ens.chemical_mods.tobytes() == st("mods").tobytes()
+        if n_chunks == 3:  # argument checking of the host path: dtype / layout / writability
+            with pytest.raises(ValueError):
+                ens.engine.mc_sim_host(1, ens.r.astype(np.float32), ens.t3, ens.t2, ens.states, ens.chemical_mods)
+            with pytest.raises(ValueError):
+                ens.engine.mc_sim_host(1, ens.r[:, ::2], ens.t3, ens.t2, ens.states, ens.chemical_mods)
+            ro = ens.states.copy()
+            ro.setflags(write=False)
+            with pytest.raises(ValueError):
+                ens.engine.mc_sim_host(1, ens.r, ens.t3, ens.t2, ro, ens.chemical_mods)
+        ens.close()
+    for n_chunks in (0, 3):
+        for a, b in zip(out[-1][:5], out[n_chunks][:5]):
+            assert a.tobytes() == b.tobytes()
+        # the initial full recompute adds with fp64 atomics in arrival order: densities agree to rounding
+        assert np.allclose(out[-1][5], out[n_chunks][5], rtol=1e-12, atol=1e-18)
+    assert not np.array_equal(out[-1][0], st("r"))
