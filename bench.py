@@ -240,7 +240,7 @@ def run_reference(args):
                 scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=workload_config(args, 0), cpu_baseline=cb,
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, cap):
@@ -385,10 +385,29 @@ def run_ours(args):
                 line["cpu_baseline"] = cb
             except Exception as e:  # never lose the GPU number to a baseline hiccup
                 line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=str(e)[:200])
-        print(json.dumps(line))
+        emit(line)
     ens.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route file descriptor 1 to stderr while the bench runs (NCCL and friends print banners to
+    stdout); `emit` writes the ONE JSON line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
@@ -408,6 +427,7 @@ def main():
     ap.add_argument("--rpb", type=int, default=0, help="replicas per thread block (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
