@@ -67,6 +67,8 @@ SYMBOLS = [
     "chromo_elastic_energy", "chromo_chi_observable", "chromo_srand", "chromo_numpy_seed",
     "chromo_mc_sim", "chromo_mc_sim_host", "chromo_get_moves", "chromo_set_moves", "chromo_last_attempts", "chromo_last_algo_bytes",
     "chromo_mc_step",
+    "chromo_cg_num_beads", "chromo_cg_chromatin", "chromo_refined_num_points", "chromo_refined_num_draws",
+    "chromo_refine_path", "chromo_enforce_spherical_confinement",
 ]
 
 
@@ -108,6 +110,17 @@ def _declare(L):
     L.chromo_mc_step.argtypes = [_vp, C.c_int64, C.c_int, C.c_double, C.c_int64, C.c_double, C.c_int,
                                  C.c_uint64, C.c_int, C.POINTER(StepReport), _pl, C.c_int64, _pd,
                                  C.c_int64, _pl, _pd, C.c_int64]
+    L.chromo_cg_num_beads.argtypes = [C.c_int64, C.c_int64]
+    L.chromo_cg_num_beads.restype = C.c_int64
+    L.chromo_cg_chromatin.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, _pd, _pd,
+                                      _pl, _pl, _pd, _pd, _pd, _pl, _pl, _pd]
+    L.chromo_refined_num_points.argtypes = [C.c_int64, C.c_int64]
+    L.chromo_refined_num_points.restype = C.c_int64
+    L.chromo_refined_num_draws.argtypes = [C.c_int64, C.c_int64]
+    L.chromo_refined_num_draws.restype = C.c_int64
+    L.chromo_refine_path.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, _pd, _pd, C.c_uint64,
+                                     C.c_double, C.c_int, _pd, _pd, _pd]
+    L.chromo_enforce_spherical_confinement.argtypes = [C.c_int, C.c_int64, C.c_int64, _pd, C.c_double, _pd]
     return L
 
 

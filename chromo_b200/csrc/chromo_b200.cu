@@ -31,6 +31,16 @@ static int fail(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
+// error sink of the other translation units (rediscretize.cu)
+int cb_set_error(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
 #define CK(call)                                                                              \
     do {                                                                                      \
         cudaError_t e_ = (call);                                                              \

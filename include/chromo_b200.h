@@ -264,6 +264,56 @@ int chromo_mc_step(chromo_ctx *ctx, int64_t replica, int move, double amp_move,
                    double *trial_rows, int64_t rows_cap,       /* [n_inds][9+nb]: r,t3,t2,states */
                    int64_t *touched, double *dtrial, int64_t touched_cap /* [n_touched],[..][nb+1] */);
 
+/* ---- coarse-grain / refine, the steps either side of the MC path (chromo/util/rediscretize.py) ----
+ * Batched over R replicas; context-free (host arrays in, host arrays out, one launch per call).
+ * `kernel_ms` (may be NULL) receives the device time of the kernel alone (CUDA events). */
+
+/* number of coarse-grained beads: len(get_cg_bead_intervals(num_beads, cg_factor)),
+ * rediscretize.py:24-54 (floor(N / cg) intervals plus one for the left-over beads); -1 on bad input */
+int64_t chromo_cg_num_beads(int64_t num_beads, int64_t cg_factor);
+
+/* get_cg_chromatin rediscretize.py:401-471 for every replica at once:
+ *   r_cg      = interval means of r / r_divisor            (get_avg_in_intervals 57-84, line 452;
+ *                                                           r_divisor = cg_factor ** (1/3))
+ *   t3_cg,t2_cg = normalised interval means of t3, t2 = t3 x e_x (e_y if t3 == e_x), normalised
+ *                                                          (get_orientations_in_intervals 87-122)
+ *   states_cg, mods_cg = most frequent value per interval and column, smallest on ties
+ *                                                          (get_majority_state_in_interval 125-160)
+ * r, t3: [R][N][3]; states, mods: [R][N][nb] (either may be NULL); outputs [R][M][.] with
+ * M = chromo_cg_num_beads(N, cg_factor). Bit-identical to the reference's numpy arithmetic. */
+int chromo_cg_chromatin(int device, int64_t R, int64_t N, int64_t nb, int64_t cg_factor,
+                        double r_divisor, const double *r, const double *t3, const int64_t *states,
+                        const int64_t *mods, double *r_cg, double *t3_cg, double *t2_cg,
+                        int64_t *states_cg, int64_t *mods_cg, double *kernel_ms);
+
+/* rows of get_refined_path(cg_r, num_beads_refined) (rediscretize.py:756-807): num_beads_refined when
+ * it is not a multiple of (num_beads_cg - 1), one fewer when it is (get_refined_intervals 565-583 gives
+ * the last bridge half a segment minus one); and the number of standard-normal TRIPLES one path draws
+ * from numpy's global generator. -1 when the reference itself would fail (fewer than 3 refined beads
+ * per coarse bond: brownian_bridge(0, ...) divides by zero). */
+int64_t chromo_refined_num_points(int64_t num_beads_cg, int64_t num_beads_refined);
+int64_t chromo_refined_num_draws(int64_t num_beads_cg, int64_t num_beads_refined);
+
+/* get_refined_path rediscretize.py:756-807 for every replica at once: free Gaussian-direction ends
+ * (gaussian_walk util/poly_paths.py:269-295) and one Brownian bridge per coarse bond (brownian_bridge
+ * 586-685) with the average step normalised to bead_spacing.
+ *   cg_r [R][M][3]; out [R][P][3], P = chromo_refined_num_points(M, num_beads_refined)
+ *   xi   [R][D][3] standard-normal deviates in the reference's draw order (replay of np.random), or
+ *        NULL: Philox4x32-10 + Box-Muller keyed by (seed, replica, draw) on the device
+ *   orientations = 0: rows are multiplied by out_scale (refine_chromatin 1056)
+ *   orientations = 1: get_refined_orientations 810-842: rows normalised, out_t2 completed as in
+ *                     chromo_cg_chromatin (pass bead_spacing = pi, the reference's default) */
+int chromo_refine_path(int device, int64_t R, int64_t num_beads_cg, int64_t num_beads_refined,
+                       double bead_spacing, const double *cg_r, const double *xi, uint64_t seed,
+                       double out_scale, int orientations, double *out, double *out_t2,
+                       double *kernel_ms);
+
+/* enforce_spherical_confinement rediscretize.py:708-753, in place on r [R][N][3]: every bead outside
+ * the sphere pulls itself and its three neighbours on either side inwards by
+ * {0.98,0.97,0.96,0.95,0.96,0.97,0.98} / (dist / rad), violations measured on the incoming path */
+int chromo_enforce_spherical_confinement(int device, int64_t R, int64_t N, double *r, double rad,
+                                         double *kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

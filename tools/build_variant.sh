@@ -16,11 +16,12 @@ fi
 F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC $*"
 cd "$tmp/chromo_b200/csrc"
 nvcc $F -c chromo_b200.cu -o "$tmp/api.o" &
+if [ -f rediscretize.cu ]; then nvcc $F -c rediscretize.cu -o "$tmp/rd.o" & else echo 'int cb_rd_absent;' > "$tmp/rd.cu"; nvcc $F -c "$tmp/rd.cu" -o "$tmp/rd.o" & fi
 nvcc $F -DCB_INST_REPLAY=1 -DCB_INST_HI=0 -c mc_inst.cu -o "$tmp/r12.o" &
 nvcc $F -DCB_INST_REPLAY=1 -DCB_INST_HI=1 -c mc_inst.cu -o "$tmp/r34.o" &
 nvcc $F -DCB_INST_REPLAY=0 -DCB_INST_HI=0 -c mc_inst.cu -o "$tmp/p12.o" &
 nvcc $F -DCB_INST_REPLAY=0 -DCB_INST_HI=1 -c mc_inst.cu -o "$tmp/p34.o" &
 wait
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$out" "$tmp/api.o" "$tmp/r12.o" "$tmp/r34.o" "$tmp/p12.o" "$tmp/p34.o"
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$out" "$tmp/api.o" "$tmp/rd.o" "$tmp/r12.o" "$tmp/r34.o" "$tmp/p12.o" "$tmp/p34.o"
 rm -rf "$tmp"
 echo "built $out from $rev"
