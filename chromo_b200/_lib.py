@@ -61,7 +61,7 @@ SYMBOLS = [
     "chromo_last_error", "chromo_version", "chromo_ctx_create", "chromo_ctx_destroy",
     "chromo_ctx_sync", "chromo_ctx_stream", "chromo_ctx_bytes", "chromo_ctx_set_table_capacity",
     "chromo_ctx_set_warps_per_replica", "chromo_ctx_set_replicas_per_block", "chromo_set_binders",
-    "chromo_set_replica_params", "chromo_set_bond_params", "chromo_set_access_volumes",
+    "chromo_set_replica_params", "chromo_set_bond_params", "chromo_set_twist_params", "chromo_set_access_volumes",
     "chromo_upload_state", "chromo_download_state", "chromo_download_density",
     "chromo_upload_density", "chromo_field_recompute", "chromo_field_energy",
     "chromo_elastic_energy", "chromo_chi_observable", "chromo_srand", "chromo_numpy_seed",
@@ -87,6 +87,7 @@ def _declare(L):
     L.chromo_set_binders.argtypes = [_vp, _pl, _pd, _pd, _pd, _pd, C.c_int64]
     L.chromo_set_replica_params.argtypes = [_vp, _pd, _pd]
     L.chromo_set_bond_params.argtypes = [_vp, C.c_int64, _pd, _pd, _pd, _pd, _pd]
+    L.chromo_set_twist_params.argtypes = [_vp, C.c_int64, _pd, _pd]
     L.chromo_set_access_volumes.argtypes = [_vp, _pd]
     L.chromo_upload_state.argtypes = [_vp, C.c_int64, C.c_int64, _pd, _pd, _pd, _pl, _pl]
     L.chromo_download_state.argtypes = [_vp, C.c_int64, C.c_int64, _pd, _pd, _pd, _pl]

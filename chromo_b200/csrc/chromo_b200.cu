@@ -57,7 +57,7 @@ struct chromo_ctx {
     std::vector<void *> allocs;
     int64_t bytes = 0;
     // owned device buffers that can be replaced
-    double *d_bond = nullptr, *d_chi = nullptr, *d_mu = nullptr, *d_bindF = nullptr, *d_access = nullptr;
+    double *d_bond = nullptr, *d_twist = nullptr, *d_chi = nullptr, *d_mu = nullptr, *d_bindF = nullptr, *d_access = nullptr;
     double *d_partial = nullptr, *d_out = nullptr;
     int *d_dcount = nullptr;
     long long *d_stage = nullptr;
@@ -93,6 +93,30 @@ static void refresh_fx_base(chromo_ctx *c) {
     int smax = 1;
     for (int a = 0; a < d.nb; a++) smax = std::max(smax, d.sites[a]);
     d.fx_base = (vmin > 0.0) ? 61 + (int)ilogb(vmin / (double)smax) : 61;
+}
+
+// kernel instantiation for (rng mode, number of binders, twist); the twist (SSTWLC) kernels are their own
+// translation units, built for one or two binders
+static int launch_sim(const McSimArgs &a, int rng_mode) {
+    const DevCtx &d = a.d;
+    if (d.twist) {
+        if (d.nb > 2) return -1000;
+        return rng_mode == CHROMO_RNG_REPLAY ? cb_mc_sim_replay_tw_12(a) : cb_mc_sim_philox_tw_12(a);
+    }
+    if (rng_mode == CHROMO_RNG_REPLAY) return d.nb <= 2 ? cb_mc_sim_replay_12(a) : cb_mc_sim_replay_34(a);
+    return d.nb <= 2 ? cb_mc_sim_philox_12(a) : cb_mc_sim_philox_34(a);
+}
+static int launch_step(const McStepArgs &a, int rng_mode) {
+    const DevCtx &d = a.d;
+    if (d.twist) {
+        if (d.nb > 2) return -1000;
+        return rng_mode == CHROMO_RNG_REPLAY ? cb_mc_step_replay_tw_12(a) : cb_mc_step_philox_tw_12(a);
+    }
+    if (rng_mode == CHROMO_RNG_REPLAY) return d.nb <= 2 ? cb_mc_step_replay_12(a) : cb_mc_step_replay_34(a);
+    return d.nb <= 2 ? cb_mc_step_philox_12(a) : cb_mc_step_philox_34(a);
+}
+static const char *launch_error(int e) {
+    return e == -1000 ? "twist (SSTWLC) kernels are built for one or two binders" : cudaGetErrorString((cudaError_t)e);
 }
 
 extern "C" const char *chromo_last_error(void) { return g_err.c_str(); }
@@ -369,6 +393,32 @@ extern "C" int chromo_set_bond_params(chromo_ctx *c, int64_t n_sets, const doubl
     c->d.bond = c->d_bond;
     c->d.bond_stride = (n_sets == 1) ? 0 : (long long)nbonds * 5;
     c->have_bonds = true;
+    return CHROMO_OK;
+}
+
+extern "C" int chromo_set_twist_params(chromo_ctx *c, int64_t n_sets, const double *eps_twist,
+                                       const double *natural_twist) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    if (!eps_twist && !natural_twist) { // back to a chain without twist
+        c->d.twist = nullptr;
+        c->d.twist_stride = 0;
+        return CHROMO_OK;
+    }
+    if (!eps_twist || !natural_twist) return fail(CHROMO_ERR_ARG, "null argument");
+    if (n_sets != 1 && n_sets != c->d.R) return fail(CHROMO_ERR_ARG, "n_sets must be 1 or n_replicas");
+    if (c->d.nb > 2) return fail(CHROMO_ERR_ARG, "twist (SSTWLC) kernels are built for one or two binders");
+    size_t nbonds = (size_t)c->d.N - 1;
+    std::vector<double> packed((size_t)n_sets * nbonds * 2);
+    for (size_t i = 0; i < (size_t)n_sets * nbonds; i++) {
+        if (!(eps_twist[i] > 0.0)) return fail(CHROMO_ERR_ARG, "Twist modulus must be positive."); // polymers.pyx:2095
+        packed[2 * i] = eps_twist[i];
+        packed[2 * i + 1] = natural_twist[i];
+    }
+    int rc = replace_buf(c, &c->d_twist, packed.data(), packed.size());
+    if (rc) return rc;
+    c->d.twist = c->d_twist;
+    c->d.twist_stride = (n_sets == 1) ? 0 : (long long)nbonds * 2;
     return CHROMO_OK;
 }
 
@@ -660,11 +710,9 @@ extern "C" int chromo_mc_sim(chromo_ctx *c, int64_t num_mc_steps, chromo_move_st
     if (moves && (rc = chromo_set_moves(c, moves))) return rc;
     if (rng_mode == CHROMO_RNG_REPLAY && numpy_seeds && (rc = chromo_numpy_seed(c, numpy_seeds))) return rc;
     McSimArgs a{d, (long long)num_mc_steps, mu_adjust_factor, (unsigned long long)seed, c->cap, c->warps, c->rpb, c->stream};
-    int e;
-    if (rng_mode == CHROMO_RNG_REPLAY) e = d.nb <= 2 ? cb_mc_sim_replay_12(a) : cb_mc_sim_replay_34(a);
-    else if (rng_mode == CHROMO_RNG_PHILOX) e = d.nb <= 2 ? cb_mc_sim_philox_12(a) : cb_mc_sim_philox_34(a);
-    else return fail(CHROMO_ERR_ARG, "unknown rng_mode %d", rng_mode);
-    if (e) return fail(CHROMO_ERR_CUDA, "mc_sim launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    if (rng_mode != CHROMO_RNG_REPLAY && rng_mode != CHROMO_RNG_PHILOX) return fail(CHROMO_ERR_ARG, "unknown rng_mode %d", rng_mode);
+    const int e = launch_sim(a, rng_mode);
+    if (e) return fail(CHROMO_ERR_CUDA, "mc_sim launch failed: %s", launch_error(e));
     CK(cudaGetLastError());
     if (moves) {
         CK(cudaMemcpyAsync(moves, d.moves, sizeof(chromo_move_state) * d.R * CHROMO_NUM_MOVES,
@@ -755,10 +803,8 @@ extern "C" int chromo_mc_sim_host(chromo_ctx *c, int64_t num_mc_steps, chromo_mo
         CB_MARK(0);
         McSimArgs a{d, (long long)num_mc_steps, mu_adjust_factor, (unsigned long long)seed, c->cap, c->warps, c->rpb, st,
                     (int)first, (int)n};
-        int e;
-        if (rng_mode == CHROMO_RNG_REPLAY) e = d.nb <= 2 ? cb_mc_sim_replay_12(a) : cb_mc_sim_replay_34(a);
-        else e = d.nb <= 2 ? cb_mc_sim_philox_12(a) : cb_mc_sim_philox_34(a);
-        if (e) return fail(CHROMO_ERR_CUDA, "mc_sim launch failed: %s", cudaGetErrorString((cudaError_t)e));
+        const int e = launch_sim(a, rng_mode);
+        if (e) return fail(CHROMO_ERR_CUDA, "mc_sim launch failed: %s", launch_error(e));
         CB_MARK(1);
         CK(cudaMemcpyAsync(r + off * 3, d.r + off * 3, cnt * 24, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(t3 + off * 3, d.t3 + off * 3, cnt * 24, cudaMemcpyDeviceToHost, st));
@@ -838,11 +884,9 @@ extern "C" int chromo_mc_step(chromo_ctx *c, int64_t replica, int move, double a
     CK(cudaMemcpyAsync(c->d_dbg, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
     McStepArgs a{d, (int)replica, move, amp_move, (int)amp_bead, mu_adjust_factor, (unsigned long long)seed,
                  force_accept, c->d_dbg, c->cap, c->stream};
-    int e;
-    if (rng_mode == CHROMO_RNG_REPLAY) e = d.nb <= 2 ? cb_mc_step_replay_12(a) : cb_mc_step_replay_34(a);
-    else if (rng_mode == CHROMO_RNG_PHILOX) e = d.nb <= 2 ? cb_mc_step_philox_12(a) : cb_mc_step_philox_34(a);
-    else return fail(CHROMO_ERR_ARG, "unknown rng_mode %d", rng_mode);
-    if (e) return fail(CHROMO_ERR_CUDA, "mc_step launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    if (rng_mode != CHROMO_RNG_REPLAY && rng_mode != CHROMO_RNG_PHILOX) return fail(CHROMO_ERR_ARG, "unknown rng_mode %d", rng_mode);
+    const int e = launch_step(a, rng_mode);
+    if (e) return fail(CHROMO_ERR_CUDA, "mc_step launch failed: %s", launch_error(e));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&h, c->d_dbg, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -149,8 +149,16 @@ __global__ void __launch_bounds__(FK_THREADS) elastic_energy_kernel(DevCtx C, do
             bend[i] = t1[i] + (-t0[i] - B.eta * perp[i]);
         }
         double tp = par - B.gamma;
-        e += (0.5 * B.eps_bend * dot3(bend, bend) + 0.5 * B.eps_par * (tp * tp)) +
-             0.5 * B.eps_perp * dot3(perp, perp);
+        double eb = (0.5 * B.eps_bend * dot3(bend, bend) + 0.5 * B.eps_par * (tp * tp)) +
+                    0.5 * B.eps_perp * dot3(perp, perp);
+        if (C.twist) { // SSTWLC.compute_E polymers.pyx:2250-2285
+            double u0[3], u1[3];
+            const double *T2 = C.t2 + (long long)rep * C.N * 3;
+            load3(T2 + 3 * (long long)b, u0);
+            load3(T2 + 3 * (long long)(b + 1), u1);
+            eb += twist_energy(C.twist + (long long)rep * C.twist_stride + 2 * (long long)b, twist_omega(u0, t0, u1, t1));
+        }
+        e += eb;
     }
     double t = block_sum(e, sh);
     if (threadIdx.x == 0) partial[(long long)rep * gridDim.x + blockIdx.x] = t;

@@ -261,6 +261,27 @@ __device__ __forceinline__ double bond_energy(const Bond &B, const double r0[3],
            0.5 * B.eps_perp * dot3(perp, perp);
 }
 
+// compute_twist_angle_omega polymers.pyx:3427-3461: t1 = t2 x t3 for both beads,
+// omega = atan2(t2_0.t1_1 - t1_0.t2_1, t1_0.t1_1 + t2_0.t2_1)
+__device__ __forceinline__ double twist_omega(const double t2_0[3], const double t3_0[3], const double t2_1[3],
+                                              const double t3_1[3]) {
+    double a[3], b[3];
+    a[0] = t2_0[1] * t3_0[2] - t2_0[2] * t3_0[1];
+    a[1] = t2_0[2] * t3_0[0] - t2_0[0] * t3_0[2];
+    a[2] = t2_0[0] * t3_0[1] - t2_0[1] * t3_0[0];
+    b[0] = t2_1[1] * t3_1[2] - t2_1[2] * t3_1[1];
+    b[1] = t2_1[2] * t3_1[0] - t2_1[0] * t3_1[2];
+    b[2] = t2_1[0] * t3_1[1] - t2_1[1] * t3_1[0];
+    return atan2(dot3(t2_0, b) - dot3(a, t2_1), dot3(a, b) + dot3(t2_0, t2_1));
+}
+// the twist term of E_pair_with_twist polymers.pyx:2050-2102; tw = {eps_twist, natural twist} of the bond
+__device__ __forceinline__ double twist_energy(const double *tw, double omega) {
+    const double pi = 3.141592653589793, two_pi = 2.0 * pi;
+    double d = omega - tw[1];
+    d -= two_pi * floor((d + pi) / two_pi);
+    return 0.5 * tw[0] * (d * d);
+}
+
 __device__ __forceinline__ void load3(const double *p, double v[3]) {
     v[0] = p[0];
     v[1] = p[1];

@@ -70,3 +70,8 @@ int cb_mc_step_replay_12(const McStepArgs &a);
 int cb_mc_step_replay_34(const McStepArgs &a);
 int cb_mc_step_philox_12(const McStepArgs &a);
 int cb_mc_step_philox_34(const McStepArgs &a);
+// SSTWLC (twist) builds of mc_inst.cu (-DCB_TWIST=1), one or two binders
+int cb_mc_sim_replay_tw_12(const McSimArgs &a);
+int cb_mc_sim_philox_tw_12(const McSimArgs &a);
+int cb_mc_step_replay_tw_12(const McStepArgs &a);
+int cb_mc_step_philox_tw_12(const McStepArgs &a);

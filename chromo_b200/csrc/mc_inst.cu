@@ -2,18 +2,37 @@
 // of binder counts.  Compile with
 //   -DCB_INST_REPLAY=0|1  -DCB_INST_HI=0|1     (HI: nb in {3,4}, else {1,2})
 #include "launch.cuh"
+#ifndef CB_TWIST
+#define CB_TWIST 0
+#endif
+#include "geometry.cuh"
+#include "params.cuh"
+#include "rng.cuh"
+#if CB_TWIST
+// the twist build of the kernels lives in its own namespace: same template arguments as the default
+// build, different symbols (kernels, and every inline function whose body depends on CB_TWIST)
+#define TW_ _tw
+namespace cb_twist_build {
 #include "mc_kernel.cuh"
+}
+using namespace cb_twist_build;
+#else
+#define TW_
+#include "mc_kernel.cuh"
+#endif
 
 #ifndef CB_INST_REPLAY
 #error "define CB_INST_REPLAY"
 #endif
 #if CB_INST_REPLAY
 typedef ReplayRng InstRng;
-#define NAME2(a, b) cb_mc_##a##_replay_##b
+#define NAME3(a, t, b) cb_mc_##a##_replay##t##_##b
 #else
 typedef PhiloxRng InstRng;
-#define NAME2(a, b) cb_mc_##a##_philox_##b
+#define NAME3(a, t, b) cb_mc_##a##_philox##t##_##b
 #endif
+#define NAME3X(a, t, b) NAME3(a, t, b)
+#define NAME2(a, b) NAME3X(a, TW_, b)
 #if CB_INST_HI
 #define NAME(a) NAME2(a, 34)
 constexpr int NB_A = 3, NB_B = 4;
@@ -55,7 +74,7 @@ static int step_one(const McStepArgs &a) {
 int NAME(sim)(const McSimArgs &a) { return a.d.nb == NB_A ? sim_one<NB_A>(a) : sim_one<NB_B>(a); }
 int NAME(step)(const McStepArgs &a) { return a.d.nb == NB_A ? step_one<NB_A>(a) : step_one<NB_B>(a); }
 
-#if defined(CB_PHASE_TIMERS) && !CB_INST_REPLAY && !CB_INST_HI
+#if defined(CB_PHASE_TIMERS) && !CB_INST_REPLAY && !CB_INST_HI && !CB_TWIST
 // development only: read and reset the phase timers of the Philox nb<=2 kernels
 extern "C" int cb_phase_read(unsigned long long *out) {
     cudaError_t e = cudaMemcpyFromSymbol(out, cb_phase_acc, sizeof(unsigned long long) * CHROMO_NUM_MOVES * CB_NPHASE);

@@ -551,17 +551,39 @@ __device__ __forceinline__ double confinement_dE_segment(const DevCtx &C, const 
 // beads optionally replaced by trial values: moved = 0 none, 1 first bead,
 // 2 second bead.  E_pair with dr / dr_par / dr_perp / bend built as in
 // bead_pair_dE_poly_forward / _reverse (polymers.pyx:1148-1175, 1253-1346).
+// SSTWLC builds (-DCB_TWIST=1, their own translation units) add the twist term of E_pair_with_twist
+// (polymers.pyx:2050-2102) to every bond energy: TwistRows carries the replica's t2 rows and its
+// {eps_twist, natural twist} rows, `t2n` the trial t2 of the moved bead.  In the default build the
+// struct is empty and nothing below changes.
+#ifndef CB_TWIST
+#define CB_TWIST 0
+#endif
+struct TwistRows {
+#if CB_TWIST
+    const double *T2, *tw;
+#endif
+};
+__device__ __forceinline__ TwistRows twist_rows(const DevCtx &C, int rep) {
+    TwistRows t;
+#if CB_TWIST
+    t.T2 = C.t2 + (long long)rep * C.N * 3;
+    t.tw = C.twist + (long long)rep * C.twist_stride;
+#endif
+    return t;
+}
 __device__ __forceinline__ double pair_energy_p(const double *Rr, const double *T3, const double *bondp, int bond,
-                                                int moved, const double rn[3], const double tn[3]);
+                                                int moved, const double rn[3], const double tn[3],
+                                                const TwistRows &TW, const double *t2n);
 __device__ __forceinline__ double pair_energy(const DevCtx &C, int rep, int bond, int moved,
-                                              const double rn[3], const double tn[3]) {
+                                              const double rn[3], const double tn[3], const double *t2n) {
     return pair_energy_p(C.r + (long long)rep * C.N * 3, C.t3 + (long long)rep * C.N * 3,
-                         C.bond + (long long)rep * C.bond_stride, bond, moved, rn, tn);
+                         C.bond + (long long)rep * C.bond_stride, bond, moved, rn, tn, twist_rows(C, rep), t2n);
 }
 
 // the same from explicit row pointers (`bondp` = the replica's bond-parameter rows)
 __device__ __forceinline__ double pair_energy_p(const double *Rr, const double *T3, const double *bondp, int bond,
-                                                int moved, const double rn[3], const double tn[3]) {
+                                                int moved, const double rn[3], const double tn[3],
+                                                const TwistRows &TW, const double *t2n) {
     double r0[3], r1[3], t0[3], t1[3];
     load3(Rr + 3 * bond, r0);
     load3(Rr + 3 * bond + 3, r1);
@@ -581,7 +603,19 @@ __device__ __forceinline__ double pair_energy_p(const double *Rr, const double *
     B.eps_perp = p[2];
     B.gamma = p[3];
     B.eta = p[4];
+#if CB_TWIST
+    double u0[3], u1[3];
+    load3(TW.T2 + 3 * bond, u0);
+    load3(TW.T2 + 3 * bond + 3, u1);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        u0[j] = moved == 1 ? t2n[j] : u0[j];
+        u1[j] = moved == 2 ? t2n[j] : u1[j];
+    }
+    return bond_energy(B, r0, r1, t0, t1) + twist_energy(TW.tw + 2 * bond, twist_omega(u0, t0, u1, t1));
+#else
     return bond_energy(B, r0, r1, t0, t1);
+#endif
 }
 
 // The state-dependent scalar half of a segment move (crank-shaft, end-pivot, slide), ONE THREAD per
@@ -594,7 +628,8 @@ __device__ __forceinline__ double pair_energy_p(const double *Rr, const double *
 // accepted attempt of the same batch.  Returns 1 without writing when the crank-shaft axis is
 // degenerate and `axis_in` is null: the caller draws one (move_funcs.pyx:229-230) and calls again.
 static __device__ CB_NOINLINE int segment_rows_prepare(const double *Rr, const double *T3, const double *bondp, int N,
-                                                       int mtype, Prop *P, const double *axis_in) {
+                                                       int mtype, Prop *P, const double *axis_in,
+                                                       const TwistRows TW) {
     const int ind0 = P->ind0, indf = P->indf;
     double M[12];
     if (mtype == CHROMO_SLIDE) {
@@ -672,8 +707,20 @@ static __device__ CB_NOINLINE int segment_rows_prepare(const double *Rr, const d
             apply_affine(M, r, rn);
             apply_rot(M, t, tn);
         }
-        const double e_trial = pair_energy_p(Rr, T3, bondp, bond, which == 0 ? 2 : 1, rn, tn);
-        const double e_cur = pair_energy_p(Rr, T3, bondp, bond, 0, rn, tn);
+        const double *t2n = nullptr;
+#if CB_TWIST
+        double u[3], un[3];
+        load3(TW.T2 + 3 * mbead, u);
+        if (mtype == CHROMO_SLIDE) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) un[j] = u[j];
+        } else {
+            apply_rot(M, u, un);
+        }
+        t2n = un;
+#endif
+        const double e_trial = pair_energy_p(Rr, T3, bondp, bond, which == 0 ? 2 : 1, rn, tn, TW, t2n);
+        const double e_cur = pair_energy_p(Rr, T3, bondp, bond, 0, rn, tn, TW, t2n);
         d[which] = e_trial - e_cur;
     }
 #pragma unroll
@@ -851,12 +898,12 @@ struct McWarp {
     __device__ __forceinline__ void rows_recompute(int mtype, int slot) {
         if (lane == 0) {
             Prop *Pp = &B.prop[slot];
-            if (segment_rows_prepare(R_(), T3_(), bond_rows(), C.N, mtype, Pp, nullptr)) {
+            if (segment_rows_prepare(R_(), T3_(), bond_rows(), C.N, mtype, Pp, nullptr, twist_rows(C, rep))) {
                 if (BATCH) rng.seek_attempt(abase + (unsigned long long)slot, Pp->used);
                 double axis[3];
                 const uint32_t d1 = rng.next31(), d2 = rng.next31();
                 degenerate_axis(d1, d2, axis);
-                (void)segment_rows_prepare(R_(), T3_(), bond_rows(), C.N, mtype, Pp, axis);
+                (void)segment_rows_prepare(R_(), T3_(), bond_rows(), C.N, mtype, Pp, axis, twist_rows(C, rep));
             }
         }
         __syncwarp();
@@ -980,13 +1027,13 @@ struct McWarp {
         if (BATCH) P.used = rng.position();
         // ---- the state-dependent half of a segment move, from the rows as they are now ----
         if ((crank || pivot || slide) && n > 0) {
-            if (segment_rows_prepare(R_(), T3_(), bond_rows(), N, mtype, &P, nullptr)) {
+            if (segment_rows_prepare(R_(), T3_(), bond_rows(), N, mtype, &P, nullptr, twist_rows(C, rep))) {
                 // degenerate crank-shaft axis: two more draws (move_funcs.pyx:229-230); in the batched
                 // mode they are draws `used`, `used + 1` of the attempt's own stream
                 double dax[3];
                 const uint32_t e1 = rng.next31(), e2 = rng.next31();
                 degenerate_axis(e1, e2, dax);
-                (void)segment_rows_prepare(R_(), T3_(), bond_rows(), N, mtype, &P, dax);
+                (void)segment_rows_prepare(R_(), T3_(), bond_rows(), N, mtype, &P, dax, twist_rows(C, rep));
             }
         }
     }
@@ -1178,7 +1225,7 @@ struct McWarp {
             const bool present = left ? (bead != 0) : (bead + 1 != N);
             if (!store && present) {
                 const int moved = (which & 1) ? 0 : (left ? 2 : 1);
-                e = pair_energy(C, rep, left ? bead - 1 : bead, moved, rc, t3n);
+                e = pair_energy(C, rep, left ? bead - 1 : bead, moved, rc, t3n, t2n);
             }
             if (which == 0) {
                 if (out) {

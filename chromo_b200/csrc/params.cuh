@@ -9,6 +9,7 @@
 //   density     [R][n_bins][nb+1] fp64, row = one voxel (fields.pxd:54), so a
 //                                 touched voxel is one 16/24/32-byte gather
 //   bond        [sets][N-1][5]    eps_bend, eps_par, eps_perp, gamma, eta
+//   twist       [sets][N-1][2]    eps_twist, natural twist (SSTWLC only)
 //   moves       [R][5]            controller / tracker state
 #pragma once
 #include <cstdint>
@@ -33,6 +34,8 @@ struct DevCtx {
     const double *access_vol; // nullptr -> vol_bin
     const double *bond;
     long long bond_stride; // 0 (shared) or (N-1)*5
+    const double *twist;   // SSTWLC: [sets][N-1][2] eps_twist, natural twist per bond; nullptr = no twist term
+    long long twist_stride; // 0 (shared) or (N-1)*2
     const double *chi;     // [R]
     const double *mu;      // [R][nb]
     double pref[CB_MAXNB], e_intra[CB_MAXNB], xpref[CB_MAXNB * CB_MAXNB];

@@ -41,7 +41,7 @@ int cb_set_error(int code, const char *fmt, ...); // chromo_b200.cu
 // ------------------------------------------------------------------------------------------------
 // coarse-graining
 // ------------------------------------------------------------------------------------------------
-#define CG_THREADS 128
+#define CG_THREADS 256
 #define CG_MAX_VALUE 16 // states / marks are small non-negative integers (sites_per_bead + 1 values)
 
 static inline __host__ __device__ int cg_row_stride(int k, int width) {
@@ -66,11 +66,35 @@ struct CgArgs {
 template <class V>
 __device__ __forceinline__ void cg_stage(V *sh, const V *src, long long b0, long long b1, int width, int k,
                                          int stride) {
-    const long long n = (b1 - b0) * width;
-    const int kw = k * width;
-    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-        const int g = (int)(i / kw), o = (int)(i - (long long)g * kw);
-        sh[(size_t)g * stride + o] = src[b0 * width + i];
+    const int n = (int)((b1 - b0) * width); // a block's rows fit shared memory: well below 2^31
+    const int kw = k * width, nt = (int)blockDim.x;
+    const int pad = stride - kw;          // 0 or 1 padding word per interval row
+    const int dg = nt / kw, dr = nt % kw; // (interval, offset) advance of a thread from one load to its next
+    src += b0 * width;
+    int i = threadIdx.x, g = i / kw, o = i % kw; // element i = row g, offset o; kept incrementally (no division per load)
+    for (; i + 7 * nt < n; i += 8 * nt) { // eight loads in flight per thread
+        V v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = src[i + u * nt];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            sh[i + u * nt + pad * g] = v[u];
+            g += dg;
+            o += dr;
+            if (o >= kw) {
+                o -= kw;
+                g++;
+            }
+        }
+    }
+    for (; i < n; i += nt) {
+        sh[i + pad * g] = src[i];
+        g += dg;
+        o += dr;
+        if (o >= kw) {
+            o -= kw;
+            g++;
+        }
     }
 }
 
@@ -112,78 +136,67 @@ __device__ __forceinline__ void cg_orient(double a[3], double t2[3]) {
 
 __global__ void __launch_bounds__(CG_THREADS) cg_reduce_kernel(const CB_GRID_CONSTANT CgArgs a) {
     CB_DYN_SMEM(smem_raw);
-    double *shd = (double *)smem_raw;
-    long long *shl = (long long *)smem_raw;
     const long long rep = blockIdx.y;
     const long long i0 = (long long)blockIdx.x * a.T;         // first interval of this block
     const long long i1 = min(a.M, i0 + (long long)a.T);       // one past the last
     const long long b0 = i0 * a.k, b1 = min(a.N, i1 * a.k);   // bead range
     const int k = (int)a.k, nb = (int)a.nb;
+    const int s3 = cg_row_stride(k, 3), sn = cg_row_stride(k, nb > 0 ? nb : 1);
+    // shared memory: r rows | t3 rows | states rows | marks rows, all staged before ONE barrier so that
+    // every load of the block is in flight together
+    double *sh_r = (double *)smem_raw, *sh_t = sh_r + (size_t)a.T * s3;
+    long long *sh_s = (long long *)(sh_t + (size_t)a.T * s3), *sh_m = sh_s + (size_t)a.T * sn;
+    cg_stage(sh_r, a.r + rep * a.N * 3, b0, b1, 3, k, s3);
+    cg_stage(sh_t, a.t3 + rep * a.N * 3, b0, b1, 3, k, s3);
+    if (a.states) cg_stage(sh_s, a.states + rep * a.N * nb, b0, b1, nb, k, sn);
+    if (a.mods) cg_stage(sh_m, a.mods + rep * a.N * nb, b0, b1, nb, k, sn);
+    __syncthreads();
     const long long me = i0 + threadIdx.x;
-    const bool active = me < i1;
-    const int cnt = active ? (int)(min(a.N, (me + 1) * a.k) - me * a.k) : 0;
-    const int s3 = cg_row_stride(k, 3);
-
-    // ---- positions: interval mean, pulled inwards by cg_factor^(1/3) (rediscretize.py:452) ----
-    cg_stage(shd, a.r + rep * a.N * 3, b0, b1, 3, k, s3);
-    __syncthreads();
-    if (active) {
-        double m[3];
-        cg_mean3(shd + (size_t)threadIdx.x * s3, cnt, m);
-        double *o = a.r_cg + (rep * a.M + me) * 3;
-        o[0] = m[0] / a.r_div;
-        o[1] = m[1] / a.r_div;
-        o[2] = m[2] / a.r_div;
+    if (me >= i1) return;
+    const int cnt = (int)(min(a.N, (me + 1) * a.k) - me * a.k);
+    double m[3], t2[3];
+    // positions: interval mean, pulled inwards by cg_factor^(1/3) (rediscretize.py:452)
+    cg_mean3(sh_r + (size_t)threadIdx.x * s3, cnt, m);
+    double *o = a.r_cg + (rep * a.M + me) * 3;
+    o[0] = m[0] / a.r_div;
+    o[1] = m[1] / a.r_div;
+    o[2] = m[2] / a.r_div;
+    // orientations
+    cg_mean3(sh_t + (size_t)threadIdx.x * s3, cnt, m);
+    cg_orient(m, t2);
+    double *o3 = a.t3_cg + (rep * a.M + me) * 3, *o2 = a.t2_cg + (rep * a.M + me) * 3;
+    for (int c = 0; c < 3; c++) {
+        o3[c] = m[c];
+        o2[c] = t2[c];
     }
-    __syncthreads();
-    // ---- orientations ----
-    cg_stage(shd, a.t3 + rep * a.N * 3, b0, b1, 3, k, s3);
-    __syncthreads();
-    if (active) {
-        double m[3], t2[3];
-        cg_mean3(shd + (size_t)threadIdx.x * s3, cnt, m);
-        cg_orient(m, t2);
-        double *o3 = a.t3_cg + (rep * a.M + me) * 3, *o2 = a.t2_cg + (rep * a.M + me) * 3;
-        for (int c = 0; c < 3; c++) {
-            o3[c] = m[c];
-            o2[c] = t2[c];
-        }
-    }
-    // ---- binding states and marks: most frequent value, smallest on ties (argmax(bincount)) ----
-    const int sn = cg_row_stride(k, nb);
+    // binding states and marks: most frequent value, smallest on ties (argmax(bincount))
     for (int which = 0; which < 2; which++) {
-        const long long *src = which == 0 ? a.states : a.mods;
+        const long long *row = (which == 0 ? sh_s : sh_m) + (size_t)threadIdx.x * sn;
         long long *dst = which == 0 ? a.states_cg : a.mods_cg;
-        if (!src) continue;
-        __syncthreads();
-        cg_stage(shl, src + rep * a.N * nb, b0, b1, nb, k, sn);
-        __syncthreads();
-        if (active) {
-            const long long *row = shl + (size_t)threadIdx.x * sn;
-            for (int c = 0; c < nb; c++) {
-                int count[CG_MAX_VALUE];
+        if (!(which == 0 ? a.states : a.mods)) continue;
+        for (int c = 0; c < nb; c++) {
+            int count[CG_MAX_VALUE];
 #pragma unroll
-                for (int v = 0; v < CG_MAX_VALUE; v++) count[v] = 0;
-                bool bad = false;
-                for (int j = 0; j < cnt; j++) {
-                    const long long v = row[j * nb + c];
-                    if (v < 0 || v >= CG_MAX_VALUE) {
-                        bad = true;
-                        continue;
-                    }
-#pragma unroll
-                    for (int w = 0; w < CG_MAX_VALUE; w++) count[w] += (w == (int)v);
+            for (int v = 0; v < CG_MAX_VALUE; v++) count[v] = 0;
+            bool bad = false;
+            for (int j = 0; j < cnt; j++) {
+                const long long v = row[j * nb + c];
+                if (v < 0 || v >= CG_MAX_VALUE) {
+                    bad = true;
+                    continue;
                 }
-                int best = 0, best_count = count[0];
 #pragma unroll
-                for (int w = 1; w < CG_MAX_VALUE; w++)
-                    if (count[w] > best_count) {
-                        best = w;
-                        best_count = count[w];
-                    }
-                if (bad) *a.err = 1;
-                dst[(rep * a.M + me) * nb + c] = cnt > 1 ? (long long)best : row[c];
+                for (int w = 0; w < CG_MAX_VALUE; w++) count[w] += (w == (int)v);
             }
+            int best = 0, best_count = count[0];
+#pragma unroll
+            for (int w = 1; w < CG_MAX_VALUE; w++)
+                if (count[w] > best_count) {
+                    best = w;
+                    best_count = count[w];
+                }
+            if (bad) *a.err = 1;
+            dst[(rep * a.M + me) * nb + c] = cnt > 1 ? (long long)best : row[c];
         }
     }
 }
@@ -191,7 +204,7 @@ __global__ void __launch_bounds__(CG_THREADS) cg_reduce_kernel(const CB_GRID_CON
 // ------------------------------------------------------------------------------------------------
 // refinement
 // ------------------------------------------------------------------------------------------------
-#define RF_WALK_CHUNK 256
+#define RF_WALK_CHUNK 32
 
 struct RefineLayout {
     long long M, Nref;
@@ -249,6 +262,8 @@ struct RefineArgs {
     double *out, *out_t2; // [R][points][3]
     int wpb;              // warps per block
     int per_warp;         // doubles of shared memory per warp
+    int G;                // lanes per inner bridge
+    long long inner_warps; // warps that carry the inner bridges of one replica
 };
 
 // production deviates: triple q of replica rep = Box-Muller of Philox4x32-10(counter (q_lo, q_hi, j, rep), key seed)
@@ -298,8 +313,9 @@ __device__ __forceinline__ void refine_store(const RefineArgs &a, long long rep,
     }
 }
 
-__device__ __forceinline__ double warp_sum(double v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+// sum over the G lanes of a group (G a power of two; every lane of the warp takes part)
+__device__ __forceinline__ double group_sum(double v, int G) {
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
@@ -311,20 +327,29 @@ __device__ __forceinline__ double linspace_at(double p0, double p1, double delta
     return any_zero ? ((double)j / (double)n) * delta + p0 : (double)j * step + p0;
 }
 
-// one warp: a Brownian bridge of n steps from p0 to p1 (rows 0..n-1 are emitted; row n = p1 belongs to
-// the next segment), rediscretize.py:634-685
+// one group of G lanes (G = 4..32, a power of two; `lane` = lane within the group): a Brownian bridge of n
+// steps from p0 to p1 (rows 0..n-1 are emitted; row n = p1 belongs to the next segment),
+// rediscretize.py:634-685.  All groups of a warp run this with the same n, so the warp-wide barriers and
+// shuffles are reached uniformly; a group without a bridge (`active` false) only keeps step.
 __device__ void refine_bridge(const RefineArgs &a, long long rep, long long n_, long long row0, long long draw0,
-                              const double *p0, const double *p1, double *sh) {
-    const int lane = threadIdx.x & 31, n = (int)n_;
+                              const double *p0, const double *p1, double *sh, int G, int lane, bool active) {
+    const int n = (int)n_;
     if (n == 1) { // trivial case: [p0, p1][:1]
-        if (lane == 0) refine_store(a, rep, row0, p0[0], p0[1], p0[2]);
+        if (lane == 0 && active) refine_store(a, rep, row0, p0[0], p0[1], p0[2]);
+        return;
+    }
+    if (!active) { // same barriers and shuffles as below, no memory traffic
+        __syncwarp();
+        __syncwarp();
+        __syncwarp();
+        (void)group_sum(0.0, G);
         return;
     }
     double *B = sh;                  // [(n + 1)][3]
     double *coef = sh + 3 * (n + 1); // [n]
     const double dt = 1.0 / (double)n, dt_sqrt = sqrt(dt);
     // increments and decay factors, all lanes
-    for (int j = lane; j < n - 1; j += 32) {
+    for (int j = lane; j < n - 1; j += G) {
         double z[3];
         refine_fetch_xi(a, rep, draw0 + j, z);
         const double t = (double)j * dt;
@@ -355,10 +380,10 @@ __device__ void refine_bridge(const RefineArgs &a, long long rep, long long n_, 
         any_zero = any_zero || step[c] == 0.0;
     }
     // B *= direct_path_length; path length of direct + B
-    for (int i = lane; i < 3 * (n + 1); i += 32) B[i] = B[i] * dpl;
+    for (int i = lane; i < 3 * (n + 1); i += G) B[i] = B[i] * dpl;
     __syncwarp();
     double len = 0.0;
-    for (int j = lane; j < n; j += 32) {
+    for (int j = lane; j < n; j += G) {
         double q[3];
         for (int c = 0; c < 3; c++) {
             const double x0 = linspace_at(p0[c], p1[c], d[c], step[c], any_zero, j, n) + B[3 * j + c];
@@ -367,12 +392,12 @@ __device__ void refine_bridge(const RefineArgs &a, long long rep, long long n_, 
         }
         len += sqrt((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]);
     }
-    len = warp_sum(len);
+    len = group_sum(len, G);
     double avg = len / (double)n;
     if (a.spacing < direct_step) avg = direct_step; // the reference prints a notice and adjusts the spacing
     const double actual_to_direct = avg / direct_step, target_to_direct = a.spacing / direct_step;
     const double den = actual_to_direct / target_to_direct;
-    for (int j = lane; j < n; j += 32) {
+    for (int j = lane; j < n; j += G) {
         double x[3];
         for (int c = 0; c < 3; c++)
             x[c] = linspace_at(p0[c], p1[c], d[c], step[c], any_zero, j, n) + B[3 * j + c] / den;
@@ -412,22 +437,42 @@ __device__ void refine_walk(const RefineArgs &a, long long rep, long long n, lon
     }
 }
 
+// lanes per inner bridge: the smallest power of two >= its number of steps, within [4, 32]
+static inline __host__ __device__ int refine_group(long long seg) {
+    int g = 4;
+    while (g < 32 && g < seg) g <<= 1;
+    return g;
+}
+
 __global__ void refine_path_kernel(const CB_GRID_CONSTANT RefineArgs a) {
     CB_DYN_SMEM(smem_raw);
-    const int warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *sh = (double *)smem_raw + (size_t)warp * a.per_warp;
     const long long rep = blockIdx.y;
-    const long long s = (long long)blockIdx.x * a.wpb + warp;
-    if (s >= a.L.nseg) return;
-    long long n, row, draw;
-    refine_segment(a.L, s, &n, &row, &draw);
+    const long long wi = (long long)blockIdx.x * a.wpb + warp; // warp index within the replica
     const double *cg = a.cg + rep * a.L.M * 3;
+    long long n, row, draw;
+    if (wi < a.inner_warps) {
+        // inner bridges 1 .. M-2 (all of L.seg steps): 32 / G of them per warp
+        const int G = a.G, gpw = 32 / G, grp = lane / G;
+        const long long s = 1 + wi * gpw + grp;
+        const bool active = s < a.L.M - 1;
+        refine_segment(a.L, active ? s : 1, &n, &row, &draw);
+        refine_bridge(a, rep, n, row, draw, cg + (s - 1) * 3, cg + s * 3, sh + (size_t)grp * 4 * (a.L.seg + 1), G,
+                      lane & (G - 1), active);
+        return;
+    }
+    // the two free ends and the last (shorter) bridge: one warp each
+    const long long k = wi - a.inner_warps;
+    const long long s = k == 0 ? 0 : k == 1 ? a.L.M - 1 : a.L.M;
+    if (k > 2 || s >= a.L.nseg) return;
+    refine_segment(a.L, s, &n, &row, &draw);
     if (s == 0) {
         refine_walk(a, rep, n, row, draw, cg, true, sh);
     } else if (s == a.L.M) {
         refine_walk(a, rep, n, row, draw, cg + (a.L.M - 1) * 3, false, sh);
     } else {
-        refine_bridge(a, rep, n, row, draw, cg + (s - 1) * 3, cg + s * 3, sh);
+        refine_bridge(a, rep, n, row, draw, cg + (s - 1) * 3, cg + s * 3, sh, 32, lane, true);
     }
 }
 
@@ -441,41 +486,51 @@ struct ConfineArgs {
     double *out;
 };
 
+#define CF_TILE 1024
 __global__ void __launch_bounds__(256) confine_kernel(const CB_GRID_CONSTANT ConfineArgs a) {
     // each bead is rescaled once per violator within three beads of it, in ascending violator order,
     // with the violation measured on the ORIGINAL path (rediscretize.py:728-752)
-    __shared__ double tile[(256 + 6) * 3];
-    __shared__ double inv_f[256 + 6]; // 1 / (dist / rad) of a violator, 0 otherwise
+    __shared__ double tile[(CF_TILE + 6) * 3];
+    __shared__ double inv_f[CF_TILE + 6]; // 1 / (dist / rad) of a violator, 0 otherwise
     const long long rep = blockIdx.y;
-    const long long j0 = (long long)blockIdx.x * 256;
+    const long long j0 = (long long)blockIdx.x * CF_TILE;
     const double *src = a.in + rep * a.N * 3;
-    const long long lo = max(0LL, j0 - 3), hi = min(a.N, j0 + 256 + 3);
-    for (long long i = lo * 3 + threadIdx.x; i < hi * 3; i += 256) tile[i - (j0 - 3) * 3] = src[i];
+    const long long lo = max(0LL, j0 - 3), hi = min(a.N, j0 + CF_TILE + 3);
+    {
+        // all of a thread's loads are issued before the first store to shared memory
+        constexpr int PER = ((CF_TILE + 6) * 3 + 255) / 256;
+        double v[PER];
+        const long long e0 = lo * 3 + threadIdx.x, e1 = hi * 3;
+#pragma unroll
+        for (int u = 0; u < PER; u++) v[u] = e0 + u * 256 < e1 ? src[e0 + u * 256] : 0.0;
+#pragma unroll
+        for (int u = 0; u < PER; u++)
+            if (e0 + u * 256 < e1) tile[e0 + u * 256 - (j0 - 3) * 3] = v[u];
+    }
+    for (int t = threadIdx.x; t < CF_TILE + 6; t += 256) inv_f[t] = 0.0; // slots outside [0, N): no violator
     __syncthreads();
-    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
-        const double *p = tile + (i - (j0 - 3)) * 3;
+    for (int t = (int)(lo - (j0 - 3)) + threadIdx.x; t < (int)(hi - (j0 - 3)); t += 256) {
+        const double *p = tile + t * 3;
         const double dist = sqrt((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]);
-        inv_f[i - (j0 - 3)] = dist > a.rad ? 1.0 / (dist / a.rad) : 0.0;
+        if (dist > a.rad) inv_f[t] = 1.0 / (dist / a.rad);
     }
     __syncthreads();
-    const long long j = j0 + threadIdx.x;
-    if (j >= a.N) return;
     const double kern[7] = {0.98, 0.97, 0.96, 0.95, 0.96, 0.97, 0.98};
-    double x = tile[(threadIdx.x + 3) * 3], y = tile[(threadIdx.x + 3) * 3 + 1], z = tile[(threadIdx.x + 3) * 3 + 2];
-    for (int o = -3; o <= 3; o++) {
-        const long long i = j + o; // violator index
-        if (i < 0 || i >= a.N) continue;
-        const double f = inv_f[threadIdx.x + 3 + o];
-        if (f == 0.0) continue;
-        const double w = kern[3 - o] * f; // bead j sits at offset j - i + 3 = 3 - o of violator i's window
-        x = x * w;
-        y = y * w;
-        z = z * w;
+    double *dst = a.out + rep * a.N * 3;
+    // one output double per thread and pass: coalesced stores
+    // (beads outside [0, N) have inv_f = 0 below: the halo slots are zeroed first)
+    const int ne = (int)(min(a.N, j0 + CF_TILE) - j0) * 3;
+    dst += j0 * 3;
+    for (int e = threadIdx.x; e < ne; e += 256) {
+        const int t = e / 3 + 3; // this bead's slot in the tile
+        double x = tile[e + 9];
+#pragma unroll
+        for (int o = -3; o <= 3; o++) {
+            const double f = inv_f[t + o]; // violator t + o
+            if (f != 0.0) x = x * (kern[3 - o] * f); // bead sits at offset 3 - o of that violator's window
+        }
+        dst[e] = x;
     }
-    double *dst = a.out + (rep * a.N + j) * 3;
-    dst[0] = x;
-    dst[1] = y;
-    dst[2] = z;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -541,14 +596,14 @@ extern "C" int chromo_cg_chromatin(int device, int64_t R, int64_t N, int64_t nb,
     if (!r || !t3 || !r_cg || !t3_cg || !t2_cg || (nb && states && !states_cg) || (nb && mods && !mods_cg))
         return cb_set_error(CHROMO_ERR_ARG, "chromo_cg_chromatin: null array");
     if (!(r_divisor > 0.0)) return cb_set_error(CHROMO_ERR_ARG, "chromo_cg_chromatin: r_divisor must be positive");
-    const int width = (int)std::max<int64_t>(3, nb);
-    if (cg_factor * width + 1 > 12000) return cb_set_error(CHROMO_ERR_ARG, "chromo_cg_chromatin: cg_factor too large");
     int rc = select_device(device);
     if (rc) return rc;
-    const size_t budget = 96 * 1024 / 8; // 64-bit words of staging per block
-    const int stride = std::max(cg_row_stride((int)cg_factor, 3), cg_row_stride((int)cg_factor, (int)std::max<int64_t>(nb, 1)));
-    const int T = (int)std::max<size_t>(1, std::min<size_t>(CG_THREADS, budget / stride));
-    const size_t smem = (size_t)T * stride * 8;
+    const size_t budget = 56 * 1024 / 8; // 64-bit words of staging per block: four blocks per SM
+    const int s3 = cg_row_stride((int)cg_factor, 3), sn = cg_row_stride((int)cg_factor, (int)std::max<int64_t>(nb, 1));
+    const size_t per_interval = 2 * (size_t)s3 + 2 * (size_t)sn;
+    if (per_interval > budget) return cb_set_error(CHROMO_ERR_ARG, "chromo_cg_chromatin: cg_factor too large");
+    const int T = (int)std::max<size_t>(1, std::min<size_t>(CG_THREADS, budget / per_interval));
+    const size_t smem = (size_t)T * per_interval * 8;
     const size_t nr = (size_t)R * N * 3, ns = (size_t)R * N * nb, ncg = (size_t)R * M * 3, nscg = (size_t)R * M * nb;
     double *d_r = nullptr, *d_t3 = nullptr, *d_rcg = nullptr, *d_t3cg = nullptr, *d_t2cg = nullptr;
     long long *d_st = nullptr, *d_md = nullptr, *d_stcg = nullptr, *d_mdcg = nullptr;
@@ -626,7 +681,9 @@ extern "C" int chromo_refine_path(int device, int64_t R, int64_t num_beads_cg, i
     if (L.seg > 4096) return cb_set_error(CHROMO_ERR_ARG, "chromo_refine_path: more than 4096 refined beads per coarse bond");
     int rc = select_device(device);
     if (rc) return rc;
-    const int per_warp = (int)std::max<long long>(4 * (L.seg + 1), 3 * RF_WALK_CHUNK);
+    const int G = refine_group(L.seg), gpw = 32 / G;
+    const long long inner_warps = (L.M - 2 + gpw - 1) / gpw, warps = inner_warps + 3;
+    const int per_warp = (int)std::max<long long>((long long)gpw * 4 * (L.seg + 1), 3 * RF_WALK_CHUNK);
     const int wpb = (int)std::max<long long>(1, std::min<long long>(8, (160 * 1024 / 8) / per_warp));
     const size_t smem = (size_t)wpb * per_warp * 8;
     const size_t ncg = (size_t)R * L.M * 3, nxi = (size_t)R * L.draws * 3, nout = (size_t)R * L.points * 3;
@@ -645,9 +702,10 @@ extern "C" int chromo_refine_path(int device, int64_t R, int64_t num_beads_cg, i
     if (orientations) RCK(dev_alloc(&d_t2, nout));
     a.L = L; a.R = R; a.spacing = bead_spacing; a.out_scale = out_scale; a.orient = orientations;
     a.cg = d_cg; a.xi = d_xi; a.seed = seed; a.out = d_out; a.out_t2 = d_t2; a.wpb = wpb; a.per_warp = per_warp;
+    a.G = G; a.inner_warps = inner_warps;
     RCK(cudaFuncSetAttribute(refine_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     timer_start(tm, kernel_ms, s);
-    CB_LAUNCH(refine_path_kernel, dim3((unsigned)((L.nseg + wpb - 1) / wpb), (unsigned)R), dim3(32 * wpb), smem, s, a);
+    CB_LAUNCH(refine_path_kernel, dim3((unsigned)((warps + wpb - 1) / wpb), (unsigned)R), dim3(32 * wpb), smem, s, a);
     RCK(cudaGetLastError());
     timer_stop(tm, kernel_ms, s);
     RCK(cudaMemcpyAsync(out, d_out, nout * 8, cudaMemcpyDeviceToHost, s));
@@ -677,7 +735,7 @@ extern "C" int chromo_enforce_spherical_confinement(int device, int64_t R, int64
     RCK(cudaMemcpyAsync(d_in, r, n * 8, cudaMemcpyHostToDevice, s));
     a.R = R; a.N = N; a.rad = rad; a.in = d_in; a.out = d_out;
     timer_start(tm, kernel_ms, s);
-    CB_LAUNCH(confine_kernel, dim3((unsigned)((N + 255) / 256), (unsigned)R), dim3(256), 0, s, a);
+    CB_LAUNCH(confine_kernel, dim3((unsigned)((N + CF_TILE - 1) / CF_TILE), (unsigned)R), dim3(256), 0, s, a);
     RCK(cudaGetLastError());
     timer_stop(tm, kernel_ms, s);
     RCK(cudaMemcpyAsync(r, d_out, n * 8, cudaMemcpyDeviceToHost, s));

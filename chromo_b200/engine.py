@@ -109,6 +109,18 @@ class Engine:
                 raise ValueError("bond parameter arrays must have N-1 entries per set")
         check(self._L.chromo_set_bond_params(self._h, n_sets, *[_lib.dptr(a) for a in arrs]))
 
+    def set_twist_params(self, eps_twist=None, natural_twist=None):
+        """SSTWLC: twist modulus and natural twist per bond ([N-1] or [R, N-1]); None switches the
+        twist term off (polymers.pyx:2000, 2088-2090)."""
+        if eps_twist is None:
+            check(self._L.chromo_set_twist_params(self._h, 0, None, None))
+            return
+        a, b = _f64(eps_twist), _f64(natural_twist)
+        n_sets = 1 if a.ndim == 1 else a.shape[0]
+        if a.size != n_sets * (self.N - 1) or b.size != a.size:
+            raise ValueError("twist parameter arrays must have N-1 entries per set")
+        check(self._L.chromo_set_twist_params(self._h, n_sets, _lib.dptr(a), _lib.dptr(b)))
+
     def set_access_volumes(self, access_vol=None):
         a = None if access_vol is None else _f64(access_vol, (self.n_bins,))
         check(self._L.chromo_set_access_volumes(self._h, _lib.dptr(a)))

@@ -64,6 +64,8 @@ class ReplicaEnsemble:
         self.engine.set_binders(self.binders, *field_prefactors)
         self.engine.set_bond_params(bond_params["eps_bend"], bond_params["eps_par"], bond_params["eps_perp"],
                                     bond_params["gamma"], bond_params["eta"])
+        if bond_params.get("eps_twist") is not None:  # SSTWLC replicas (polymers.pyx:1889-2319)
+            self.engine.set_twist_params(bond_params["eps_twist"], bond_params["natural_twist"])
         if access_vol is not None:
             self.engine.set_access_volumes(access_vol)
         self.chi = np.ascontiguousarray(np.broadcast_to(np.asarray(chi, dtype=float), (self.R,)))

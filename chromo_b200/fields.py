@@ -76,6 +76,8 @@ class FieldBase:
                        max_binders=poly.max_binders)
             e.set_binders(binder_dicts(poly), *self._prefactors(poly.num_binders))
             e.set_bond_params(poly.eps_bend, poly.eps_par, poly.eps_perp, poly.gamma, poly.eta)
+            if getattr(poly, "eps_twist", None) is not None:  # SSTWLC
+                e.set_twist_params(poly.eps_twist, poly.natural_twist)
             self._engine, self._engine_poly = e, poly
         return self._engine
 

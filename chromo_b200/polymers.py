@@ -290,6 +290,8 @@ class SSWLC(PolymerBase):
             bd = binder_dicts(self)
             e.set_binders(bd, *_zero_prefactors(self.num_binders))
             e.set_bond_params(self.eps_bend, self.eps_par, self.eps_perp, self.gamma, self.eta)
+            if getattr(self, "eps_twist", None) is not None:  # SSTWLC
+                e.set_twist_params(self.eps_twist, self.natural_twist)
             self._engine = e
         return self._engine
 
@@ -330,6 +332,47 @@ class SSWLC(PolymerBase):
                                          np.random.default_rng(np.random.randint(2 ** 31)))
         t3, t2 = paths.estimate_tangents_from_coordinates(r)
         return cls(name, r, t3=t3, t2=t2, bead_length=step_lengths, **kwargs)
+
+
+LENGTH_BP = 0.332                      # polymers.pyx:38
+NATURAL_TWIST_BARE = 2 * np.pi / 10.5  # polymers.pyx:40
+
+
+class SSTWLC(SSWLC):
+    """Stretchable, shearable wormlike chain with twist (polymers.pyx:1889-2319): every bond energy
+    carries 0.5 * eps_twist * wrap(omega - natural twist)^2 (E_pair_with_twist 2050-2102), in the MC
+    kernel (`-DCB_TWIST` builds) and in `compute_E`."""
+
+    def __init__(self, name, r, *, bead_length, lp, lt, bead_rad=5, t3=empty_2d, t2=empty_2d,
+                 states=mty_2d_int, binder_names=empty_1d, chemical_mods=mty_2d_int,
+                 chemical_mod_names=empty_1d, log_path="", max_binders=-1):
+        self.lt = float(lt)
+        super().__init__(name, r, bead_length=bead_length, lp=lp, bead_rad=bead_rad, t3=t3, t2=t2, states=states,
+                         binder_names=binder_names, chemical_mods=chemical_mods,
+                         chemical_mod_names=chemical_mod_names, log_path=log_path, max_binders=max_binders)
+        self.required_attrs = np.array(["name", "r", "t3", "t2", "states", "binder_names", "num_binders",
+                                        "beads", "num_beads", "lp", "lt", "bead_rad"])
+        self._arrays = np.array(['r', 't3', 't2', 'states', 'bead_length', 'chemical_mods'])
+        self.check_attrs()
+
+    def _find_parameters(self, bead_length):
+        """polymers.pyx:1957-2001: the SSWLC parameters plus eps_twist = lt / (delta * lp); the natural
+        twist of a bond is bead_length * NATURAL_TWIST_BARE / LENGTH_BP (2088-2090)."""
+        super()._find_parameters(bead_length)
+        self.eps_twist = self.lt / (self.delta * self.lp)
+        self.natural_twist = np.asarray(bead_length, dtype=float) * NATURAL_TWIST_BARE / LENGTH_BP
+
+    def compute_E_no_twist(self):
+        """polymers.pyx:2287-2319: the elastic energy without the twist term."""
+        e = self._polymer_engine()
+        e.set_twist_params(None)
+        try:
+            return super().compute_E()
+        finally:
+            e.set_twist_params(self.eps_twist, self.natural_twist)
+
+    def __str__(self):
+        return f"Polymer_Class<SSTWLC>, {PolymerBase.__str__(self)}"
 
 
 class Chromatin(SSWLC):

@@ -154,6 +154,15 @@ int chromo_set_replica_params(chromo_ctx *ctx, const double *chi, const double *
 int chromo_set_bond_params(chromo_ctx *ctx, int64_t n_sets, const double *eps_bend,
                            const double *eps_par, const double *eps_perp, const double *gamma,
                            const double *eta);
+/* SSTWLC._find_parameters / E_pair_with_twist (polymers.pyx:1957-2001, 2050-2102): per bond the twist
+ * modulus eps_twist = lt / (delta * lp) and the natural twist bead_length * NATURAL_TWIST_BARE /
+ * LENGTH_BP; [n_sets][N-1] each, n_sets = 1 (shared) or n_replicas.  Once set, every bond energy of
+ * chromo_mc_sim / chromo_mc_step / chromo_elastic_energy carries the twist term
+ * 0.5 * eps_twist * wrap(omega - natural_twist)^2 with omega = compute_twist_angle_omega
+ * (polymers.pyx:3427-3461).  Both pointers NULL: back to a chain without twist.  One or two binders. */
+int chromo_set_twist_params(chromo_ctx *ctx, int64_t n_sets, const double *eps_twist,
+                            const double *natural_twist);
+
 /* access_vols[n_bins] (fields.pyx:523-525, 714-770); NULL = vol_bin everywhere */
 int chromo_set_access_volumes(chromo_ctx *ctx, const double *access_vol);
 

@@ -266,7 +266,29 @@ static double E_pair(const oc_sim *s, const double *bend, double dr_par,
            0.5 * s->eps_perp[b] * dot3(dr_perp, dr_perp);
 }
 
-/* SSWLC.compute_E polymers.pyx:1348-1381 */
+/* compute_twist_angle_omega polymers.pyx:3427-3461 */
+static double twist_omega(const double *t2_0, const double *t3_0, const double *t2_1, const double *t3_1)
+{
+    double t1_0[3], t1_1[3];
+    t1_0[0] = t2_0[1] * t3_0[2] - t2_0[2] * t3_0[1];
+    t1_0[1] = t2_0[2] * t3_0[0] - t2_0[0] * t3_0[2];
+    t1_0[2] = t2_0[0] * t3_0[1] - t2_0[1] * t3_0[0];
+    t1_1[0] = t2_1[1] * t3_1[2] - t2_1[2] * t3_1[1];
+    t1_1[1] = t2_1[2] * t3_1[0] - t2_1[0] * t3_1[2];
+    t1_1[2] = t2_1[0] * t3_1[1] - t2_1[1] * t3_1[0];
+    return atan2(dot3(t2_0, t1_1) - dot3(t1_0, t2_1), dot3(t1_0, t1_1) + dot3(t2_0, t2_1));
+}
+
+/* the twist term of E_pair_with_twist polymers.pyx:2050-2102 (0 for chains without twist) */
+static double E_twist(const oc_sim *s, double omega, int64_t b)
+{
+    const double two_pi = 2 * M_PI;
+    double d = omega - s->twist0[b];
+    d -= two_pi * floor((d + M_PI) / two_pi);
+    return 0.5 * s->eps_twist[b] * (d * d);
+}
+
+/* SSWLC.compute_E polymers.pyx:1348-1381; SSTWLC.compute_E 2250-2285 */
 double oc_poly_E(const oc_sim *s)
 {
     double E = 0;
@@ -280,7 +302,11 @@ double oc_poly_E(const oc_sim *s)
         dr_par = dot3(t0, dr);
         for (j = 0; j < 3; j++) dr_perp[j] = dr[j] - t0[j] * dr_par;
         for (j = 0; j < 3; j++) bend[j] = t1[j] + (-t0[j] - s->eta[i - 1] * dr_perp[j]);
-        E += E_pair(s, bend, dr_par, dr_perp, i - 1);
+        if (s->eps_twist)
+            E += E_pair(s, bend, dr_par, dr_perp, i - 1) +
+                 E_twist(s, twist_omega(&s->t2[3 * (i - 1)], t0, &s->t2[3 * i], t1), i - 1);
+        else
+            E += E_pair(s, bend, dr_par, dr_perp, i - 1);
     }
     return E;
 }
@@ -288,7 +314,8 @@ double oc_poly_E(const oc_sim *s)
 /* bead_pair_dE_poly_forward polymers.pyx:1177-1277 */
 static double pair_dE_forward(const oc_sim *s, const double *r_0, const double *r_1,
                               const double *test_r_1, const double *t3_0,
-                              const double *t3_1, const double *test_t3_1, int64_t b)
+                              const double *t3_1, const double *test_t3_1, const double *t2_0,
+                              const double *t2_1, const double *test_t2_1, int64_t b)
 {
     double dr[3], dr_test[3], dr_perp[3], dr_perp_test[3], bend[3], bend_test[3];
     double dr_par, dr_par_test;
@@ -305,6 +332,10 @@ static double pair_dE_forward(const oc_sim *s, const double *r_0, const double *
         bend_test[i] = test_t3_1[i] - t3_0[i] - dr_perp_test[i] * s->eta[b];
         bend[i] = t3_1[i] - t3_0[i] - dr_perp[i] * s->eta[b];
     }
+    if (s->eps_twist) /* bead_pair_dE_poly_forward_with_twist polymers.pyx:2104-2175 */
+        return (E_pair(s, bend_test, dr_par_test, dr_perp_test, b) +
+                E_twist(s, twist_omega(t2_0, t3_0, test_t2_1, test_t3_1), b)) -
+               (E_pair(s, bend, dr_par, dr_perp, b) + E_twist(s, twist_omega(t2_0, t3_0, t2_1, t3_1), b));
     return E_pair(s, bend_test, dr_par_test, dr_perp_test, b) -
            E_pair(s, bend, dr_par, dr_perp, b);
 }
@@ -312,7 +343,8 @@ static double pair_dE_forward(const oc_sim *s, const double *r_0, const double *
 /* bead_pair_dE_poly_reverse polymers.pyx:1279-1346 */
 static double pair_dE_reverse(const oc_sim *s, const double *r_0, const double *test_r_0,
                               const double *r_1, const double *t3_0,
-                              const double *test_t3_0, const double *t3_1, int64_t b)
+                              const double *test_t3_0, const double *t3_1, const double *t2_0,
+                              const double *test_t2_0, const double *t2_1, int64_t b)
 {
     double dr[3], dr_test[3], dr_perp[3], dr_perp_test[3], bend[3], bend_test[3];
     double dr_par, dr_par_test;
@@ -329,6 +361,10 @@ static double pair_dE_reverse(const oc_sim *s, const double *r_0, const double *
         bend_test[i] = t3_1[i] - test_t3_0[i] - dr_perp_test[i] * s->eta[b];
         bend[i] = t3_1[i] - t3_0[i] - dr_perp[i] * s->eta[b];
     }
+    if (s->eps_twist) /* bead_pair_dE_poly_reverse_with_twist polymers.pyx:2177-2248 */
+        return (E_pair(s, bend_test, dr_par_test, dr_perp_test, b) +
+                E_twist(s, twist_omega(test_t2_0, test_t3_0, t2_1, t3_1), b)) -
+               (E_pair(s, bend, dr_par, dr_perp, b) + E_twist(s, twist_omega(t2_0, t3_0, t2_1, t3_1), b));
     return E_pair(s, bend_test, dr_par_test, dr_perp_test, b) -
            E_pair(s, bend, dr_par, dr_perp, b);
 }
@@ -340,11 +376,13 @@ static double continuous_dE_poly(const oc_sim *s, int64_t ind0, int64_t indf)
     if (ind0 != 0)
         dE += pair_dE_forward(s, &s->r[3 * (ind0 - 1)], &s->r[3 * ind0], &s->r_trial[3 * ind0],
                               &s->t3[3 * (ind0 - 1)], &s->t3[3 * ind0],
-                              &s->t3_trial[3 * ind0], ind0 - 1);
+                              &s->t3_trial[3 * ind0], &s->t2[3 * (ind0 - 1)], &s->t2[3 * ind0],
+                              &s->t2_trial[3 * ind0], ind0 - 1);
     if (indf != s->N)
         dE += pair_dE_reverse(s, &s->r[3 * (indf - 1)], &s->r_trial[3 * (indf - 1)],
                               &s->r[3 * indf], &s->t3[3 * (indf - 1)],
-                              &s->t3_trial[3 * (indf - 1)], &s->t3[3 * indf], indf - 1);
+                              &s->t3_trial[3 * (indf - 1)], &s->t3[3 * indf], &s->t2[3 * (indf - 1)],
+                              &s->t2_trial[3 * (indf - 1)], &s->t2[3 * indf], indf - 1);
     return dE;
 }
 

@@ -96,6 +96,9 @@ typedef struct {
     double last_dE_poly, last_dE_field;
     int64_t last_accept;
     double last_u;
+    /* --- SSTWLC twist (polymers.pyx:1889-2319); NULL for SSWLC / Chromatin --- */
+    double *eps_twist;                       /* [N-1] lt / (delta * lp), polymers.pyx:2000 */
+    double *twist0;                          /* [N-1] bead_length * NATURAL_TWIST_BARE / LENGTH_BP, 2088-2090 */
 } oc_sim;
 
 /* RNG */

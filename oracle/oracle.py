@@ -70,6 +70,7 @@ class Sim(C.Structure):
         ("crng", GlibcRand), ("mt", MT19937),
         ("last_dE_poly", C.c_double), ("last_dE_field", C.c_double),
         ("last_accept", C.c_int64), ("last_u", C.c_double),
+        ("eps_twist", _pd), ("twist0", _pd),
     ]
 
 
@@ -345,6 +346,11 @@ class OracleSim:
                                             _p(self.mods, _pl))
         for name in ("eps_bend", "eps_par", "eps_perp", "gamma", "eta"):
             setattr(s, name, _p(self.bp[name], _pd))
+        if spec.get("lt") is not None:  # SSTWLC: twist modulus and natural twist per bond (polymers.pyx:2000, 2088-2090)
+            bl = np.asarray(spec["bead_length"], dtype=float)
+            self.eps_twist = f64(spec["lt"] / ((bl / spec["lp"]) * spec["lp"]))
+            self.twist0 = f64(bl * (2 * np.pi / 10.5) / 0.332)
+            s.eps_twist, s.twist0 = _p(self.eps_twist, _pd), _p(self.twist0, _pd)
         s.max_binders = spec.get("max_binders", -1)
         s.mu_adjust_factor = mu_adjust_factor
         s.bead_vol = (4 / 3) * np.pi * spec["bead_rad"] ** 3  # beads.py:415
@@ -491,7 +497,9 @@ def ref_objects(spec: dict):
         max_binders=spec.get("max_binders", -1),
     )
     r = np.ascontiguousarray(spec["r"], dtype=float).copy()
-    if spec["lp"] == 53.0:
+    if spec.get("lt") is not None:
+        poly = ply.SSTWLC("replica", r, lp=float(spec["lp"]), lt=float(spec["lt"]), **kw)
+    elif spec["lp"] == 53.0:
         poly = ply.Chromatin("replica", r, **kw)
     else:
         poly = ply.SSWLC("replica", r, lp=float(spec["lp"]), **kw)

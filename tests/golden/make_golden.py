@@ -25,6 +25,8 @@ OUT = Path(__file__).resolve().parent
 def spec_to_npz(spec):
     meta = dict(N=spec["N"], nb=spec["nb"], lp=spec["lp"], bead_rad=spec["bead_rad"],
                 binders=spec["binders"], field=spec["field"], max_binders=spec["max_binders"])
+    if spec.get("lt") is not None:
+        meta["lt"] = spec["lt"]
     arrs = {k: np.asarray(spec[k]) for k in ("r", "t3", "t2", "states", "mods", "bead_length")}
     arrs["meta"] = np.array(json.dumps(meta))
     return arrs
@@ -164,6 +166,16 @@ if __name__ == "__main__":
     golden_csv("snapshot_sswlc", O.make_spec(N=25, nb=1, seed=12, binders=[dict(O.NULL_READER)], confine="",
                                              grid=4, random_states=False, lp=10.0), "homopolymer")
     if only == ["csv"]:
+        sys.exit(0)
+    # SSTWLC (twist, polymers.pyx:1889-2319): HP1 chain with a twist persistence length
+    tw = dict(O.make_spec(N=220, nb=1, seed=7), lt=100.0)
+    tw2 = dict(O.make_spec(N=180, nb=2, seed=8, cross_talk=-1.0, lp=30.0), lt=60.0)
+    golden_static("static_tw", tw)
+    golden_static("static_tw2", tw2)
+    golden_moves("moves_tw", tw, 400, 105)
+    golden_moves("moves_tw2", tw2, 300, 106)
+    golden_mc_sim("mcsim_tw", dict(O.make_spec(N=220, nb=1, seed=7, random_states=False), lt=100.0), 12, 24, 34)
+    if only == ["twist"]:
         sys.exit(0)
     # C1-like: homopolymer, null_reader, periodic box (confine_type="")
     c1 = O.make_spec(N=200, nb=1, seed=1, binders=[dict(O.NULL_READER)], confine="", grid=8,

@@ -24,6 +24,9 @@ def engine_from_spec(spec, R=1, device=0, chi=None, mu=None):
     e.set_binders(spec["binders"], pref, e_intra, xpref)
     bp = O.bond_params(spec["bead_length"], spec["lp"])
     e.set_bond_params(bp["eps_bend"], bp["eps_par"], bp["eps_perp"], bp["gamma"], bp["eta"])
+    if spec.get("lt") is not None:  # SSTWLC (polymers.pyx:2000, 2088-2090)
+        bl = np.asarray(spec["bead_length"], dtype=float)
+        e.set_twist_params(spec["lt"] / ((bl / spec["lp"]) * spec["lp"]), bl * (2 * np.pi / 10.5) / 0.332)
     e.set_replica_params(chi=(f["chi"] if f is not None else 1.0) if chi is None else chi,
                          mu=[b["chemical_potential"] for b in spec["binders"]] if mu is None else mu)
     tile = lambda a: np.broadcast_to(np.asarray(a), (R,) + np.asarray(a).shape).copy()

@@ -14,5 +14,7 @@ g++ $FLAGS -DCB_INST_REPLAY=1 -DCB_INST_HI=0 -c "$src/mc_inst.cu" -o "$out/r12.o
 g++ $FLAGS -DCB_INST_REPLAY=1 -DCB_INST_HI=1 -c "$src/mc_inst.cu" -o "$out/r34.o" &
 g++ $FLAGS -DCB_INST_REPLAY=0 -DCB_INST_HI=0 -c "$src/mc_inst.cu" -o "$out/p12.o" &
 g++ $FLAGS -DCB_INST_REPLAY=0 -DCB_INST_HI=1 -c "$src/mc_inst.cu" -o "$out/p34.o" &
+g++ $FLAGS -DCB_INST_REPLAY=1 -DCB_INST_HI=0 -DCB_TWIST=1 -c "$src/mc_inst.cu" -o "$out/rt12.o" &
+g++ $FLAGS -DCB_INST_REPLAY=0 -DCB_INST_HI=0 -DCB_TWIST=1 -c "$src/mc_inst.cu" -o "$out/pt12.o" &
 wait
-g++ -shared -pthread -o "$here/libchromo_emu.so" "$out/api.o" "$out/rd.o" "$out/r12.o" "$out/r34.o" "$out/p12.o" "$out/p34.o"
+g++ -shared -pthread -o "$here/libchromo_emu.so" "$out/api.o" "$out/rd.o" "$out/r12.o" "$out/r34.o" "$out/p12.o" "$out/p34.o" "$out/rt12.o" "$out/pt12.o"

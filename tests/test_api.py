@@ -25,11 +25,15 @@ def build(spec, lazy=False):
         objs.append(o)
     binders = bnd.make_binder_collection(objs)
     N, nb = spec["N"], spec["nb"]
-    p = ply.Chromatin("c", spec["r"].copy(), bead_length=spec["bead_length"], t3=spec["t3"].copy(),
-                      t2=spec["t2"].copy(), states=spec["states"].reshape(N, nb).copy(),
-                      binder_names=np.array([b["name"] for b in spec["binders"]]),
-                      chemical_mods=spec["mods"].reshape(N, nb).copy(),
-                      chemical_mod_names=np.array([f"m{j}" for j in range(nb)]))
+    kw = dict(bead_length=spec["bead_length"], t3=spec["t3"].copy(),
+              t2=spec["t2"].copy(), states=spec["states"].reshape(N, nb).copy(),
+              binder_names=np.array([b["name"] for b in spec["binders"]]),
+              chemical_mods=spec["mods"].reshape(N, nb).copy(),
+              chemical_mod_names=np.array([f"m{j}" for j in range(nb)]))
+    if spec.get("lt") is not None:  # twist: polymers.pyx:1889
+        p = ply.SSTWLC("c", spec["r"].copy(), lp=spec["lp"], lt=spec["lt"], **kw)
+    else:
+        p = ply.Chromatin("c", spec["r"].copy(), **kw)
     f = spec["field"]
     field = fld.UniformDensityField([p], binders, f["x_width"], f["nx"], f["y_width"], f["ny"], f["z_width"],
                                     f["nz"], confine_type=f["confine_type"], confine_length=f["confine_length"],
@@ -37,7 +41,7 @@ def build(spec, lazy=False):
     return p, binders, field
 
 
-@pytest.mark.parametrize("name", ["static_c2", "static_c3"])
+@pytest.mark.parametrize("name", ["static_c2", "static_c3", "static_tw2"])
 def test_construction_and_energies(backend, name):
     spec, g = load_golden(name)
     p, binders, field = build(spec)
@@ -51,9 +55,14 @@ def test_construction_and_energies(backend, name):
     assert np.array_equal([b["interaction_energy_intranucleosome"] for b in bd], g["e_intra"])
     assert close(field.compute_E(p), float(g["E_field"]))
     assert close(p.compute_E(), float(g["E_poly"]))
+    if "lt" in spec:  # SSTWLC: the twist term is separable (compute_E_no_twist polymers.pyx:2287-2319)
+        twist = p.compute_E() - p.compute_E_no_twist()
+        assert twist > 0 and close(p.compute_E(), float(g["E_poly"]))  # the term is restored afterwards
+        with pytest.raises(Exception, match="Twist modulus must be positive"):
+            p._polymer_engine().set_twist_params(np.zeros(spec["N"] - 1), p.natural_twist)
 
 
-@pytest.mark.parametrize("name", ["mcsim_c2", "mcsim_c3"])
+@pytest.mark.parametrize("name", ["mcsim_c2", "mcsim_c3", "mcsim_tw"])
 def test_mc_sim_drop_in(backend, name):
     """all_moves + SimpleControl + mc_sim, replaying the reference's RNG streams."""
     from chromo_b200.mc import get_amplitude_bounds, mc_controller as ctrl, set_rng_mode

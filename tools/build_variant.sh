@@ -21,7 +21,9 @@ nvcc $F -DCB_INST_REPLAY=1 -DCB_INST_HI=0 -c mc_inst.cu -o "$tmp/r12.o" &
 nvcc $F -DCB_INST_REPLAY=1 -DCB_INST_HI=1 -c mc_inst.cu -o "$tmp/r34.o" &
 nvcc $F -DCB_INST_REPLAY=0 -DCB_INST_HI=0 -c mc_inst.cu -o "$tmp/p12.o" &
 nvcc $F -DCB_INST_REPLAY=0 -DCB_INST_HI=1 -c mc_inst.cu -o "$tmp/p34.o" &
+nvcc $F -DCB_INST_REPLAY=1 -DCB_INST_HI=0 -DCB_TWIST=1 -c mc_inst.cu -o "$tmp/rt12.o" &
+nvcc $F -DCB_INST_REPLAY=0 -DCB_INST_HI=0 -DCB_TWIST=1 -c mc_inst.cu -o "$tmp/pt12.o" &
 wait
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$out" "$tmp/api.o" "$tmp/rd.o" "$tmp/r12.o" "$tmp/r34.o" "$tmp/p12.o" "$tmp/p34.o"
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$out" "$tmp/api.o" "$tmp/rd.o" "$tmp/r12.o" "$tmp/r34.o" "$tmp/p12.o" "$tmp/p34.o" "$tmp/rt12.o" "$tmp/pt12.o"
 rm -rf "$tmp"
 echo "built $out from $rev"
