@@ -42,15 +42,16 @@ def swap_decisions(chi: np.ndarray, phi: np.ndarray, round_index: int, seed: int
     (1,2),(3,4).. on odd rounds.
     """
     chi = np.asarray(chi, dtype=float).copy()
+    phi = np.asarray(phi, dtype=float)
     order = np.argsort(chi, kind="stable")  # ladder position -> replica id
     start = round_index % 2
-    pairs = [(order[p], order[p + 1]) for p in range(start, len(chi) - 1, 2)]
-    u = _uniforms(seed, round_index, len(pairs))
-    for (a, b), ui in zip(pairs, u):
-        dE = (chi[a] - chi[b]) * (phi[b] - phi[a])
-        with np.errstate(over="ignore"):
-            if ui < np.exp(-dE):
-                chi[a], chi[b] = chi[b], chi[a]
+    a, b = order[start:len(chi) - 1:2], order[start + 1::2]  # disjoint pairs: decided all at once
+    b = b[:len(a)]
+    u = _uniforms(seed, round_index, len(a))
+    dE = (chi[a] - chi[b]) * (phi[b] - phi[a])
+    with np.errstate(over="ignore"):
+        swap = u < np.exp(-dE)
+    chi[a[swap]], chi[b[swap]] = chi[b[swap]], chi[a[swap]]
     return chi
 
 

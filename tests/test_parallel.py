@@ -36,6 +36,32 @@ def test_swap_rule():
     assert abs(acc - np.exp(-1.0)) < 0.03
 
 
+def _swap_loop(chi, phi, round_index, seed):
+    """Pair-by-pair statement of the exchange rule (the checker of the vectorised form)."""
+    chi = np.asarray(chi, dtype=float).copy()
+    order = np.argsort(chi, kind="stable")
+    pairs = [(order[p], order[p + 1]) for p in range(round_index % 2, len(chi) - 1, 2)]
+    u = par._uniforms(seed, round_index, len(pairs))
+    for (a, b), ui in zip(pairs, u):
+        with np.errstate(over="ignore"):
+            if ui < np.exp(-(chi[a] - chi[b]) * (phi[b] - phi[a])):
+                chi[a], chi[b] = chi[b], chi[a]
+    return chi
+
+
+def test_vectorised_swaps_equal_the_pairwise_rule():
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 7, 64, 4096):
+        chi = rng.permutation(np.geomspace(0.25, 4.0, n))
+        for rnd in range(4):
+            phi = rng.normal(size=n) * 3
+            want = _swap_loop(chi, phi, rnd, seed=5)
+            got = par.swap_decisions(chi, phi, rnd, seed=5)
+            assert np.array_equal(got, want), (n, rnd)
+            chi = got
+    assert np.array_equal(par.swap_decisions(np.array([1.0]), np.array([0.0]), 0, 1), [1.0])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -34,6 +34,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default="", help="run only the cases whose name starts with this (e.g. C2)")
     a = ap.parse_args()
     pk, src = peak()
     rng = np.random.default_rng(0)
@@ -41,6 +42,8 @@ def main():
     for name, R, N, k, nb in (("C2 1024 x 10000 beads, cg 5", 1024, 10000, 5, 1),
                               ("C3 1024 x 10000 beads, 2 binders, cg 10", 1024, 10000, 10, 2),
                               ("C4 16 x 400000 beads, cg 40", 16, 400000, 40, 1)):
+        if a.only and not name.startswith(a.only):
+            continue
         r = rng.standard_normal((R, N, 3))
         t3 = rng.standard_normal((R, N, 3))
         st = rng.integers(0, 3, (R, N, nb))
