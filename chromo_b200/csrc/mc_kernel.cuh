@@ -206,7 +206,7 @@ __device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin, boo
 // and +w/V*{1,state'} at its trial position to the 8 voxels around each.
 //   kind 0: trial = M r (crank-shaft, end-pivot)   kind 1: trial = r + t (slide)
 //   kind 2: trial position = current position, state' = newst (binding)
-// G lanes share a bead (G = 16/8/4/2/1 by segment length).  A bead whose current
+// G lanes share a bead (G = 16/8/4/2/1 by the beads left to do).  A bead whose current
 // and trial positions fall in the same cell (most slides and small rotations,
 // every binding move) has 8 merged units -- one per voxel corner l (bit0 x,
 // bit1 y, bit2 z), trial minus current -- otherwise 16 units (k = 0 current /
@@ -221,12 +221,18 @@ __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, Warp
     const double *Rr = C.r + (long long)rep * C.N * 3;
     const signed char *ST = C.states + (long long)rep * C.N * NB;
     const double *dens_rows = C.density + (long long)rep * C.n_bins * NCOL;
-    const int G = n <= 2 ? 16 : n <= 4 ? 8 : n <= 8 ? 4 : n <= 16 ? 2 : 1;
-    const int per_iter = 32 / G;
-    const int sub = lane & (G - 1);
     const bool checked = P > 1 || 16 * n > H.limit;
     int out_t = 0, out_c = 0;
+    int per_iter;
     for (int base = 0; base < n; base += per_iter) {
+        // lanes per bead, chosen per iteration from the beads still to do: an underfull last iteration
+        // spreads each bead's 16 units over more lanes instead of leaving lanes idle; 17..24 beads go as
+        // 16 beads on 2 lanes each now and the rest on 4..16 lanes each next time (10-12 units per lane
+        // instead of 16).  The table cells are fixed point, so the split does not change any result.
+        const int rem = n - base;
+        const int G = rem <= 2 ? 16 : rem <= 4 ? 8 : rem <= 8 ? 4 : rem <= 24 ? 2 : 1;
+        per_iter = 32 / G;
+        const int sub = lane & (G - 1);
         const int i = base + lane / G;
         if (i >= n) continue;
         const int bead = ind0 + i;

@@ -175,26 +175,44 @@ __global__ void __launch_bounds__(CG_THREADS) cg_reduce_kernel(const CB_GRID_CON
         long long *dst = which == 0 ? a.states_cg : a.mods_cg;
         if (!(which == 0 ? a.states : a.mods)) continue;
         for (int c = 0; c < nb; c++) {
+            // occurrence counts of the values 0..15 packed as 16 bytes (two 64-bit words): one shift
+            // and add per bead; intervals longer than 255 beads are counted in chunks
+            unsigned long long lo = 0, hi = 0;
             int count[CG_MAX_VALUE];
+            bool bad = false, wide = cnt > 255;
+            if (wide) {
 #pragma unroll
-            for (int v = 0; v < CG_MAX_VALUE; v++) count[v] = 0;
-            bool bad = false;
-            for (int j = 0; j < cnt; j++) {
-                const long long v = row[j * nb + c];
-                if (v < 0 || v >= CG_MAX_VALUE) {
-                    bad = true;
-                    continue;
-                }
-#pragma unroll
-                for (int w = 0; w < CG_MAX_VALUE; w++) count[w] += (w == (int)v);
+                for (int v = 0; v < CG_MAX_VALUE; v++) count[v] = 0;
             }
-            int best = 0, best_count = count[0];
-#pragma unroll
-            for (int w = 1; w < CG_MAX_VALUE; w++)
-                if (count[w] > best_count) {
-                    best = w;
-                    best_count = count[w];
+            int vmax = 0;
+            for (int j0 = 0; j0 < cnt; j0 += 255) {
+                const int j1 = min(cnt, j0 + 255);
+                for (int j = j0; j < j1; j++) {
+                    const long long v = row[j * nb + c];
+                    if (v < 0 || v >= CG_MAX_VALUE) {
+                        bad = true;
+                        continue;
+                    }
+                    vmax = max(vmax, (int)v);
+                    const unsigned long long one = 1ull << (8 * ((int)v & 7));
+                    lo += v < 8 ? one : 0ull;
+                    hi += v < 8 ? 0ull : one;
                 }
+                if (wide) {
+#pragma unroll
+                    for (int w = 0; w < CG_MAX_VALUE; w++)
+                        count[w] += (int)(((w < 8 ? lo : hi) >> (8 * (w & 7))) & 0xffull);
+                    lo = hi = 0;
+                }
+            }
+            int best = 0, best_count = -1;
+            for (int w = 0; w <= vmax; w++) { // argmax(bincount): the smallest value among the most frequent
+                const int cw = wide ? count[w] : (int)(((w < 8 ? lo : hi) >> (8 * (w & 7))) & 0xffull);
+                if (cw > best_count) {
+                    best = w;
+                    best_count = cw;
+                }
+            }
             if (bad) *a.err = 1;
             dst[(rep * a.M + me) * nb + c] = cnt > 1 ? (long long)best : row[c];
         }
@@ -516,21 +534,33 @@ __global__ void __launch_bounds__(256) confine_kernel(const CB_GRID_CONSTANT Con
     }
     __syncthreads();
     const double kern[7] = {0.98, 0.97, 0.96, 0.95, 0.96, 0.97, 0.98};
-    double *dst = a.out + rep * a.N * 3;
-    // one output double per thread and pass: coalesced stores
-    // (beads outside [0, N) have inv_f = 0 below: the halo slots are zeroed first)
-    const int ne = (int)(min(a.N, j0 + CF_TILE) - j0) * 3;
-    dst += j0 * 3;
-    for (int e = threadIdx.x; e < ne; e += 256) {
-        const int t = e / 3 + 3; // this bead's slot in the tile
-        double x = tile[e + 9];
+    // (beads outside [0, N) have inv_f = 0: the halo slots were zeroed first)
+    const int nbeads = (int)(min(a.N, j0 + CF_TILE) - j0);
+    // one thread per bead: its window factors once, applied to the three coordinates in place
+    for (int b = threadIdx.x; b < nbeads; b += 256) {
+        double *p = tile + (b + 3) * 3;
+        double x = p[0], y = p[1], z = p[2];
+        bool any = false;
 #pragma unroll
         for (int o = -3; o <= 3; o++) {
-            const double f = inv_f[t + o]; // violator t + o
-            if (f != 0.0) x = x * (kern[3 - o] * f); // bead sits at offset 3 - o of that violator's window
+            const double f = inv_f[b + 3 + o]; // violator b + o
+            if (f != 0.0) {
+                const double w = kern[3 - o] * f; // bead sits at offset 3 - o of that violator's window
+                x = x * w;
+                y = y * w;
+                z = z * w;
+                any = true;
+            }
         }
-        dst[e] = x;
+        if (any) {
+            p[0] = x;
+            p[1] = y;
+            p[2] = z;
+        }
     }
+    __syncthreads();
+    double *dst = a.out + (rep * a.N + j0) * 3;
+    for (int e = threadIdx.x; e < nbeads * 3; e += 256) dst[e] = tile[e + 9]; // coalesced
 }
 
 // ------------------------------------------------------------------------------------------------
