@@ -139,7 +139,7 @@ def test_ensemble_coarse_graining_matches_oracle(backend, R, N, k, nb):
             assert np.array_equal(out[name][i], want), (name, i)
 
 
-@pytest.mark.parametrize("R,M,n_ref", [(3, 6, 100), (2, 20, 613), (4, 3, 9)])
+@pytest.mark.parametrize("R,M,n_ref", [(3, 6, 100), (2, 20, 613), (4, 3, 9), (2, 2, 40), (2, 300, 1000), (1, 5, 4000)])
 def test_ensemble_refinement_matches_oracle(backend, R, M, n_ref):
     import chromo_b200.util.rediscretize as rd
     rng = np.random.default_rng(R + M + n_ref)

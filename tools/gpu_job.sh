@@ -1,5 +1,6 @@
 set -x
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests/test_rediscretize.py -m gpu -x -q ) > gpurun_out/gpu_tests_rd.log 2>&1
-tail -4 gpurun_out/gpu_tests_rd.log
-timeout 600 python tools/rediscretize_bench.py --out gpurun_out/rediscretize_bench.json > gpurun_out/rd_bench.log 2>&1
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_rediscretize.py -m gpu -x -q -k "not c2_ensemble" > gpurun_out/sanitizer_memcheck_rd.log 2>&1; echo "memcheck rd rc=$?"
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_rediscretize.py -m gpu -x -q -k "not c2_ensemble" > gpurun_out/sanitizer_racecheck_rd.log 2>&1; echo "racecheck rd rc=$?"
+timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity.py tests/test_api.py -m gpu -x -q -k "tw" > gpurun_out/sanitizer_memcheck_tw.log 2>&1; echo "memcheck twist rc=$?"
+tail -4 gpurun_out/sanitizer_memcheck_rd.log gpurun_out/sanitizer_racecheck_rd.log gpurun_out/sanitizer_memcheck_tw.log
