@@ -257,6 +257,48 @@ def get_refined_orientations(t3_cg: np.ndarray, num_beads_refined: int, seed: Op
     return t3[0], t2[0]
 
 
+def brownian_bridge(N: int, p0: np.ndarray, p1: np.ndarray, avg_step_target: Optional[float] = None) -> np.ndarray:
+    """rediscretize.py:586-685: N steps from p0 to p1 (N + 1 points), average step normalised to
+    `avg_step_target`.  Runs as the bridge segment of a two-bead path on the device and consumes
+    numpy's generator like the reference (N - 1 Gaussian triples)."""
+    p0, p1 = np.asarray(p0, dtype=float), np.asarray(p1, dtype=float)
+    if N == 1:
+        return np.array([p0, p1])
+    if avg_step_target is None:
+        raise NotImplementedError("brownian_bridge without a step target is not used by the pipeline")
+    L = _lib.lib()
+    n_ref = 2 * N + 2  # two coarse beads: free end of N + 1 steps, then one bridge of N steps
+    h1 = N + 1
+    xi = np.ones((1, h1 + N - 1, 3))
+    xi[0, h1:] = np.random.standard_normal((N - 1, 3))
+    out = np.empty((1, int(L.chromo_refined_num_points(2, n_ref)), 3))
+    check(L.chromo_refine_path(0, 1, 2, n_ref, float(avg_step_target), dptr(np.ascontiguousarray([[p0, p1]])),
+                               dptr(xi), 0, 1.0, 0, dptr(out), None, None))
+    return np.vstack([out[0, h1:h1 + N], p1])
+
+
+def gaussian_walk_from_point(start, N, step_size):
+    """rediscretize.py:688-705: N unit-direction Gaussian steps of length `step_size` away from `start`
+    (N + 1 points), as the free end of a two-bead path on the device."""
+    step = np.unique(np.asarray(step_size, dtype=float))
+    if len(step) != 1:
+        raise NotImplementedError("one step length per walk")
+    if N == 0:
+        return np.asarray(start, dtype=float)[None].copy()
+    L = _lib.lib()
+    start = np.asarray(start, dtype=float)
+    n_ref = 2 * N + 6  # free end of N + 3 steps; the walk is its first N
+    h1 = N + 3
+    D = int(L.chromo_refined_num_draws(2, n_ref))
+    xi = np.ones((1, D, 3))
+    xi[0, :N] = np.random.standard_normal((N, 3))
+    out = np.empty((1, int(L.chromo_refined_num_points(2, n_ref)), 3))
+    check(L.chromo_refine_path(0, 1, 2, n_ref, float(step[0]), dptr(np.ascontiguousarray([[start, start + 1.0]])),
+                               dptr(xi), 0, 1.0, 0, dptr(out), None, None))
+    # the free end is emitted end-first: rows h1-1 ... 0 hold points 1 ... h1
+    return np.vstack([start, out[0, :h1][::-1][:N]])
+
+
 def enforce_spherical_confinement(r: np.ndarray, rad: float) -> np.ndarray:
     """rediscretize.py:708-753 (in place, returns `r`)."""
     buf = np.ascontiguousarray(r, dtype=np.float64)

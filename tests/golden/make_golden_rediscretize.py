@@ -122,5 +122,15 @@ out.update(dict(rc_nref=np.array(n_ref), rc_mods=np.vstack([md, md[:1]]), rc_r=n
                 rc_grid=np.array([uref.nx, uref.ny, uref.nz, uref.x_width, uref.y_width, uref.z_width,
                                   uref.confine_length])))
 
+# ---- the two path primitives on their own (appended last: earlier vectors keep their random inputs) ----
+for i, (N, tgt) in enumerate([(1, 2.0), (2, 0.5), (5, 8.0), (33, 3.0), (200, 16.5)]):
+    p0, p1 = rng.standard_normal(3) * 10, rng.standard_normal(3) * 10
+    np.random.seed(300 + i)
+    out[f"bb{i}_out"] = quiet(ref.brownian_bridge, N, p0, p1, tgt)
+    np.random.seed(400 + i)
+    out[f"gw{i}_out"] = ref.gaussian_walk_from_point(p0, N, np.array([tgt] * N))
+    out[f"bb{i}_in"] = np.concatenate([[N, tgt], p0, p1])
+out["bb_n"] = np.array(5)
+
 np.savez_compressed(Path(__file__).resolve().parent / "rediscretize.npz", **out)
 print("wrote rediscretize.npz with", len(out), "arrays")

@@ -116,6 +116,18 @@ def test_refined_paths_match_reference(backend, gold):
         assert rel_close(t3, gold[f"rf{i}_t3"]) and rel_close(t2, gold[f"rf{i}_t2"])
 
 
+def test_path_primitives_match_reference(backend, gold):
+    """brownian_bridge / gaussian_walk_from_point under the reference's numpy seeds."""
+    import chromo_b200.util.rediscretize as rd
+    for i in range(int(gold["bb_n"])):
+        v = gold[f"bb{i}_in"]
+        N, tgt, p0, p1 = int(v[0]), float(v[1]), v[2:5], v[5:8]
+        np.random.seed(300 + i)
+        assert rel_close(rd.brownian_bridge(N, p0, p1, tgt), gold[f"bb{i}_out"])
+        np.random.seed(400 + i)
+        assert rel_close(rd.gaussian_walk_from_point(p0, N, np.array([tgt] * N)), gold[f"gw{i}_out"])
+
+
 def test_confinement_matches_reference(backend, gold):
     import chromo_b200.util.rediscretize as rd
     for i in range(int(gold["cf_n"])):
