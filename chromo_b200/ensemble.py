@@ -57,6 +57,8 @@ class ReplicaEnsemble:
         self.chemical_mods = np.ascontiguousarray(chemical_mods, dtype=np.int64).reshape(self.R, self.N, self.nb)
         self.binders = [dict(b) for b in binders]
         self.grid = grid
+        self.bead_vol, self.max_binders, self.bond_params = bead_vol, max_binders, dict(bond_params)
+        self.min_spacing, self.device = min_spacing, device
         self.engine = Engine(self.R, self.N, self.nb, grid=grid, bead_vol=bead_vol, max_binders=max_binders,
                              device=device)
         if field_prefactors is None:
@@ -203,6 +205,76 @@ class ReplicaEnsemble:
     def replica_to_csv(self, i: int, path, **kwargs):
         """Replica `i` in the reference's CSV schema (polymers.pyx:575-684)."""
         return self.replica_polymer(i, **kwargs).to_csv(str(path))
+
+    # ---- coarse-grain / refine (SURVEY 8f.2; chromo/util/rediscretize.py) -------------
+    def _uniform_bonds(self, n_bonds):
+        """Bond parameters of a re-discretised chain: the reference gives every bond of the new chain
+        the first bond's length (rediscretize.py:447-449, 1059-1060), so uniform parameters carry over."""
+        out = {}
+        for k, v in self.bond_params.items():
+            if v is None:
+                continue
+            v = np.asarray(v, dtype=float)
+            if not np.all(v == v[..., :1]):
+                raise NotImplementedError("re-discretisation needs one bond length per chain")
+            out[k] = np.repeat(v[..., :1], n_bonds, axis=-1)
+        return out
+
+    def _like(self, r, t3, t2, states, mods, grid):
+        N = r.shape[1]
+        spacing = 16.5 if self.min_spacing is None else self.min_spacing
+        g = dict(grid, vf_limit=self.grid.get("vf_limit", 0.5))
+        return ReplicaEnsemble(r, t3, t2, states, mods, binders=self.binders, bond_params=self._uniform_bonds(N - 1),
+                               grid=g, bead_vol=self.bead_vol, chi=self.chi, mu=self.mu, max_binders=self.max_binders,
+                               moves=default_moves(self.R, N, spacing), min_spacing=self.min_spacing,
+                               device=self.device)
+
+    def coarse_grained(self, cg_factor: int):
+        """Every replica coarse-grained by `cg_factor` (get_cg_chromatin + get_cg_udf, rediscretize.py:
+        199-272, 401-471) in one launch; returns a new ensemble on the coarser grid."""
+        from .util import rediscretize as rd
+        self.engine.sync()
+        self.pull()
+        cg = rd.coarse_grain_ensemble(self.r, self.t3, self.states, self.chemical_mods, cg_factor, self.device)
+        return self._like(cg["r"], cg["t3"], cg["t2"], cg["states"], cg["chemical_mods"],
+                          rd.cg_grid(self.grid, cg_factor))
+
+    def refined(self, num_beads_refined: int, bead_spacing: float, chemical_mods, seed: Optional[int] = 0,
+                binding_equilibration: int = 0):
+        """Every replica refined to `num_beads_refined` beads (refine_chromatin + refine_udf,
+        rediscretize.py:845-900, 994-1107): Brownian bridges between the coarse beads, scaled outwards,
+        pulled back into a spherical confinement, states reset to 0 and -- optionally -- equilibrated by
+        `binding_equilibration` binding-state attempts per replica in one launch of the MC kernel."""
+        from .util import rediscretize as rd
+        self.engine.sync()
+        self.pull()
+        M, g = self.N, self.grid
+        if rd.refined_num_points(M, num_beads_refined) != num_beads_refined:
+            raise ValueError("num_beads_refined must not be a multiple of (coarse beads - 1): the reference's "
+                             "path then has one bead fewer (rediscretize.py:571)")
+        fine_grid = rd.refined_grid(dict(nx=g["nx"], ny=g["ny"], nz=g["nz"], dx=g["x_width"] / g["nx"],
+                                         dy=g["y_width"] / g["ny"], dz=g["z_width"] / g["nz"],
+                                         confine_type=g["confine_type"], confine_length=g["confine_length"]),
+                                    num_beads_refined / M)
+        rad = fine_grid["confine_length"] if fine_grid["confine_type"] == "Spherical" else 0.0
+        fine = rd.refine_ensemble(self.r, self.t3, num_beads_refined, bead_spacing, confine_length=rad, seed=seed,
+                                  device=self.device)
+        mods = np.ascontiguousarray(np.broadcast_to(np.asarray(chemical_mods, dtype=np.int64).reshape(
+            (-1, num_beads_refined, self.nb)), (self.R, num_beads_refined, self.nb)))
+        ens = self._like(fine["r"], fine["t3"], fine["t2"], np.zeros_like(mods), mods, fine_grid)
+        if binding_equilibration > 0:  # rediscretize.py:1093-1106: binding-only attempts, one bead each
+            keep = ens.moves.copy()
+            mv = keep.copy()
+            mv["move_on"][:] = 0
+            mv["move_on"][:, 4], mv["num_per_cycle"][:, 4], mv["controller"][:, 4] = 1, binding_equilibration, 0
+            ens.moves = mv
+            ens.engine.set_moves(mv)
+            ens.mc_sim(1, 1.0, 0 if seed is None else seed, sync_host=False)
+            ens.engine.sync()
+            ens.pull()
+            ens.moves = keep
+            ens.engine.set_moves(keep)
+        return ens
 
     def close(self):
         self.engine.close()

@@ -248,3 +248,39 @@ def test_c2_ensemble_round_trip_properties(cuda_backend):
     scaling = ((N + 1) / M) ** (1 / 3)
     assert np.allclose(ref["r"][:, starts], out["r"][:Rr, :M - 1] * scaling, rtol=1e-15, atol=0)
     assert np.allclose(np.linalg.norm(ref["t3"], axis=2), 1, atol=1e-14)
+
+
+def test_ensemble_pipeline_coarse_grain_mc_refine(backend):
+    """The chromosome-scale workflow on a small ensemble: coarse-grain every replica, run MC on the
+    coarse chains, refine back with a binding equilibration; mass is conserved at each stage."""
+    import math
+    import oracle as O
+    from chromo_b200.ensemble import ReplicaEnsemble, default_moves
+    from chromo_b200.util import poly_paths as paths
+    rng = np.random.default_rng(2)
+    R, N, k = 2, 240, 4
+    Rc = 120.0
+    r = paths.confined_gaussian_walk(N, np.full(N - 1, 16.5), "Spherical", Rc, rng, replicas=R)
+    t3, t2 = paths.estimate_tangents_from_coordinates(r)
+    mods = paths.synthetic_marks(N, 1, rng, replicas=R)
+    hp1 = dict(O.HP1)
+    grid = dict(x_width=2.4 * Rc, nx=10, y_width=2.4 * Rc, ny=10, z_width=2.4 * Rc, nz=10, confine_type="Spherical",
+                confine_length=Rc, vf_limit=0.5)
+    ens = ReplicaEnsemble(r, t3, t2, np.zeros((R, N, 1), dtype=np.int64), mods, binders=[hp1],
+                          bond_params=O.bond_params(np.full(N - 1, 16.5), 53.0), grid=grid,
+                          bead_vol=(4 / 3) * math.pi * 125.0, moves=default_moves(R, N, 16.5), min_spacing=16.5)
+    cg = ens.coarse_grained(k)
+    assert cg.N == N // k and cg.grid["nx"] == int(round(10 / k ** (1 / 3))) + 1
+    want = RO.cg_arrays(r[0], t3[0], ens.states[0], mods[0], k, k ** (1 / 3))
+    assert np.array_equal(cg.r[0], want[0]) and np.array_equal(cg.chemical_mods[0], want[4])
+    vol = lambda e: e.grid["x_width"] * e.grid["y_width"] * e.grid["z_width"] / (e.grid["nx"] * e.grid["ny"] * e.grid["nz"])
+    assert np.allclose(cg.density()[..., 0].sum(axis=1) * vol(cg), cg.N, rtol=1e-9)
+    cg.mc_sim(1, 1.0, 5)
+    fine = cg.refined(N + 1, 16.5, np.concatenate([mods, mods[:, :1]], axis=1), seed=9, binding_equilibration=100)
+    assert fine.N == N + 1 and fine.states.min() >= 0 and fine.states.max() <= 2 and fine.states.sum() > 0
+    assert np.all(np.linalg.norm(fine.r, axis=2) <= fine.grid["confine_length"] * 1.02)
+    d = fine.density()
+    assert np.allclose(d[..., 0].sum(axis=1) * vol(fine), fine.N, rtol=1e-9)
+    assert np.allclose(d[..., 1].sum(axis=1) * vol(fine), fine.states[..., 0].sum(axis=1), rtol=1e-9)
+    for e in (fine, cg, ens):
+        e.close()
