@@ -65,5 +65,12 @@ def test_no_gpu_is_an_error_not_a_fallback():
         from chromo_b200.engine import Engine
         with pytest.raises(_lib.ChromoError):
             Engine(1, 10, 1, grid=None, bead_vol=1.0)
+        # the context-free entry points (coarse-grain / refine) refuse as well
+        import numpy as np
+        import chromo_b200.util.rediscretize as rd
+        with pytest.raises(_lib.ChromoError, match="no CUDA device|no CPU fallback"):
+            rd.coarse_grain_ensemble(np.zeros((1, 10, 3)), np.ones((1, 10, 3)), None, None, 2)
+        with pytest.raises(_lib.ChromoError, match="no CUDA device|no CPU fallback"):
+            rd.get_refined_path(np.zeros((3, 3)), 10, 1.0)
     finally:
         _lib._LIB = None
