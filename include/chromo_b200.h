@@ -119,11 +119,12 @@ int64_t chromo_ctx_bytes(chromo_ctx *ctx);
  * capacity in effect through *cap_out (may be NULL). */
 int chromo_ctx_set_table_capacity(chromo_ctx *ctx, int64_t cap, int64_t *cap_out);
 /* Tuning knob: warps that work on one replica in the production (Philox) MC
- * kernel, 1 or 2 (default 1; 0 = leave unchanged).  With 2, the bead-row stage of
+ * kernel, 1 or 2 (0 = leave unchanged; default 2 while at most 4 replicas share an SM,
+ * i.e. n_replicas <= 4 x SM count, else 1).  With 2, the bead-row stage of
  * attempt j+1 overlaps the density stage of attempt j; attempts still take
  * effect strictly in order and the results are bit-identical to 1 warp (on
- * B200 the second warp currently costs more in instruction-cache misses than
- * the overlap gains at 7 replicas per SM; it pays when few replicas are resident).  The
+ * B200 the second warp costs more in instruction-cache misses than the overlap
+ * gains at 7 replicas per SM, and gains 4-40 % when 1-4 replicas share an SM).  The
  * replayed-RNG kernels (sequential streams) always use 1.  Re-chooses the table
  * capacity.  Returns the value in effect through *warps_out (may be NULL). */
 int chromo_ctx_set_warps_per_replica(chromo_ctx *ctx, int64_t warps, int64_t *warps_out);
