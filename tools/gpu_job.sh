@@ -1,6 +1,10 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python bench.py --beads 400000 --replicas 148 --sweeps 5 --steps 4 --warmup 3 --ref-warm 100 --e2e-steps 1 --no-cpu-baseline > gpurun_out/bench_c4_148x400k.json 2> gpurun_out/bench_c4.err
-cat gpurun_out/bench_c4_148x400k.json | cut -c1-1500; tail -3 gpurun_out/bench_c4.err
-timeout 600 python bench.py --beads 1000 --replicas 1024 --sweeps 200 --steps 5 --no-cpu-baseline > gpurun_out/bench_c1_1024x1000.json 2> gpurun_out/bench_c1.err
-cat gpurun_out/bench_c1_1024x1000.json | cut -c1-1500
+( time timeout 1200 python -m pytest tests -m gpu -x -q --durations=8 ) > gpurun_out/gpu_tests_r01_final.log 2>&1
+tail -15 gpurun_out/gpu_tests_r01_final.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -3 gpurun_out/smoke.log
+timeout 600 python bench.py > gpurun_out/bench_r01_final.json 2> gpurun_out/bench_r01_final.err
+cat gpurun_out/bench_r01_final.json | cut -c1-300
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r01_final_ref.json 2> gpurun_out/bench_r01_final_ref.err
+cat gpurun_out/bench_r01_final_ref.json | cut -c1-300
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_v14_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu_v14.log 2>&1
