@@ -94,8 +94,9 @@ def make_inputs(R: int, N: int, seed: int, pinned: bool):
     return r, t3, t2, states, mods, grid
 
 
-def bond_params(N: int, spacing=16.5, lp=53.0):
-    """SSWLC._find_parameters (polymers.pyx:1545-1601) for uniform spacing."""
+def bond_params(N: int, spacing=16.5, lp=53.0, lt=None):
+    """SSWLC._find_parameters (polymers.pyx:1545-1601) for uniform spacing; with `lt` also the twist
+    parameters of SSTWLC (polymers.pyx:2000, 2088-2090)."""
     import numpy as np
     from chromo_b200.util import dss_params as tab
     d = spacing / lp
@@ -104,6 +105,9 @@ def bond_params(N: int, spacing=16.5, lp=53.0):
                 eps_par=np.interp(d, tab[:, 0], tab[:, 3]) / (d * lp ** 2),
                 eps_perp=np.interp(d, tab[:, 0], tab[:, 4]) / (d * lp ** 2),
                 eta=np.interp(d, tab[:, 0], tab[:, 5]) / lp)
+    if lt is not None:
+        vals["eps_twist"] = lt / (d * lp)
+        vals["natural_twist"] = spacing * (2 * np.pi / 10.5) / 0.332
     return {k: np.full(N - 1, v) for k, v in vals.items()}
 
 
@@ -245,11 +249,20 @@ def run_reference(args):
 
 def workload_config(args, cap):
     Rc, nx, W = workload_params(args.beads)
-    return dict(workload=f"C2: chromatin {args.beads} beads, HP1 on H3K9me3 (synthetic marks), chi=1, mu=-1.2, "
-                         f"{args.replicas} replicas per GPU, {nx}^3 voxels, spherical confinement R={Rc:.1f} nm",
+    label = {10000: "C2", 400000: "C4-sized", 1000: "C1-sized"}.get(args.beads, "custom size")
+    if args.beads == 10000 and args.replicas != 1024:
+        label = "C2-sized"
+    twist = f", SSTWLC twist lt={args.lt:g}" if getattr(args, "lt", None) is not None else ""
+    state_mb = args.replicas * args.beads * 74 / 1e6   # r, t3, t2 fp64 + states, marks int8
+    field_mb = args.replicas * nx ** 3 * 16 / 1e6      # (bead, HP1) fp64 per voxel
+    fits = state_mb + field_mb <= 126
+    return dict(workload=f"{label}: chromatin {args.beads} beads, HP1 on H3K9me3 (synthetic marks), chi=1, mu=-1.2, "
+                         f"{args.replicas} replicas per GPU, {nx}^3 voxels, spherical confinement R={Rc:.1f} nm{twist}",
                 replicas_per_gpu=args.replicas, beads=args.beads, grid=nx, sweeps_per_step=args.sweeps,
                 attempts_per_sweep=ATTEMPTS_PER_SWEEP, rng="philox4x32-10", table_slots=cap,
-                l2="working set (state 737 MB + field 152 MB per GPU at C2) exceeds the 126 MB L2; no flush needed",
+                l2=(f"working set (state {state_mb:.0f} MB + field {field_mb:.0f} MB per GPU) "
+                    + ("FITS the 126 MB L2: not a cold-cache number" if fits
+                       else "exceeds the 126 MB L2; no flush needed")),
                 parallelism=f"replica-sharded x{args.gpus}")
 
 
@@ -272,7 +285,7 @@ def run_ours(args):
     R, N, S, K, Wm = args.replicas, args.beads, args.sweeps, args.steps, max(args.warmup, 3)
 
     r, t3, t2, states, mods, grid = make_inputs(R, N, 1234 + rank, pinned=True)
-    ens = ReplicaEnsemble(r, t3, t2, states, mods, binders=[dict(HP1)], bond_params=bond_params(N), grid=grid,
+    ens = ReplicaEnsemble(r, t3, t2, states, mods, binders=[dict(HP1)], bond_params=bond_params(N, lt=args.lt), grid=grid,
                           bead_vol=(4 / 3) * math.pi * 5.0 ** 3, chi=1.0, mu=[-1.2],
                           moves=default_moves(R, N, 16.5), device=local)
     eng = ens.engine
@@ -425,6 +438,8 @@ def main():
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0, help="warps per replica in the MC kernel (0 = library default)")
     ap.add_argument("--rpb", type=int, default=0, help="replicas per thread block (0 = library default)")
+    ap.add_argument("--lt", type=float, default=None, help="twist persistence length: run the SSTWLC kernels "
+                    "(not the headline configuration; the reference arm ignores it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     quiet_stdout()
