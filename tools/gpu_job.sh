@@ -1,5 +1,4 @@
 set -x
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests/test_rediscretize.py -m gpu -x -q ) > gpurun_out/gpu_tests_rd.log 2>&1
-tail -4 gpurun_out/gpu_tests_rd.log
-timeout 600 python tools/rediscretize_bench.py --out gpurun_out/rediscretize_bench.json > gpurun_out/rd_bench.log 2>&1
+timeout 600 python bench.py --lt 100 --no-cpu-baseline > gpurun_out/bench_twist_n1.json 2> gpurun_out/bench_twist.err
+cat gpurun_out/bench_twist_n1.json | cut -c1-400; tail -3 gpurun_out/bench_twist.err
