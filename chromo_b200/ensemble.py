@@ -290,8 +290,10 @@ class ReplicaEnsemble:
         grid = f0._grid()
         bd = binder_dicts(p0)
         pre = f0._prefactors(p0.num_binders)
-        bond = {k: np.stack([getattr(p, k) for p in polymers]) for k in
-                ("eps_bend", "eps_par", "eps_perp", "gamma", "eta")}
+        keys = ("eps_bend", "eps_par", "eps_perp", "gamma", "eta")
+        if getattr(p0, "eps_twist", None) is not None:  # SSTWLC replicas keep their twist term
+            keys += ("eps_twist", "natural_twist")
+        bond = {k: np.stack([getattr(p, k) for p in polymers]) for k in keys}
         if all(np.array_equal(bond["eps_bend"][0], b) for b in bond["eps_bend"]):
             bond = {k: v[0] for k, v in bond.items()}
         moves = None

@@ -237,3 +237,21 @@ def test_against_live_reference(backend):
         assert np.allclose(p.r, np.asarray(rp.r), rtol=0, atol=tol)
         assert np.array_equal(p.states, np.asarray(rp.states))
         assert close(field.compute_E(p), rfield.compute_E(rp), 1e-9 if backend == "emu" else 1e-7)
+
+
+def test_ensemble_from_twisted_polymers_keeps_the_twist_term(backend):
+    """ReplicaEnsemble.from_polymers on SSTWLC replicas: the batched elastic energy is each polymer's
+    own compute_E (twist included), and a short mc_sim runs the twist kernels."""
+    from chromo_b200.ensemble import ReplicaEnsemble
+    spec, g = load_golden("static_tw")
+    built = [build(spec) for _ in range(2)]
+    polys, fields = [b[0] for b in built], [b[2] for b in built]
+    polys[1].t2[...] = np.cross(polys[1].t3, [0.0, 0.0, 1.0])
+    polys[1].t2[...] /= np.linalg.norm(polys[1].t2, axis=1)[:, None]
+    ens = ReplicaEnsemble.from_polymers(polys, fields)
+    E = ens.elastic_energy()
+    assert close(E[0], float(g["E_poly"])) and close(E[0], polys[0].compute_E())
+    assert close(E[1], polys[1].compute_E()) and not close(E[0], E[1])
+    ens.mc_sim(1, 1.0, 3)
+    assert np.isfinite(ens.elastic_energy()).all() and ens.acceptance()["crank_shaft"] > 0
+    ens.close()

@@ -253,6 +253,8 @@ def test_two_warps_per_replica_match_one(backend, oracle_mod, case):
         spec = O.make_spec(N=120, nb=1, seed=23, random_states=False)
         spec["field"] = dict(spec["field"], nx=0, ny=0, nz=0)
         sweeps, per_cycle = 6, (30, 1, 60, 60, 10)
+    if backend == "emu":  # the CPU emulation runs ~1 ms per attempt: fewer sweeps there, all of them on the GPU
+        sweeps = max(2, sweeps // 2)
     R = 3
     out = []
     dens0 = None
@@ -323,7 +325,7 @@ def test_host_array_path_matches_resident_path(backend, oracle_mod):
                               moves=default_moves(R, N, 16.5), **kw)
         ens.engine.set_replicas_per_block(2)
         for k in range(2):
-            ens.mc_sim(2, 1.0, 77 + k, n_chunks=n_chunks)
+            ens.mc_sim(1 if backend == "emu" else 2, 1.0, 77 + k, n_chunks=n_chunks)
         out[n_chunks] = (ens.r.copy(), ens.t3.copy(), ens.t2.copy(), ens.states.copy(), ens.moves.copy(),
                          ens.density().copy())
         assert ens.chemical_mods.tobytes() == st("mods").tobytes()
