@@ -235,7 +235,7 @@ def test_philox_is_deterministic_and_consistent(backend, oracle_mod):
     assert 0.2 < acc < 0.95
 
 
-@pytest.mark.parametrize("case", ["mixed", "dense", "no_field"])
+@pytest.mark.parametrize("case", ["mixed", "dense", "no_field", "twist"])
 def test_two_warps_per_replica_match_one(backend, oracle_mod, case):
     """The production kernel with two warps per replica (stage 1 of attempt j+1
     overlapping stage 2 of attempt j, redone when an accepted attempt changed
@@ -249,6 +249,9 @@ def test_two_warps_per_replica_match_one(backend, oracle_mod, case):
     elif case == "dense":
         spec = O.make_spec(N=40, nb=1, seed=22, random_states=True)
         sweeps, per_cycle = 8, (30, 5, 60, 60, 30)
+    elif case == "twist":  # the SSTWLC builds of the kernels
+        spec = dict(O.make_spec(N=150, nb=1, seed=24, random_states=True), lt=80.0)
+        sweeps, per_cycle = 4, (30, 1, 60, 60, 10)
     else:
         spec = O.make_spec(N=120, nb=1, seed=23, random_states=False)
         spec["field"] = dict(spec["field"], nx=0, ny=0, nz=0)
