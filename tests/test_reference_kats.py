@@ -154,3 +154,24 @@ def test_from_point():
         if 100 < ind0 < N - 100:
             frac_right = np.mean(sel > ind0)
             assert 0.4 < frac_right < 0.6                 # either side with probability 1/2
+
+
+# ---- the same convention through the CUDA path (full density recompute of beads placed at the KAT points) ----
+def test_voxel_super_indices_through_the_kernels(backend):
+    from gpu_common import engine_from_spec
+    spec = O.make_spec(N=4, nb=1, seed=0, grid=5, confine="")
+    W = spec["field"]["x_width"]
+    d = W / 5
+    s = O.OracleSim(spec)
+    cases = [([-W / 2 + 0.25 * d] * 3, {0, 4, 20, 24, 100, 104, 120, 124}),
+             ([-W / 2 + 2.75 * d, -W / 2 + 2.25 * d, -W / 2 + 0.25 * d], {12, 13, 7, 8, 112, 113, 107, 108}),
+             ([-W / 2 + 1.75 * d, -W / 2 + 3.75 * d, -W / 2 + 2.75 * d], {66, 67, 71, 72, 91, 92, 96, 97})]
+    for point, want in cases:
+        spec["r"] = np.tile(np.asarray(point, dtype=float), (4, 1))
+        e = engine_from_spec(spec, R=1)
+        dens = e.density()[0]
+        assert set(np.nonzero(dens[:, 0])[0]) == want
+        idx, w = s.bin_point(point)
+        vol_bin = d ** 3
+        assert np.allclose(dens[idx, 0] * vol_bin, 4 * w, rtol=1e-12)  # four beads, the oracle's weights
+        e.close()
