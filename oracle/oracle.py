@@ -231,6 +231,9 @@ def confined_walk(N, step, R, rng):
     (poly_paths.py:298-335): unit Gaussian-direction steps of length `step`,
     re-drawn while the bead would leave the sphere of radius R."""
     r = np.zeros((N, 3))
+    if 0 < R < step:  # the first step from the origin can never stay inside: fail instead of looping for ever
+        raise ValueError(f"a walk with steps of {step} does not fit a sphere of radius {R:.3g} "
+                         f"(pass confine=\"\" or more beads)")
     for i in range(1, N):
         while True:
             d = rng.standard_normal(3)
