@@ -107,3 +107,18 @@ def test_wide_windows(backend):
             omv[i].bead_amp_lo = min(omv[i].bead_amp_lo, ab)
     e_cap = {}
     _replay_both(spec, 4, per_cycle=(8, 4, 8, 12, 6), tweak=tweak, backend=backend)
+
+
+@pytest.mark.parametrize("N", [2, 5, 60])
+def test_twisted_chains(backend, N):
+    """SSTWLC (twist term in every bond energy, polymers.pyx:1889-2319) on the shortest chains -- every
+    end-of-chain special case with the trial t2 in play -- and on a chain with wide windows; replayed
+    against the oracle."""
+    spec = dict(O.make_spec(N=N, nb=1, seed=40 + N, grid=4, confine=""), lt=70.0)
+
+    def wide(mv, omv):
+        if N >= 60:
+            for i, a in ((0, 40), (2, 30), (3, 25)):
+                mv["amp_bead"][:, i] = a
+                omv[i].amp_bead = a
+    _replay_both(spec, 12, per_cycle=(8, 4, 8, 10, 3), move_on=(1, int(N >= 4), 1, 1, 1), tweak=wide, backend=backend)
