@@ -219,6 +219,8 @@ extern "C" int chromo_ctx_create(chromo_ctx **out, int device, const chromo_shap
     if ((rc = dev_alloc(c, &d.glibc, (size_t)d.R * CB_GLIBC_WORDS))) return rc;
     if ((rc = dev_alloc(c, &d.mt, (size_t)d.R * CB_MT_WORDS))) return rc;
     if ((rc = dev_alloc(c, &d.philox_ctr, (size_t)d.R))) return rc;
+    d.rep_offset = 0u;
+    d.batch = 32;
     if ((rc = dev_alloc(c, &d.tan_inds, RN))) return rc;
     if ((rc = dev_alloc(c, &d.sel_bits, (size_t)d.R * ((d.N + 31) / 32)))) return rc;
     if ((rc = dev_alloc(c, &d.st_new, RN))) return rc;
@@ -325,6 +327,34 @@ extern "C" int chromo_ctx_set_replicas_per_block(chromo_ctx *c, int64_t rpb, int
         choose_table(c);
     }
     if (rpb_out) *rpb_out = c->rpb;
+    return CHROMO_OK;
+}
+extern "C" int chromo_ctx_set_replica_offset(chromo_ctx *c, int64_t offset) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    if (offset < 0 || offset > 0xffffffffLL - c->d.R) return fail(CHROMO_ERR_ARG, "replica offset out of range");
+    c->d.rep_offset = (unsigned)offset;
+    return CHROMO_OK;
+}
+extern "C" int chromo_ctx_set_batch_size(chromo_ctx *c, int64_t batch) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    if (batch < 1 || batch > 32) return fail(CHROMO_ERR_ARG, "batch size must be in [1, 32]");
+    c->d.batch = (int)batch;
+    return CHROMO_OK;
+}
+extern "C" int chromo_get_rng_counters(chromo_ctx *c, int64_t first, int64_t n, uint64_t *counters) {
+    if (!c || !counters) return fail(CHROMO_ERR_ARG, "null argument");
+    if (first < 0 || n < 0 || first + n > c->d.R) return fail(CHROMO_ERR_ARG, "replica range out of bounds");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(counters, c->d.philox_ctr + first, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+extern "C" int chromo_set_rng_counters(chromo_ctx *c, int64_t first, int64_t n, const uint64_t *counters) {
+    if (!c || !counters) return fail(CHROMO_ERR_ARG, "null argument");
+    if (first < 0 || n < 0 || first + n > c->d.R) return fail(CHROMO_ERR_ARG, "replica range out of bounds");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->d.philox_ctr + first, counters, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return CHROMO_OK;
 }
 extern "C" void *chromo_ctx_stream(chromo_ctx *c) { return c ? (void *)c->stream : nullptr; }

@@ -1625,7 +1625,7 @@ __device__ __forceinline__ unsigned long long rng_load<PhiloxRng>(PhiloxRng &rng
                                                                   int rep, int, unsigned long long seed) {
     rng.k0 = (uint32_t)seed;
     rng.k1 = (uint32_t)(seed >> 32);
-    rng.rep = (uint32_t)rep;
+    rng.rep = C.rep_offset + (uint32_t)rep; // global replica index: shards of an ensemble draw different streams
     rng.seek_attempt(C.philox_ctr[rep]);
     return C.philox_ctr[rep]; // attempts this replica has ever made
 }
@@ -1678,7 +1678,7 @@ __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, 1)
     long long a0 = 0;
     if (active)
         for (int m = 0; m < CHROMO_NUM_MOVES; m++) a0 += B.mv[m].num_attempt;
-    constexpr int BS = Rng::kBatched ? 32 : 1;
+    const int BS = Rng::kBatched ? C.batch : 1;
     for (long long k = 0; k < num_mc_steps; k++)
         for (int m = 0; m < CHROMO_NUM_MOVES; m++) {
             if (active) {

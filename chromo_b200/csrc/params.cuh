@@ -48,6 +48,8 @@ struct DevCtx {
     uint32_t *glibc;                 // [R][GLIBC_WORDS]
     uint32_t *mt;                    // [R][MT_WORDS]
     unsigned long long *philox_ctr;  // [R]
+    unsigned rep_offset;             // global index of replica 0 (key of the production streams)
+    int batch;                       // attempts prepared at once in the production kernels (1..32)
     int *tan_inds;                   // [R][N]   tangent-rotation large path
     uint32_t *sel_bits;              // [R][ceil(N/32)]
     signed char *st_new;             // [R][N]   binding large path

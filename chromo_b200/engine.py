@@ -265,6 +265,27 @@ class Engine:
         check(self._L.chromo_ctx_set_replicas_per_block(self._h, int(rpb), C.byref(out)))
         return int(out.value)
 
+    def set_replica_offset(self, offset: int) -> None:
+        """Global index of this context's replica 0: the production streams are keyed by
+        (seed, global replica, attempt), so the shards of one ensemble draw different numbers."""
+        check(self._L.chromo_ctx_set_replica_offset(self._h, int(offset)))
+
+    def set_batch_size(self, batch: int) -> None:
+        """Attempts prepared at once by the production kernels (1..32; test knob, results do not depend on it)."""
+        check(self._L.chromo_ctx_set_batch_size(self._h, int(batch)))
+
+    def rng_counters(self) -> np.ndarray:
+        """Attempts made so far per replica = position of its production random stream."""
+        out = np.zeros(self.R, dtype=np.uint64)
+        check(self._L.chromo_get_rng_counters(self._h, 0, self.R, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def set_rng_counters(self, counters) -> None:
+        a = np.ascontiguousarray(counters, dtype=np.uint64)
+        if a.shape != (self.R,):
+            raise ValueError(f"counters must have shape ({self.R},)")
+        check(self._L.chromo_set_rng_counters(self._h, 0, self.R, a.ctypes.data_as(C.POINTER(C.c_uint64))))
+
     def sync(self):
         check(self._L.chromo_ctx_sync(self._h))
 

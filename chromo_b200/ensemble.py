@@ -47,7 +47,8 @@ class ReplicaEnsemble:
     def __init__(self, r, t3, t2, states, chemical_mods, *, binders: Sequence[dict], bond_params: dict,
                  grid: Optional[dict], bead_vol: float, chi=1.0, mu=None, max_binders: int = -1,
                  moves: Optional[np.ndarray] = None, min_spacing: Optional[float] = None,
-                 access_vol=None, device: int = 0, field_prefactors=None):
+                 access_vol=None, device: int = 0, field_prefactors=None, assume_fully_accessible: int = 1,
+                 replica_offset: int = 0):
         self.r = np.ascontiguousarray(r, dtype=np.float64)
         self.R, self.N = self.r.shape[0], self.r.shape[1]
         self.t3 = np.ascontiguousarray(t3, dtype=np.float64)
@@ -68,8 +69,16 @@ class ReplicaEnsemble:
                                     bond_params["gamma"], bond_params["eta"])
         if bond_params.get("eps_twist") is not None:  # SSTWLC replicas (polymers.pyx:1889-2319)
             self.engine.set_twist_params(bond_params["eps_twist"], bond_params["natural_twist"])
+        self.assume_fully_accessible = assume_fully_accessible
+        if access_vol is None and assume_fully_accessible != 1 and grid is not None and grid.get("nx", 0):
+            from .fields import accessible_volumes
+            access_vol = accessible_volumes(grid, 20, assume_fully_accessible)  # fields.pyx:714-770
         if access_vol is not None:
             self.engine.set_access_volumes(access_vol)
+        self.replica_offset = int(replica_offset)
+        if replica_offset:
+            self.engine.set_replica_offset(replica_offset)
+        self._host_stale = False  # the device state is ahead of the host arrays (sync_host=False calls)
         self.chi = np.ascontiguousarray(np.broadcast_to(np.asarray(chi, dtype=float), (self.R,)))
         if mu is None:
             mu = [b["chemical_potential"] for b in self.binders]
@@ -92,7 +101,9 @@ class ReplicaEnsemble:
             return pref, e_intra, xpref
         vol_bin = grid["x_width"] * grid["y_width"] * grid["z_width"] / (grid["nx"] * grid["ny"] * grid["nz"])
         for i, b in enumerate(binders):
-            v_int = (4.0 / 3.0) * np.pi * b["interaction_radius"] ** 3
+            v_int = b.get("interaction_volume", None)
+            if v_int is None:
+                v_int = (4.0 / 3.0) * np.pi * b["interaction_radius"] ** 3
             pref[i] = 0.5 * b["interaction_energy"] * v_int * vol_bin
             e_intra[i] = b["interaction_energy"] * (1 - v_int / vol_bin)
             for j, nxt in enumerate(binders):
@@ -104,10 +115,12 @@ class ReplicaEnsemble:
     def push(self):
         """Upload the host arrays (user-visible state) to the device."""
         self.engine.upload(self.r, self.t3, self.t2, self.states, self.chemical_mods)
+        self._host_stale = False
 
     def pull(self):
         """Refresh the host arrays from the device."""
         self.engine.download_into(self.r, self.t3, self.t2, self.states)
+        self._host_stale = False
 
     def set_params(self, chi=None, mu=None):
         if chi is not None:
@@ -127,6 +140,12 @@ class ReplicaEnsemble:
         queued."""
         mode = {"philox": RNG_PHILOX, "replay": RNG_REPLAY}[rng]
         ns = ((random_seed if numpy_seeds is None else numpy_seeds) if mode == RNG_REPLAY else None)
+        if sync_host and self._host_stale:
+            # device-resident calls ran since the host arrays were last refreshed: the host-array call
+            # below would upload the OLD configuration over the advanced one (and its density)
+            self.engine.sync()
+            self.pull()
+            self.moves = self.engine.get_moves()
         if sync_host and n_chunks >= 0:
             self.engine.mc_sim_host(num_mc_steps, self.r, self.t3, self.t2, self.states, self.chemical_mods,
                                     self.moves, mu_adjust_factor, random_seed, mode, numpy_seeds=ns,
@@ -138,6 +157,7 @@ class ReplicaEnsemble:
         else:
             self.engine.mc_sim(num_mc_steps, None, mu_adjust_factor, random_seed, mode,
                                numpy_seeds=numpy_seeds if mode == RNG_REPLAY else None)
+            self._host_stale = True
 
     def sync(self):
         self.engine.sync()
@@ -171,7 +191,8 @@ class ReplicaEnsemble:
             self.pull()
             self.moves = self.engine.get_moves()
         np.savez(path, r=self.r, t3=self.t3, t2=self.t2, states=self.states, chemical_mods=self.chemical_mods,
-                 moves=self.moves.view(np.uint8).reshape(self.R, -1), chi=self.chi, mu=self.mu)
+                 moves=self.moves.view(np.uint8).reshape(self.R, -1), chi=self.chi, mu=self.mu,
+                 rng_counters=self.engine.rng_counters())
 
     def load_snapshot(self, path):
         """Restore the state written by `save_snapshot` (same R, N, nb) and upload it; the
@@ -185,6 +206,8 @@ class ReplicaEnsemble:
         self.moves = np.ascontiguousarray(z["moves"]).view(MOVE_DTYPE).reshape(self.R, NUM_MOVES).copy()
         self.engine.set_moves(self.moves)
         self.set_params(chi=z["chi"], mu=z["mu"])
+        if "rng_counters" in z.files:  # continue the production streams instead of replaying them
+            self.engine.set_rng_counters(z["rng_counters"])
         self.push()
         if self.grid is not None and self.grid.get("nx", 0):
             self.engine.field_recompute(clamp=True)
@@ -227,7 +250,8 @@ class ReplicaEnsemble:
         return ReplicaEnsemble(r, t3, t2, states, mods, binders=self.binders, bond_params=self._uniform_bonds(N - 1),
                                grid=g, bead_vol=self.bead_vol, chi=self.chi, mu=self.mu, max_binders=self.max_binders,
                                moves=default_moves(self.R, N, spacing), min_spacing=self.min_spacing,
-                               device=self.device)
+                               device=self.device, assume_fully_accessible=self.assume_fully_accessible,
+                               replica_offset=self.replica_offset)
 
     def coarse_grained(self, cg_factor: int):
         """Every replica coarse-grained by `cg_factor` (get_cg_chromatin + get_cg_udf, rediscretize.py:
@@ -289,6 +313,13 @@ class ReplicaEnsemble:
         st = lambda name: np.stack([getattr(p, name) for p in polymers])
         grid = f0._grid()
         bd = binder_dicts(p0)
+        # the field's own binder table (fields.pyx:687-712 reads it from the DataFrame snapshot) carries
+        # what a re-discretised ensemble needs to rebuild its prefactors on another grid
+        for b, rec in zip(bd, getattr(f0, "binder_dict", None) or []):
+            b["interaction_energy"] = float(rec["interaction_energy"])
+            b["interaction_volume"] = float(rec["interaction_volume"])
+            b["interaction_radius"] = float((3.0 * rec["interaction_volume"] / (4.0 * np.pi)) ** (1.0 / 3.0))
+            b["cross_talk"] = dict(rec.get("cross_talk_interaction_energy", {}) or {})
         pre = f0._prefactors(p0.num_binders)
         keys = ("eps_bend", "eps_par", "eps_perp", "gamma", "eta")
         if getattr(p0, "eps_twist", None) is not None:  # SSTWLC replicas keep their twist term
@@ -304,5 +335,6 @@ class ReplicaEnsemble:
                   grid=grid, bead_vol=p0.beads[0].vol, chi=[getattr(f, "chi", 1.0) for f in fields], mu=mu,
                   max_binders=p0.max_binders, moves=moves, min_spacing=float(np.min(p0.bead_length)),
                   access_vol=None if getattr(f0, "assume_fully_accessible", 1) == 1 else f0.access_vols,
-                  device=device, field_prefactors=pre)
+                  device=device, field_prefactors=pre,
+                  assume_fully_accessible=getattr(f0, "assume_fully_accessible", 1))
         return ens

@@ -37,6 +37,37 @@ def _zero_prefactors(nb):
     return np.zeros(nb), np.zeros(nb), np.zeros((nb, nb))
 
 
+def accessible_volumes(grid, n_side=20, assume_fully_accessible=1):
+    """Per-voxel accessible volume of a grid description (get_accessible_volumes fields.pyx:714-770).
+    With assume_fully_accessible == 0 and a spherical confinement, voxels cut by the sphere get
+    vol_bin * (fraction of an n_side^3 sub-grid, anchored at the voxel corner, that lies inside)."""
+    nx, ny, nz = int(grid["nx"]), int(grid["ny"]), int(grid["nz"])
+    n_bins = nx * ny * nz
+    dx, dy, dz = grid["x_width"] / nx, grid["y_width"] / ny, grid["z_width"] / nz
+    vol_bin = grid["x_width"] * grid["y_width"] * grid["z_width"] / n_bins
+    vols = np.full(n_bins, vol_bin)
+    if assume_fully_accessible == 1 or grid.get("confine_type", "") != "Spherical":
+        return vols
+    R = float(grid["confine_length"])
+    ii = np.arange(n_bins)
+    ix, iy, iz = ii % nx, (ii // nx) % ny, ii // (nx * ny)
+    # voxel centres, get_voxel_coords fields.pyx:772-803
+    centre = np.stack([(ix - (nx - 1) / 2) * dx, (iy - (ny - 1) / 2) * dy, (iz - (nz - 1) / 2) * dz], axis=1)
+    # voxels cut by the sphere, get_split_voxels fields.pyx:805-840
+    buffer_dist = np.sqrt(2) / 4 * max(dx, dy, dz)
+    dist = np.sqrt(centre[:, 0] ** 2 + centre[:, 1] ** 2 + centre[:, 2] ** 2)
+    split = ~((dist < R - buffer_dist) | (dist > R + buffer_dist))
+    # n_side^3 sub-grid anchored at the voxel corner, define_voxel_subgrid 842-880
+    k = np.arange(n_side, dtype=float)
+    sub = np.stack(np.meshgrid(k * (dx / n_side), k * (dy / n_side), k * (dz / n_side), indexing="ij"),
+                   -1).reshape(-1, 3)
+    corner = centre - np.array([dx / 2, dy / 2, dz / 2])
+    for b in np.nonzero(split)[0]:  # get_frac_accessible fields.pyx:882-951
+        inside = np.linalg.norm(corner[b] + sub, axis=1) < R
+        vols[b] = vol_bin * (inside.sum() / float(len(sub)))
+    return vols
+
+
 class FieldBase:
     """A discretization of space for computing energies (fields.pyx:46-202)."""
 
@@ -185,30 +216,12 @@ class UniformDensityField(FieldBase):
                     self.binders.at[i, 'cross_talk_field_energy_prefactor'][nxt] = 0
 
     def get_accessible_volumes(self, n_side, assume_fully_accessible):
-        """Per-voxel accessible volume (fields.pyx:714-770).  With
-        assume_fully_accessible == 0 and a spherical confinement, voxels cut by
-        the sphere get vol_bin * (fraction of an n_side^3 sub-grid inside)."""
-        vols = np.full(self.n_bins, self.vol_bin)
-        if assume_fully_accessible == 1 or self.confine_type != "Spherical":
-            return vols
-        ii = np.arange(self.n_bins)
-        ix, iy, iz = ii % self.nx, (ii // self.nx) % self.ny, ii // (self.nx * self.ny)
-        # voxel centres, get_voxel_coords fields.pyx:772-803
-        centre = np.stack([(ix - (self.nx - 1) / 2) * self.dx, (iy - (self.ny - 1) / 2) * self.dy,
-                           (iz - (self.nz - 1) / 2) * self.dz], axis=1)
-        # voxels cut by the sphere, get_split_voxels fields.pyx:805-840
-        buffer_dist = np.sqrt(2) / 4 * max(self.dx, self.dy, self.dz)
-        dist = np.sqrt(centre[:, 0] ** 2 + centre[:, 1] ** 2 + centre[:, 2] ** 2)
-        split = ~((dist < self.confine_length - buffer_dist) | (dist > self.confine_length + buffer_dist))
-        # n_side^3 sub-grid anchored at the voxel corner, define_voxel_subgrid 842-880
-        k = np.arange(n_side, dtype=float)
-        sub = np.stack(np.meshgrid(k * (self.dx / n_side), k * (self.dy / n_side), k * (self.dz / n_side),
-                                   indexing="ij"), -1).reshape(-1, 3)
-        corner = centre - np.array([self.dx / 2, self.dy / 2, self.dz / 2])
-        for b in np.nonzero(split)[0]:  # get_frac_accessible fields.pyx:882-951
-            inside = np.linalg.norm(corner[b] + sub, axis=1) < self.confine_length
-            vols[b] = self.vol_bin * (inside.sum() / float(len(sub)))
-        return vols
+        """Per-voxel accessible volume (fields.pyx:714-770)."""
+        return accessible_volumes(self._grid_geometry(), n_side, assume_fully_accessible)
+
+    def _grid_geometry(self):
+        return dict(nx=self.nx, ny=self.ny, nz=self.nz, x_width=self.x_width, y_width=self.y_width,
+                    z_width=self.z_width, confine_type=self.confine_type, confine_length=self.confine_length)
 
     def get_dict(self):
         return {"x_width": self.x_width, "y_width": self.y_width, "z_width": self.z_width, "nx": self.nx,

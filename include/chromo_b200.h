@@ -135,6 +135,20 @@ int chromo_ctx_set_warps_per_replica(chromo_ctx *ctx, int64_t warps, int64_t *wa
  * do not depend on it.  Re-chooses the table capacity.  Returns the value in
  * effect through *rpb_out (may be NULL). */
 int chromo_ctx_set_replicas_per_block(chromo_ctx *ctx, int64_t rpb, int64_t *rpb_out);
+/* Index of this context's replica 0 in the whole ensemble.  The production
+ * random streams are keyed by (seed, GLOBAL replica index, attempt): a shard of
+ * a multi-GPU ensemble must set its offset (chromo_b200.parallel does), or
+ * replica j of every shard would draw the same numbers.  Default 0. */
+int chromo_ctx_set_replica_offset(chromo_ctx *ctx, int64_t offset);
+/* Test / debugging knob: attempts of one move type whose state-independent half
+ * is prepared at once by the lanes of a warp in the production kernels, 1..32
+ * (default 32).  Results must not depend on it (tests/test_philox_parity.py). */
+int chromo_ctx_set_batch_size(chromo_ctx *ctx, int64_t batch);
+/* Attempts every replica has made so far = position of its production random
+ * stream (counters[n] for replicas [first, first+n)).  Saved and restored with a
+ * snapshot so that a resumed run continues the stream instead of replaying it. */
+int chromo_get_rng_counters(chromo_ctx *ctx, int64_t first, int64_t n, uint64_t *counters);
+int chromo_set_rng_counters(chromo_ctx *ctx, int64_t first, int64_t n, const uint64_t *counters);
 
 /* ---- parameters -------------------------------------------------------- */
 /* Reader-protein tables.

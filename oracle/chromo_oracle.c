@@ -35,6 +35,7 @@ void oc_srand(oc_glibc_rand *s, uint32_t seed)
 {
     int32_t *r = s->r;
     int i;
+    s->alt = NULL; /* srand() selects the reference's streams */
     if (seed == 0) seed = 1;
     r[0] = (int32_t)seed;
     for (i = 1; i < 31; i++) {
@@ -49,14 +50,76 @@ void oc_srand(oc_glibc_rand *s, uint32_t seed)
     for (i = 0; i < 310; i++) (void)oc_rand(s);
 }
 
+/* ---- the product's production streams (chromo_b200/csrc/rng.cuh, PhiloxRng) ---- */
+void oc_philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    int i;
+    for (i = 0; i < 10; i++) { /* Philox4x32-10 (Salmon et al., SC'11) */
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static void philox_seek(oc_philox *p, uint64_t attempt)
+{
+    p->attempt = attempt;
+    p->pos = 0;
+}
+
+static uint32_t philox_next32(oc_philox *p)
+{
+    uint32_t w = p->pos & 3u;
+    if (w == 0)
+        oc_philox_block((uint32_t)p->attempt, (uint32_t)(p->attempt >> 32), p->pos >> 2, p->rep,
+                        p->k0, p->k1, p->blk);
+    p->pos++;
+    return p->blk[w];
+}
+
+/* PhiloxRng::randint: np.random.randint's masked rejection on the stream's 32-bit words */
+static int64_t philox_randint(oc_philox *p, int64_t high)
+{
+    uint32_t rng = (uint32_t)(high - 1), mask = rng, v;
+    if (rng == 0) return 0;
+    mask |= mask >> 1;
+    mask |= mask >> 2;
+    mask |= mask >> 4;
+    mask |= mask >> 8;
+    mask |= mask >> 16;
+    do {
+        v = philox_next32(p) & mask;
+    } while (v > rng);
+    return (int64_t)v;
+}
+
+void oc_philox_init(oc_sim *s, uint64_t seed, uint32_t replica, uint64_t next_attempt)
+{
+    s->philox.k0 = (uint32_t)seed;
+    s->philox.k1 = (uint32_t)(seed >> 32);
+    s->philox.rep = replica;
+    s->philox.next_attempt = next_attempt;
+    philox_seek(&s->philox, next_attempt);
+    s->crng.alt = &s->philox;
+}
+
 int32_t oc_rand(oc_glibc_rand *s)
 {
     uint32_t *r = (uint32_t *)s->r;
+    if (s->alt) return (int32_t)(philox_next32((oc_philox *)s->alt) >> 1); /* PhiloxRng::next31 */
+    {
     uint32_t val = r[s->f] += r[s->b];
     int32_t result = (int32_t)(val >> 1);
     if (++s->f >= 31) s->f = 0;
     if (++s->b >= 31) s->b = 0;
     return result;
+    }
 }
 
 static double oc_uniform(oc_glibc_rand *g)
@@ -691,10 +754,33 @@ static void check_bead_bounds(int64_t b0, int64_t b1, int64_t N, int64_t *ind0, 
 }
 
 /* uniform_sample_unit_sphere(_inplace) linalg.pyx:23-59 */
-static void sample_sphere(oc_glibc_rand *g, double v[3])
+static void sample_sphere_exact(oc_glibc_rand *g, double v[3])
 {
     double phi = oc_uniform(g) * (2.0 * M_PI);
     double theta = acos(oc_uniform(g) * 2 - 1);
+    v[0] = cos(phi) * sin(theta);
+    v[1] = sin(phi) * sin(theta);
+    v[2] = cos(theta);
+}
+
+/* the same point; with the production streams in the product's closed form
+ * (geometry.cuh unit_sphere_point<false>: cos(theta) = x = 2 u2 - 1,
+ * sin(theta) = sqrt((1 - x)(1 + x)), sincospi(2 u1)) */
+static void sample_sphere(oc_glibc_rand *g, double v[3])
+{
+    double phi, theta;
+    if (g->alt) {
+        double u1 = oc_uniform(g), u2 = oc_uniform(g);
+        double x = u2 * 2.0 - 1.0;
+        double st = sqrt((1.0 - x) * (1.0 + x));
+        double a = M_PI * (u1 * 2.0);
+        v[0] = cos(a) * st;
+        v[1] = sin(a) * st;
+        v[2] = x;
+        return;
+    }
+    phi = oc_uniform(g) * (2.0 * M_PI);
+    theta = acos(oc_uniform(g) * 2 - 1);
     v[0] = cos(phi) * sin(theta);
     v[1] = sin(phi) * sin(theta);
     v[2] = cos(theta);
@@ -765,7 +851,7 @@ static void crank_axis(oc_sim *s, int64_t ind0, int64_t indf, double dir[3])
     for (i = 0; i < 3; i++) dir[i] = s->r[3 * a + i] - s->r[3 * b + i];
     mag = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
     if (mag < 1E-5) {
-        sample_sphere(&s->crng, dir);
+        sample_sphere_exact(&s->crng, dir); /* the product keeps libm's acos here (geometry.cuh degenerate_axis) */
     } else {
         double scaling = 1.0 / mag;
         for (i = 0; i < 3; i++) dir[i] = dir[i] * scaling;
@@ -893,7 +979,8 @@ int64_t oc_propose(oc_sim *s, int move, double amp_move, int64_t amp_bead, int64
         n = indf - ind0;
         for (i = 0; i < n; i++) {
             inds[i] = ind0 + i;
-            s->states_trial[inds[i] * s->nb + binder] = oc_mt_randint(&s->mt, 0, tails + 1);
+            s->states_trial[inds[i] * s->nb + binder] =
+                g->alt ? philox_randint((oc_philox *)g->alt, tails + 1) : oc_mt_randint(&s->mt, 0, tails + 1);
         }
         return n;
     }
@@ -992,8 +1079,13 @@ void oc_update_amplitudes(oc_move *mv)
 int oc_mc_step(oc_sim *s, oc_move *mv, int move, int64_t *inds)
 {
     int check_field = (s->field_active && move != OC_TANGENT);
-    double dE = 0, exp_dE, u, dEp, dEf = 0;
+    double dE = 0, exp_dE, u = 0, dEp, dEf = 0;
     int64_t n;
+    const int prod = s->crng.alt != NULL;
+    if (prod) { /* production streams: attempt t has its own stream, whose draw 0 is the Metropolis uniform */
+        philox_seek(&s->philox, s->philox.next_attempt++);
+        u = oc_uniform(&s->crng);
+    }
     mv->num_attempt += 1; /* MCAdapter.propose moves.pyx:151 */
     n = oc_propose(s, move, mv->amp_move, mv->amp_bead, inds);
     if (n == 0) return -1;
@@ -1006,7 +1098,7 @@ int oc_mc_step(oc_sim *s, oc_move *mv, int move, int64_t *inds)
     s->last_dE_poly = dEp;
     s->last_dE_field = dEf;
     exp_dE = exp(-dE);
-    u = oc_uniform(&s->crng);
+    if (!prod) u = oc_uniform(&s->crng);
     s->last_u = u;
     if (u < exp_dE) {
         oc_accept(s, mv, move, inds, n);

@@ -30,7 +30,25 @@ enum { OC_CONFINE_NONE = 0, OC_CONFINE_SPHERICAL = 1, OC_CONFINE_CUBICAL = 2 };
 typedef struct {
     int32_t r[34];
     int f, b;
+    void *alt;   /* NULL: the reference's streams.  Else an oc_philox: the product's
+                    production streams (see below), every draw comes from there */
 } oc_glibc_rand;
+
+/* The product's PRODUCTION random streams, restated (chromo_b200/csrc/rng.cuh,
+ * PhiloxRng): draw i of attempt t of replica r is word (i & 3) of
+ * Philox4x32-10(counter = (t_lo, t_hi, i >> 2, r), key = seed).  Draw 0 of an
+ * attempt is its Metropolis uniform, the proposal's draws follow in the
+ * reference's order; binding states come from the same
+ * stream (masked rejection on 32-bit words) instead of numpy's MT19937, and
+ * sphere points use the closed form cos(theta) = 2u-1 (the reference calls
+ * acos).  This is NOT the reference's RNG: it exists so that the kernel that is
+ * benchmarked can be replayed attempt for attempt on the CPU. */
+typedef struct {
+    uint32_t k0, k1, rep, pos;
+    uint64_t attempt;       /* stream in use */
+    uint64_t next_attempt;  /* attempts this replica has made (persists across mc_sim calls) */
+    uint32_t blk[4];
+} oc_philox;
 
 /* numpy legacy RandomState (MT19937) -- move_funcs.pyx:819 np.random.randint */
 typedef struct {
@@ -99,6 +117,8 @@ typedef struct {
     /* --- SSTWLC twist (polymers.pyx:1889-2319); NULL for SSWLC / Chromatin --- */
     double *eps_twist;                       /* [N-1] lt / (delta * lp), polymers.pyx:2000 */
     double *twist0;                          /* [N-1] bead_length * NATURAL_TWIST_BARE / LENGTH_BP, 2088-2090 */
+    /* --- production streams (crng.alt points here when in use) --- */
+    oc_philox philox;
 } oc_sim;
 
 /* RNG */
@@ -107,6 +127,8 @@ int32_t oc_rand(oc_glibc_rand *s);
 void oc_mt_seed(oc_mt19937 *s, uint32_t seed);
 uint32_t oc_mt_next(oc_mt19937 *s);
 int64_t oc_mt_randint(oc_mt19937 *s, int64_t low, int64_t high);
+void oc_philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]);
+void oc_philox_init(oc_sim *s, uint64_t seed, uint32_t replica, uint64_t next_attempt);
 
 /* A1: per-bead binning */
 void oc_bin_point(const oc_sim *s, const double xyz[3], int64_t idx[8], double w[8]);

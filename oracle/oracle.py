@@ -28,7 +28,12 @@ _pl = C.POINTER(C.c_int64)
 
 
 class GlibcRand(C.Structure):
-    _fields_ = [("r", C.c_int32 * 34), ("f", C.c_int), ("b", C.c_int)]
+    _fields_ = [("r", C.c_int32 * 34), ("f", C.c_int), ("b", C.c_int), ("alt", C.c_void_p)]
+
+
+class Philox(C.Structure):
+    _fields_ = [("k0", C.c_uint32), ("k1", C.c_uint32), ("rep", C.c_uint32), ("pos", C.c_uint32),
+                ("attempt", C.c_uint64), ("next_attempt", C.c_uint64), ("blk", C.c_uint32 * 4)]
 
 
 class MT19937(C.Structure):
@@ -71,6 +76,7 @@ class Sim(C.Structure):
         ("last_dE_poly", C.c_double), ("last_dE_field", C.c_double),
         ("last_accept", C.c_int64), ("last_u", C.c_double),
         ("eps_twist", _pd), ("twist0", _pd),
+        ("philox", Philox),
     ]
 
 
@@ -96,6 +102,8 @@ def lib():
         L.oc_mt_next.restype = C.c_uint32
         L.oc_mt_randint.argtypes = [C.POINTER(MT19937), C.c_int64, C.c_int64]
         L.oc_mt_randint.restype = C.c_int64
+        L.oc_philox_block.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
+        L.oc_philox_init.argtypes = [ps, C.c_uint64, C.c_uint32, C.c_uint64]
         L.oc_bin_point.argtypes = [ps, _pd, _pl, _pd]
         L.oc_update_all_densities.argtypes = [ps, C.c_int]
         L.oc_field_E.argtypes = [ps]
@@ -411,6 +419,17 @@ class OracleSim:
 
     def np_seed(self, seed):
         self.L.oc_mt_seed(C.byref(self.s.mt), seed)
+
+    def use_production_streams(self, seed, replica=0, next_attempt=0):
+        """Draw from the product's production streams (Philox4x32-10 keyed by seed and replica, one
+        stream per attempt; chromo_b200/csrc/rng.cuh) instead of the reference's rand() / MT19937, so
+        that a production-mode run of the product can be replayed attempt for attempt.  `srand`
+        switches back."""
+        self.L.oc_philox_init(C.byref(self.s), seed, replica, next_attempt)
+
+    @property
+    def attempts_made(self):
+        return int(self.s.philox.next_attempt)
 
     # -- A1
     def bin_point(self, xyz):

@@ -138,6 +138,61 @@ def test_replay_matches_oracle_at_c2_size(cuda_backend):
     ens.close()
 
 
+def _check_against_production_oracle(ens, g, binders, start, reps, sweeps, seed, offset=0):
+    """replicas `reps` of a production-mode run against the oracle drawing from the same streams"""
+    for rep in reps:
+        spec = dict(start["spec"](rep))
+        o = O.OracleSim(spec)
+        o.use_production_streams(seed, offset + rep)
+        mv = O.make_moves(ens.N, 16.5)
+        o.mc_sim(mv, sweeps, 0)
+        assert [int(x) for x in ens.moves["num_success"][rep]] == [m.num_success for m in mv], rep
+        assert [int(x) for x in ens.moves["amp_bead"][rep]] == [m.amp_bead for m in mv]
+        assert [float(x) for x in ens.moves["amp_move"][rep]] == [m.amp_move for m in mv]
+        assert np.array_equal(ens.states[rep], o.states)
+        assert np.allclose(ens.r[rep], o.r, rtol=0, atol=1e-7)
+        assert np.allclose(ens.t3[rep], o.t3, rtol=0, atol=1e-7)
+
+
+def test_production_run_matches_oracle_at_c2_size(cuda_backend):
+    """The benchmarked instantiation (Philox streams, batches of 32 prepared attempts, 7 replicas per block,
+    default table) at N = 10,000 for 6 sweeps: same accept / reject counts, controller state, binding states
+    and positions as the oracle run sequentially on the same streams."""
+    R = 16
+    ens, g, binders, Rc = _ensemble(R, 10_000, nb=1, seed=6)
+    assert ens.engine.set_replicas_per_block(7) == 7
+    r0, t30, t20, st0 = ens.r.copy(), ens.t3.copy(), ens.t2.copy(), ens.states.copy()
+    start = dict(spec=lambda rep: dict(N=10_000, nb=1, r=r0[rep], t3=t30[rep], t2=t20[rep], states=st0[rep],
+                                       mods=ens.chemical_mods[rep], bead_length=np.full(9_999, 16.5), lp=53.0,
+                                       bead_rad=5.0, binders=binders, max_binders=-1, field=dict(g, chi=1.0)))
+    ens.mc_sim(6, 1.0, 31337, sync_host=True)
+    _check_against_production_oracle(ens, g, binders, start, (0, 6, 7, 15), 6, 31337)
+    ens.close()
+
+
+def test_bench_ensemble_replays_against_oracle(cuda_backend):
+    """The bench's own ensemble (bench.make_inputs: 1,024 replicas x 10,000 beads, marks from the reference's
+    H3K9me3 track, default launch shape: 7 replicas per block, 147 blocks) for 5 sweeps; three of its replicas
+    replayed on the CPU."""
+    import bench
+    from chromo_b200.ensemble import ReplicaEnsemble, default_moves
+    R, N = 1024, 10_000
+    r, t3, t2, states, mods, grid = bench.make_inputs(R, N, 1234, pinned=False)
+    binders = [dict(bench.HP1)]
+    ens = ReplicaEnsemble(r.copy(), t3.copy(), t2.copy(), states.copy(), mods, binders=binders,
+                          bond_params=bench.bond_params(N), grid=grid, bead_vol=(4 / 3) * math.pi * 125.0, chi=1.0,
+                          mu=[-1.2], moves=default_moves(R, N, 16.5))
+    assert ens.engine.set_replicas_per_block(0) == 7
+    start = dict(spec=lambda rep: dict(N=N, nb=1, r=r[rep], t3=t3[rep], t2=t2[rep], states=states[rep],
+                                       mods=mods[rep], bead_length=np.full(N - 1, 16.5), lp=53.0, bead_rad=5.0,
+                                       binders=binders, max_binders=-1, field=dict(grid, chi=1.0)))
+    ens.mc_sim(5, 1.0, 2024, sync_host=False)
+    ens.sync()
+    ens.pull()
+    _check_against_production_oracle(ens, grid, binders, start, (0, 511, 1023), 5, 2024)
+    ens.close()
+
+
 def test_replica_exchange_single_rank(cuda_backend):
     """C5 on one rank: chi ladder, labels move, configurations do not."""
     from chromo_b200.parallel import ReplicaExchange
