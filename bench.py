@@ -5,13 +5,22 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
 
 Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): chromatin, 10,000 beads
-per replica, HP1 on synthetic H3K9me3 marks, chi = 1, mu = -1.2, spherical
-confinement, 21^3 voxel grid, canonical 161-attempt sweep (30 crank-shaft, 1
-end-pivot, 60 slide, 60 tangent-rotation, 10 binding) with SimpleControl, and
-1,024 replicas PER GPU (weak scaling: replicas shard across ranks, no data-path
-collective).  One bench "step" = one `mc_sim` call of --sweeps MC sweeps
-(default 50; the reference's own scripts call mc_sim with 1,000-6,000 sweeps per
-snapshot) over every replica = R * sweeps * 161 move attempts.
+per replica, HP1 on the first 10,000 entries of the reference's H3K9me3 track
+(chromo/chemical_mods/HNCFF683HCZ_H3K9me3_methyl.txt), chi = 1, mu = -1.2,
+spherical confinement, 21^3 voxel grid, canonical 161-attempt sweep (30
+crank-shaft, 1 end-pivot, 60 slide, 60 tangent-rotation, 10 binding) with
+SimpleControl, and 1,024 replicas PER GPU (weak scaling: replicas shard across
+ranks, no data-path collective).  One bench "step" = one `mc_sim` call of
+--sweeps MC sweeps (default 50; the reference's own scripts call mc_sim with
+1,000-6,000 sweeps per snapshot) over every replica = R * sweeps * 161 attempts.
+
+Equal work: SimpleControl keeps widening the bead windows for ~5,000 sweeps until
+crank-shaft, end-pivot and slide sit at their upper bound of 150 beads and
+tangent rotation at ~14 (profiles/stationary_amplitudes.json); throughput at that
+state is half of what it is 500 sweeps in.  BOTH arms therefore START from that
+state (controllers on), print the bead windows they ended with, and our arm's
+line fails (exit code 3, line still printed) if the CPU leg and the GPU differ by
+more than 2 %.
 
 value : attempts/s with the state resident in HBM (CUDA events on the kernel's
         stream around K back-to-back mc_sim launches, max over ranks).
@@ -62,17 +71,55 @@ HP1 = dict(name="HP1", sites_per_bead=2, bind_energy_mod=-0.01, bind_energy_no_m
            interaction_energy=-4.0, chemical_potential=-1.2, interaction_radius=3.0, cross_talk={"PRC1": 0.0})
 
 
-def make_inputs(R: int, N: int, seed: int, pinned: bool):
-    """Synthetic replicas: confined Gaussian-direction walks, central-difference
-    tangents, blocky 0/1/2 marks, all binding states 0."""
+def stationary_state():
+    """Controller state both arms start from: where SimpleControl settles on this workload
+    (tools/stationary_state.py, measured over 10,000 sweeps of 1,024 replicas)."""
+    st = dict(amp_bead=[150, 150, 150, 14, 1], amp_move=[0.5238, 0.701, 4.1266, 0.4022, 0.0])
+    try:
+        d = json.loads((ROOT / "profiles" / "stationary_amplitudes.json").read_text())
+        st = dict(amp_bead=[int(x) for x in d["amp_bead"]], amp_move=[float(x) for x in d["amp_move"]])
+    except Exception:
+        pass
+    return st
+
+
+def stationary_moves(R: int, N: int, first: int = 0):
+    """[R,5] controller records of replicas first .. first+R at the stationary state (bead windows clipped to
+    the chain's bounds).  The stationary ensemble is a spread, not a point: the rotation / translation
+    amplitudes of crank-shaft, end-pivot and slide cycle through [lo, hi] (acceptance stays above 0.5 with the
+    window pinned at its bound), and the tangent-rotation window hovers between 14 and 15 beads (mean 14.4).
+    Replica i gets a deterministic phase of that cycle, the same in both arms."""
     import numpy as np
+    from chromo_b200.ensemble import default_moves
+    mv = default_moves(R, N, 16.5)
+    st = stationary_state()
+    idx = first + np.arange(R)
+    phase = (idx * 0.6180339887498949) % 1.0
+    for i in range(5):
+        lo_b, hi_b = int(mv["bead_amp_lo"][0, i]), int(mv["bead_amp_hi"][0, i])
+        lo_m, hi_m = float(mv["move_amp_lo"][0, i]), float(mv["move_amp_hi"][0, i])
+        mv["amp_bead"][:, i] = max(lo_b, min(int(st["amp_bead"][i]), hi_b))
+        mv["amp_move"][:, i] = max(lo_m, min(st["amp_move"][i], hi_m))
+        mv["acceptance_rate"][:, i] = 0.5
+        if i in (0, 1, 2) and hi_m > lo_m:  # geometric sawtooth lo -> hi (x 1/0.95 per sweep)
+            mv["amp_move"][:, i] = lo_m * (hi_m / lo_m) ** phase
+    if st["amp_bead"][3] == 14:
+        mv["amp_bead"][:, 3] = np.clip(np.where(idx % 5 < 2, 15, 14), int(mv["bead_amp_lo"][0, 3]), int(mv["bead_amp_hi"][0, 3]))
+    return mv
+
+
+def make_inputs(R: int, N: int, seed: int, pinned: bool, nb: int = 1):
+    """Synthetic replicas: confined Gaussian-direction walks, central-difference tangents, the first N
+    entries of the reference's mark track(s) (the same for every replica), all binding states 0."""
+    import numpy as np
+    from chromo_b200.util import chemical_mods
     from chromo_b200.util import poly_paths as paths
     rng = np.random.default_rng(seed)
     Rc, nx, W = workload_params(N)
     r = paths.confined_gaussian_walk(N, np.full(N - 1, 16.5), "Spherical", Rc, rng, replicas=R)
     t3, t2 = paths.estimate_tangents_from_coordinates(r)
-    mods = paths.synthetic_marks(N, 1, rng, replicas=R)
-    states = np.zeros((R, N, 1), dtype=np.int64)
+    mods = chemical_mods.first_beads(N, chemical_mods.TRACKS[:nb], replicas=R)
+    states = np.zeros((R, N, nb), dtype=np.int64)
     if pinned:
         import torch
 
@@ -165,9 +212,8 @@ class ClockSampler:
 
 # ---------------------------------------------------------------- CPU baseline
 def _ref_worker(args):
-    """One host core: the reference's Cython mc_sim on one replica of the workload.
-    Warm-up sweeps let SimpleControl bring the amplitudes to their working point
-    (segments grow from ~7 to ~30 beads), as they are in the GPU arm's timed region."""
+    """One host core: the reference's Cython mc_sim on one replica of the workload, started from the
+    controllers' stationary state like the GPU arm (a few warm-up sweeps decorrelate the replicas)."""
     rank, N, warm, sweeps, reps, kind = args
     import numpy as np
     sys.path.insert(0, str(ROOT / "oracle"))
@@ -183,6 +229,11 @@ def _ref_worker(args):
         ctrl, mc, mcs, sh = M["mc_controller"], M["mc"], M["mc_sim"], M["shim"]
         bb, mb = mc.get_amplitude_bounds([poly])
         cs = ctrl.all_moves("/tmp/chromo_bench", bb.bounds, mb.bounds, ctrl.SimpleControl)
+        st = stationary_moves(1, N, first=rank)
+        for i, c in enumerate(cs):
+            c.move.amp_bead = int(st["amp_bead"][0, i])
+            c.move.amp_move = float(st["amp_move"][0, i])
+            c.move.acceptance_tracker.acceptance_rate = 0.5
         sh.c_srand(rank + 1)
         with np.errstate(over="ignore"):
             mcs.mc_sim([poly], df, warm, cs, field, 1.0, rank)
@@ -194,6 +245,10 @@ def _ref_worker(args):
     else:
         o = O.OracleSim(spec, srand_seed=rank + 1)
         mv = O.make_moves(N, 16.5)
+        st = stationary_moves(1, N, first=rank)
+        for i in range(5):
+            mv[i].amp_bead, mv[i].amp_move = int(st["amp_bead"][0, i]), float(st["amp_move"][0, i])
+            mv[i].acceptance_rate = 0.5
         o.mc_sim(mv, warm, rank)
         for k in range(reps):
             t0 = time.perf_counter()
@@ -224,8 +279,8 @@ def cpu_reference_sample(N: int, sweeps: int, warm: int, reps: int = 1, cores: i
     amp = [sum(a[i] for _, _, a in res) / len(res) for i in range(5)]
     cb = dict(value=value, unit=UNIT, cores=cores, kind=kind,
               sample=f"{cores} processes (one per host core) x {sweeps} MC sweeps ({sweeps * ATTEMPTS_PER_SWEEP} attempts "
-                     f"each) of one N={N} HP1 replica, after {warm} warm-up sweeps that bring SimpleControl to its "
-                     f"working point; wall time of mc_sim only",
+                     f"each) of one N={N} HP1 replica, started at SimpleControl's stationary state (bead windows "
+                     f"150/150/150/14/1) + {warm} untimed sweeps; wall time of mc_sim only",
               single_core=max(a / min(t) for a, t, _ in res), amp_bead_mean=[round(x, 2) for x in amp])
     return cb, per_rep
 
@@ -242,12 +297,12 @@ def run_reference(args):
     line = dict(metric=METRIC, value=v, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * sum(t for _, t in timed) / len(timed), higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=workload_config(args, 0), cpu_baseline=cb,
+                config=workload_config(args), cpu_baseline=cb, amp_bead_mean=cb.get("amp_bead_mean"),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
 
 
-def workload_config(args, cap):
+def workload_config(args):
     Rc, nx, W = workload_params(args.beads)
     label = {10000: "C2", 400000: "C4-sized", 1000: "C1-sized"}.get(args.beads, "custom size")
     if args.beads == 10000 and args.replicas != 1024:
@@ -256,10 +311,12 @@ def workload_config(args, cap):
     state_mb = args.replicas * args.beads * 74 / 1e6   # r, t3, t2 fp64 + states, marks int8
     field_mb = args.replicas * nx ** 3 * 16 / 1e6      # (bead, HP1) fp64 per voxel
     fits = state_mb + field_mb <= 126
-    return dict(workload=f"{label}: chromatin {args.beads} beads, HP1 on H3K9me3 (synthetic marks), chi=1, mu=-1.2, "
-                         f"{args.replicas} replicas per GPU, {nx}^3 voxels, spherical confinement R={Rc:.1f} nm{twist}",
+    st = stationary_state()
+    return dict(workload=f"{label}: chromatin {args.beads} beads, HP1 on H3K9me3 (first {args.beads} entries of the "
+                         f"reference's track), chi=1, mu=-1.2, {args.replicas} replicas per GPU, {nx}^3 voxels, "
+                         f"spherical confinement R={Rc:.1f} nm, SimpleControl started at its stationary state{twist}",
                 replicas_per_gpu=args.replicas, beads=args.beads, grid=nx, sweeps_per_step=args.sweeps,
-                attempts_per_sweep=ATTEMPTS_PER_SWEEP, rng="philox4x32-10", table_slots=cap,
+                attempts_per_sweep=ATTEMPTS_PER_SWEEP, start_amp_bead=st["amp_bead"], start_amp_move=st["amp_move"],
                 l2=(f"working set (state {state_mb:.0f} MB + field {field_mb:.0f} MB per GPU) "
                     + ("FITS the 126 MB L2: not a cold-cache number" if fits
                        else "exceeds the 126 MB L2; no flush needed")),
@@ -270,7 +327,7 @@ def workload_config(args, cap):
 def run_ours(args):
     import numpy as np
     import torch
-    from chromo_b200.ensemble import ReplicaEnsemble, default_moves
+    from chromo_b200.ensemble import ReplicaEnsemble
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -287,7 +344,8 @@ def run_ours(args):
     r, t3, t2, states, mods, grid = make_inputs(R, N, 1234 + rank, pinned=True)
     ens = ReplicaEnsemble(r, t3, t2, states, mods, binders=[dict(HP1)], bond_params=bond_params(N, lt=args.lt), grid=grid,
                           bead_vol=(4 / 3) * math.pi * 5.0 ** 3, chi=1.0, mu=[-1.2],
-                          moves=default_moves(R, N, 16.5), device=local)
+                          moves=stationary_moves(R, N, first=rank * R), device=local,
+                          replica_offset=rank * R)  # every rank's replicas draw their own random streams
     eng = ens.engine
     warps = eng.set_warps_per_replica(args.warps)
     rpb = eng.set_replicas_per_block(args.rpb)
@@ -302,8 +360,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput --------------------------------------
-    # untimed: let SimpleControl bring the amplitudes to their working point (same for the CPU arm)
-    ens.mc_sim(args.ref_warm, 1.0, 99, sync_host=False)
+    # both arms start at SimpleControl's stationary state; the warm-up steps decorrelate the replicas
     for w in range(Wm):
         ens.mc_sim(S, 1.0, 100 + w, sync_host=False)
     barrier()
@@ -311,32 +368,35 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    algo_bytes, attempts = [], []
     ev[0].record(stream)
     for k in range(K):
         ens.mc_sim(S, 1.0, 1000 + k, sync_host=False)
         ev[k + 1].record(stream)
+        # per-launch counters (a stream sync + two 8 KB reads: microseconds against a ~100 ms launch)
+        algo_bytes.append(eng.last_algo_bytes())
+        attempts.append(eng.last_attempts())
     eng.sync()
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = ev[0].elapsed_time(ev[K])
     kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
-    attempts_last = eng.last_attempts()
-    algo_bytes_last = eng.last_algo_bytes()
     ens.sync()
     acc = ens.acceptance()
     amp_bead_mean = [float(x) for x in ens.moves["amp_bead"].mean(axis=0)]
     barrier()
 
     # ---- end to end through the host-facing call --------------------------
-    h2d = (3 * R * N * 24 + 2 * R * N * 1 * 8) * world  # r, t3, t2 + states, chemical_mods (int64), all ranks
-    d2h = (3 * R * N * 24 + R * N * 1 * 8) * world      # r, t3, t2 + states, all ranks
+    # per call: r, t3, t2 (fp64) and states (int64) go host -> device and come back; the marks go up once
+    # per ensemble (they never change: ReplicaEnsemble.mc_sim keeps them resident)
+    h2d = (3 * R * N * 24 + R * N * 1 * 8) * world
+    d2h = (3 * R * N * 24 + R * N * 1 * 8) * world
     Ke = max(1, min(K, args.e2e_steps))
-    # replica chunks of the pipelined host path (the library's automatic rule, include/chromo_b200.h)
     nblk = -(-R // rpb)
     e2e_chunks = 4
     while e2e_chunks > 1 and e2e_chunks * -(-nblk // e2e_chunks) > torch.cuda.get_device_properties(local).multi_processor_count:
         e2e_chunks -= 1
-    ens.mc_sim(S, 1.0, 5000, sync_host=True)
+    ens.mc_sim(S, 1.0, 5000, sync_host=True)  # (refreshes the host arrays from the device first)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -358,6 +418,7 @@ def run_ours(args):
     value = attempts_step * K / (ms_total * 1e-3)
     e2e = attempts_step * Ke / (e2e_ms * 1e-3)
 
+    rc = 0
     if rank == 0:
         peaks, peak_src = 6650.0, "fallback"
         try:
@@ -365,43 +426,68 @@ def run_ours(args):
             peaks, peak_src = float(mp["hbm_gbs"]), "measured"
         except Exception:
             pass
+        # roofline of the dominant kernel: algorithmic bytes of ALL timed launches / their summed CUDA-event time
         k_ms = sum(kernel_ms) / len(kernel_ms)
-        achieved = algo_bytes_last / (kernel_ms[-1] * 1e-3) / 1e9
+        bytes_launch = sum(algo_bytes) / len(algo_bytes)
+        attempts_launch = sum(attempts) / len(attempts)
+        achieved = sum(algo_bytes) / (sum(kernel_ms) * 1e-3) / 1e9
         traffic = None
         try:
             tr = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
             per_attempt = tr.get("mc_sim_kernel", {}).get("dram_bytes_per_attempt")
-            traffic = per_attempt * attempts_last if per_attempt else None  # ncu DRAM bytes, scaled to this launch
+            # ncu dram__bytes_read + dram__bytes_write of one launch at THIS working point, per attempt
+            traffic = per_attempt * attempts_launch if per_attempt else None
         except Exception:
             pass
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=Wm,
             ms_per_step=ms_total / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-            data="synthetic", config=dict(workload_config(args, cap), warps_per_replica=warps, replicas_per_block=rpb),
+            data="synthetic", config=workload_config(args),
+            launch=dict(warps_per_replica=warps, replicas_per_block=rpb, table_slots=cap, rng="philox4x32-10"),
             e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=Ke,
                      ms_per_step=e2e_ms / Ke, replica_chunks=e2e_chunks,
+                     h2d_gbs_per_gpu=h2d / world / (e2e_ms / Ke * 1e-3) / 1e9,
+                     d2h_gbs_per_gpu=d2h / world / (e2e_ms / Ke * 1e-3) / 1e9,
                      path="chromo_mc_sim_host: pinned host arrays -> device -> kernel -> host, pipelined over replica chunks"),
             gpu_launches=K + 4 * e2e_chunks * Ke,  # e2e: per replica chunk 2 narrowing kernels, the MC kernel, 1 widening
             clocks=clocks,
             roofline=dict(bound="hbm", achieved=achieved, peak=peaks, unit="GB/s", frac=achieved / peaks,
-                          traffic=traffic, peak_source=peak_src, kernel="mc_sim_kernel<PhiloxRng,1>",
-                          kernel_ms=k_ms, algorithmic_bytes_per_launch=algo_bytes_last,
-                          bytes_per_attempt=algo_bytes_last / max(1, attempts_last),
-                          note="latency-bound (serial moves per replica, one warp each); see DESIGN.md"),
+                          traffic=traffic, peak_source=peak_src, kernel=f"mc_sim_kernel<PhiloxRng,1,{warps}>",
+                          kernel_ms=k_ms, algorithmic_bytes_per_launch=bytes_launch,
+                          attempts_per_launch=attempts_launch,
+                          bytes_per_attempt=bytes_launch / max(1.0, attempts_launch),
+                          note="achieved = sum of algorithmic bytes of the timed launches / sum of their CUDA-event "
+                               "times; latency-bound (serial moves per replica); see DESIGN.md"),
             acceptance={k: round(float(v), 4) for k, v in acc.items()},
             amp_bead_mean=[round(x, 2) for x in amp_bead_mean],
             hbm_bytes=eng.bytes(),
         )
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cb, _ = cpu_reference_sample(N, args.ref_sweeps, args.ref_warm)
+                # the same code path and start state as `--impl reference`: 1 untimed + 12 timed repetitions
+                cb, per_rep = cpu_reference_sample(N, args.ref_sweeps, args.ref_warm, reps=13)
+                cb["value"] = sum(v for v, _ in per_rep[1:]) / len(per_rep[1:])
                 line["cpu_baseline"] = cb
+                ours, theirs = line["amp_bead_mean"], cb["amp_bead_mean"]
+                # bead windows within 2 %; the tangent-rotation window is an integer hovering between 14 and 15,
+                # so a handful of CPU replicas can sit up to one bead from the GPU's 1,024-replica mean
+                diff = max(abs(a - b) / max(abs(a), abs(b), 1e-9) for i, (a, b) in enumerate(zip(ours, theirs)) if i != 3)
+                tdiff = abs(ours[3] - theirs[3])
+                ok = diff <= 0.02 and tdiff <= 1.0
+                line["equal_work"] = dict(amp_bead_gpu=ours, amp_bead_cpu=theirs, max_rel_diff=round(diff, 4),
+                                          tangent_window_diff_beads=round(tdiff, 2), ok=ok)
+                if not ok:
+                    rc = 3
+                    print(f"bench.py: the arms did NOT do equal work: bead windows {ours} (GPU) vs {theirs} (CPU)",
+                          file=sys.stderr)
             except Exception as e:  # never lose the GPU number to a baseline hiccup
                 line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=str(e)[:200])
         emit(line)
     ens.close()
     if dist is not None:
         dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
 
 
 _REAL_STDOUT = None
@@ -433,8 +519,8 @@ def main():
     ap.add_argument("--beads", type=int, default=10000)
     ap.add_argument("--sweeps", type=int, default=50, help="MC sweeps (161 attempts each) per bench step")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--ref-sweeps", type=int, default=100, help="MC sweeps per process in the CPU reference sample")
-    ap.add_argument("--ref-warm", type=int, default=400, help="warm-up sweeps of the CPU reference (controller settles)")
+    ap.add_argument("--ref-sweeps", type=int, default=20, help="MC sweeps per process and repetition in the CPU reference sample")
+    ap.add_argument("--ref-warm", type=int, default=10, help="untimed sweeps of the CPU reference after the stationary start")
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0, help="warps per replica in the MC kernel (0 = library default)")
     ap.add_argument("--rpb", type=int, default=0, help="replicas per thread block (0 = library default)")

@@ -60,6 +60,7 @@ struct chromo_ctx {
     double *d_bond = nullptr, *d_twist = nullptr, *d_chi = nullptr, *d_mu = nullptr, *d_bindF = nullptr, *d_access = nullptr;
     double *d_partial = nullptr, *d_out = nullptr;
     int *d_dcount = nullptr;
+    int *d_bad = nullptr; // set by the narrowing kernel when a state / mark is out of range
     long long *d_stage = nullptr;
     int64_t stage_elems = 0;
     // host-array path (chromo_mc_sim_host): one stream + int64 staging buffer per replica chunk
@@ -79,6 +80,7 @@ struct chromo_ctx {
     double roundK = 0.0;
     double min_access_vol = 0.0; // smallest positive per-voxel volume (0: uniform voxels)
     bool have_binders = false, have_bonds = false, have_state = false;
+    bool have_mods = false; // every replica's chemical_mods have been uploaded
     int64_t last_attempts = 0;
     int sm_count = 148;
     size_t smem_optin = 227 * 1024; // largest block
@@ -219,6 +221,7 @@ extern "C" int chromo_ctx_create(chromo_ctx **out, int device, const chromo_shap
     if ((rc = dev_alloc(c, &d.glibc, (size_t)d.R * CB_GLIBC_WORDS))) return rc;
     if ((rc = dev_alloc(c, &d.mt, (size_t)d.R * CB_MT_WORDS))) return rc;
     if ((rc = dev_alloc(c, &d.philox_ctr, (size_t)d.R))) return rc;
+    if ((rc = dev_alloc(c, &c->d_bad, (size_t)1))) return rc;
     d.rep_offset = 0u;
     d.batch = 32;
     if ((rc = dev_alloc(c, &d.tan_inds, RN))) return rc;
@@ -487,15 +490,32 @@ static int check_range(chromo_ctx *c, int64_t first, int64_t n) {
     return 0;
 }
 
+// largest value a state / mark may take: the binding free-energy table is [nb][S1][S1]
+static int value_limit(const chromo_ctx *c) {
+    int hi = 0;
+    for (int a = 0; a < c->d.nb; a++) hi = std::max(hi, c->d.sites[a]);
+    return c->have_binders ? hi : 127;
+}
+static int check_bad_values(chromo_ctx *c) {
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (bad) {
+        CK(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
+        return fail(CHROMO_ERR_ARG, "states / chemical_mods must lie in [0, %d] (the largest sites_per_bead)", value_limit(c));
+    }
+    return 0;
+}
 static int upload_i64_as_i8(chromo_ctx *c, signed char *dst, const int64_t *src, size_t n) {
     for (size_t o = 0; o < n; o += (size_t)c->stage_elems) {
         size_t m = std::min(n - o, (size_t)c->stage_elems);
         CK(cudaMemcpyAsync(c->d_stage, src + o, m * 8, cudaMemcpyHostToDevice, c->stream));
-        CB_LAUNCH(narrow_i64_kernel, (unsigned)((m + 255) / 256), 256, 0, c->stream, (const long long *)c->d_stage, dst + o, (long long)m);
+        CB_LAUNCH(narrow_i64_kernel, (unsigned)((m + 255) / 256), 256, 0, c->stream, (const long long *)c->d_stage, dst + o, (long long)m,
+                  value_limit(c), c->d_bad);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(c->stream));
     }
-    return 0;
+    return check_bad_values(c);
 }
 static int download_i8_as_i64(chromo_ctx *c, int64_t *dst, const signed char *src, size_t n) {
     for (size_t o = 0; o < n; o += (size_t)c->stage_elems) {
@@ -523,6 +543,7 @@ extern "C" int chromo_upload_state(chromo_ctx *c, int64_t first, int64_t n, cons
     if (mods && (rc = upload_i64_as_i8(c, d.mods + off * d.nb, mods, cnt * d.nb))) return rc;
     CK(cudaStreamSynchronize(c->stream));
     c->have_state = true;
+    if (mods && first == 0 && n == d.R) c->have_mods = true;
     return CHROMO_OK;
 }
 
@@ -764,7 +785,8 @@ extern "C" int chromo_mc_sim_host(chromo_ctx *c, int64_t num_mc_steps, chromo_mo
                                   const uint32_t *numpy_seeds, double *r, double *t3, double *t2,
                                   int64_t *states, const int64_t *mods, int64_t n_chunks) {
     if (!c) return fail(CHROMO_ERR_ARG, "null context");
-    if (!r || !t3 || !t2 || !states || !mods) return fail(CHROMO_ERR_ARG, "null host array");
+    if (!r || !t3 || !t2 || !states) return fail(CHROMO_ERR_ARG, "null host array");
+    if (!mods && !c->have_mods) return fail(CHROMO_ERR_ARG, "chemical_mods were never uploaded to this context");
     if (num_mc_steps < 0) return fail(CHROMO_ERR_ARG, "negative num_mc_steps");
     if (rng_mode != CHROMO_RNG_REPLAY && rng_mode != CHROMO_RNG_PHILOX) return fail(CHROMO_ERR_ARG, "unknown rng_mode %d", rng_mode);
     if (n_chunks < 0 || n_chunks > 64) return fail(CHROMO_ERR_ARG, "n_chunks must be in [0, 64]");
@@ -832,9 +854,13 @@ extern "C" int chromo_mc_sim_host(chromo_ctx *c, int64_t num_mc_steps, chromo_mo
         CK(cudaMemcpyAsync(d.t3 + off * 3, t3 + off * 3, cnt * 24, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d.t2 + off * 3, t2 + off * 3, cnt * 24, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(stage, states + off * d.nb, cs * 8, cudaMemcpyHostToDevice, st));
-        CB_LAUNCH(narrow_i64_kernel, (unsigned)((cs + 255) / 256), 256, 0, st, (const long long *)stage, d.states + off * d.nb, (long long)cs);
-        CK(cudaMemcpyAsync(stage, mods + off * d.nb, cs * 8, cudaMemcpyHostToDevice, st));
-        CB_LAUNCH(narrow_i64_kernel, (unsigned)((cs + 255) / 256), 256, 0, st, (const long long *)stage, d.mods + off * d.nb, (long long)cs);
+        CB_LAUNCH(narrow_i64_kernel, (unsigned)((cs + 255) / 256), 256, 0, st, (const long long *)stage, d.states + off * d.nb, (long long)cs,
+                  value_limit(c), c->d_bad);
+        if (mods) { // NULL: mc_sim never modifies the marks, the copy already on the device is current
+            CK(cudaMemcpyAsync(stage, mods + off * d.nb, cs * 8, cudaMemcpyHostToDevice, st));
+            CB_LAUNCH(narrow_i64_kernel, (unsigned)((cs + 255) / 256), 256, 0, st, (const long long *)stage, d.mods + off * d.nb, (long long)cs,
+                      value_limit(c), c->d_bad);
+        }
         CK(cudaEventRecord(c->chunk_uploaded[k], st));
         CB_MARK(0);
         McSimArgs a{d, (long long)num_mc_steps, mu_adjust_factor, (unsigned long long)seed, c->cap, c->warps, c->rpb, st,
@@ -862,6 +888,8 @@ extern "C" int chromo_mc_sim_host(chromo_ctx *c, int64_t num_mc_steps, chromo_mo
     }
 #endif
 #undef CB_MARK
+    if ((rc = check_bad_values(c))) return rc;
+    if (mods) c->have_mods = true;
     if (moves) {
         CK(cudaMemcpyAsync(moves, d.moves, sizeof(chromo_move_state) * d.R * CHROMO_NUM_MOVES,
                            cudaMemcpyDeviceToHost, c->stream));

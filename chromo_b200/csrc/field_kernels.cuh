@@ -179,7 +179,17 @@ __global__ void widen_i8_kernel(const signed char *src, long long *dst, long lon
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
 }
-__global__ void narrow_i64_kernel(const long long *src, signed char *dst, long long n) {
+// Values index the binding free-energy table (binding_dE_poly): anything outside [0, hi] (hi = the largest
+// sites_per_bead) is clamped and reported through *bad, and the call that uploaded it fails with
+// CHROMO_ERR_ARG instead of reading out of bounds on the device.
+__global__ void narrow_i64_kernel(const long long *src, signed char *dst, long long n, int hi, int *bad) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = (signed char)src[i];
+    if (i < n) {
+        long long v = src[i];
+        if (v < 0 || v > hi) {
+            *bad = 1;
+            v = v < 0 ? 0 : hi;
+        }
+        dst[i] = (signed char)v;
+    }
 }

@@ -213,17 +213,22 @@ __device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin, boo
 // 1 trial, corner l); the lanes of the bead split the units evenly.
 // Returns the confinement counters of get_confinement_dE (fields.pyx:160-193):
 // x = # trial positions outside, y = # current positions outside (this lane's).
-template <int NB>
+// KIND >= 0: the move's kind at compile time (the hot, single-pass instance of each move type);
+// KIND < 0: `kind_rt` decides (the one out-of-line copy behind the rare partition passes).
+template <int NB, int KIND, bool ONEPASS>
 __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
-                                          int kind, int ind0, int n, int binder,
-                                          const signed char *newst, int P, int p, double scale) {
+                                          int kind_rt, int ind0, int n, int binder,
+                                          const signed char *newst, int P_rt, int p, double scale) {
     constexpr int NCOL = NB + 1;
+    const int kind = KIND >= 0 ? KIND : kind_rt;
+    const int P = ONEPASS ? 1 : P_rt;
     const double *Rr = C.r + (long long)rep * C.N * 3;
     const signed char *ST = C.states + (long long)rep * C.N * NB;
     const double *dens_rows = C.density + (long long)rep * C.n_bins * NCOL;
     const bool checked = P > 1 || 16 * n > H.limit;
     int out_t = 0, out_c = 0;
     int per_iter;
+#pragma unroll 1
     for (int base = 0; base < n; base += per_iter) {
         // lanes per bead, chosen per iteration from the beads still to do: an underfull last iteration
         // spreads each bead's 16 units over more lanes instead of leaving lanes idle; 17..24 beads go as
@@ -424,13 +429,59 @@ __device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTabl
 // the delta-rho rows afterwards (used by the commit).  Moves whose touched set
 // overflows the table are re-scattered in hash-partition passes inside stage 2.
 // ddbl[a] = change in the number of doubly-bound beads (count_doubly_bound).
-template <int NB>
+template <int NB, int KIND>
 __device__ __forceinline__ int2 field_scatter(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
-                                              int kind, int ind0, int n, int binder, const signed char *newst) {
+                                              int ind0, int n, int binder, const signed char *newst) {
     const double scale = pow2_double(fx_exponent(C, n));
-    const int2 conf = scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, 1, 0, scale);
+    const int2 conf = scatter_pass<NB, KIND, true>(C, H, S, rep, lane, KIND, ind0, n, binder, newst, 1, 0, scale);
     __syncwarp();
     return conf;
+}
+// one partition pass of a move whose touched set overflowed the table (rare): the single out-of-line copy
+template <int NB>
+__device__ CB_NOINLINE void scatter_pass_cold(const DevCtx &C, HashTable H, WarpSh *Sp, int rep, int lane, int kind,
+                                              int ind0, int n, int binder, const signed char *newst, int P, int p,
+                                              double scale) {
+    (void)scatter_pass<NB, -1, false>(C, H, *Sp, rep, lane, kind, ind0, n, binder, newst, P, p, scale);
+}
+// the touched set does not fit the table (rare): re-scatter in P = 2, 4, ... hash-partition passes
+// (voxels with bin % P == p per pass; the energy is a sum over voxels).  Returns P; the table ends empty.
+template <int NB, bool DEBUG>
+__device__ CB_NOINLINE int field_energy_multipass(const DevCtx &C, HashTable H, WarpSh *Sp, int rep, int lane, int kind,
+                                                  int ind0, int n, int binder, const signed char *newst, double chi,
+                                                  FieldSums<NB> *Fp, DebugOut *dbg) {
+    constexpr int NCOL = NB + 1;
+    WarpSh &S = *Sp;
+    FieldSums<NB> &F = *Fp;
+    const int fxe = fx_exponent(C, n);
+    const double scale = pow2_double(fxe), inv_scale = pow2_double(-fxe);
+    const bool want_cross = C.any_cross != 0;
+    int P = 1;
+    bool failed = true;
+    while (failed) {
+        P *= 2;
+#pragma unroll
+        for (int a = 0; a < NB; a++) F.sq[a] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NB * NB; a++) F.cross[a] = 0.0;
+        F.chi = 0.0;
+        if (DEBUG && lane == 0) dbg->n_touched = 0;
+        failed = false;
+        for (int p = 0; p < P; p++) {
+            table_clear(H, S, NCOL, lane);
+            scatter_pass_cold<NB>(C, H, &S, rep, lane, kind, ind0, n, binder, newst, P, p, scale);
+            __syncwarp();
+            if (S.overflow) {
+                failed = true;
+                break;
+            }
+            table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross, inv_scale);
+            if (lane == 0) S.last_U = (p == 0 ? 0 : S.last_U) + S.count;
+            if (DEBUG) table_debug_dump(C, H, S, lane, dbg, inv_scale);
+        }
+    }
+    table_clear(H, S, NCOL, lane);
+    return P;
 }
 template <int NB, bool DEBUG>
 __device__ __forceinline__ double field_finish(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
@@ -438,8 +489,7 @@ __device__ __forceinline__ double field_finish(const DevCtx &C, HashTable &H, Wa
                                                int2 conf, const int *ddbl, DebugOut *dbg) {
     constexpr int NCOL = NB + 1;
     const double chi = C.chi[rep];
-    const int fxe = fx_exponent(C, n);
-    const double scale = pow2_double(fxe), inv_scale = pow2_double(-fxe);
+    const double inv_scale = pow2_double(-fx_exponent(C, n));
     FieldSums<NB> F;
     const bool want_cross = C.any_cross != 0;
 #pragma unroll
@@ -454,30 +504,7 @@ __device__ __forceinline__ double field_finish(const DevCtx &C, HashTable &H, Wa
         if (lane == 0) S.last_U = S.count;
         if (DEBUG) table_debug_dump(C, H, S, lane, dbg, inv_scale);
     } else {
-        bool failed = true;
-        while (failed) { // rare: the touched set does not fit the table
-            P *= 2;
-#pragma unroll
-            for (int a = 0; a < NB; a++) F.sq[a] = 0.0;
-#pragma unroll
-            for (int a = 0; a < NB * NB; a++) F.cross[a] = 0.0;
-            F.chi = 0.0;
-            if (DEBUG && lane == 0) dbg->n_touched = 0;
-            failed = false;
-            for (int p = 0; p < P; p++) {
-                table_clear(H, S, NCOL, lane);
-                (void)scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, P, p, scale);
-                __syncwarp();
-                if (S.overflow) {
-                    failed = true;
-                    break;
-                }
-                table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross, inv_scale);
-                if (lane == 0) S.last_U = (p == 0 ? 0 : S.last_U) + S.count;
-                if (DEBUG) table_debug_dump(C, H, S, lane, dbg, inv_scale);
-            }
-        }
-        table_clear(H, S, NCOL, lane);
+        P = field_energy_multipass<NB, DEBUG>(C, H, &S, rep, lane, kind, ind0, n, binder, newst, chi, &F, dbg);
     }
     if (lane == 0) S.passes = P;
     // ---- reduce and assemble in the reference's order ----
@@ -519,7 +546,7 @@ __device__ CB_NOINLINE void field_commit_multipass(const DevCtx &C, HashTable H,
     const double scale = pow2_double(fxe), inv_scale = pow2_double(-fxe);
     for (int p = 0; p < passes; p++) {
         table_clear(H, S, NB + 1, lane);
-        (void)scatter_pass<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst, passes, p, scale);
+        scatter_pass_cold<NB>(C, H, Sp, rep, lane, kind, ind0, n, binder, newst, passes, p, scale);
         __syncwarp();
         table_commit(C, H, S, rep, lane, inv_scale);
     }
@@ -856,7 +883,9 @@ struct McWarp {
     // did an attempt that committed after this warp's previous turn change rows that stage 1 of
     // attempt `slot` has read?  Writes of a segment move: beads [ind0, indf); reads: one more bead
     // on either side.  Tangent rotation: the selected beads; reads: their neighbours as well.
-    __device__ __forceinline__ bool stale(int mtype, int slot) const {
+    template <int MT>
+    __device__ __forceinline__ bool stale(int slot) const {
+        constexpr int mtype = MT;
         if (NW == 1) return false;
         const unsigned accepted = *(volatile unsigned *)&B.accepted;
         const Prop &P = B.prop[slot];
@@ -901,7 +930,9 @@ struct McWarp {
         return __any_sync(FULL_MASK, hit);
     }
     // one thread redoes the state-dependent half of attempt `slot` from the rows as they are now
-    __device__ __forceinline__ void rows_recompute(int mtype, int slot) {
+    template <int MT>
+    __device__ __forceinline__ void rows_recompute(int slot) {
+        constexpr int mtype = MT;
         if (lane == 0) {
             Prop *Pp = &B.prop[slot];
             if (segment_rows_prepare(R_(), T3_(), bond_rows(), C.N, mtype, Pp, nullptr, twist_rows(C, rep))) {
@@ -917,7 +948,9 @@ struct McWarp {
 
     // ======================================================== prepare
     // lanes [0, cnt) of warp 0 each prepare one attempt of move type `mtype`
-    __device__ __forceinline__ void prepare(int mtype, int cnt) {
+    template <int MT>
+    __device__ __forceinline__ void prepare(int cnt) {
+        constexpr int mtype = MT;
         if (lane >= cnt) return;
         const int N = C.N;
         Prop &P = B.prop[lane];
@@ -926,9 +959,9 @@ struct McWarp {
             rng.seek_attempt(abase + (unsigned long long)lane);
             P.u = u01(rng.next31()); // Metropolis uniform: draw 0 of the attempt's own stream
         }
-        const bool crank = mtype == CHROMO_CRANK_SHAFT, pivot = mtype == CHROMO_END_PIVOT;
-        const bool slide = mtype == CHROMO_SLIDE, bind = mtype == CHROMO_CHANGE_BINDING_STATE;
-        const bool tangent = mtype == CHROMO_TANGENT_ROTATION;
+        constexpr bool crank = mtype == CHROMO_CRANK_SHAFT, pivot = mtype == CHROMO_END_PIVOT;
+        constexpr bool slide = mtype == CHROMO_SLIDE, bind = mtype == CHROMO_CHANGE_BINDING_STATE;
+        constexpr bool tangent = mtype == CHROMO_TANGENT_ROTATION;
         double amp = 0.0;
         uint32_t d1 = 0, d2 = 0;
         int b0 = 0, lhs = 0, binder = 0, ind0 = 0, indf = 0, k = 0, bead = 0;
@@ -1315,13 +1348,15 @@ struct McWarp {
     }
 
     // ---- attempt `slot` of the batch (mc_step, mc_sim.pyx:106-182) ------------
-    __device__ __forceinline__ void attempt(int mtype, int slot) {
+    template <int MT>
+    __device__ __forceinline__ void attempt(int slot) {
+        constexpr int mtype = MT;
         const int N = C.N;
         const Prop &P = B.prop[slot];
-        const bool tangent = mtype == CHROMO_TANGENT_ROTATION;
+        constexpr bool tangent = mtype == CHROMO_TANGENT_ROTATION;
         const int ind0 = P.ind0, n = P.n;
         const int binder = mtype == CHROMO_CHANGE_BINDING_STATE ? P.aux : 0;
-        const int kind = mtype == CHROMO_SLIDE ? 1 : (mtype == CHROMO_CHANGE_BINDING_STATE ? 2 : 0);
+        constexpr int kind = mtype == CHROMO_SLIDE ? 1 : (mtype == CHROMO_CHANGE_BINDING_STATE ? 2 : 0);
         const unsigned long long att = abase + (unsigned long long)slot;
         if (n <= 0) { // mc_sim.pyx:151-152: counted, nothing else happens
             wait_turn(slot);
@@ -1339,7 +1374,7 @@ struct McWarp {
         // stage 1 may run ahead of the attempt's turn unless it needs sequential draws or the
         // replica-wide HBM scratch (large tangent / binding moves)
         bool my_turn = !(NW > 1 && (tangent ? presel : (kind != 2 || n <= CB_NEWST)));
-        const bool segmove = !tangent && kind != 2;
+        constexpr bool segmove = !tangent && kind != 2;
         unsigned seen = 0u; // accepted attempts of the batch whose writes the prepared map / elastic dE reflect
         CB_T0();
         if (my_turn) wait_turn(slot);
@@ -1353,7 +1388,7 @@ struct McWarp {
                     // the map and the elastic dE were prepared with the batch; redo them if an attempt
                     // accepted since then wrote this segment's rows or its neighbours'
                     const unsigned now = accepted_before(slot);
-                    if (rows_changed(now & ~seen, slot)) rows_recompute(mtype, slot);
+                    if (rows_changed(now & ~seen, slot)) rows_recompute<MT>(slot);
                     seen = now;
                     if (lane < 12) S.M[lane] = P.M[lane];
                     dE_poly = P.dE_poly;
@@ -1373,7 +1408,7 @@ struct McWarp {
                 if (kind == 2) dE_poly = binding_dE_poly(ind0, n, binder, newst, ddbl);
                 CB_LAP(13);
                 if (C.field_active) {
-                    conf = field_scatter<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst);
+                    conf = field_scatter<NB, kind>(C, H, S, rep, lane, ind0, n, binder, newst);
                     CB_LAP(14);
                 } else if (kind != 2 && C.confine_type != CHROMO_CONFINE_NONE)
                     dE_field = confinement_dE_segment(C, S, rep, lane, kind, ind0, n);
@@ -1410,7 +1445,7 @@ struct McWarp {
             wait_turn(slot);
             CB_LAP(2);
             my_turn = true;
-            if (segmove ? !rows_changed(accepted_before(slot) & ~seen, slot) : !stale(mtype, slot)) break;
+            if (segmove ? !rows_changed(accepted_before(slot) & ~seen, slot) : !stale<MT>(slot)) break;
             if (!tangent && C.field_active) table_clear(H, S, NCOL, lane); // rows changed under stage 1: redo it
             CB_LAP(3);
         }
@@ -1495,7 +1530,9 @@ struct McWarp {
     }
 
     // pull the rows a later attempt will read towards the SM while this one runs
-    __device__ __forceinline__ void prefetch_attempt(int mtype, const Prop &P, int slot) {
+    template <int MT>
+    __device__ __forceinline__ void prefetch_attempt(const Prop &P, int slot) {
+        constexpr int mtype = MT;
         const int N = C.N;
         int first, count;
         if (mtype == CHROMO_TANGENT_ROTATION) {
@@ -1537,10 +1574,11 @@ struct McWarp {
 
     // a batch of `cnt` attempts of one move type: prepare (lanes of warp 0), then the warps take
     // the attempts round-robin
-    __device__ __forceinline__ void run(int mtype, int cnt) {
+    template <int MT>
+    __device__ __forceinline__ void run(int cnt) {
         CB_T0();
         if (wid == 0) {
-            prepare(mtype, cnt);
+            prepare<MT>(cnt);
             if (lane == 0) {
                 *(volatile int *)&B.token = 0;
                 *(volatile unsigned *)&B.accepted = 0u;
@@ -1552,15 +1590,28 @@ struct McWarp {
 #pragma unroll 1
         for (int j = wid; j < cnt; j += NW) {
             CB_T0();
-            if (j + NW < cnt) prefetch_attempt(mtype, B.prop[j + NW], j + NW);
+            if (j + NW < cnt) prefetch_attempt<MT>(B.prop[j + NW], j + NW);
             CB_LAP(0);
-            attempt(mtype, j);
+            attempt<MT>(j);
         }
         abase += (unsigned long long)cnt;
         {
             CB_T0();
             block_sync();
             CB_LAP(9);
+        }
+    }
+
+    // One copy of the attempt code PER MOVE TYPE: a move type's loop is then a compact, contiguous piece of
+    // SASS (the generic copy interleaved all five, and the hot path of one type was spread over the whole
+    // 160 KB kernel: 13 % instruction-cache misses with one warp per replica, 33 % with two).
+    __device__ __forceinline__ void run_type(int mtype, int cnt) {
+        switch (mtype) {
+        case CHROMO_CRANK_SHAFT: run<CHROMO_CRANK_SHAFT>(cnt); break;
+        case CHROMO_END_PIVOT: run<CHROMO_END_PIVOT>(cnt); break;
+        case CHROMO_SLIDE: run<CHROMO_SLIDE>(cnt); break;
+        case CHROMO_TANGENT_ROTATION: run<CHROMO_TANGENT_ROTATION>(cnt); break;
+        default: run<CHROMO_CHANGE_BINDING_STATE>(cnt); break;
         }
     }
 
@@ -1685,7 +1736,7 @@ __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, 1)
                 if (B.mv[m].move_on == 1) {
                     const int npc = B.mv[m].num_per_cycle;
 #pragma unroll 1
-                    for (int j0 = 0; j0 < npc; j0 += BS) W.run(m, min(BS, npc - j0));
+                    for (int j0 = 0; j0 < npc; j0 += BS) W.run_type(m, min(BS, npc - j0));
                 }
                 W.update_amplitudes(m); // also for moves that are off (mc_sim.pyx:103)
             }
@@ -1743,7 +1794,7 @@ __global__ void __launch_bounds__(32) mc_step_kernel(const CB_GRID_CONSTANT DevC
     const unsigned long long abase0 = rng_load<Rng>(rng, C, B, rep, lane, seed);
     __syncwarp();
     McWarp<Rng, true, NB, 1> W{C, B, S, H, rng, rep, lane, 0, 0, mu_adjust, force_accept, dbg, abase0};
-    W.run(mtype, 1);
+    W.run_type(mtype, 1);
     __syncwarp();
     rng_store<Rng>(C, B, rep, lane, W.abase);
 }

@@ -225,9 +225,10 @@ class Engine:
         """mc_sim on HOST arrays in the reference's layouts, in place (r, t3, t2 [R,N,3] f64; states,
         mods [R,N,nb] int64): upload, kernel and download pipelined over replica chunks
         (chromo_mc_sim_host).  The arrays must be C-contiguous and of exactly these dtypes -- they are
-        written through their own memory, no copies are made."""
+        written through their own memory, no copies are made.  `mods=None`: the marks already on the
+        device are current (mc_sim never modifies them)."""
         for name, a, dt in (("r", r, np.float64), ("t3", t3, np.float64), ("t2", t2, np.float64),
-                            ("states", states, np.int64), ("mods", mods, np.int64)):
+                            ("states", states, np.int64)) + ((("mods", mods, np.int64),) if mods is not None else ()):
             want = self.R * self.N * (3 if dt is np.float64 else self.nb)
             if not isinstance(a, np.ndarray) or a.dtype != dt or not a.flags.c_contiguous or a.size != want:
                 raise ValueError(f"`{name}` must be a C-contiguous {np.dtype(dt).name} array of {want} elements")
@@ -245,7 +246,7 @@ class Engine:
         check(self._L.chromo_mc_sim_host(self._h, int(num_mc_steps), mp, float(mu_adjust_factor),
                                          int(seed) & 0xFFFFFFFFFFFFFFFF, int(rng_mode), _lib.uptr(ns),
                                          _lib.dptr(r), _lib.dptr(t3), _lib.dptr(t2), _lib.lptr(states),
-                                         _lib.lptr(mods), int(n_chunks)))
+                                         _lib.lptr(mods) if mods is not None else None, int(n_chunks)))
 
     def set_table_capacity(self, cap: int = 0) -> int:
         """Slots of the per-replica shared-memory delta-density hash (0 = auto)."""

@@ -116,11 +116,16 @@ class ReplicaEnsemble:
         """Upload the host arrays (user-visible state) to the device."""
         self.engine.upload(self.r, self.t3, self.t2, self.states, self.chemical_mods)
         self._host_stale = False
+        self._mods_resident = True  # mc_sim never modifies chemical_mods: later host-array calls leave them on the device
 
     def pull(self):
         """Refresh the host arrays from the device."""
         self.engine.download_into(self.r, self.t3, self.t2, self.states)
         self._host_stale = False
+
+    def marks_changed(self):
+        """Call after editing `chemical_mods` on the host: the next host-array `mc_sim` uploads them again."""
+        self._mods_resident = False
 
     def set_params(self, chi=None, mu=None):
         if chi is not None:
@@ -147,9 +152,12 @@ class ReplicaEnsemble:
             self.pull()
             self.moves = self.engine.get_moves()
         if sync_host and n_chunks >= 0:
-            self.engine.mc_sim_host(num_mc_steps, self.r, self.t3, self.t2, self.states, self.chemical_mods,
+            # the marks go up again only after `marks_changed()` (the reference never writes them either)
+            self.engine.mc_sim_host(num_mc_steps, self.r, self.t3, self.t2, self.states,
+                                    None if self._mods_resident else self.chemical_mods,
                                     self.moves, mu_adjust_factor, random_seed, mode, numpy_seeds=ns,
                                     n_chunks=n_chunks)
+            self._mods_resident = True
         elif sync_host:
             self.push()
             self.engine.mc_sim(num_mc_steps, self.moves, mu_adjust_factor, random_seed, mode, numpy_seeds=ns)

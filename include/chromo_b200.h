@@ -246,7 +246,10 @@ int chromo_set_moves(chromo_ctx *ctx, const chromo_move_state *moves /* [R][5] *
  * serialised by the driver.  The voxel densities are the field's state, not the
  * polymers' (fields.pxd:54): they stay on the device between calls, exactly as
  * with chromo_upload_state + chromo_mc_sim + chromo_download_state, whose result
- * this call reproduces bit for bit (each replica has its own RNG stream). */
+ * this call reproduces bit for bit (each replica has its own RNG stream).
+ * `mods` may be NULL once every replica's marks have been uploaded (by an earlier
+ * call of this function or by chromo_upload_state over all replicas): mc_sim never
+ * modifies chemical_mods, so the copy on the device stays current. */
 int chromo_mc_sim_host(chromo_ctx *ctx, int64_t num_mc_steps, chromo_move_state *moves,
                        double mu_adjust_factor, uint64_t seed, int rng_mode,
                        const uint32_t *numpy_seeds, double *r, double *t3, double *t2,

@@ -306,6 +306,11 @@ def test_error_behaviour(backend, oracle_mod):
         e.mc_step(5, 0, 0.1, 3)
     with pytest.raises(ValueError, match="Confinement type"):
         Engine(1, 10, 1, grid=dict(spec["field"], confine_type="Ellipsoidal"), bead_vol=1.0)
+    bad = spec["states"].copy()
+    bad[3, 0] = 3  # above sites_per_bead = 2: would index past the binding free-energy table
+    with pytest.raises(_lib.ChromoError, match="must lie in"):
+        e.upload(spec["r"][None], spec["t3"][None], spec["t2"][None], bad[None], spec["mods"][None])
+    e.upload(spec["r"][None], spec["t3"][None], spec["t2"][None], spec["states"][None], spec["mods"][None])
     e2 = Engine(1, 10, 1, grid=None, bead_vol=1.0)
     with pytest.raises(_lib.ChromoError, match="set_binders"):
         e2.mc_sim(1, None, 1.0, 0, PHILOX)
