@@ -527,8 +527,12 @@ def main():
     ap.add_argument("--lt", type=float, default=None, help="twist persistence length: run the SSTWLC kernels "
                     "(not the headline configuration; the reference arm ignores it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lib", default=None, help="development: load this build of libchromo_b200.so (A/B timing)")
     args = ap.parse_args()
     quiet_stdout()
+    if args.lib:
+        from chromo_b200 import _lib
+        _lib.use_library(args.lib)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -87,14 +87,14 @@ struct chromo_ctx {
     size_t smem_sm = 228 * 1024;    // per SM
 };
 
-// exponent base of the MC kernel's fixed-point delta-density cells (mc_kernel.cuh, fx_exponent):
-// floor(log2(2^61 * V_min / max_state))
+// exponent base of the MC kernel's fixed-point delta-density cells (mc_kernel.cuh, fx_format):
+// floor(log2(V_min / max_state))
 static void refresh_fx_base(chromo_ctx *c) {
     DevCtx &d = c->d;
     double vmin = (d.access_vol && c->min_access_vol > 0.0) ? c->min_access_vol : d.vol_bin;
     int smax = 1;
     for (int a = 0; a < d.nb; a++) smax = std::max(smax, d.sites[a]);
-    d.fx_base = (vmin > 0.0) ? 61 + (int)ilogb(vmin / (double)smax) : 61;
+    d.fx_base = (vmin > 0.0) ? (int)ilogb(vmin / (double)smax) : 0;
 }
 
 // kernel instantiation for (rng mode, number of binders, twist); the twist (SSTWLC) kernels are their own

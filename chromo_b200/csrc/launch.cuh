@@ -8,12 +8,20 @@
 #include "cuda_emu.h"
 #else
 #include <cuda_runtime.h>
+#include <cstdint>
 #define CB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define CB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define CB_NOINLINE __noinline__
 #define CB_GRID_CONSTANT __grid_constant__
 __device__ __forceinline__ void cb_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cb_backoff() { __nanosleep(20); }
+// 32-bit shared-state-space addresses for the fire-and-forget atomic adds of the delta-density cells: a
+// generic pointer costs a 64-bit address computation and a generic-to-shared conversion per atomic
+typedef uint32_t cb_saddr;
+__device__ __forceinline__ cb_saddr cb_shared_addr(const void *p) { return (cb_saddr)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cb_red_add_u32(cb_saddr a, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 // named barrier `id` (1..15) for `count` threads of the block
 __device__ __forceinline__ void cb_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");

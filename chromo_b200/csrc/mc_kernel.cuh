@@ -53,6 +53,9 @@ __device__ unsigned long long cb_phase_acc[CHROMO_NUM_MOVES][CB_NPHASE];
 #define CB_LAP(ph) do { } while (0)
 #endif
 
+#ifndef CB_MIN_BLOCKS
+#define CB_MIN_BLOCKS 1 // resident blocks per SM the register allocation aims for (A/B knob)
+#endif
 #ifndef CB_UNIT_UNROLL
 #define CB_UNIT_UNROLL 1 // voxel-contribution loop of scatter_pass (A/B knob)
 #endif
@@ -108,7 +111,8 @@ static_assert(CB_KSEL <= CB_TAN_SMALL, "prepared bead sets are staged in shared 
 struct HashTable {
     int *keys;      // [cap]
     int *list;      // [cap]   occupied slots, in claim order
-    uint32_t *vals; // [cap][ncol][2]  delta-rho in 64-bit fixed point (low word, high word)
+    uint32_t *vals; // [cap][ncol][2]  delta-rho in fixed point (two words per cell, see Fx)
+    cb_saddr vals_s; // the same as a shared-state-space address
     int cap, limit; // cap: any size >= 128 (not necessarily a power of two)
 };
 
@@ -127,30 +131,53 @@ __device__ __forceinline__ int warp_sum_int(int v) {
 // Shared memory has no native 64-bit or floating-point atomic add on sm_100a
 // (both compile to ATOMS.CAST.SPIN loops, three dependent shared-memory round
 // trips per try -- the top stall of the v3-v6 profiles).  The delta-rho of a move
-// is therefore accumulated as a 64-bit integer in units of 2^-E through TWO
-// native 32-bit ATOMS.ADD: the low word's returned old value gives the carry,
-// the high-word add is fire-and-forget.  E is chosen per move from the segment
-// length so that the sum cannot overflow (fx_exponent); at n = 16 beads the
-// quantum is 2^-70 nm^-3, finer than the fp64 ulp of a single w/V term, and
-// the result no longer depends on the order in which lanes arrive
-// (bit-reproducible runs).
-__device__ __forceinline__ void fx_add(uint32_t *cell, long long v) {
+// is therefore accumulated as an integer in units of 2^-E, split into two
+// INDEPENDENT 32-bit words -- word 0 collects the low 20 bits of every term
+// (unsigned; 2n <= 4096 terms per cell cannot overflow it), word 1 the terms'
+// arithmetic shift right by 20 (two's complement; the final sum fits) -- so that
+// a term is two fire-and-forget native atomic adds with no carry to wait for
+// (v8-v14 took the carry from the low word's returned value: two dependent round
+// trips).  E is chosen per move from the segment length so that the sum cannot
+// overflow (fx_format): at n = 32 beads the quantum is 2^-57 nm^-3, a factor 2^20
+// below the 1e-9 relative tolerance on a 1e-5 nm^-3 term, and the result does not
+// depend on the order in which lanes arrive (bit-reproducible runs).  Moves of more
+// than 2,048 beads (no reference workload has them) keep the exact 64-bit form
+// with a carry (lo_bits = 0).
+struct Fx {
+    double scale, inv_scale;
+    int lo_bits;
+};
+// 2^e as a double
+__device__ __forceinline__ double pow2_double(int e) { return __hiloint2double((1023 + e) << 20, 0); }
+// every voxel receives at most 2n terms of magnitude <= max_state / V_min = 2^-fx_base per move
+// (C.fx_base = floor(log2(V_min / max_state)), host): scaled by 2^E the sum stays below 2^(29 + lo_bits)
+// (2^61 in the 64-bit form)
+__device__ __forceinline__ Fx fx_format(const DevCtx &C, int n) {
+    Fx f;
+    f.lo_bits = n <= 2048 ? 20 : 0;
+    const int e = (f.lo_bits ? 28 + f.lo_bits : 60) + C.fx_base - (n > 1 ? 32 - __clz(n - 1) : 0);
+    f.scale = pow2_double(e);
+    f.inv_scale = pow2_double(-e);
+    return f;
+}
+static __device__ CB_NOINLINE void fx_add_carry(uint32_t *cell, long long v) {
     const uint32_t lo = (uint32_t)v, hi = (uint32_t)((unsigned long long)v >> 32);
     const uint32_t old = atomicAdd(&cell[0], lo);
     const uint32_t carry = (uint32_t)(old + lo) < lo ? 1u : 0u;
     atomicAdd(&cell[1], hi + carry);
 }
-__device__ __forceinline__ double fx_read(const uint32_t *cell, double inv_scale) {
-    const long long v = (long long)(((unsigned long long)cell[1] << 32) | (unsigned long long)cell[0]);
-    return (double)v * inv_scale;
+__device__ __forceinline__ void fx_add(uint32_t *cell, cb_saddr cell_s, long long v, int lo_bits) {
+    if (lo_bits) {
+        cb_red_add_u32(cell_s, (uint32_t)v & 0xFFFFFu);
+        cb_red_add_u32(cell_s + 4, (uint32_t)(v >> 20));
+    } else {
+        fx_add_carry(cell, v);
+    }
 }
-// 2^e as a double
-__device__ __forceinline__ double pow2_double(int e) { return __hiloint2double((1023 + e) << 20, 0); }
-// every voxel receives at most 2n terms of magnitude <= max_state / V_min per
-// move; C.fx_base = floor(log2(2^61 * V_min / max_state)) (host), so with
-// E = fx_base - ceil(log2(n)) the sum stays below 2^62 in magnitude.
-__device__ __forceinline__ int fx_exponent(const DevCtx &C, int n) {
-    return C.fx_base - (n > 1 ? 32 - __clz(n - 1) : 0);
+__device__ __forceinline__ double fx_read(const uint32_t *cell, const Fx &f) {
+    const long long v = f.lo_bits ? ((long long)(int)cell[1] << 20) + (long long)cell[0]
+                                  : (long long)(((unsigned long long)cell[1] << 32) | (unsigned long long)cell[0]);
+    return (double)v * f.inv_scale;
 }
 
 // ---------------------------------------------------------------- hash table
@@ -183,9 +210,10 @@ __device__ __forceinline__ void table_clear(HashTable &H, WarpSh &S, int ncol, i
 // case.  `checked` (moves that could overflow the table: 16 n > limit): -1 once
 // the overflow flag is up; the flag rises when `limit` slots are taken, at most
 // 32 more claims can be in flight, so the table never fills and every claimed
-// slot is listed (table_clear relies on that).
-__device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin, bool checked) {
+// slot is listed (table_clear relies on that).  `fresh`: this call claimed the slot.
+__device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin, bool checked, bool &fresh) {
     uint32_t slot = __umulhi((uint32_t)bin * 2654435761u, (uint32_t)H.cap);
+    fresh = false;
     if (checked && *(volatile int *)&S.overflow) return -1;
     while (true) {
         const int prev = atomicCAS(&H.keys[slot], HASH_EMPTY, bin);
@@ -194,10 +222,42 @@ __device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin, boo
             const int pos = atomicAdd(&S.count, 1);
             H.list[pos] = (int)slot;
             if (checked && pos + 1 >= H.limit) S.overflow = 1;
+            fresh = true;
             return (int)slot;
         }
         slot = slot + 1 == (uint32_t)H.cap ? 0u : slot + 1;
     }
+}
+
+// w / V_access in fixed point: exact division by the constant voxel volume, or by the per-voxel one (out of
+// line: only fields with assume_fully_accessible = 0 have it); |x| <= 1e-18 terms are dropped (quirk 3)
+static __device__ CB_NOINLINE double div_access(const double *access_vol, int bin, double w) {
+    return w / access_vol[bin];
+}
+template <bool GEN>
+__device__ __forceinline__ long long fx_term(const DevCtx &C, double w, int bin, double scale) {
+    const double d = (GEN && C.access_vol) ? div_access(C.access_vol, bin, w) : div_const(w, C.vol_bin, C.inv_vol_bin);
+    return fabs(d) > 1E-18 ? __double2ll_rn(d * scale) : 0ll;
+}
+// one voxel contribution: `v` to the bead column (unless `no_bead`), v * mult[m] to binder column m
+template <int NB, bool GEN>
+__device__ __forceinline__ void unit_add(const DevCtx &C, HashTable &H, WarpSh &S, const double *dens_rows,
+                                         bool checked, int P, int p, int bin, long long v, bool no_bead,
+                                         const int mult[NB], int lo_bits_rt) {
+    constexpr int NCOL = NB + 1;
+    const int lo_bits = GEN ? lo_bits_rt : 20;
+    if (GEN && P > 1 && (bin & (P - 1)) != p) return;
+    bool fresh; // the voxel joins the touched set even when its term is zero (fields.pyx:1499-1520)
+    const int slot = table_claim(H, S, bin, checked, fresh);
+    if (slot < 0) return;
+    if (fresh) cb_prefetch(dens_rows + (long long)bin * NCOL); // the density row is needed by table_energy
+    if (v == 0) return;
+    uint32_t *cell = H.vals + (size_t)slot * NCOL * 2;
+    const cb_saddr cell_s = H.vals_s + (cb_saddr)slot * (NCOL * 8);
+    if (!no_bead) fx_add(cell, cell_s, v, lo_bits);
+#pragma unroll
+    for (int m = 0; m < NB; m++)
+        if (mult[m] != 0) fx_add(cell + 2 * (1 + m), cell_s + 8 * (1 + m), v * (long long)mult[m], lo_bits);
 }
 
 // ---------------------------------------------------------- scatter of a move
@@ -206,125 +266,134 @@ __device__ __forceinline__ int table_claim(HashTable &H, WarpSh &S, int bin, boo
 // and +w/V*{1,state'} at its trial position to the 8 voxels around each.
 //   kind 0: trial = M r (crank-shaft, end-pivot)   kind 1: trial = r + t (slide)
 //   kind 2: trial position = current position, state' = newst (binding)
-// G lanes share a bead (G = 16/8/4/2/1 by the beads left to do).  A bead whose current
-// and trial positions fall in the same cell (most slides and small rotations,
-// every binding move) has 8 merged units -- one per voxel corner l (bit0 x,
-// bit1 y, bit2 z), trial minus current -- otherwise 16 units (k = 0 current /
-// 1 trial, corner l); the lanes of the bead split the units evenly.
+// v15: two passes per chunk of up to 32 beads.
+//   pass 1  the 8 voxels of the bead's CURRENT cell, G = 1/2/4/8 lanes per bead (by the beads left to
+//           do): trial minus current for a bead whose trial position falls in the same cell ("merged":
+//           most slides and small rotations, every binding move), minus current otherwise;
+//   pass 2  the 8 voxels of the TRIAL cell of the (few) beads that left their cell, 8 lanes per bead --
+//           one corner each -- whatever the segment length: the owner lane hands the trial cell over by
+//           shuffles.
+// (v14 walked 16 contributions per lane as soon as ONE bead of the chunk had left its cell, with most
+// lanes idle in the second half, and selected cell / weight per contribution at run time.)
 // Returns the confinement counters of get_confinement_dE (fields.pyx:160-193):
 // x = # trial positions outside, y = # current positions outside (this lane's).
-// KIND >= 0: the move's kind at compile time (the hot, single-pass instance of each move type);
-// KIND < 0: `kind_rt` decides (the one out-of-line copy behind the rare partition passes).
-template <int NB, int KIND, bool ONEPASS>
+// GEN = false: the hot instance (uniform voxel volumes, a single pass, at most 2,048 beads: every reference
+// workload); GEN = true: the general one behind scatter_pass_cold (per-voxel accessible volumes, partition
+// passes, the 64-bit cell format).
+template <int NB, bool GEN, int KIND_CT>
 __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
                                           int kind_rt, int ind0, int n, int binder,
-                                          const signed char *newst, int P_rt, int p, double scale) {
+                                          const signed char *newst, int P, int p, const Fx &fx) {
     constexpr int NCOL = NB + 1;
-    const int kind = KIND >= 0 ? KIND : kind_rt;
-    const int P = ONEPASS ? 1 : P_rt;
+    // KIND_CT = 2: binding moves; 0: crank-shaft / end-pivot / slide (kind_rt tells which); -1: kind_rt decides
+    const int kind = KIND_CT == 2 ? 2 : (KIND_CT == 0 ? (kind_rt == 1 ? 1 : 0) : kind_rt);
     const double *Rr = C.r + (long long)rep * C.N * 3;
     const signed char *ST = C.states + (long long)rep * C.N * NB;
     const double *dens_rows = C.density + (long long)rep * C.n_bins * NCOL;
     const bool checked = P > 1 || 16 * n > H.limit;
+    const int nxy = C.nx * C.ny;
+    const double scale = fx.scale;
+    const int lo_bits = fx.lo_bits;
     int out_t = 0, out_c = 0;
     int per_iter;
 #pragma unroll 1
     for (int base = 0; base < n; base += per_iter) {
-        // lanes per bead, chosen per iteration from the beads still to do: an underfull last iteration
-        // spreads each bead's 16 units over more lanes instead of leaving lanes idle; 17..24 beads go as
-        // 16 beads on 2 lanes each now and the rest on 4..16 lanes each next time (10-12 units per lane
-        // instead of 16).  The table cells are fixed point, so the split does not change any result.
         const int rem = n - base;
-        const int G = rem <= 2 ? 16 : rem <= 4 ? 8 : rem <= 8 ? 4 : rem <= 24 ? 2 : 1;
+        const int G = rem <= 4 ? 8 : rem <= 8 ? 4 : rem <= 16 ? 2 : 1;
         per_iter = 32 / G;
         const int sub = lane & (G - 1);
         const int i = base + lane / G;
-        if (i >= n) continue;
-        const int bead = ind0 + i;
-        double x[3];
-        load3(Rr + 3 * bead, x);
-        int mult[NB]; // column m+1 receives (column-0 term) * mult[m]
+        const bool active = i < n;
+        int mult[NB]; // binder column m receives (bead-column term) * mult[m]
+        int clo[3], chi[3], tlo[3], thi[3];
+        double cw[3], tw[3];
+        bool merged = true;
 #pragma unroll
-        for (int m = 0; m < NB; m++) mult[m] = ST[bead * NB + m];
-        int loc[3], hic[3], lot[3], hit[3];
-        double wc[3], wt[3];
-        bin_axes(C, x, loc, hic, wc);
-        bool same = true;
-        if (kind == 2) {
-            // state change only: the bead column cancels exactly (quirk 4), the
-            // binder's column gets w/V * (s' - s)
+        for (int m = 0; m < NB; m++) mult[m] = 0;
 #pragma unroll
-            for (int m = 0; m < NB; m++) mult[m] = (m == binder) ? (int)newst[i] - mult[m] : 0;
+        for (int j = 0; j < 3; j++) tlo[j] = thi[j] = 0, tw[j] = 0.0;
+        if (active) {
+            const int bead = ind0 + i;
+            double x[3];
+            load3(Rr + 3 * bead, x);
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
-                lot[j] = loc[j];
-                hit[j] = hic[j];
-                wt[j] = wc[j];
-            }
-        } else {
-            double y[3];
-            if (kind == 0) apply_affine(S.M, x, y);
-            else
-                for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
-            if (p == 0 && sub == 0) {
-                if (C.confine_type == CHROMO_CONFINE_SPHERICAL) {
-                    out_t += sqrt(dot3(y, y)) > C.confine_length;
-                    out_c += sqrt(dot3(x, x)) > C.confine_length;
-                } else if (C.confine_type == CHROMO_CONFINE_CUBICAL) {
-                    // fields.pyx:178-193: the current configuration is never counted
-                    for (int j = 0; j < 3; j++) out_t += (fabs(y[j]) > C.confine_length / 2);
-                }
-            }
-            bin_axes(C, y, lot, hit, wt);
-            same = loc[0] == lot[0] && loc[1] == lot[1] && loc[2] == lot[2];
-        }
-        const int nunits = same ? 8 : 16;
-        const int cpl = max(nunits / G, 1);
-        const int u0 = sub * cpl, u1 = min(u0 + cpl, nunits);
-        // a lane that walks all 8 corners starts at a lane-dependent corner, so that
-        // neighbouring beads (which mostly share a cell) do not hit one slot together
-        const int rot = cpl >= 8 ? (lane / G) & 7 : 0;
-#pragma unroll cb_unit_unroll
-        for (int u = u0; u < u1; u++) {
-            const int k = u >> 3, l = ((u & 7) + rot) & 7;
-            const int bx = l & 1, by = (l >> 1) & 1, bz = l >> 2;
-            // voxel index and weights (products in the reference's order (x*y)*z)
-            const int ix = k ? (bx ? hit[0] : lot[0]) : (bx ? hic[0] : loc[0]);
-            const int iy = k ? (by ? hit[1] : lot[1]) : (by ? hic[1] : loc[1]);
-            const int iz = k ? (bz ? hit[2] : lot[2]) : (bz ? hic[2] : loc[2]);
-            const int bin = ix + C.nx * (iy + C.ny * iz);
-            if (P > 1 && (bin & (P - 1)) != p) continue;
-            const int slot = table_claim(H, S, bin, checked);
-            if (slot < 0) continue;
-            cb_prefetch(dens_rows + (long long)bin * NCOL); // the density row is needed by table_energy
-            const double w_c = (bx ? 1.0 - wc[0] : wc[0]) * (by ? 1.0 - wc[1] : wc[1]) * (bz ? 1.0 - wc[2] : wc[2]);
-            const double w_t = (bx ? 1.0 - wt[0] : wt[0]) * (by ? 1.0 - wt[1] : wt[1]) * (bz ? 1.0 - wt[2] : wt[2]);
-            // w / V_access: exact division by the constant voxel volume, or by the per-voxel one;
-            // |x| <= 1e-18 terms are dropped (quirk 3)
-            double d_c, d_t;
-            if (C.access_vol) {
-                const double V = C.access_vol[bin];
-                d_c = w_c / V;
-                d_t = w_t / V;
-            } else {
-                d_c = div_const(w_c, C.vol_bin, C.inv_vol_bin);
-                d_t = div_const(w_t, C.vol_bin, C.inv_vol_bin);
-            }
-            const long long f_c = fabs(d_c) > 1E-18 ? __double2ll_rn(d_c * scale) : 0ll;
-            const long long f_t = fabs(d_t) > 1E-18 ? __double2ll_rn(d_t * scale) : 0ll;
-            long long v0, vs; // bead column; base of the binder columns
+            for (int m = 0; m < NB; m++) mult[m] = ST[bead * NB + m];
+            bin_axes(C, x, clo, chi, cw);
             if (kind == 2) {
-                v0 = 0;
-                vs = f_c;
-            } else {
-                v0 = same ? f_t - f_c : (k ? f_t : -f_c);
-                vs = v0;
-            }
-            uint32_t *cell = H.vals + (size_t)slot * NCOL * 2;
-            if (v0 != 0) fx_add(cell, v0);
+                // state change only: the bead column cancels exactly (quirk 4), the binder's column gets
+                // w/V * (s' - s)
 #pragma unroll
-            for (int m = 0; m < NB; m++)
-                if (mult[m] != 0 && vs != 0) fx_add(cell + 2 * (1 + m), vs * (long long)mult[m]);
+                for (int m = 0; m < NB; m++) mult[m] = (m == binder) ? (int)newst[i] - mult[m] : 0;
+            } else {
+                double y[3];
+                if (kind == 0) apply_affine(S.M, x, y);
+                else
+                    for (int j = 0; j < 3; j++) y[j] = x[j] + S.M[4 * j + 3];
+                if (p == 0 && sub == 0) {
+                    if (C.confine_type == CHROMO_CONFINE_SPHERICAL) {
+                        out_t += sqrt(dot3(y, y)) > C.confine_length;
+                        out_c += sqrt(dot3(x, x)) > C.confine_length;
+                    } else if (C.confine_type == CHROMO_CONFINE_CUBICAL) {
+                        // fields.pyx:178-193: the current configuration is never counted
+                        for (int j = 0; j < 3; j++) out_t += (fabs(y[j]) > C.confine_length / 2);
+                    }
+                }
+                bin_axes(C, y, tlo, thi, tw);
+                merged = clo[0] == tlo[0] && clo[1] == tlo[1] && clo[2] == tlo[2];
+            }
+            // ---- pass 1: the current cell's corners l (bit0 x, bit1 y, bit2 z), this lane's share ----
+            const int cpl = 8 / G;
+            // a lane that walks all 8 corners starts at a lane-dependent corner, so that neighbouring
+            // beads (which mostly share a cell) do not hit one slot together
+            const int rot = G == 1 ? (lane & 7) : 0;
+            const int yl = C.nx * clo[1], yh = C.nx * chi[1], zl = nxy * clo[2], zh = nxy * chi[2];
+#pragma unroll 1
+            for (int u = sub * cpl; u < (sub + 1) * cpl; u++) {
+                const int l = (u + rot) & 7;
+                const bool bx = l & 1, by = l & 2, bz = l & 4;
+                const int bin = (bx ? chi[0] : clo[0]) + (by ? yh : yl) + (bz ? zh : zl);
+                // products in the reference's order (x*y)*z
+                const double w_c = ((bx ? 1.0 - cw[0] : cw[0]) * (by ? 1.0 - cw[1] : cw[1])) * (bz ? 1.0 - cw[2] : cw[2]);
+                const long long f_c = fx_term<GEN>(C, w_c, bin, scale);
+                long long v;
+                if (kind == 2) {
+                    v = f_c;
+                } else {
+                    const double w_t = ((bx ? 1.0 - tw[0] : tw[0]) * (by ? 1.0 - tw[1] : tw[1])) * (bz ? 1.0 - tw[2] : tw[2]);
+                    const long long f_t = fx_term<GEN>(C, w_t, bin, scale);
+                    v = merged ? f_t - f_c : -f_c;
+                }
+                unit_add<NB, GEN>(C, H, S, dens_rows, checked, P, p, bin, v, kind == 2, mult, lo_bits);
+            }
+        }
+        // ---- pass 2: the trial cell of the beads that left theirs, one corner per lane ----
+        if (kind != 2) {
+            unsigned left = __ballot_sync(FULL_MASK, active && !merged && sub == 0);
+#pragma unroll 1
+            while (left) {
+                const int owner = (int)__fns(left, 0, (lane >> 3) + 1); // the (lane / 8)-th bead of this round
+                const bool has = owner >= 0 && owner < 32;
+                const int src = has ? owner : 0;
+                int qlo[3], qhi[3], qm[NB];
+                double qw[3];
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    qlo[j] = __shfl_sync(FULL_MASK, tlo[j], src);
+                    qhi[j] = __shfl_sync(FULL_MASK, thi[j], src);
+                    qw[j] = __shfl_sync(FULL_MASK, tw[j], src);
+                }
+#pragma unroll
+                for (int m = 0; m < NB; m++) qm[m] = __shfl_sync(FULL_MASK, mult[m], src);
+                if (has) {
+                    const int l = lane & 7;
+                    const bool bx = l & 1, by = l & 2, bz = l & 4;
+                    const int bin = (bx ? qhi[0] : qlo[0]) + C.nx * (by ? qhi[1] : qlo[1]) + nxy * (bz ? qhi[2] : qlo[2]);
+                    const double w_t = ((bx ? 1.0 - qw[0] : qw[0]) * (by ? 1.0 - qw[1] : qw[1])) * (bz ? 1.0 - qw[2] : qw[2]);
+                    unit_add<NB, GEN>(C, H, S, dens_rows, checked, P, p, bin, fx_term<GEN>(C, w_t, bin, scale), false, qm, lo_bits);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) left &= left - 1; // the four beads just done
+            }
         }
     }
     return make_int2(out_t, out_c);
@@ -341,7 +410,7 @@ struct FieldSums {
 template <int NB>
 __device__ __forceinline__ void table_energy(const DevCtx &C, const HashTable &H, const WarpSh &S,
                                              int rep, double chi, int lane, FieldSums<NB> &F,
-                                             bool want_cross, double inv_scale) {
+                                             bool want_cross, const Fx &fx) {
     constexpr int NCOL = NB + 1;
     int cnt = S.count;
     const double *dens = C.density + (long long)rep * C.n_bins * NCOL;
@@ -353,7 +422,7 @@ __device__ __forceinline__ void table_energy(const DevCtx &C, const HashTable &H
 #pragma unroll
         for (int c = 0; c < NCOL; c++) {
             rho[c] = row[c];
-            const double dr = fx_read(H.vals + ((size_t)slot * NCOL + c) * 2, inv_scale);
+            const double dr = fx_read(H.vals + ((size_t)slot * NCOL + c) * 2, fx);
             if (c == 0) dr0 = dr;
             rn[c] = rho[c] + dr;
         }
@@ -386,17 +455,17 @@ __device__ __forceinline__ void table_energy(const DevCtx &C, const HashTable &H
 }
 // update_affected_densities fields.pyx:1968-1975 for the voxels in the table
 __device__ __forceinline__ void table_commit(const DevCtx &C, const HashTable &H, const WarpSh &S,
-                                             int rep, int lane, double inv_scale) {
+                                             int rep, int lane, const Fx &fx) {
     int cnt = S.count;
     double *dens = C.density + (long long)rep * C.n_bins * C.ncol;
     for (int j = lane; j < cnt; j += 32) {
         int slot = H.list[j];
         double *row = dens + (long long)H.keys[slot] * C.ncol;
-        for (int c = 0; c < C.ncol; c++) row[c] += fx_read(H.vals + ((size_t)slot * C.ncol + c) * 2, inv_scale);
+        for (int c = 0; c < C.ncol; c++) row[c] += fx_read(H.vals + ((size_t)slot * C.ncol + c) * 2, fx);
     }
 }
 __device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTable &H, const WarpSh &S,
-                                              int lane, DebugOut *dbg, double inv_scale) {
+                                              int lane, DebugOut *dbg, const Fx &fx) {
     int cnt = S.count;
     long long base = dbg->n_touched;
     for (int j = lane; j < cnt; j += 32) {
@@ -405,7 +474,7 @@ __device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTabl
             int slot = H.list[j];
             dbg->touched[o] = H.keys[slot];
             for (int c = 0; c < C.ncol; c++)
-                dbg->dtrial[o * C.ncol + c] = fx_read(H.vals + ((size_t)slot * C.ncol + c) * 2, inv_scale);
+                dbg->dtrial[o * C.ncol + c] = fx_read(H.vals + ((size_t)slot * C.ncol + c) * 2, fx);
         }
     }
     __syncwarp();
@@ -429,59 +498,22 @@ __device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTabl
 // the delta-rho rows afterwards (used by the commit).  Moves whose touched set
 // overflows the table are re-scattered in hash-partition passes inside stage 2.
 // ddbl[a] = change in the number of doubly-bound beads (count_doubly_bound).
-template <int NB, int KIND>
+// the general scatter, out of line: one copy serves fields with per-voxel accessible volumes, the partition
+// passes of a move whose touched set overflowed the table and moves of more than 2,048 beads
+template <int NB>
+__device__ CB_NOINLINE int2 scatter_pass_cold(const DevCtx &C, HashTable H, WarpSh *Sp, int rep, int lane, int kind,
+                                              int ind0, int n, int binder, const signed char *newst, int P, int p) {
+    return scatter_pass<NB, true, -1>(C, H, *Sp, rep, lane, kind, ind0, n, binder, newst, P, p, fx_format(C, n));
+}
+template <int NB>
 __device__ __forceinline__ int2 field_scatter(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
-                                              int ind0, int n, int binder, const signed char *newst) {
-    const double scale = pow2_double(fx_exponent(C, n));
-    const int2 conf = scatter_pass<NB, KIND, true>(C, H, S, rep, lane, KIND, ind0, n, binder, newst, 1, 0, scale);
+                                              int kind, int ind0, int n, int binder, const signed char *newst) {
+    int2 conf;
+    if (C.access_vol || n > 2048) conf = scatter_pass_cold<NB>(C, H, &S, rep, lane, kind, ind0, n, binder, newst, 1, 0);
+    else if (kind == 2) conf = scatter_pass<NB, false, 2>(C, H, S, rep, lane, kind, ind0, n, binder, newst, 1, 0, fx_format(C, n));
+    else conf = scatter_pass<NB, false, 0>(C, H, S, rep, lane, kind, ind0, n, binder, newst, 1, 0, fx_format(C, n));
     __syncwarp();
     return conf;
-}
-// one partition pass of a move whose touched set overflowed the table (rare): the single out-of-line copy
-template <int NB>
-__device__ CB_NOINLINE void scatter_pass_cold(const DevCtx &C, HashTable H, WarpSh *Sp, int rep, int lane, int kind,
-                                              int ind0, int n, int binder, const signed char *newst, int P, int p,
-                                              double scale) {
-    (void)scatter_pass<NB, -1, false>(C, H, *Sp, rep, lane, kind, ind0, n, binder, newst, P, p, scale);
-}
-// the touched set does not fit the table (rare): re-scatter in P = 2, 4, ... hash-partition passes
-// (voxels with bin % P == p per pass; the energy is a sum over voxels).  Returns P; the table ends empty.
-template <int NB, bool DEBUG>
-__device__ CB_NOINLINE int field_energy_multipass(const DevCtx &C, HashTable H, WarpSh *Sp, int rep, int lane, int kind,
-                                                  int ind0, int n, int binder, const signed char *newst, double chi,
-                                                  FieldSums<NB> *Fp, DebugOut *dbg) {
-    constexpr int NCOL = NB + 1;
-    WarpSh &S = *Sp;
-    FieldSums<NB> &F = *Fp;
-    const int fxe = fx_exponent(C, n);
-    const double scale = pow2_double(fxe), inv_scale = pow2_double(-fxe);
-    const bool want_cross = C.any_cross != 0;
-    int P = 1;
-    bool failed = true;
-    while (failed) {
-        P *= 2;
-#pragma unroll
-        for (int a = 0; a < NB; a++) F.sq[a] = 0.0;
-#pragma unroll
-        for (int a = 0; a < NB * NB; a++) F.cross[a] = 0.0;
-        F.chi = 0.0;
-        if (DEBUG && lane == 0) dbg->n_touched = 0;
-        failed = false;
-        for (int p = 0; p < P; p++) {
-            table_clear(H, S, NCOL, lane);
-            scatter_pass_cold<NB>(C, H, &S, rep, lane, kind, ind0, n, binder, newst, P, p, scale);
-            __syncwarp();
-            if (S.overflow) {
-                failed = true;
-                break;
-            }
-            table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross, inv_scale);
-            if (lane == 0) S.last_U = (p == 0 ? 0 : S.last_U) + S.count;
-            if (DEBUG) table_debug_dump(C, H, S, lane, dbg, inv_scale);
-        }
-    }
-    table_clear(H, S, NCOL, lane);
-    return P;
 }
 template <int NB, bool DEBUG>
 __device__ __forceinline__ double field_finish(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
@@ -489,7 +521,7 @@ __device__ __forceinline__ double field_finish(const DevCtx &C, HashTable &H, Wa
                                                int2 conf, const int *ddbl, DebugOut *dbg) {
     constexpr int NCOL = NB + 1;
     const double chi = C.chi[rep];
-    const double inv_scale = pow2_double(-fx_exponent(C, n));
+    const Fx fx = fx_format(C, n);
     FieldSums<NB> F;
     const bool want_cross = C.any_cross != 0;
 #pragma unroll
@@ -500,11 +532,34 @@ __device__ __forceinline__ double field_finish(const DevCtx &C, HashTable &H, Wa
     if (DEBUG && lane == 0) dbg->n_touched = 0;
     int P = 1;
     if (!S.overflow) {
-        table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross, inv_scale);
+        table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross, fx);
         if (lane == 0) S.last_U = S.count;
-        if (DEBUG) table_debug_dump(C, H, S, lane, dbg, inv_scale);
+        if (DEBUG) table_debug_dump(C, H, S, lane, dbg, fx);
     } else {
-        P = field_energy_multipass<NB, DEBUG>(C, H, &S, rep, lane, kind, ind0, n, binder, newst, chi, &F, dbg);
+        bool failed = true;
+        while (failed) { // rare: the touched set does not fit the table
+            P *= 2;
+#pragma unroll
+            for (int a = 0; a < NB; a++) F.sq[a] = 0.0;
+#pragma unroll
+            for (int a = 0; a < NB * NB; a++) F.cross[a] = 0.0;
+            F.chi = 0.0;
+            if (DEBUG && lane == 0) dbg->n_touched = 0;
+            failed = false;
+            for (int p = 0; p < P; p++) {
+                table_clear(H, S, NCOL, lane);
+                (void)scatter_pass_cold<NB>(C, H, &S, rep, lane, kind, ind0, n, binder, newst, P, p);
+                __syncwarp();
+                if (S.overflow) {
+                    failed = true;
+                    break;
+                }
+                table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross, fx);
+                if (lane == 0) S.last_U = (p == 0 ? 0 : S.last_U) + S.count;
+                if (DEBUG) table_debug_dump(C, H, S, lane, dbg, fx);
+            }
+        }
+        table_clear(H, S, NCOL, lane);
     }
     if (lane == 0) S.passes = P;
     // ---- reduce and assemble in the reference's order ----
@@ -542,13 +597,12 @@ __device__ CB_NOINLINE void field_commit_multipass(const DevCtx &C, HashTable H,
                                                    const signed char *newst) {
     WarpSh &S = *Sp;
     const int passes = S.passes;
-    const int fxe = fx_exponent(C, n);
-    const double scale = pow2_double(fxe), inv_scale = pow2_double(-fxe);
+    const Fx fx = fx_format(C, n);
     for (int p = 0; p < passes; p++) {
         table_clear(H, S, NB + 1, lane);
-        scatter_pass_cold<NB>(C, H, Sp, rep, lane, kind, ind0, n, binder, newst, passes, p, scale);
+        (void)scatter_pass_cold<NB>(C, H, Sp, rep, lane, kind, ind0, n, binder, newst, passes, p);
         __syncwarp();
-        table_commit(C, H, S, rep, lane, inv_scale);
+        table_commit(C, H, S, rep, lane, fx);
     }
 }
 
@@ -883,9 +937,7 @@ struct McWarp {
     // did an attempt that committed after this warp's previous turn change rows that stage 1 of
     // attempt `slot` has read?  Writes of a segment move: beads [ind0, indf); reads: one more bead
     // on either side.  Tangent rotation: the selected beads; reads: their neighbours as well.
-    template <int MT>
-    __device__ __forceinline__ bool stale(int slot) const {
-        constexpr int mtype = MT;
+    __device__ __forceinline__ bool stale(int mtype, int slot) const {
         if (NW == 1) return false;
         const unsigned accepted = *(volatile unsigned *)&B.accepted;
         const Prop &P = B.prop[slot];
@@ -930,9 +982,7 @@ struct McWarp {
         return __any_sync(FULL_MASK, hit);
     }
     // one thread redoes the state-dependent half of attempt `slot` from the rows as they are now
-    template <int MT>
-    __device__ __forceinline__ void rows_recompute(int slot) {
-        constexpr int mtype = MT;
+    __device__ __forceinline__ void rows_recompute(int mtype, int slot) {
         if (lane == 0) {
             Prop *Pp = &B.prop[slot];
             if (segment_rows_prepare(R_(), T3_(), bond_rows(), C.N, mtype, Pp, nullptr, twist_rows(C, rep))) {
@@ -948,9 +998,7 @@ struct McWarp {
 
     // ======================================================== prepare
     // lanes [0, cnt) of warp 0 each prepare one attempt of move type `mtype`
-    template <int MT>
-    __device__ __forceinline__ void prepare(int cnt) {
-        constexpr int mtype = MT;
+    __device__ __forceinline__ void prepare(int mtype, int cnt) {
         if (lane >= cnt) return;
         const int N = C.N;
         Prop &P = B.prop[lane];
@@ -959,9 +1007,9 @@ struct McWarp {
             rng.seek_attempt(abase + (unsigned long long)lane);
             P.u = u01(rng.next31()); // Metropolis uniform: draw 0 of the attempt's own stream
         }
-        constexpr bool crank = mtype == CHROMO_CRANK_SHAFT, pivot = mtype == CHROMO_END_PIVOT;
-        constexpr bool slide = mtype == CHROMO_SLIDE, bind = mtype == CHROMO_CHANGE_BINDING_STATE;
-        constexpr bool tangent = mtype == CHROMO_TANGENT_ROTATION;
+        const bool crank = mtype == CHROMO_CRANK_SHAFT, pivot = mtype == CHROMO_END_PIVOT;
+        const bool slide = mtype == CHROMO_SLIDE, bind = mtype == CHROMO_CHANGE_BINDING_STATE;
+        const bool tangent = mtype == CHROMO_TANGENT_ROTATION;
         double amp = 0.0;
         uint32_t d1 = 0, d2 = 0;
         int b0 = 0, lhs = 0, binder = 0, ind0 = 0, indf = 0, k = 0, bead = 0;
@@ -1138,7 +1186,7 @@ struct McWarp {
     __device__ __forceinline__ void segment_commit(int kind, int ind0, int n, int binder,
                                                    const signed char *newst) {
         if (C.field_active) {
-            if (S.passes == 1) table_commit(C, H, S, rep, lane, pow2_double(-fx_exponent(C, n)));
+            if (S.passes == 1) table_commit(C, H, S, rep, lane, fx_format(C, n));
             else field_commit_multipass<NB>(C, H, &S, rep, lane, kind, ind0, n, binder, newst);
         }
         if (kind == 2) {
@@ -1348,15 +1396,13 @@ struct McWarp {
     }
 
     // ---- attempt `slot` of the batch (mc_step, mc_sim.pyx:106-182) ------------
-    template <int MT>
-    __device__ __forceinline__ void attempt(int slot) {
-        constexpr int mtype = MT;
+    __device__ __forceinline__ void attempt(int mtype, int slot) {
         const int N = C.N;
         const Prop &P = B.prop[slot];
-        constexpr bool tangent = mtype == CHROMO_TANGENT_ROTATION;
+        const bool tangent = mtype == CHROMO_TANGENT_ROTATION;
         const int ind0 = P.ind0, n = P.n;
         const int binder = mtype == CHROMO_CHANGE_BINDING_STATE ? P.aux : 0;
-        constexpr int kind = mtype == CHROMO_SLIDE ? 1 : (mtype == CHROMO_CHANGE_BINDING_STATE ? 2 : 0);
+        const int kind = mtype == CHROMO_SLIDE ? 1 : (mtype == CHROMO_CHANGE_BINDING_STATE ? 2 : 0);
         const unsigned long long att = abase + (unsigned long long)slot;
         if (n <= 0) { // mc_sim.pyx:151-152: counted, nothing else happens
             wait_turn(slot);
@@ -1374,7 +1420,7 @@ struct McWarp {
         // stage 1 may run ahead of the attempt's turn unless it needs sequential draws or the
         // replica-wide HBM scratch (large tangent / binding moves)
         bool my_turn = !(NW > 1 && (tangent ? presel : (kind != 2 || n <= CB_NEWST)));
-        constexpr bool segmove = !tangent && kind != 2;
+        const bool segmove = !tangent && kind != 2;
         unsigned seen = 0u; // accepted attempts of the batch whose writes the prepared map / elastic dE reflect
         CB_T0();
         if (my_turn) wait_turn(slot);
@@ -1388,7 +1434,7 @@ struct McWarp {
                     // the map and the elastic dE were prepared with the batch; redo them if an attempt
                     // accepted since then wrote this segment's rows or its neighbours'
                     const unsigned now = accepted_before(slot);
-                    if (rows_changed(now & ~seen, slot)) rows_recompute<MT>(slot);
+                    if (rows_changed(now & ~seen, slot)) rows_recompute(mtype, slot);
                     seen = now;
                     if (lane < 12) S.M[lane] = P.M[lane];
                     dE_poly = P.dE_poly;
@@ -1408,7 +1454,7 @@ struct McWarp {
                 if (kind == 2) dE_poly = binding_dE_poly(ind0, n, binder, newst, ddbl);
                 CB_LAP(13);
                 if (C.field_active) {
-                    conf = field_scatter<NB, kind>(C, H, S, rep, lane, ind0, n, binder, newst);
+                    conf = field_scatter<NB>(C, H, S, rep, lane, kind, ind0, n, binder, newst);
                     CB_LAP(14);
                 } else if (kind != 2 && C.confine_type != CHROMO_CONFINE_NONE)
                     dE_field = confinement_dE_segment(C, S, rep, lane, kind, ind0, n);
@@ -1445,7 +1491,7 @@ struct McWarp {
             wait_turn(slot);
             CB_LAP(2);
             my_turn = true;
-            if (segmove ? !rows_changed(accepted_before(slot) & ~seen, slot) : !stale<MT>(slot)) break;
+            if (segmove ? !rows_changed(accepted_before(slot) & ~seen, slot) : !stale(mtype, slot)) break;
             if (!tangent && C.field_active) table_clear(H, S, NCOL, lane); // rows changed under stage 1: redo it
             CB_LAP(3);
         }
@@ -1530,9 +1576,7 @@ struct McWarp {
     }
 
     // pull the rows a later attempt will read towards the SM while this one runs
-    template <int MT>
-    __device__ __forceinline__ void prefetch_attempt(const Prop &P, int slot) {
-        constexpr int mtype = MT;
+    __device__ __forceinline__ void prefetch_attempt(int mtype, const Prop &P, int slot) {
         const int N = C.N;
         int first, count;
         if (mtype == CHROMO_TANGENT_ROTATION) {
@@ -1574,11 +1618,10 @@ struct McWarp {
 
     // a batch of `cnt` attempts of one move type: prepare (lanes of warp 0), then the warps take
     // the attempts round-robin
-    template <int MT>
-    __device__ __forceinline__ void run(int cnt) {
+    __device__ __forceinline__ void run(int mtype, int cnt) {
         CB_T0();
         if (wid == 0) {
-            prepare<MT>(cnt);
+            prepare(mtype, cnt);
             if (lane == 0) {
                 *(volatile int *)&B.token = 0;
                 *(volatile unsigned *)&B.accepted = 0u;
@@ -1590,28 +1633,15 @@ struct McWarp {
 #pragma unroll 1
         for (int j = wid; j < cnt; j += NW) {
             CB_T0();
-            if (j + NW < cnt) prefetch_attempt<MT>(B.prop[j + NW], j + NW);
+            if (j + NW < cnt) prefetch_attempt(mtype, B.prop[j + NW], j + NW);
             CB_LAP(0);
-            attempt<MT>(j);
+            attempt(mtype, j);
         }
         abase += (unsigned long long)cnt;
         {
             CB_T0();
             block_sync();
             CB_LAP(9);
-        }
-    }
-
-    // One copy of the attempt code PER MOVE TYPE: a move type's loop is then a compact, contiguous piece of
-    // SASS (the generic copy interleaved all five, and the hot path of one type was spread over the whole
-    // 160 KB kernel: 13 % instruction-cache misses with one warp per replica, 33 % with two).
-    __device__ __forceinline__ void run_type(int mtype, int cnt) {
-        switch (mtype) {
-        case CHROMO_CRANK_SHAFT: run<CHROMO_CRANK_SHAFT>(cnt); break;
-        case CHROMO_END_PIVOT: run<CHROMO_END_PIVOT>(cnt); break;
-        case CHROMO_SLIDE: run<CHROMO_SLIDE>(cnt); break;
-        case CHROMO_TANGENT_ROTATION: run<CHROMO_TANGENT_ROTATION>(cnt); break;
-        default: run<CHROMO_CHANGE_BINDING_STATE>(cnt); break;
         }
     }
 
@@ -1653,6 +1683,7 @@ struct McWarp {
 __device__ __forceinline__ HashTable carve_table(unsigned char *dyn, int cap, int ncol) {
     HashTable H;
     H.vals = (uint32_t *)dyn;
+    H.vals_s = cb_shared_addr(dyn);
     H.keys = (int *)(dyn + (size_t)cap * ncol * 8);
     H.list = H.keys + cap;
     H.cap = cap;
@@ -1699,7 +1730,7 @@ __device__ __forceinline__ void rng_store<PhiloxRng>(const DevCtx &C, ReplicaSh 
 // barrier after each): the kernel is bound by instruction fetch (140 KB of SASS against a
 // 32 KB L1.5 instruction cache), and warps that run the same move type share its code.
 template <class Rng, int NB, int NW>
-__global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, 1)
+__global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, CB_MIN_BLOCKS)
     mc_sim_kernel(const CB_GRID_CONSTANT DevCtx C, long long num_mc_steps, double mu_adjust,
                   unsigned long long seed, int cap, int rpb, int rep0, int rep_end) {
     CB_DYN_SMEM(dyn);
@@ -1736,7 +1767,7 @@ __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, 1)
                 if (B.mv[m].move_on == 1) {
                     const int npc = B.mv[m].num_per_cycle;
 #pragma unroll 1
-                    for (int j0 = 0; j0 < npc; j0 += BS) W.run_type(m, min(BS, npc - j0));
+                    for (int j0 = 0; j0 < npc; j0 += BS) W.run(m, min(BS, npc - j0));
                 }
                 W.update_amplitudes(m); // also for moves that are off (mc_sim.pyx:103)
             }
@@ -1794,7 +1825,7 @@ __global__ void __launch_bounds__(32) mc_step_kernel(const CB_GRID_CONSTANT DevC
     const unsigned long long abase0 = rng_load<Rng>(rng, C, B, rep, lane, seed);
     __syncwarp();
     McWarp<Rng, true, NB, 1> W{C, B, S, H, rng, rep, lane, 0, 0, mu_adjust, force_accept, dbg, abase0};
-    W.run_type(mtype, 1);
+    W.run(mtype, 1);
     __syncwarp();
     rng_store<Rng>(C, B, rep, lane, W.abase);
 }

@@ -41,7 +41,7 @@ struct DevCtx {
     double pref[CB_MAXNB], e_intra[CB_MAXNB], xpref[CB_MAXNB * CB_MAXNB];
     int sites[CB_MAXNB];
     int any_cross; // some cross-talk prefactor is non-zero
-    int fx_base;   // fixed-point exponent base of the delta-density cells (mc_kernel.cuh, fx_exponent)
+    int fx_base;   // floor(log2(V_min / max_state)): exponent base of the fixed-point delta-density cells (fx_format)
     const double *bindF; // [nb][S1][S1]
     int S1;
     chromo_move_state *moves;        // [R][5]

@@ -100,6 +100,24 @@ static inline int __any_sync(unsigned, int pred) {
     return r;
 }
 
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    unsigned base = threadIdx.x & ~31u;
+    emu_blk->slots[threadIdx.x] = pred ? 1 : 0;
+    emu_warp_wait();
+    unsigned r = 0;
+    for (int i = 0; i < 32 && base + i < blockDim.x; i++) r |= (unsigned)(emu_blk->slots[base + i] & 1) << i;
+    emu_warp_wait();
+    return r;
+}
+// position of the `offset`-th set bit of `mask` at or above `base` (offset >= 1), 0xffffffff if there is none
+static inline unsigned __fns(unsigned mask, unsigned base, int offset) {
+    for (unsigned b = base; b < 32; b++)
+        if ((mask >> b) & 1u)
+            if (--offset == 0) return b;
+    return 0xffffffffu;
+}
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+
 static inline int atomicCAS(int *a, int cmp, int val) {
     __atomic_compare_exchange_n(a, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
     return cmp;
@@ -139,6 +157,9 @@ static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 #define CB_NOINLINE __attribute__((noinline))
 #define CB_GRID_CONSTANT
 static inline void cb_prefetch(const void *) {}
+typedef uintptr_t cb_saddr;
+static inline cb_saddr cb_shared_addr(const void *p) { return (cb_saddr)p; }
+static inline void cb_red_add_u32(cb_saddr a, uint32_t v) { __atomic_fetch_add((uint32_t *)a, v, __ATOMIC_SEQ_CST); }
 static inline void cb_backoff() { sched_yield(); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline double __longlong_as_double(long long v) {

@@ -30,7 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--replicas", type=int, default=1024)
     ap.add_argument("--beads", type=int, default=10000)
-    ap.add_argument("--warm", type=int, default=400)
+    ap.add_argument("--warm", type=int, default=100)
     ap.add_argument("--sweeps", type=int, default=20)
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0, help="warps per replica (0 = library default)")
@@ -44,7 +44,7 @@ def main():
     r, t3, t2, states, mods, grid = bench.make_inputs(R, N, 1234, pinned=False)
     ens = ReplicaEnsemble(r, t3, t2, states, mods, binders=[dict(bench.HP1)], bond_params=bench.bond_params(N),
                           grid=grid, bead_vol=(4 / 3) * math.pi * 5.0 ** 3, chi=1.0, mu=[-1.2],
-                          moves=default_moves(R, N, 16.5), device=0)
+                          moves=bench.stationary_moves(R, N), device=0)
     eng = ens.engine
     warps = eng.set_warps_per_replica(a.warps)
     rpb = eng.set_replicas_per_block(a.rpb) if hasattr(eng._L, "chromo_ctx_set_replicas_per_block") else 1

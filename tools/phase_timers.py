@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--lib", required=True)
     ap.add_argument("--replicas", type=int, default=1024)
     ap.add_argument("--beads", type=int, default=10000)
-    ap.add_argument("--warm", type=int, default=400)
+    ap.add_argument("--warm", type=int, default=100)
     ap.add_argument("--sweeps", type=int, default=20)
     ap.add_argument("--warps", default="1,2")
     ap.add_argument("--out", default=None)
@@ -46,7 +46,7 @@ def main():
     for w in [int(x) for x in a.warps.split(",")]:
         ens = ReplicaEnsemble(r.copy(), t3.copy(), t2.copy(), states.copy(), mods, binders=[dict(bench.HP1)],
                               bond_params=bench.bond_params(N), grid=grid, bead_vol=(4 / 3) * math.pi * 5.0 ** 3,
-                              chi=1.0, mu=[-1.2], moves=default_moves(R, N, 16.5), device=0)
+                              chi=1.0, mu=[-1.2], moves=bench.stationary_moves(R, N), device=0)
         eng = ens.engine
         eng.set_warps_per_replica(w)
         cap = eng.set_table_capacity(0)
