@@ -65,7 +65,8 @@ SYMBOLS = [
     "chromo_set_replica_params", "chromo_set_bond_params", "chromo_set_twist_params", "chromo_set_access_volumes",
     "chromo_upload_state", "chromo_download_state", "chromo_download_density",
     "chromo_upload_density", "chromo_field_recompute", "chromo_field_energy",
-    "chromo_elastic_energy", "chromo_chi_observable", "chromo_srand", "chromo_numpy_seed",
+    "chromo_elastic_energy", "chromo_chi_observable", "chromo_exchange_init", "chromo_exchange_observable",
+    "chromo_exchange_step", "chromo_exchange_state", "chromo_srand", "chromo_numpy_seed",
     "chromo_mc_sim", "chromo_mc_sim_host", "chromo_get_moves", "chromo_set_moves", "chromo_last_attempts", "chromo_last_algo_bytes",
     "chromo_mc_step",
     "chromo_cg_num_beads", "chromo_cg_chromatin", "chromo_refined_num_points", "chromo_refined_num_draws",
@@ -102,6 +103,10 @@ def _declare(L):
     L.chromo_field_energy.argtypes = [_vp, _pd, _pd, _pl, _pd]
     L.chromo_elastic_energy.argtypes = [_vp, _pd]
     L.chromo_chi_observable.argtypes = [_vp, _pd]
+    L.chromo_exchange_init.argtypes = [_vp, _pd, C.c_int64, C.c_int64, C.c_int64]
+    L.chromo_exchange_observable.argtypes = [_vp, C.c_void_p]
+    L.chromo_exchange_step.argtypes = [_vp, C.c_void_p, C.c_int64, C.c_uint64]
+    L.chromo_exchange_state.argtypes = [_vp, C.POINTER(C.c_int32), _pd, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.chromo_srand.argtypes = [_vp, _pu]
     L.chromo_numpy_seed.argtypes = [_vp, _pu]
     L.chromo_mc_sim.argtypes = [_vp, C.c_int64, _vp, C.c_double, C.c_uint64, C.c_int, _pu]

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <cstdlib>
@@ -61,6 +62,11 @@ struct chromo_ctx {
     double *d_partial = nullptr, *d_out = nullptr;
     int *d_dcount = nullptr;
     int *d_bad = nullptr; // set by the narrowing kernel when a state / mark is out of range
+    // replica exchange (chromo_exchange_*): the chi ladder(s), the replica on every rung, counters
+    double *d_ex_ladder = nullptr;
+    int *d_ex_rung = nullptr;
+    unsigned long long *d_ex_counters = nullptr;
+    int64_t ex_total = 0, ex_first = 0, ex_ladder_len = 0;
     long long *d_stage = nullptr;
     int64_t stage_elems = 0;
     // host-array path (chromo_mc_sim_host): one stream + int64 staging buffer per replica chunk
@@ -671,6 +677,87 @@ extern "C" int chromo_chi_observable(chromo_ctx *c, double *Phi) {
     CK(cudaMemcpyAsync(out.data(), c->d_out, out.size() * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     for (int r = 0; r < d.R; r++) Phi[r] = out[(size_t)r * d.ncol + d.nb];
+    return CHROMO_OK;
+}
+
+// ---------------------------------------------------------- replica exchange
+extern "C" int chromo_exchange_init(chromo_ctx *c, const double *chi_by_replica, int64_t n_total, int64_t first,
+                                    int64_t ladder_len) {
+    if (!c || !chi_by_replica) return fail(CHROMO_ERR_ARG, "null argument");
+    DevCtx &d = c->d;
+    if (n_total < 1 || first < 0 || first + d.R > n_total) return fail(CHROMO_ERR_ARG, "this context's replicas [first, first + R) must lie in [0, n_total)");
+    if (ladder_len <= 0) ladder_len = n_total;
+    if (n_total % ladder_len) return fail(CHROMO_ERR_ARG, "n_total must be a multiple of ladder_len");
+    if (n_total > 0x7fffffffLL) return fail(CHROMO_ERR_ARG, "too many replicas");
+    CK(cudaSetDevice(c->device));
+    // rung k of ladder l = the k-th smallest chi among replicas [l * ladder_len, (l + 1) * ladder_len)
+    std::vector<double> ladder((size_t)n_total);
+    std::vector<int> rung((size_t)n_total);
+    for (int64_t l = 0; l < n_total / ladder_len; l++) {
+        std::vector<int> idx((size_t)ladder_len);
+        for (int64_t i = 0; i < ladder_len; i++) idx[(size_t)i] = (int)(l * ladder_len + i);
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return chi_by_replica[x] < chi_by_replica[y]; });
+        for (int64_t i = 0; i < ladder_len; i++) {
+            rung[(size_t)(l * ladder_len + i)] = idx[(size_t)i];
+            ladder[(size_t)(l * ladder_len + i)] = chi_by_replica[idx[(size_t)i]];
+        }
+    }
+    int rc;
+    if (c->ex_total != n_total) {
+        if ((rc = dev_alloc(c, &c->d_ex_ladder, (size_t)n_total))) return rc;
+        if ((rc = dev_alloc(c, &c->d_ex_rung, (size_t)n_total))) return rc;
+        if (!c->d_ex_counters && (rc = dev_alloc(c, &c->d_ex_counters, (size_t)2))) return rc;
+    }
+    c->ex_total = n_total;
+    c->ex_first = first;
+    c->ex_ladder_len = ladder_len;
+    CK(cudaMemcpyAsync(c->d_ex_ladder, ladder.data(), (size_t)n_total * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_ex_rung, rung.data(), (size_t)n_total * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->d_ex_counters, 0, 16, c->stream));
+    if (!c->d_chi && (rc = dev_alloc(c, &c->d_chi, (size_t)d.R))) return rc;
+    CK(cudaMemcpyAsync(c->d_chi, chi_by_replica + first, (size_t)d.R * 8, cudaMemcpyHostToDevice, c->stream));
+    d.chi = c->d_chi;
+    CK(cudaStreamSynchronize(c->stream));
+    return CHROMO_OK;
+}
+
+extern "C" int chromo_exchange_observable(chromo_ctx *c, double *phi_dev) {
+    if (!c || !phi_dev) return fail(CHROMO_ERR_ARG, "null argument");
+    if (!c->d.field_active) return fail(CHROMO_ERR_STATE, "context has no field");
+    CK(cudaSetDevice(c->device));
+    DevCtx &d = c->d;
+    int rc = field_reduce(c, 1);
+    if (rc) return rc;
+    CB_LAUNCH(pick_column_kernel, (d.R + 127) / 128, 128, 0, c->stream, (const double *)c->d_out, phi_dev, d.R, d.ncol, d.nb);
+    CK(cudaGetLastError());
+    return CHROMO_OK; // asynchronous: ordered on the context's stream
+}
+
+extern "C" int chromo_exchange_step(chromo_ctx *c, const double *phi_all_dev, int64_t round, uint64_t seed) {
+    if (!c || !phi_all_dev) return fail(CHROMO_ERR_ARG, "null argument");
+    if (c->ex_total <= 0) return fail(CHROMO_ERR_STATE, "call chromo_exchange_init first");
+    if (round < 0) return fail(CHROMO_ERR_ARG, "negative round");
+    CK(cudaSetDevice(c->device));
+    const long long pairs = (c->ex_total + 1) / 2;
+    CB_LAUNCH(exchange_kernel, (unsigned)((pairs + 127) / 128), 128, 0, c->stream, phi_all_dev,
+              (const double *)c->d_ex_ladder, c->d_ex_rung, c->d_chi, (long long)c->ex_total, (long long)c->ex_ladder_len,
+              (long long)c->ex_first, c->d.R, (long long)round, (unsigned long long)seed, c->d_ex_counters);
+    CK(cudaGetLastError());
+    return CHROMO_OK; // asynchronous: the next mc_sim on this context's stream sees the new chi
+}
+
+extern "C" int chromo_exchange_state(chromo_ctx *c, int32_t *rung_replica, double *chi_local, uint64_t *pairs_tried,
+                                     uint64_t *swaps_accepted) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    if (c->ex_total <= 0) return fail(CHROMO_ERR_STATE, "call chromo_exchange_init first");
+    CK(cudaSetDevice(c->device));
+    unsigned long long cnt[2] = {0, 0};
+    if (rung_replica) CK(cudaMemcpyAsync(rung_replica, c->d_ex_rung, (size_t)c->ex_total * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (chi_local) CK(cudaMemcpyAsync(chi_local, c->d_chi, (size_t)c->d.R * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(cnt, c->d_ex_counters, 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (pairs_tried) *pairs_tried = cnt[0];
+    if (swaps_accepted) *swaps_accepted = cnt[1];
     return CHROMO_OK;
 }
 

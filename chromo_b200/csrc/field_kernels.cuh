@@ -5,6 +5,7 @@
 // they are bit-reproducible run to run.
 #pragma once
 #include "geometry.cuh"
+#include "rng.cuh"
 #include "launch.cuh"
 #include "params.cuh"
 
@@ -191,5 +192,43 @@ __global__ void narrow_i64_kernel(const long long *src, signed char *dst, long l
             v = v < 0 ? 0 : hi;
         }
         dst[i] = (signed char)v;
+    }
+}
+
+// ------------------------------------------------------------ replica exchange
+// column `col` of the per-replica reduction results -> a caller-owned device buffer
+__global__ void pick_column_kernel(const double *out, double *dst, int R, int ncol, int col) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) dst[r] = out[(size_t)r * ncol + col];
+}
+
+// One even / odd round of neighbour swaps on a chi ladder, decided identically on every rank from the
+// all-gathered observable Phi_g = sum_bins (V/v) phi^2 (global replica id g).  The Hamiltonian sampled by the
+// moves is H0 + chi Phi (nonspecific_interact_dE fields.pyx:1829-1840), so exchanging the chi LABELS of the
+// replicas on rungs k, k+1 changes the total energy by (chi_k - chi_{k+1}) (Phi_b - Phi_a); it is accepted
+// with probability min(1, exp(-dE)).  ladder[k] is the k-th smallest chi, rung_replica[k] the replica that
+// holds it; rungs are grouped in independent ladders of `ladder_len` (no pair across a boundary).  One
+// thread per pair: pairs are disjoint, so the permutation is updated in place.  The uniform of pair p in
+// round t is word 0 of Philox4x32-10(counter = (p, t_lo, t_hi, 'EXCH'), key = seed): the same on every rank.
+__global__ void exchange_kernel(const double *phi_all, const double *ladder, int *rung_replica, double *chi_local,
+                                long long n_total, long long ladder_len, long long first, int R, long long round,
+                                unsigned long long seed, unsigned long long *counters) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long k = (round & 1) + 2 * p;
+    if (k + 1 >= n_total) return;
+    if ((k + 1) % ladder_len == 0) return; // rungs k and k+1 belong to different ladders
+    const int a = rung_replica[k], b = rung_replica[k + 1];
+    const double dE = (ladder[k] - ladder[k + 1]) * (phi_all[b] - phi_all[a]);
+    uint32_t o[4];
+    philox4x32_10((uint32_t)p, (uint32_t)round, (uint32_t)((unsigned long long)round >> 32), 0x45584348u,
+                  (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    const double u = (double)(o[0] >> 1) / CB_RAND_MAX;
+    atomicAdd(&counters[0], 1ull);
+    if (u < exp(-dE)) {
+        rung_replica[k] = b;
+        rung_replica[k + 1] = a;
+        if (b >= first && b < first + R) chi_local[b - first] = ladder[k];
+        if (a >= first && a < first + R) chi_local[a - first] = ladder[k + 1];
+        atomicAdd(&counters[1], 1ull);
     }
 }

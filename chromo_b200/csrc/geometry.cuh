@@ -44,8 +44,11 @@ __device__ __forceinline__ void bin_axis(double x, double half_width, double wid
                                          double half_step, double d, double inv_d, int n, int &ind_lo,
                                          int &ind_hi, double &w_lo) {
     double a = x + half_width;
-    double m = fmod_exact(a, width, inv_width);
-    if (m != 0.0 && m < 0.0) m = m + width; // Python modulo: result takes the divisor's sign
+    double m = a; // a % width == a for 0 <= a < width: every bead of a confined chain, no division needed
+    if (!(a >= 0.0 && a < width)) {
+        m = fmod_exact(a, width, inv_width);
+        if (m != 0.0 && m < 0.0) m = m + width; // Python modulo: result takes the divisor's sign
+    }
     double xs = m - half_step;
     double q = div_const(xs, d, inv_d); // == xs / d
     double fl = floor(q);

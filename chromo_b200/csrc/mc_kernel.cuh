@@ -155,7 +155,10 @@ __device__ __forceinline__ double pow2_double(int e) { return __hiloint2double((
 __device__ __forceinline__ Fx fx_format(const DevCtx &C, int n) {
     Fx f;
     f.lo_bits = n <= 2048 ? 20 : 0;
-    const int e = (f.lo_bits ? 28 + f.lo_bits : 60) + C.fx_base - (n > 1 ? 32 - __clz(n - 1) : 0);
+    // E <= 58 in the two-word form: a term the reference drops (|w/V| <= 1e-18, quirk 3) then rounds to 0 by
+    // itself (1e-18 * 2^58 = 0.29), so the hot path needs no explicit threshold
+    int e = (f.lo_bits ? 28 + f.lo_bits : 60) + C.fx_base - (n > 1 ? 32 - __clz(n - 1) : 0);
+    if (f.lo_bits) e = min(e, 58);
     f.scale = pow2_double(e);
     f.inv_scale = pow2_double(-e);
     return f;
@@ -168,8 +171,13 @@ static __device__ CB_NOINLINE void fx_add_carry(uint32_t *cell, long long v) {
 }
 __device__ __forceinline__ void fx_add(uint32_t *cell, cb_saddr cell_s, long long v, int lo_bits) {
     if (lo_bits) {
+#ifdef CB_DBG_GENERIC_ATOMICS
+        atomicAdd(&cell[0], (uint32_t)v & 0xFFFFFu);
+        atomicAdd(&cell[1], (uint32_t)(v >> 20));
+#else
         cb_red_add_u32(cell_s, (uint32_t)v & 0xFFFFFu);
         cb_red_add_u32(cell_s + 4, (uint32_t)(v >> 20));
+#endif
     } else {
         fx_add_carry(cell, v);
     }
@@ -237,6 +245,7 @@ static __device__ CB_NOINLINE double div_access(const double *access_vol, int bi
 template <bool GEN>
 __device__ __forceinline__ long long fx_term(const DevCtx &C, double w, int bin, double scale) {
     const double d = (GEN && C.access_vol) ? div_access(C.access_vol, bin, w) : div_const(w, C.vol_bin, C.inv_vol_bin);
+    if (!GEN) return __double2ll_rn(d * scale); // (the 1e-18 threshold is implied by the format, see fx_format)
     return fabs(d) > 1E-18 ? __double2ll_rn(d * scale) : 0ll;
 }
 // one voxel contribution: `v` to the bead column (unless `no_bead`), v * mult[m] to binder column m
@@ -251,7 +260,7 @@ __device__ __forceinline__ void unit_add(const DevCtx &C, HashTable &H, WarpSh &
     const int slot = table_claim(H, S, bin, checked, fresh);
     if (slot < 0) return;
     if (fresh) cb_prefetch(dens_rows + (long long)bin * NCOL); // the density row is needed by table_energy
-    if (v == 0) return;
+    if (GEN && v == 0) return;
     uint32_t *cell = H.vals + (size_t)slot * NCOL * 2;
     const cb_saddr cell_s = H.vals_s + (cb_saddr)slot * (NCOL * 8);
     if (!no_bead) fx_add(cell, cell_s, v, lo_bits);
@@ -464,10 +473,13 @@ __device__ __forceinline__ void table_commit(const DevCtx &C, const HashTable &H
         for (int c = 0; c < C.ncol; c++) row[c] += fx_read(H.vals + ((size_t)slot * C.ncol + c) * 2, fx);
     }
 }
+// instrumentation of the single-step kernel: the voxels in the table and their delta-rho rows, appended after
+// the `base` entries of the earlier partition passes (S.last_U already counts this pass)
 __device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTable &H, const WarpSh &S,
                                               int lane, DebugOut *dbg, const Fx &fx) {
-    int cnt = S.count;
-    long long base = dbg->n_touched;
+    __syncwarp();
+    const int cnt = __shfl_sync(FULL_MASK, S.count, 0);
+    const long long base = __shfl_sync(FULL_MASK, S.last_U - S.count, 0); // lane 0 wrote last_U itself
     for (int j = lane; j < cnt; j += 32) {
         long long o = base + j;
         if (o < dbg->touched_cap) {
@@ -477,7 +489,6 @@ __device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTabl
                 dbg->dtrial[o * C.ncol + c] = fx_read(H.vals + ((size_t)slot * C.ncol + c) * 2, fx);
         }
     }
-    __syncwarp();
     if (lane == 0) dbg->n_touched = base + cnt;
     __syncwarp();
 }
@@ -498,10 +509,12 @@ __device__ __forceinline__ void table_debug_dump(const DevCtx &C, const HashTabl
 // the delta-rho rows afterwards (used by the commit).  Moves whose touched set
 // overflows the table are re-scattered in hash-partition passes inside stage 2.
 // ddbl[a] = change in the number of doubly-bound beads (count_doubly_bound).
-// the general scatter, out of line: one copy serves fields with per-voxel accessible volumes, the partition
-// passes of a move whose touched set overflowed the table and moves of more than 2,048 beads
+// the general scatter: fields with per-voxel accessible volumes, the partition passes of a move whose touched
+// set overflowed the table, moves of more than 2,048 beads.  (Inlined into its three callers, two of which
+// are themselves out of line: as a separate out-of-line function it lost table entries on B200 -- warp-level
+// primitives behind a call from a loop with divergent lanes -- although the CPU emulation was clean.)
 template <int NB>
-__device__ CB_NOINLINE int2 scatter_pass_cold(const DevCtx &C, HashTable H, WarpSh *Sp, int rep, int lane, int kind,
+__device__ __forceinline__ int2 scatter_pass_cold(const DevCtx &C, HashTable H, WarpSh *Sp, int rep, int lane, int kind,
                                               int ind0, int n, int binder, const signed char *newst, int P, int p) {
     return scatter_pass<NB, true, -1>(C, H, *Sp, rep, lane, kind, ind0, n, binder, newst, P, p, fx_format(C, n));
 }
@@ -514,6 +527,44 @@ __device__ __forceinline__ int2 field_scatter(const DevCtx &C, HashTable &H, War
     else conf = scatter_pass<NB, false, 0>(C, H, S, rep, lane, kind, ind0, n, binder, newst, 1, 0, fx_format(C, n));
     __syncwarp();
     return conf;
+}
+// the touched set does not fit the table (rare): re-scatter in P = 2, 4, ... hash-partition passes
+// (voxels with bin % P == p per pass; the energy is a sum over voxels).  Returns P; the table ends empty.
+template <int NB, bool DEBUG>
+__device__ CB_NOINLINE int field_energy_multipass(const DevCtx &C, HashTable H, WarpSh *Sp, int rep, int lane, int kind,
+                                                  int ind0, int n, int binder, const signed char *newst, double chi,
+                                                  FieldSums<NB> *Fp, DebugOut *dbg) {
+    constexpr int NCOL = NB + 1;
+    WarpSh &S = *Sp;
+    FieldSums<NB> &F = *Fp;
+    const Fx fx = fx_format(C, n);
+    const bool want_cross = C.any_cross != 0;
+    int P = 1;
+    bool failed = true;
+    while (failed) {
+        P *= 2;
+#pragma unroll
+        for (int a = 0; a < NB; a++) F.sq[a] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NB * NB; a++) F.cross[a] = 0.0;
+        F.chi = 0.0;
+        if (DEBUG && lane == 0) dbg->n_touched = 0;
+        failed = false;
+        for (int p = 0; p < P; p++) {
+            table_clear(H, S, NCOL, lane);
+            (void)scatter_pass_cold<NB>(C, H, &S, rep, lane, kind, ind0, n, binder, newst, P, p);
+            __syncwarp();
+            if (S.overflow) {
+                failed = true;
+                break;
+            }
+            table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross, fx);
+            if (lane == 0) S.last_U = (p == 0 ? 0 : S.last_U) + S.count;
+            if (DEBUG) table_debug_dump(C, H, S, lane, dbg, fx);
+        }
+    }
+    table_clear(H, S, NCOL, lane);
+    return P;
 }
 template <int NB, bool DEBUG>
 __device__ __forceinline__ double field_finish(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
@@ -536,30 +587,7 @@ __device__ __forceinline__ double field_finish(const DevCtx &C, HashTable &H, Wa
         if (lane == 0) S.last_U = S.count;
         if (DEBUG) table_debug_dump(C, H, S, lane, dbg, fx);
     } else {
-        bool failed = true;
-        while (failed) { // rare: the touched set does not fit the table
-            P *= 2;
-#pragma unroll
-            for (int a = 0; a < NB; a++) F.sq[a] = 0.0;
-#pragma unroll
-            for (int a = 0; a < NB * NB; a++) F.cross[a] = 0.0;
-            F.chi = 0.0;
-            if (DEBUG && lane == 0) dbg->n_touched = 0;
-            failed = false;
-            for (int p = 0; p < P; p++) {
-                table_clear(H, S, NCOL, lane);
-                (void)scatter_pass_cold<NB>(C, H, &S, rep, lane, kind, ind0, n, binder, newst, P, p);
-                __syncwarp();
-                if (S.overflow) {
-                    failed = true;
-                    break;
-                }
-                table_energy<NB>(C, H, S, rep, chi, lane, F, want_cross, fx);
-                if (lane == 0) S.last_U = (p == 0 ? 0 : S.last_U) + S.count;
-                if (DEBUG) table_debug_dump(C, H, S, lane, dbg, fx);
-            }
-        }
-        table_clear(H, S, NCOL, lane);
+        P = field_energy_multipass<NB, DEBUG>(C, H, &S, rep, lane, kind, ind0, n, binder, newst, chi, &F, dbg);
     }
     if (lane == 0) S.passes = P;
     // ---- reduce and assemble in the reference's order ----
@@ -1782,7 +1810,9 @@ __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, CB_MIN_BLOCKS)
             // The block's replicas enter the next move type together.  (Measured on B200: skipping
             // the barrier before the short move types -- 1 end-pivot, 10 binding attempts -- costs
             // more in lost instruction-cache sharing than the wait for the slowest replica does.)
+#ifndef CB_NO_TYPE_BARRIER
             __syncthreads();
+#endif
         }
     if (!active) return;
     long long a1 = 0;

@@ -213,6 +213,32 @@ int chromo_elastic_energy(chromo_ctx *ctx, double *E);
  * (nonspecific_interact_dE fields.pyx:1829-1840).  Uses the current densities. */
 int chromo_chi_observable(chromo_ctx *ctx, double *Phi);
 
+/* ---- replica exchange on the device (SURVEY.md 8b `exchange_step`, 8e) ---
+ * Parallel tempering over chi for an ensemble sharded over GPUs: replica g of
+ * n_total lives in the context that covers [first, first + R).  The reference has
+ * no such step (its runs are independent processes); this is BASELINE config 5.
+ * One round, all on the context's stream and without any host round trip:
+ *   1. chromo_exchange_observable(ctx, phi_local_dev)   Phi of the local replicas
+ *      into a caller-owned DEVICE buffer [R];
+ *   2. the caller all-gathers the shards into phi_all_dev [n_total] (NCCL over
+ *      NVLink: 8 B per replica; chromo_b200.parallel does it with
+ *      torch.distributed on the same stream);
+ *   3. chromo_exchange_step(ctx, phi_all_dev, round, seed)   every rank decides the
+ *      same even / odd neighbour swaps on the ladder (a counter-based uniform per
+ *      pair and round), updates its copy of the rung -> replica permutation and
+ *      the chi of its own replicas.  Labels move, configurations never do.
+ * chromo_exchange_init sets the ladder from chi_by_replica[n_total] (the chi of
+ * every GLOBAL replica); replicas [l * ladder_len, (l+1) * ladder_len) form ladder l
+ * (ladder_len <= 0: one ladder of n_total rungs). */
+int chromo_exchange_init(chromo_ctx *ctx, const double *chi_by_replica, int64_t n_total, int64_t first,
+                         int64_t ladder_len);
+int chromo_exchange_observable(chromo_ctx *ctx, double *phi_local_dev);
+int chromo_exchange_step(chromo_ctx *ctx, const double *phi_all_dev, int64_t round, uint64_t seed);
+/* Synchronising read-back for checks: rung_replica[n_total] (global replica on each rung),
+ * chi_local[R], pairs tried and swaps accepted since chromo_exchange_init (any may be NULL). */
+int chromo_exchange_state(chromo_ctx *ctx, int32_t *rung_replica, double *chi_local, uint64_t *pairs_tried,
+                          uint64_t *swaps_accepted);
+
 /* ---- RNG --------------------------------------------------------------- */
 /* REPLAY: seed each replica's glibc rand() state, as srand(seed) would. */
 int chromo_srand(chromo_ctx *ctx, const uint32_t *seeds /* [R] */);

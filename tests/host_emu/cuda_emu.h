@@ -134,6 +134,9 @@ static inline double atomicAdd(double *a, double v) {
     return o;
 }
 static inline unsigned atomicAdd(unsigned *a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long *a, unsigned long long v) {
+    return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST);
+}
 static inline long long __double2ll_rn(double x) { return llrint(x); } // default rounding mode: to nearest even
 static inline double __hiloint2double(int hi, int lo) {
     uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;

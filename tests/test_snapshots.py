@@ -143,7 +143,7 @@ def test_ensemble_snapshot_round_trip(backend, tmp_path):
     for a in ("r", "t3", "t2", "states", "chemical_mods", "chi", "mu"):
         assert np.array_equal(getattr(ens, a), getattr(ens2, a)), a
     assert ens2.moves.tobytes() == moves.tobytes()
-    assert np.allclose(ens2.density(), dens, rtol=1e-9, atol=1e-18)
+    assert np.allclose(ens2.density(), dens, rtol=1e-9, atol=1e-15)  # incremental updates are fixed point (quantum ~1e-17, mc_kernel.cuh fx_format)
     # any replica of the batch exports to the reference's CSV schema
     csv = tmp_path / "Chr-2-0.csv"
     ens2.replica_to_csv(1, csv, bead_length=specs[1]["bead_length"])
