@@ -384,6 +384,7 @@ def run_ours(args):
     ens.sync()
     acc = ens.acceptance()
     amp_bead_mean = [float(x) for x in ens.moves["amp_bead"].mean(axis=0)]
+    hbm_bytes = eng.bytes()
     barrier()
 
     # ---- end to end through the host-facing call --------------------------
@@ -408,6 +409,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
     barrier()
+
+    # ---- extra legs: strong scaling of C2 and the C5 replica-exchange ladder ---------------
+    extra = {}
+    if not args.no_extra_legs:
+        ens.close()
+        ens = None
+        extra = extra_legs(args, rank, world, local, dist, (r, t3, t2, states, mods, grid))
 
     # ---- reduce over ranks --------------------------------------------------
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
@@ -460,7 +468,8 @@ def run_ours(args):
                                "times; latency-bound (serial moves per replica); see DESIGN.md"),
             acceptance={k: round(float(v), 4) for k, v in acc.items()},
             amp_bead_mean=[round(x, 2) for x in amp_bead_mean],
-            hbm_bytes=eng.bytes(),
+            hbm_bytes=hbm_bytes,
+            **extra,
         )
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -483,11 +492,118 @@ def run_ours(args):
             except Exception as e:  # never lose the GPU number to a baseline hiccup
                 line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=str(e)[:200])
         emit(line)
-    ens.close()
+    if ens is not None:
+        ens.close()
     if dist is not None:
         dist.destroy_process_group()
     if rc:
         sys.exit(rc)
+
+
+def extra_legs(args, rank, world, local, dist, inputs):
+    """Two more numbers on the same line (every rank takes part; the values are maxima over ranks):
+    strong_scaling  C2 with 1,024 replicas IN TOTAL, split over the ranks (the main value is weak scaling);
+    c5_exchange     BASELINE config 5: 4,096 replicas in total, 256 chi ladders of 16 rungs (geometric 0.25 .. 4:
+                    ~35 % of the neighbour swaps accepted), one exchange round every 10 sweeps INSIDE the timed
+                    region: device observable -> NCCL all-gather (8 B per replica) -> swap kernel, no host trip."""
+    import numpy as np
+    import torch
+    from chromo_b200 import parallel as par
+    from chromo_b200.ensemble import ReplicaEnsemble
+    N, S = args.beads, args.sweeps
+    r, t3, t2, states, mods, grid = inputs
+    dev = torch.device("cuda", local)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def rank_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    out = {}
+    # ---- strong scaling: the same 1,024 replicas as one GPU runs, R / world per rank ----
+    total = args.replicas
+    if world > 1 and total % world == 0:
+        Rs = total // world
+        sl = slice(0, Rs)
+        ens = ReplicaEnsemble(r[sl].copy(), t3[sl].copy(), t2[sl].copy(), states[sl].copy(), mods[sl], binders=[dict(HP1)],
+                              bond_params=bond_params(N, lt=args.lt), grid=grid, bead_vol=(4 / 3) * math.pi * 5.0 ** 3,
+                              chi=1.0, mu=[-1.2], moves=stationary_moves(Rs, N, first=rank * Rs), device=local,
+                              replica_offset=rank * Rs)
+        stream = torch.cuda.ExternalStream(ens.engine.stream(), device=local)
+        for w in range(3):
+            ens.mc_sim(S, 1.0, 300 + w, sync_host=False)
+        ens.engine.sync()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        Ks = 4
+        e0.record(stream)
+        for k in range(Ks):
+            ens.mc_sim(S, 1.0, 400 + k, sync_host=False)
+        e1.record(stream)
+        ens.engine.sync()
+        torch.cuda.synchronize()
+        ms = rank_max(e0.elapsed_time(e1))
+        out["strong_scaling"] = dict(value=total * S * ATTEMPTS_PER_SWEEP * Ks / (ms * 1e-3), unit=UNIT, replicas_total=total,
+                                     replicas_per_gpu=Rs, steps=Ks, ms_per_step=ms / Ks, launch=dict(
+                                         warps_per_replica=ens.engine.set_warps_per_replica(0),
+                                         replicas_per_block=ens.engine.set_replicas_per_block(0)))
+        ens.close()
+    # ---- C5: replica exchange ----
+    total5, L = 4096, 16
+    if total5 % world == 0 and (total5 // world) % L == 0 and N <= 20000:
+        R5 = total5 // world
+        r5, t35, t25, st5, md5, _ = make_inputs(R5, N, 4321 + rank, pinned=False)
+        ladder = np.tile(np.geomspace(0.25, 4.0, L), total5 // L)
+        ens = ReplicaEnsemble(r5, t35, t25, st5, md5, binders=[dict(HP1)], bond_params=bond_params(N), grid=grid,
+                              bead_vol=(4 / 3) * math.pi * 5.0 ** 3, chi=ladder[rank * R5:(rank + 1) * R5], mu=[-1.2],
+                              moves=stationary_moves(R5, N, first=rank * R5), device=local, replica_offset=rank * R5)
+        ex = par.ReplicaExchange(ens, ladder, n_total=total5, seed=11, device=dev, ladder_len=L)
+        stream = torch.cuda.ExternalStream(ens.engine.stream(), device=local)
+        sweeps, rounds = 10, 6
+        ens.mc_sim(100, 1.0, 499, sync_host=False)  # the rungs drift apart before the ladder is exercised
+        for w in range(4):  # warm-up: kernels, NCCL communicator
+            ens.mc_sim(sweeps, 1.0, 500 + w, sync_host=False)
+            ex.step()
+        _, _, tried0, acc0 = ex.state()
+        sync_all()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * rounds + 2)]
+        ev[0].record(stream)
+        for k in range(rounds):
+            ens.mc_sim(sweeps, 1.0, 600 + k, sync_host=False)
+            ev[1 + 2 * k].record(stream)
+            ex.step()
+            ev[2 + 2 * k].record(stream)
+        ens.engine.sync()
+        torch.cuda.synchronize()
+        ms = rank_max(ev[0].elapsed_time(ev[2 * rounds]))
+        ex_us = rank_max(1e3 * sum(ev[1 + 2 * k].elapsed_time(ev[2 + 2 * k]) for k in range(rounds)) / rounds)
+        rung, chi_local, tried, acc = ex.state()
+        same = True
+        if dist is not None:  # every rank must hold the same permutation
+            a = torch.as_tensor(rung.astype(np.int64), device=dev)
+            lo, hi = a.clone(), a.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            same = bool(torch.equal(lo, hi))
+        phi = ex.phi_all.cpu().numpy()
+        by_rung = np.stack([phi[rung[l0:l0 + L]] for l0 in range(0, total5, L)]).mean(axis=0)
+        out["c5_exchange"] = dict(
+            value=total5 * sweeps * ATTEMPTS_PER_SWEEP * rounds / (ms * 1e-3), unit=UNIT, replicas_total=total5,
+            replicas_per_gpu=R5, ladders=total5 // L, rungs_per_ladder=L, chi_range=[0.25, 4.0],
+            sweeps_between_exchanges=sweeps, rounds=rounds, ms_per_round=ms / rounds, exchange_us_per_round=ex_us,
+            swap_acceptance=(acc - acc0) / max(1, tried - tried0), ladders_identical_on_all_ranks=same,
+            labels_are_permutations=bool(all(sorted(rung[l0:l0 + L]) == list(range(l0, l0 + L)) for l0 in range(0, total5, L))),
+            mean_phi_first_rung=float(by_rung[0]), mean_phi_last_rung=float(by_rung[-1]),
+            collective="all_gather_into_tensor over NCCL, 8 B per replica, on the kernel stream" if world > 1 else "none (one rank)")
+        ens.close()
+    return out
 
 
 _REAL_STDOUT = None
@@ -527,6 +643,7 @@ def main():
     ap.add_argument("--lt", type=float, default=None, help="twist persistence length: run the SSTWLC kernels "
                     "(not the headline configuration; the reference arm ignores it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the strong-scaling and C5 exchange legs")
     ap.add_argument("--lib", default=None, help="development: load this build of libchromo_b200.so (A/B timing)")
     args = ap.parse_args()
     quiet_stdout()

@@ -194,16 +194,29 @@ def test_bench_ensemble_replays_against_oracle(cuda_backend):
 
 
 def test_replica_exchange_single_rank(cuda_backend):
-    """C5 on one rank: chi ladder, labels move, configurations do not."""
-    from chromo_b200.parallel import ReplicaExchange
-    R = 16
+    """C5 on one rank, decided on the device: four ladders of 8 rungs, labels move, configurations do not; the
+    kernel's decisions equal the host statement of the rule; mean Phi decreases with chi along the ladders."""
+    from chromo_b200 import parallel as par
+    R, L = 32, 8
     ens, g, binders, Rc = _ensemble(R, 2_000, nb=1, seed=5)
-    ladder = np.geomspace(0.25, 4.0, R)
-    ex = ReplicaExchange(ens, ladder, seed=3)
-    swaps = 0
-    for rnd in range(6):
-        ens.mc_sim(2, 1.0, 100 + rnd, sync_host=False)
-        swaps += ex.step()
-    assert np.array_equal(np.sort(ex.chi), ladder) and swaps > 0
+    ladder = np.tile(np.geomspace(0.25, 4.0, L), R // L)
+    ex = par.ReplicaExchange(ens, ladder, seed=3, ladder_len=L)
+    chi = ladder.copy()
+    phi_by_rung = np.zeros(L)
+    for rnd in range(12):
+        ens.mc_sim(20, 1.0, 100 + rnd, sync_host=False)
+        ex.step()
+        rung, chi_local, tried, acc = ex.state()
+        phi = ex.phi_all.cpu().numpy()
+        chi = par.swap_decisions(chi, phi, rnd, 3, L)
+        assert np.array_equal(chi_local, chi)
+        if rnd >= 6:
+            for l0 in range(0, R, L):
+                phi_by_rung += phi[rung[l0:l0 + L]]
+    assert acc > 0 and tried == 6 * 4 * 4 + 6 * 4 * 3
+    for l0 in range(0, R, L):
+        assert np.array_equal(np.sort(chi[l0:l0 + L]), ladder[:L])
+    # a larger chi penalises dense voxels: Phi = sum (V/v) phi^2 falls along the ladder
+    assert phi_by_rung[0] > phi_by_rung[-1]
     _invariants(ens, g, Rc)
     ens.close()

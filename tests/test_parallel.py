@@ -36,15 +36,19 @@ def test_swap_rule():
     assert abs(acc - np.exp(-1.0)) < 0.03
 
 
-def _swap_loop(chi, phi, round_index, seed):
-    """Pair-by-pair statement of the exchange rule (the checker of the vectorised form)."""
+def _swap_loop(chi, phi, round_index, seed, ladder_len=0):
+    """Pair-by-pair statement of the exchange rule (the checker of the vectorised form and of the kernel)."""
     chi = np.asarray(chi, dtype=float).copy()
-    order = np.argsort(chi, kind="stable")
-    pairs = [(order[p], order[p + 1]) for p in range(round_index % 2, len(chi) - 1, 2)]
-    u = par._uniforms(seed, round_index, len(pairs))
-    for (a, b), ui in zip(pairs, u):
+    n = len(chi)
+    L = n if ladder_len <= 0 else ladder_len
+    order = np.concatenate([l0 + np.argsort(chi[l0:l0 + L], kind="stable") for l0 in range(0, n, L)])
+    u = par._uniforms(seed, round_index, (n + 1) // 2)
+    for p, k in enumerate(range(round_index % 2, n - 1, 2)):
+        if (k + 1) % L == 0:
+            continue
+        a, b = order[k], order[k + 1]
         with np.errstate(over="ignore"):
-            if ui < np.exp(-(chi[a] - chi[b]) * (phi[b] - phi[a])):
+            if u[p] < np.exp(-(chi[a] - chi[b]) * (phi[b] - phi[a])):
                 chi[a], chi[b] = chi[b], chi[a]
     return chi
 
@@ -58,6 +62,8 @@ def test_vectorised_swaps_equal_the_pairwise_rule():
             want = _swap_loop(chi, phi, rnd, seed=5)
             got = par.swap_decisions(chi, phi, rnd, seed=5)
             assert np.array_equal(got, want), (n, rnd)
+            if n % 4 == 0 and n > 4:  # independent ladders of n / 4 rungs
+                assert np.array_equal(par.swap_decisions(chi, phi, rnd, 5, n // 4), _swap_loop(chi, phi, rnd, 5, n // 4))
             chi = got
     assert np.array_equal(par.swap_decisions(np.array([1.0]), np.array([0.0]), 0, 1), [1.0])
 
@@ -105,3 +111,69 @@ def test_exchange_is_identical_on_all_ranks():
     assert np.array_equal(res[0], res[1])                     # same decisions everywhere
     assert np.array_equal(np.sort(res[0][-1]), np.linspace(0.0, 2.0, n_total))  # labels permuted
     assert not np.array_equal(res[0][-1], np.linspace(0.0, 2.0, n_total))       # and something moved
+
+
+# ---- the device path (chromo_exchange_*), world_size 2 over gloo, kernels on the CPU emulation ------------------
+def _device_worker(rank, world, port, q, emu_lib):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle as O
+        from chromo_b200 import _lib
+        from chromo_b200.ensemble import ReplicaEnsemble, default_moves
+        _lib.use_library(emu_lib)
+        R, N, L = 4, 60, 4  # 4 replicas per rank, two ladders of 4 rungs
+        n_total = R * world
+        specs = [O.make_spec(N=N, nb=1, seed=70 + rank * R + i) for i in range(R)]
+        st = lambda k: np.stack([s[k] for s in specs])
+        ens = ReplicaEnsemble(st("r"), st("t3"), st("t2"), st("states"), st("mods"), binders=specs[0]["binders"],
+                              bond_params=O.bond_params(specs[0]["bead_length"], 53.0), grid=specs[0]["field"],
+                              bead_vol=(4 / 3) * np.pi * 125.0, moves=default_moves(R, N, 16.5),
+                              replica_offset=rank * R)
+        ladder = np.tile(np.array([0.5, 1.0, 2.0, 4.0]), n_total // L)[np.random.default_rng(1).permutation(n_total)]
+        ladder = np.concatenate([np.random.default_rng(2 + l).permutation([0.5, 1.0, 2.0, 4.0]) for l in range(n_total // L)])
+        ex = par.ReplicaExchange(ens, ladder, n_total=n_total, seed=17, device="cpu", ladder_len=L)
+        chi = ladder.copy()
+        hist = []
+        for rnd in range(6):
+            ens.mc_sim(1, 1.0, 100 + rnd, sync_host=False)
+            ex.step()
+            ens.engine.sync()
+            phi = ex.phi_all.numpy().copy()  # what every rank decided on
+            assert np.allclose(phi[ex.mine], ens.engine.chi_observable(), rtol=1e-12)
+            chi = par.swap_decisions(chi, phi, rnd, 17, L)  # host statement of the same round
+            rung, chi_local, tried, acc = ex.state()
+            assert np.array_equal(chi_local, chi[ex.mine]), (rank, rnd)
+            hist.append((phi, rung.copy(), chi.copy(), tried, acc))
+        # the kernel's chi is what the next mc_sim uses
+        assert np.array_equal(ens.chi, chi[ex.mine])
+        q.put((rank, hist))
+        ens.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_device_exchange_world2(emu_lib):
+    """chromo_exchange_observable -> all-gather -> chromo_exchange_step on two ranks: every rank holds the same
+    permutation, it equals the host statement of the rule, labels stay a permutation of the ladders."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_device_worker, args=(r, world, port, q, str(emu_lib))) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    moved = 0
+    for (phi0, rung0, chi0, t0, a0), (phi1, rung1, chi1, t1, a1) in zip(res[0], res[1]):
+        assert np.array_equal(phi0, phi1) and np.array_equal(rung0, rung1) and np.array_equal(chi0, chi1)
+        assert (t0, a0) == (t1, a1)
+        for l0 in range(0, 8, 4):  # each ladder keeps its own rungs and replicas
+            assert sorted(chi0[l0:l0 + 4]) == [0.5, 1.0, 2.0, 4.0]
+            assert sorted(rung0[l0:l0 + 4]) == list(range(l0, l0 + 4))
+        moved = a0
+    assert res[0][-1][3] == 3 * 4 + 3 * 2  # pairs tried: even rounds 2 per ladder, odd rounds 1 per ladder
+    assert moved > 0
