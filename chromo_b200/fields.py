@@ -51,8 +51,10 @@ def accessible_volumes(grid, n_side=20, assume_fully_accessible=1):
     R = float(grid["confine_length"])
     ii = np.arange(n_bins)
     ix, iy, iz = ii % nx, (ii // nx) % ny, ii // (nx * ny)
-    # voxel centres, get_voxel_coords fields.pyx:772-803
-    centre = np.stack([(ix - (nx - 1) / 2) * dx, (iy - (ny - 1) / 2) * dy, (iz - (nz - 1) / 2) * dz], axis=1)
+    # voxel "centres", get_voxel_coords fields.pyx:772-803.  `(n - 1) / 2` there divides two C longs with
+    # Python semantics, i.e. FLOORS: on an even grid the reference's centres sit half a voxel below the
+    # geometric ones, and the accessible volumes follow from those (reproduced, SURVEY quirk list)
+    centre = np.stack([(ix - (nx - 1) // 2) * dx, (iy - (ny - 1) // 2) * dy, (iz - (nz - 1) // 2) * dz], axis=1)
     # voxels cut by the sphere, get_split_voxels fields.pyx:805-840
     buffer_dist = np.sqrt(2) / 4 * max(dx, dy, dz)
     dist = np.sqrt(centre[:, 0] ** 2 + centre[:, 1] ** 2 + centre[:, 2] ** 2)

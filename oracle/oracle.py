@@ -191,6 +191,39 @@ def field_prefactors(binders: list, vol_bin: float):
     return pref, e_intra, xpref
 
 
+def accessible_volumes(fld: dict, n_side: int = 20) -> np.ndarray:
+    """UniformDensityField.get_accessible_volumes (fields.pyx:714-770) restated: with
+    assume_fully_accessible = 0 and a spherical confinement, a voxel cut by the sphere
+    (get_split_voxels 805-840: centre within sqrt(2)/4 of the largest voxel edge of the surface) keeps the
+    fraction of an n_side^3 sub-grid -- anchored at the voxel's lower corner, define_voxel_subgrid 842-880 --
+    that lies strictly inside (get_frac_accessible 882-951); every other voxel keeps vol_bin.  Pinned by the
+    `access_vols` array of tests/golden/static_av.npz (the reference's own output)."""
+    nx, ny, nz = fld["nx"], fld["ny"], fld["nz"]
+    n_bins = nx * ny * nz
+    dx, dy, dz = fld["x_width"] / nx, fld["y_width"] / ny, fld["z_width"] / nz
+    vol_bin = fld["x_width"] * fld["y_width"] * fld["z_width"] / n_bins
+    vols = np.full(n_bins, vol_bin)
+    if fld.get("assume_fully_accessible", 1) == 1 or fld.get("confine_type", "") != "Spherical":
+        return vols
+    R = fld["confine_length"]
+    buf = np.sqrt(2) / 4 * max(dx, dy, dz)
+    k = np.arange(n_side, dtype=float)
+    for b in range(n_bins):
+        ix, iy, iz = b % nx, (b // nx) % ny, b // (nx * ny)
+        # get_voxel_coords fields.pyx:795-799: `(nxyz[j] - 1) / 2` on C longs is FLOOR division (cdivision
+        # False, language_level 2): for an even grid the "centres" sit half a voxel below the true ones
+        c = np.array([(ix - (nx - 1) // 2) * dx, (iy - (ny - 1) // 2) * dy, (iz - (nz - 1) // 2) * dz])
+        dist = np.sqrt(c[0] ** 2 + c[1] ** 2 + c[2] ** 2)
+        if dist < R - buf or dist > R + buf:
+            continue
+        corner = c - np.array([dx / 2, dy / 2, dz / 2])
+        gx, gy, gz = np.meshgrid(corner[0] + k * (dx / n_side), corner[1] + k * (dy / n_side),
+                                 corner[2] + k * (dz / n_side), indexing="ij")
+        inside = np.sqrt(gx ** 2 + gy ** 2 + gz ** 2) < R
+        vols[b] = vol_bin * (inside.sum() / float(n_side ** 3))
+    return vols
+
+
 def amplitude_bounds(N: int, min_spacing: float):
     """get_amplitude_bounds, mc/__init__.py:295-332."""
     bead = {
@@ -382,7 +415,7 @@ class OracleSim:
                 s.half_width[j] = 0.5 * widths[j]
                 s.half_step[j] = 0.5 * (widths[j] / ns[j])
             s.vol_bin = widths[0] * widths[1] * widths[2] / n_bins
-            self.access_vol = np.full(n_bins, s.vol_bin)
+            self.access_vol = np.ascontiguousarray(accessible_volumes(fld))  # uniform unless assume_fully_accessible = 0
             s.confine_type = CONFINE[fld.get("confine_type", "")]
             s.confine_length = fld.get("confine_length", 0.0)
             s.chi = fld.get("chi", 1.0)
@@ -532,7 +565,8 @@ def ref_objects(spec: dict):
         field = fld.UniformDensityField(
             [poly], df, f["x_width"], f["nx"], f["y_width"], f["ny"], f["z_width"], f["nz"],
             confine_type=f.get("confine_type", ""), confine_length=f.get("confine_length", 0.0),
-            chi=f.get("chi", 1.0), vf_limit=f.get("vf_limit", 0.5))
+            chi=f.get("chi", 1.0), vf_limit=f.get("vf_limit", 0.5),
+            assume_fully_accessible=f.get("assume_fully_accessible", 1))
     mods = dict(polymers=ply, binders=bnd, fields=fld,
                 mc_sim=importlib.import_module("chromo.mc.mc_sim"),
                 mc_controller=importlib.import_module("chromo.mc.mc_controller"),

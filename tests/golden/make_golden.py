@@ -49,6 +49,9 @@ def golden_static(name, spec):
                             dtype=float)
     out["vol_bin"] = field.vol_bin
     out["bead_vol"] = poly.beads[0].vol
+    if spec["field"].get("assume_fully_accessible", 1) == 0:
+        av = field.access_vols  # {bin: volume} (fields.pyx:714-770)
+        out["access_vols"] = np.array([av[i] for i in range(field.n_bins)], dtype=float)
     np.savez_compressed(OUT / f"{name}.npz", **out)
     print(name, "E_field", out["E_field"], "E_poly", out["E_poly"])
 
@@ -161,6 +164,21 @@ def golden_csv(name, spec, polymer_name):
 
 if __name__ == "__main__":
     only = sys.argv[1:]  # e.g. `make_golden.py csv`: just the snapshot CSVs
+    if only == ["av"]:
+        # per-voxel accessible volumes (assume_fully_accessible = 0, fields.pyx:714-951): the voxels cut by
+        # the confining sphere are smaller, every w / V_access of the polymer's outer shell changes
+        av = O.make_spec(N=300, nb=1, seed=41)
+        av["field"] = dict(av["field"], assume_fully_accessible=0)
+        av2 = O.make_spec(N=200, nb=2, seed=42, cross_talk=-1.0, grid=7)
+        av2["field"] = dict(av2["field"], assume_fully_accessible=0)
+        golden_static("static_av", av)
+        golden_static("static_av2", av2)
+        golden_moves("moves_av", av, 300, 141)
+        golden_moves("moves_av2", av2, 250, 142)
+        avs = O.make_spec(N=300, nb=1, seed=41, random_states=False)
+        avs["field"] = dict(avs["field"], assume_fully_accessible=0)
+        golden_mc_sim("mcsim_av", avs, 10, 25, 35)
+        sys.exit(0)
     # snapshot CSVs: two-binder chromatin and a null_reader SSWLC (lp != 53 -> the SSWLC class)
     golden_csv("snapshot_chromatin", O.make_spec(N=40, nb=2, seed=11, cross_talk=-1.5), "Chr-1")
     golden_csv("snapshot_sswlc", O.make_spec(N=25, nb=1, seed=12, binders=[dict(O.NULL_READER)], confine="",

@@ -29,6 +29,9 @@ def engine_from_spec(spec, R=1, device=0, chi=None, mu=None):
         e.set_twist_params(spec["lt"] / ((bl / spec["lp"]) * spec["lp"]), bl * (2 * np.pi / 10.5) / 0.332)
     e.set_replica_params(chi=(f["chi"] if f is not None else 1.0) if chi is None else chi,
                          mu=[b["chemical_potential"] for b in spec["binders"]] if mu is None else mu)
+    if f is not None and f.get("assume_fully_accessible", 1) == 0:  # per-voxel accessible volumes (fields.pyx:714-951)
+        from chromo_b200.fields import accessible_volumes
+        e.set_access_volumes(accessible_volumes(f, 20, 0))
     tile = lambda a: np.broadcast_to(np.asarray(a), (R,) + np.asarray(a).shape).copy()
     e.upload(tile(spec["r"]), tile(spec["t3"]), tile(spec["t2"]), tile(spec["states"]), tile(spec["mods"]))
     if f is not None and f["nx"] * f["ny"] * f["nz"] > 0:

@@ -120,6 +120,34 @@ def test_c4_chromosome_scale(cuda_backend):
     ens.close()
 
 
+def test_c4_fine_grid(cuda_backend):
+    """C4 on the fine 130^3 grid (2.2 M voxels per replica): nothing in the kernels scans the grid
+    per move (the reference clears and walks all of it twice per move, fields.pyx:1223-1226, 1971-1975), so a
+    fine grid costs HBM footprint only.  Same invariants, the oracle agrees on the occupied voxels and the total
+    energies of one replica, and a short production run equals the oracle's on the same streams."""
+    ens, g, binders, Rc = _ensemble(2, 400_000, nb=1, seed=8, grid=130)
+    r0, t30, t20, st0 = ens.r.copy(), ens.t3.copy(), ens.t2.copy(), ens.states.copy()
+    spec0 = dict(N=400_000, nb=1, r=r0[1], t3=t30[1], t2=t20[1], states=st0[1], mods=ens.chemical_mods[1],
+                 bead_length=np.full(399_999, 16.5), lp=53.0, bead_rad=5.0, binders=binders, max_binders=-1,
+                 field=dict(g, chi=1.0))
+    ens.mc_sim(2, 1.0, 41, sync_host=True)
+    _invariants(ens, g, Rc)
+    o = O.OracleSim(_spec_of(ens, g, binders, 1))
+    d = ens.density()[1]
+    assert np.array_equal(d != 0, o.density != 0)
+    assert close(ens.field_energy()[1], o.field_E())
+    assert close(ens.elastic_energy()[1], o.poly_E())
+    # the same two sweeps on the CPU, from the same production streams
+    o2 = O.OracleSim(spec0)
+    o2.use_production_streams(41, 1)
+    mv = O.make_moves(400_000, 16.5)
+    o2.mc_sim(mv, 2, 0)
+    assert [int(x) for x in ens.moves["num_success"][1]] == [m.num_success for m in mv]
+    assert np.array_equal(ens.states[1], o2.states)
+    assert np.allclose(ens.r[1], o2.r, rtol=0, atol=1e-7)
+    ens.close()
+
+
 def test_replay_matches_oracle_at_c2_size(cuda_backend):
     """A replayed mc_sim at N = 10,000 reproduces the oracle's accept/reject
     counts and final configuration (the oracle needs ~0.2 s per 1,000 attempts here)."""

@@ -11,9 +11,9 @@ import pytest
 
 from common import close, close_dE, huge_scale, load_golden, split
 
-STATIC = ["static_c1", "static_c2", "static_c3", "static_c4", "static_tw", "static_tw2"]
-MOVES = ["moves_c1", "moves_c2", "moves_c3", "moves_c4", "moves_tw", "moves_tw2"]
-MCSIM = ["mcsim_c1", "mcsim_c2", "mcsim_c3", "mcsim_tw"]
+STATIC = ["static_c1", "static_c2", "static_c3", "static_c4", "static_tw", "static_tw2", "static_av", "static_av2"]
+MOVES = ["moves_c1", "moves_c2", "moves_c3", "moves_c4", "moves_tw", "moves_tw2", "moves_av", "moves_av2"]
+MCSIM = ["mcsim_c1", "mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_av"]
 
 
 @pytest.mark.parametrize("name", STATIC)
@@ -32,7 +32,7 @@ def test_static(oracle_mod, name):
     assert np.array_equal(s.density, g["density_after_E"])
     assert close(s.poly_E(), float(g["E_poly"]))
     # mass conservation (validate_density_calculation.ipynb): sum(rho*V) = N
-    assert abs(s.density[:, 0].sum() * s.s.vol_bin - spec["N"]) < 1e-9 * spec["N"]
+    assert abs((s.density[:, 0] * s.access_vol).sum() - spec["N"]) < 1e-9 * spec["N"]  # (V = the accessible volume)
 
 
 @pytest.mark.parametrize("name", MOVES)
@@ -118,3 +118,14 @@ def test_rng_known_answers(oracle_mod):
     a = [int(np.random.randint(0, 3)) for _ in range(500)]
     b = [O.lib().oc_mt_randint(C.byref(mt), 0, 3) for _ in range(500)]
     assert a == b
+
+
+@pytest.mark.parametrize("name", ["static_av", "static_av2"])
+def test_accessible_volumes_match_the_reference(oracle_mod, name):
+    """get_accessible_volumes (fields.pyx:714-951) restated in the oracle AND in the product's host code, against
+    the reference's own output -- including its floor-divided voxel centres on an even grid."""
+    from chromo_b200.fields import accessible_volumes
+    spec, g = load_golden(name)
+    assert np.array_equal(oracle_mod.accessible_volumes(spec["field"]), g["access_vols"])
+    assert np.array_equal(accessible_volumes(spec["field"], 20, 0), g["access_vols"])
+    assert (g["access_vols"] != float(g["vol_bin"])).sum() > 20

@@ -19,9 +19,9 @@ import pytest
 from common import close, close_dE, huge_scale, load_golden, split
 from gpu_common import engine_from_spec, moves_array
 
-STATIC = ["static_c1", "static_c2", "static_c3", "static_c4", "static_tw", "static_tw2"]
-MOVES = ["moves_c1", "moves_c2", "moves_c3", "moves_c4", "moves_tw", "moves_tw2"]
-MCSIM = ["mcsim_c1", "mcsim_c2", "mcsim_c3", "mcsim_tw"]
+STATIC = ["static_c1", "static_c2", "static_c3", "static_c4", "static_tw", "static_tw2", "static_av", "static_av2"]
+MOVES = ["moves_c1", "moves_c2", "moves_c3", "moves_c4", "moves_tw", "moves_tw2", "moves_av", "moves_av2"]
+MCSIM = ["mcsim_c1", "mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_av"]
 REPLAY, PHILOX = 1, 0
 
 
@@ -39,8 +39,8 @@ def test_full_recompute_and_total_energies(backend, name):
     for rep in range(3):
         assert close(E[rep], float(g["E_field"]))
         assert close(Ep[rep], float(g["E_poly"]))
-    vol_bin = float(g["vol_bin"])
-    assert np.allclose(d[..., 0].sum(axis=1) * vol_bin, spec["N"], rtol=1e-12)  # mass conservation
+    vols = g["access_vols"] if "access_vols" in g else float(g["vol_bin"])  # per-voxel volumes of the *_av cases
+    assert np.allclose((d[..., 0] * vols).sum(axis=1), spec["N"], rtol=1e-12)  # mass conservation
     e.close()
 
 
