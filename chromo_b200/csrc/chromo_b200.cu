@@ -87,6 +87,7 @@ struct chromo_ctx {
     double min_access_vol = 0.0; // smallest positive per-voxel volume (0: uniform voxels)
     bool have_binders = false, have_bonds = false, have_state = false;
     bool have_mods = false; // every replica's chemical_mods have been uploaded
+    bool force_l2_density = false; // test knob: full recompute through the L2-atomic kernel even on a small grid
     int64_t last_attempts = 0;
     int sm_count = 148;
     size_t smem_optin = 227 * 1024; // largest block
@@ -605,6 +606,30 @@ static int launch_recompute(chromo_ctx *c, int clamp) {
     if (!d.field_active) return fail(CHROMO_ERR_STATE, "context has no field");
     if (!c->have_state) return fail(CHROMO_ERR_STATE, "upload the polymer state first");
     size_t n = (size_t)d.R * d.n_bins * d.ncol;
+    const size_t priv_bytes = (size_t)d.n_bins * 16;
+    if (priv_bytes <= c->smem_optin && !c->force_l2_density) {
+        // the grid fits one block's shared memory: privatised, bit-reproducible accumulation (field_kernels.cuh)
+        double vmin = (d.access_vol && c->min_access_vol > 0.0) ? c->min_access_vol : d.vol_bin;
+        int smax = 1;
+        for (int a = 0; a < d.nb; a++) smax = std::max(smax, d.sites[a]);
+        int sbits = 0;
+        while ((1 << sbits) < smax) sbits++;
+        const long long chunks = ((long long)d.N + 65535) / 65536;
+        int cbits = 0;
+        while ((1LL << cbits) < chunks) cbits++;
+        const int fx_e = 61 - sbits - std::max(0, cbits - 2) + (int)ilogb(vmin);
+        dim3 grid(d.R, d.ncol);
+        int lrc = 0;
+        DISPATCH_NB(d.nb, {
+            auto k = density_private_kernel<NB>;
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)priv_bytes);
+            if (e != cudaSuccess) lrc = (int)e;
+            else CB_LAUNCH(k, grid, FK_PRIV_THREADS, priv_bytes, c->stream, d, clamp, fx_e);
+        });
+        if (lrc) return fail(CHROMO_ERR_CUDA, "density_private_kernel: %s", cudaGetErrorString((cudaError_t)lrc));
+        CK(cudaGetLastError());
+        return 0;
+    }
     CK(cudaMemsetAsync(d.density, 0, n * 8, c->stream));
     dim3 grid((d.N + FK_THREADS - 1) / FK_THREADS, d.R);
     DISPATCH_NB(d.nb, { auto k = density_scatter_kernel<NB>; CB_LAUNCH(k, grid, FK_THREADS, 0, c->stream, d); });

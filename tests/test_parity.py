@@ -227,9 +227,9 @@ def test_philox_is_deterministic_and_consistent(backend, oracle_mod):
             assert np.allclose(n3, 1.0, atol=1e-9)
         e.close()
     assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
-    # the initial full recompute uses fp64 atomics at L2 (order-dependent in the last ulp); the MC
-    # kernel's own updates are order-independent (see test_two_warps_per_replica_match_one)
-    assert np.allclose(runs[0][2], runs[1][2], rtol=1e-12, atol=1e-15 * runs[0][2].max())
+    # the full recompute (shared-memory privatised, fixed point) and the MC kernel's own updates are both
+    # independent of the order in which lanes arrive: the densities of two runs are identical to the last bit
+    assert np.array_equal(runs[0][2], runs[1][2])
     assert not np.array_equal(runs[0][0][0], runs[0][0][1])
     acc = runs[0][3]["num_success"].sum() / runs[0][3]["num_attempt"].sum()
     assert 0.2 < acc < 0.95
@@ -350,6 +350,6 @@ def test_host_array_path_matches_resident_path(backend, oracle_mod):
     for n_chunks in (0, 3):
         for a, b in zip(out[-1][:5], out[n_chunks][:5]):
             assert a.tobytes() == b.tobytes()
-        # the initial full recompute adds with fp64 atomics in arrival order: densities agree to rounding
-        assert np.allclose(out[-1][5], out[n_chunks][5], rtol=1e-12, atol=1e-18)
+        # full recompute and incremental updates are order-independent: identical densities for any chunking
+        assert np.array_equal(out[-1][5], out[n_chunks][5])
     assert not np.array_equal(out[-1][0], st("r"))

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out/r02
 T=${1:-v15}
-python -m pytest tests -m gpu -x -q > gpurun_out/r02/gpu_tests_$T.log 2>&1
+python -m pytest tests -m gpu -q > gpurun_out/r02/gpu_tests_$T.log 2>&1
 tail -3 gpurun_out/r02/gpu_tests_$T.log
 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/r02/bench_ref_$T.json 2> gpurun_out/r02/bench_ref_$T.err
 python bench.py --steps 10 --warmup 3 > gpurun_out/r02/bench_$T.json 2> gpurun_out/r02/bench_$T.err
