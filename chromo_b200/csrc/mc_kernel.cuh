@@ -88,7 +88,7 @@ struct WarpSh {
     int overflow;
     int last_U;                      // touched voxels of the last field dE (all passes)
     int passes;
-    uint32_t draws[16];              // per-bead axis draws of tangent rotation (8 beads per chunk)
+    uint32_t draws[32];              // per-bead axis draws of tangent rotation (16 beads per chunk)
     signed char newst[CB_NEWST];     // new binding states (small path)
 };
 
@@ -423,6 +423,7 @@ __device__ __forceinline__ void table_energy(const DevCtx &C, const HashTable &H
     constexpr int NCOL = NB + 1;
     int cnt = S.count;
     const double *dens = C.density + (long long)rep * C.n_bins * NCOL;
+    const double chi_Vv = chi * (C.vol_bin / C.bead_vol); // chi * (V / v_bead) of a uniform voxel: one division per move
     for (int j = lane; j < cnt; j += 32) {
         int slot = H.list[j];
         int bin = H.keys[slot];
@@ -451,14 +452,15 @@ __device__ __forceinline__ void table_energy(const DevCtx &C, const HashTable &H
                     F.cross[a * NB + b] += t;
                 }
         }
-        double V = C.access_vol ? C.access_vol[bin] : C.vol_bin;
+        // chi * (V_access / v_bead) * phi^2 (fields.pyx:1829-1840), evaluated as (chi * (V / v)) * (phi * phi)
+        const double k = C.access_vol ? chi * (C.access_vol[bin] / C.bead_vol) : chi_Vv;
         double vf0 = rho[0] * C.bead_vol;
         double vf1 = vf0 + (dr0 * C.bead_vol);
         double e = 0.0;
         if (vf1 > C.vf_limit) e += CB_E_HUGE_FIELD * vf1;
-        else e += chi * (V / C.bead_vol) * (vf1 * vf1);
+        else e += k * (vf1 * vf1);
         if (vf0 > C.vf_limit) e -= CB_E_HUGE_FIELD * vf0;
-        else e -= chi * (V / C.bead_vol) * (vf0 * vf0);
+        else e -= k * (vf0 * vf0);
         F.chi += e;
     }
 }
@@ -1307,11 +1309,11 @@ struct McWarp {
     // per selected bead: own random axis, rotate t3/t2, both adjacent bonds
     // against the CURRENT neighbours (polymers.pyx:1075-1080; quirk 8); never
     // touches the field (mc_sim.pyx:145).
-    // One bead is evaluated by 4 lanes (one bond energy each: left bond trial /
-    // as is, right bond trial / as is), up to 8 beads per call.  The axis comes
-    // either from the prepared record (`axfix`, the common single-bead case) or
-    // from per-bead draws.  New tangents of chunk bead j go to out[6j..6j+5]
-    // (shared) when `out` is given, or straight to global memory when `store`.
+    // One bead is evaluated by 2 lanes -- its left bond and its right bond, each with the bead's trial
+    // tangents and as it is -- up to 16 beads per call (v14: 4 lanes per bead, 8 beads per call: the typical
+    // window of 14 needed two calls with a nearly empty second one).  The axis comes either from the prepared
+    // record (`axfix`, the common single-bead case) or from per-bead draws.  New tangents of chunk bead j go
+    // to out[6j..6j+5] (shared) when `out` is given, or straight to global memory when `store`.
     // Returns acc_in + the chunk's dE on all lanes (bead-by-bead sum).
     __device__ __forceinline__ double tangent_chunk(const int *beads, int cnt, const uint32_t *draws,
                                                     const double *axfix, double sn, double cs, double *out,
@@ -1319,8 +1321,8 @@ struct McWarp {
         const double *Rr = R_();
         double *T3 = T3_(), *T2 = T2_();
         const int N = C.N;
-        const int j = lane >> 2, which = lane & 3;
-        double e = 0.0;
+        const int j = lane >> 1, right = lane & 1;
+        double dside = 0.0;
         if (j < cnt) {
             const int bead = beads[j];
             double Rm[9], t3c[3], t2c[3], t3n[3], t2n[3], rc[3], axis[3];
@@ -1336,13 +1338,16 @@ struct McWarp {
             load3(Rr + 3 * bead, rc);
             apply_rot3(Rm, t3c, t3n);
             apply_rot3(Rm, t2c, t2n);
-            const bool left = which < 2;
-            const bool present = left ? (bead != 0) : (bead + 1 != N);
+            const bool present = right ? (bead + 1 != N) : (bead != 0);
             if (!store && present) {
-                const int moved = (which & 1) ? 0 : (left ? 2 : 1);
-                e = pair_energy(C, rep, left ? bead - 1 : bead, moved, rc, t3n, t2n);
+                // E(bond with the bead's trial tangents) - E(bond as it is); the bead is the second bead of
+                // its left bond and the first of its right bond
+                const int bond = right ? bead : bead - 1;
+                const double e_trial = pair_energy(C, rep, bond, right ? 1 : 2, rc, t3n, t2n);
+                const double e_cur = pair_energy(C, rep, bond, 0, rc, t3n, t2n);
+                dside = e_trial - e_cur;
             }
-            if (which == 0) {
+            if (!right) {
                 if (out) {
                     store3(out + 6 * j, t3n);
                     store3(out + 6 * j + 3, t2n);
@@ -1362,23 +1367,21 @@ struct McWarp {
             }
         }
         // per bead: (0 + (E_left' - E_left)) + (E_right' - E_right); then bead by bead
-        const double l0 = __shfl_down_sync(FULL_MASK, e, 1), r0 = __shfl_down_sync(FULL_MASK, e, 2),
-                     r1 = __shfl_down_sync(FULL_MASK, e, 3);
-        const double d = (e - l0) + (r0 - r1); // valid on which == 0 lanes
+        const double d = dside + __shfl_down_sync(FULL_MASK, dside, 1); // valid on the left-bond lanes
         double tot = acc_in;
-        for (int b = 0; b < cnt; b++) tot += __shfl_sync(FULL_MASK, d, 4 * b);
+        for (int b = 0; b < cnt; b++) tot += __shfl_sync(FULL_MASK, d, 2 * b);
         return tot;
     }
 
-    // k > 1 beads, 8 per chunk: energies or stores.  The two axis draws of bead b are draws
+    // k > 1 beads, 16 per chunk: energies or stores.  The two axis draws of bead b are draws
     // `first + 2b`, `first + 2b + 1` of the attempt's stream: with the counter-based generator
     // (`par`) every bead's lane fetches its own, otherwise lane 0 draws them in order.
     __device__ __forceinline__ double tangent_eval_multi(const int *inds, int k, double sn, double cs,
                                                          bool small, bool store, bool par,
                                                          unsigned long long att, uint32_t first) {
         double dE_poly = 0.0;
-        for (int base = 0; base < k; base += 8) {
-            const int cnt = min(8, k - base);
+        for (int base = 0; base < k; base += 16) {
+            const int cnt = min(16, k - base);
             if (BATCH && par) {
                 if (lane < cnt) {
                     Rng g = rng;
