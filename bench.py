@@ -585,6 +585,19 @@ def extra_legs(args, rank, world, local, dist, inputs):
         ms = rank_max(ev[0].elapsed_time(ev[2 * rounds]))
         ex_us = rank_max(1e3 * sum(ev[1 + 2 * k].elapsed_time(ev[2 + 2 * k]) for k in range(rounds)) / rounds)
         rung, chi_local, tried, acc = ex.state()
+        phi = ex.phi_all.cpu().numpy().copy()
+        # the exchange machinery alone: back-to-back rounds with the ranks in lockstep (inside the run above the
+        # all-gather also waits for the slowest rank's sweeps -- that wait is load imbalance, not exchange cost)
+        sync_all()
+        reps = 20
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record(stream)
+        for k in range(reps):
+            ex.step()
+        x1.record(stream)
+        ens.engine.sync()
+        torch.cuda.synchronize()
+        ex_alone_us = rank_max(1e3 * x0.elapsed_time(x1) / reps)
         same = True
         if dist is not None:  # every rank must hold the same permutation
             a = torch.as_tensor(rung.astype(np.int64), device=dev)
@@ -592,12 +605,12 @@ def extra_legs(args, rank, world, local, dist, inputs):
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             same = bool(torch.equal(lo, hi))
-        phi = ex.phi_all.cpu().numpy()
         by_rung = np.stack([phi[rung[l0:l0 + L]] for l0 in range(0, total5, L)]).mean(axis=0)
         out["c5_exchange"] = dict(
             value=total5 * sweeps * ATTEMPTS_PER_SWEEP * rounds / (ms * 1e-3), unit=UNIT, replicas_total=total5,
             replicas_per_gpu=R5, ladders=total5 // L, rungs_per_ladder=L, chi_range=[0.25, 4.0],
-            sweeps_between_exchanges=sweeps, rounds=rounds, ms_per_round=ms / rounds, exchange_us_per_round=ex_us,
+            sweeps_between_exchanges=sweeps, rounds=rounds, ms_per_round=ms / rounds,
+            exchange_us_per_round=ex_alone_us, exchange_us_per_round_incl_wait_for_slowest_rank=ex_us,
             swap_acceptance=(acc - acc0) / max(1, tried - tried0), ladders_identical_on_all_ranks=same,
             labels_are_permutations=bool(all(sorted(rung[l0:l0 + L]) == list(range(l0, l0 + L)) for l0 in range(0, total5, L))),
             mean_phi_first_rung=float(by_rung[0]), mean_phi_last_rung=float(by_rung[-1]),
@@ -648,8 +661,9 @@ def main():
     args = ap.parse_args()
     quiet_stdout()
     if args.lib:
-        from chromo_b200 import _lib
-        _lib.use_library(args.lib)
+        sys.path.insert(0, str(ROOT / "tests"))
+        import devlib
+        devlib.use_library(args.lib)
     if args.impl == "reference":
         run_reference(args)
     else:

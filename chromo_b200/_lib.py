@@ -135,14 +135,6 @@ def _declare(L):
     return L
 
 
-def use_library(path):
-    """TEST HOOK: bind a specific build of the C ABI (tests/host_emu uses it to
-    debug kernel logic on a GPU-less box).  The package itself never calls it."""
-    global _LIB
-    _LIB = _declare(C.CDLL(str(path)))
-    return _LIB
-
-
 def lib():
     """The CUDA library.  Fails loudly when it has not been built."""
     global _LIB

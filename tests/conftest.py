@@ -51,7 +51,8 @@ def backend(request, emu_lib):
     sm_100a library ("cuda", GPU box) for the duration of one test."""
     from chromo_b200 import _lib
     if request.param == "emu":
-        _lib.use_library(emu_lib)
+        import devlib
+        devlib.use_library(emu_lib)
     else:
         _lib._LIB = None
         _lib.lib()

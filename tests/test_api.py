@@ -37,11 +37,12 @@ def build(spec, lazy=False):
     f = spec["field"]
     field = fld.UniformDensityField([p], binders, f["x_width"], f["nx"], f["y_width"], f["ny"], f["z_width"],
                                     f["nz"], confine_type=f["confine_type"], confine_length=f["confine_length"],
-                                    chi=f["chi"], vf_limit=f["vf_limit"])
+                                    chi=f["chi"], vf_limit=f["vf_limit"],
+                                    assume_fully_accessible=f.get("assume_fully_accessible", 1))
     return p, binders, field
 
 
-@pytest.mark.parametrize("name", ["static_c2", "static_c3", "static_tw2"])
+@pytest.mark.parametrize("name", ["static_c2", "static_c3", "static_tw2", "static_av"])
 def test_construction_and_energies(backend, name):
     spec, g = load_golden(name)
     p, binders, field = build(spec)
@@ -255,3 +256,26 @@ def test_ensemble_from_twisted_polymers_keeps_the_twist_term(backend):
     ens.mc_sim(1, 1.0, 3)
     assert np.isfinite(ens.elastic_energy()).all() and ens.acceptance()["crank_shaft"] > 0
     ens.close()
+
+
+def test_ensemble_from_polymers_coarse_grains_and_refines(backend):
+    """from_polymers -> coarse_grained -> refined (the workflow INTEGRATION.md advertises): the ensemble carries
+    the binders' interaction parameters, so the prefactors are rebuilt on the coarser / finer grid, and the
+    field's accessible-volume setting with them."""
+    from chromo_b200.ensemble import ReplicaEnsemble
+    spec, g = load_golden("static_av2")  # two binders with cross-talk, assume_fully_accessible = 0
+    built = [build(spec) for _ in range(2)]
+    polys, fields = [b[0] for b in built], [b[2] for b in built]
+    ens = ReplicaEnsemble.from_polymers(polys, fields)
+    assert ens.assume_fully_accessible == 0
+    pre = ens.prefactors_from_binders(ens.binders, ens.grid)
+    assert np.allclose(pre[0], g["field_pref"]) and np.allclose(pre[1], g["e_intra"]) and np.allclose(pre[2], g["xpref"])
+    cg = ens.coarse_grained(4)
+    assert cg.N == spec["N"] // 4 and cg.assume_fully_accessible == 0
+    E = cg.field_energy()
+    assert np.isfinite(E).all() and E[0] == E[1]
+    cg.mc_sim(1, 1.0, 3)
+    fine = cg.refined(spec["N"] + 1, 16.5, np.concatenate([spec["mods"], spec["mods"][:1]])[None], seed=4)
+    assert fine.N == spec["N"] + 1 and fine.assume_fully_accessible == 0 and np.isfinite(fine.field_energy()).all()
+    for e in (fine, cg, ens):
+        e.close()

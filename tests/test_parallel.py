@@ -121,7 +121,8 @@ def _device_worker(rank, world, port, q, emu_lib):
         import oracle as O
         from chromo_b200 import _lib
         from chromo_b200.ensemble import ReplicaEnsemble, default_moves
-        _lib.use_library(emu_lib)
+        import devlib
+        devlib.use_library(emu_lib)
         R, N, L = 4, 60, 4  # 4 replicas per rank, two ladders of 4 rungs
         n_total = R * world
         specs = [O.make_spec(N=N, nb=1, seed=70 + rank * R + i) for i in range(R)]

@@ -107,7 +107,7 @@ def test_mc_sim_replay(backend, name):
     final configuration."""
     exact = backend == "emu"
     spec, g = load_golden(name)
-    R = 2
+    R = 1 if exact else 2  # (the CPU emulation runs ~1 ms per attempt and replica)
     e = engine_from_spec(spec, R=R)
     mv = moves_array(spec, R, tuple(int(x) for x in g["per_cycle"]))
     e.srand(int(g["srand_seed"]))
@@ -128,7 +128,7 @@ def test_mc_sim_replay(backend, name):
     assert np.allclose(e.density()[0], g["final_density"], rtol=1e-9, atol=1e-9 / vol_bin)
     E, _, _, _ = e.field_energy()
     assert close(E[0], float(g["E_field"]), 1e-9 if exact else 1e-7)
-    assert close(e.elastic_energy()[1], float(g["E_poly"]), 1e-9 if exact else 1e-7)
+    assert close(e.elastic_energy()[R - 1], float(g["E_poly"]), 1e-9 if exact else 1e-7)
     e.close()
 
 
@@ -212,7 +212,7 @@ def test_philox_is_deterministic_and_consistent(backend, oracle_mod):
     for _ in range(2):
         e = engine_from_spec(spec, R=R)
         mv = moves_array(spec, R)
-        e.mc_sim(4, mv, 1.0, 77, PHILOX)
+        e.mc_sim(2 if backend == "emu" else 4, mv, 1.0, 77, PHILOX)
         r, t3, t2, st = e.download()
         dens = e.density()
         runs.append((r, st, dens, mv.copy()))
@@ -322,7 +322,7 @@ def test_host_array_path_matches_resident_path(backend, oracle_mod):
     upload + mc_sim + download bit for bit, for any chunking: replicas have their own streams."""
     from chromo_b200.ensemble import ReplicaEnsemble, default_moves
     O = oracle_mod
-    R, N = 9, 60
+    R, N = (5 if backend == "emu" else 9), 60
     specs = [O.make_spec(N=N, nb=1, seed=50 + i) for i in range(R)]
     st = lambda k: np.stack([s[k] for s in specs])
     kw = dict(binders=specs[0]["binders"], bond_params=O.bond_params(specs[0]["bead_length"], 53.0),

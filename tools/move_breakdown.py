@@ -40,7 +40,9 @@ def main():
     R, N = a.replicas, a.beads
     if a.lib:
         from chromo_b200 import _lib
-        _lib.use_library(a.lib)
+        sys.path.insert(0, str(ROOT / "tests"))
+        import devlib
+        devlib.use_library(a.lib)
     r, t3, t2, states, mods, grid = bench.make_inputs(R, N, 1234, pinned=False)
     ens = ReplicaEnsemble(r, t3, t2, states, mods, binders=[dict(bench.HP1)], bond_params=bench.bond_params(N),
                           grid=grid, bead_vol=(4 / 3) * math.pi * 5.0 ** 3, chi=1.0, mu=[-1.2],

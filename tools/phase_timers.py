@@ -38,7 +38,9 @@ def main():
     ap.add_argument("--warps", default="1,2")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    _lib.use_library(a.lib)
+    sys.path.insert(0, str(ROOT / "tests"))
+    import devlib
+    devlib.use_library(a.lib)
     L = C.CDLL(a.lib)
     R, N = a.replicas, a.beads
     r, t3, t2, states, mods, grid = bench.make_inputs(R, N, 1234, pinned=False)
