@@ -351,6 +351,15 @@ extern "C" int chromo_ctx_set_batch_size(chromo_ctx *c, int64_t batch) {
     c->d.batch = (int)batch;
     return CHROMO_OK;
 }
+extern "C" int chromo_ctx_set_fast_field(chromo_ctx *c, int64_t n_points) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    if (n_points < 0 || n_points > 1000000) return fail(CHROMO_ERR_ARG, "n_points out of range");
+    if (n_points > 0 && !c->d.field_active) return fail(CHROMO_ERR_STATE, "context has no field");
+    n_points += n_points % 2; // fields.pyx:603
+    c->d.fast_n = (int)n_points;
+    for (int j = 0; j < 3; j++) c->d.fast_sbw[j] = n_points ? c->d.dxyz[j] / (double)n_points : 0.0;
+    return CHROMO_OK;
+}
 extern "C" int chromo_get_rng_counters(chromo_ctx *c, int64_t first, int64_t n, uint64_t *counters) {
     if (!c || !counters) return fail(CHROMO_ERR_ARG, "null argument");
     if (first < 0 || n < 0 || first + n > c->d.R) return fail(CHROMO_ERR_ARG, "replica range out of bounds");

@@ -58,6 +58,29 @@ __device__ __forceinline__ void bin_axis(double x, double half_width, double wid
     ind_hi = (ind_lo + 1 >= n) ? ind_lo + 1 - n : ind_lo + 1;
 }
 
+// fast_field = 1 (init_fast_field fields.pyx:577-671, get_change_in_density_quickly 1235-1368): the position is
+// quantised to sub-bin i = floor((x + W/2) / sbw) % (n_points n) (numpy floor, Python modulo) and binned from the
+// sub-bin's lower edge x_i = (i - n_points/2) sbw: ind = floor(x_i / d), weight 1 - (x_i / d - ind).  The
+// reference reads these from per-axis tables built once; the same IEEE operations here give the same doubles.
+__device__ __forceinline__ void bin_axis_fast(double x, double half_width, double sbw, double d, int n, int npts,
+                                              int &ind_lo, int &ind_hi, double &w_lo) {
+    const double nsub = (double)npts * (double)n;
+    double f = floor((x + half_width) / sbw);
+    double sub = fmod(f, nsub);
+    if (sub != 0.0 && sub < 0.0) sub += nsub;
+    const double xi = ((double)((long long)sub - npts / 2) * sbw) / d;
+    const double fl = floor(xi);
+    const int ind = (int)fl;
+    w_lo = 1.0 - (xi - fl);
+    ind_lo = (ind == -1) ? n - 1 : ind;
+    ind_hi = (ind_lo + 1 >= n) ? ind_lo + 1 - n : ind_lo + 1;
+}
+static __device__ CB_NOINLINE void bin_axes_fast(const DevCtx &C, const double p[3], int lo[3], int hi[3], double wl[3]) {
+    bin_axis_fast(p[0], C.half_width[0], C.fast_sbw[0], C.dxyz[0], C.nx, C.fast_n, lo[0], hi[0], wl[0]);
+    bin_axis_fast(p[1], C.half_width[1], C.fast_sbw[1], C.dxyz[1], C.ny, C.fast_n, lo[1], hi[1], wl[1]);
+    bin_axis_fast(p[2], C.half_width[2], C.fast_sbw[2], C.dxyz[2], C.nz, C.fast_n, lo[2], hi[2], wl[2]);
+}
+
 // lower / upper voxel index and lower-voxel weight along each axis
 __device__ __forceinline__ void bin_axes(const DevCtx &C, const double p[3], int lo[3], int hi[3],
                                          double wl[3]) {

@@ -246,6 +246,7 @@ template <bool GEN>
 __device__ __forceinline__ long long fx_term(const DevCtx &C, double w, int bin, double scale) {
     const double d = (GEN && C.access_vol) ? div_access(C.access_vol, bin, w) : div_const(w, C.vol_bin, C.inv_vol_bin);
     if (!GEN) return __double2ll_rn(d * scale); // (the 1e-18 threshold is implied by the format, see fx_format)
+    if (C.fast_n) return __double2ll_rn(d * scale); // fast_field adds every term (fields.pyx:1350-1366)
     return fabs(d) > 1E-18 ? __double2ll_rn(d * scale) : 0ll;
 }
 // one voxel contribution: `v` to the bead column (unless `no_bead`), v * mult[m] to binder column m
@@ -327,7 +328,8 @@ __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, Warp
             load3(Rr + 3 * bead, x);
 #pragma unroll
             for (int m = 0; m < NB; m++) mult[m] = ST[bead * NB + m];
-            bin_axes(C, x, clo, chi, cw);
+            if (GEN && C.fast_n) bin_axes_fast(C, x, clo, chi, cw);
+            else bin_axes(C, x, clo, chi, cw);
             if (kind == 2) {
                 // state change only: the bead column cancels exactly (quirk 4), the binder's column gets
                 // w/V * (s' - s)
@@ -347,7 +349,8 @@ __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, Warp
                         for (int j = 0; j < 3; j++) out_t += (fabs(y[j]) > C.confine_length / 2);
                     }
                 }
-                bin_axes(C, y, tlo, thi, tw);
+                if (GEN && C.fast_n) bin_axes_fast(C, y, tlo, thi, tw);
+                else bin_axes(C, y, tlo, thi, tw);
                 merged = clo[0] == tlo[0] && clo[1] == tlo[1] && clo[2] == tlo[2];
             }
             // ---- pass 1: the current cell's corners l (bit0 x, bit1 y, bit2 z), this lane's share ----
@@ -524,7 +527,7 @@ template <int NB>
 __device__ __forceinline__ int2 field_scatter(const DevCtx &C, HashTable &H, WarpSh &S, int rep, int lane,
                                               int kind, int ind0, int n, int binder, const signed char *newst) {
     int2 conf;
-    if (C.access_vol || n > 2048) conf = scatter_pass_cold<NB>(C, H, &S, rep, lane, kind, ind0, n, binder, newst, 1, 0);
+    if (C.access_vol || n > 2048 || C.fast_n) conf = scatter_pass_cold<NB>(C, H, &S, rep, lane, kind, ind0, n, binder, newst, 1, 0);
     else if (kind == 2) conf = scatter_pass<NB, false, 2>(C, H, S, rep, lane, kind, ind0, n, binder, newst, 1, 0, fx_format(C, n));
     else conf = scatter_pass<NB, false, 0>(C, H, S, rep, lane, kind, ind0, n, binder, newst, 1, 0, fx_format(C, n));
     __syncwarp();

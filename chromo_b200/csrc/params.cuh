@@ -48,6 +48,8 @@ struct DevCtx {
     uint32_t *glibc;                 // [R][GLIBC_WORDS]
     uint32_t *mt;                    // [R][MT_WORDS]
     unsigned long long *philox_ctr;  // [R]
+    int fast_n;                      // fast_field: sub-bins per voxel edge (even), 0 = exact binning
+    double fast_sbw[3];              // fast_field: sub-bin widths dx / n_points (fields.pyx:604-606)
     unsigned rep_offset;             // global index of replica 0 (key of the production streams)
     int batch;                       // attempts prepared at once in the production kernels (1..32)
     int *tan_inds;                   // [R][N]   tangent-rotation large path

@@ -275,6 +275,11 @@ class Engine:
         """Attempts prepared at once by the production kernels (1..32; test knob, results do not depend on it)."""
         check(self._L.chromo_ctx_set_batch_size(self._h, int(batch)))
 
+    def set_fast_field(self, n_points: int) -> None:
+        """fast_field = 1 of the reference's UniformDensityField: sub-bin quantised binning in the dE path
+        (`n_points` sub-bins per voxel edge; 0 switches it off)."""
+        check(self._L.chromo_ctx_set_fast_field(self._h, int(n_points)))
+
     def rng_counters(self) -> np.ndarray:
         """Attempts made so far per replica = position of its production random stream."""
         out = np.zeros(self.R, dtype=np.uint64)

@@ -48,7 +48,7 @@ class ReplicaEnsemble:
                  grid: Optional[dict], bead_vol: float, chi=1.0, mu=None, max_binders: int = -1,
                  moves: Optional[np.ndarray] = None, min_spacing: Optional[float] = None,
                  access_vol=None, device: int = 0, field_prefactors=None, assume_fully_accessible: int = 1,
-                 replica_offset: int = 0):
+                 replica_offset: int = 0, fast_field_points: int = 0):
         self.r = np.ascontiguousarray(r, dtype=np.float64)
         self.R, self.N = self.r.shape[0], self.r.shape[1]
         self.t3 = np.ascontiguousarray(t3, dtype=np.float64)
@@ -75,6 +75,9 @@ class ReplicaEnsemble:
             access_vol = accessible_volumes(grid, 20, assume_fully_accessible)  # fields.pyx:714-770
         if access_vol is not None:
             self.engine.set_access_volumes(access_vol)
+        self.fast_field_points = int(fast_field_points)
+        if self.fast_field_points:
+            self.engine.set_fast_field(self.fast_field_points)
         self.replica_offset = int(replica_offset)
         if replica_offset:
             self.engine.set_replica_offset(replica_offset)
@@ -259,7 +262,7 @@ class ReplicaEnsemble:
                                grid=g, bead_vol=self.bead_vol, chi=self.chi, mu=self.mu, max_binders=self.max_binders,
                                moves=default_moves(self.R, N, spacing), min_spacing=self.min_spacing,
                                device=self.device, assume_fully_accessible=self.assume_fully_accessible,
-                               replica_offset=self.replica_offset)
+                               replica_offset=self.replica_offset, fast_field_points=self.fast_field_points)
 
     def coarse_grained(self, cg_factor: int):
         """Every replica coarse-grained by `cg_factor` (get_cg_chromatin + get_cg_udf, rediscretize.py:
@@ -344,5 +347,6 @@ class ReplicaEnsemble:
                   max_binders=p0.max_binders, moves=moves, min_spacing=float(np.min(p0.bead_length)),
                   access_vol=None if getattr(f0, "assume_fully_accessible", 1) == 1 else f0.access_vols,
                   device=device, field_prefactors=pre,
-                  assume_fully_accessible=getattr(f0, "assume_fully_accessible", 1))
+                  assume_fully_accessible=getattr(f0, "assume_fully_accessible", 1),
+                  fast_field_points=int(getattr(f0, "n_points", 0)) if getattr(f0, "fast_field", 0) == 1 else 0)
         return ens

@@ -5,8 +5,8 @@ Constructor signatures, attribute names and error behaviour follow the
 reference.  The voxel densities live in HBM; `field.density` is a host copy
 refreshed after every device call that changes it.  All energy evaluation
 happens in the CUDA kernels (chromo_b200/csrc) -- nothing here computes a dE.
-Out of scope: `fast_field=1` (a CPU-only approximation that changes binning
-results, fields.pyx:577-671), Reconstructor, neighbour-bin helpers.
+`fast_field=1` (sub-bin quantised binning in the dE path, fields.pyx:577-671, 1235-1368) is a
+kernel option (`chromo_ctx_set_fast_field`).  Out of scope: Reconstructor, neighbour-bin helpers.
 """
 from __future__ import annotations
 
@@ -163,9 +163,6 @@ class UniformDensityField(FieldBase):
         if len(polymers) != 1:
             raise NotImplementedError("chromo_b200 evaluates one polymer per field (fields.pyx:53-59); "
                                       "use chromo_b200.ensemble.ReplicaEnsemble for many replicas.")
-        if fast_field == 1:
-            raise NotImplementedError("fast_field=1 (precomputed sub-bin weights, fields.pyx:577-671) is a "
-                                      "CPU-only approximation that changes binning results; not provided.")
         self.x_width, self.y_width, self.z_width = float(x_width), float(y_width), float(z_width)
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
         self.init_grid()
@@ -255,6 +252,8 @@ class UniformDensityField(FieldBase):
         e = super()._engine_for(poly)
         if fresh and self.assume_fully_accessible != 1:
             e.set_access_volumes(self.access_vols)
+        if fresh and self.fast_field == 1:  # sub-bin quantised binning in the dE path (fields.pyx:577-671, 1235-1368)
+            e.set_fast_field(self.n_points)
         return e
 
     # ---- full recompute / total energy (A8) ----------------------------------

@@ -144,6 +144,11 @@ int chromo_ctx_set_replica_offset(chromo_ctx *ctx, int64_t offset);
  * is prepared at once by the lanes of a warp in the production kernels, 1..32
  * (default 32).  Results must not depend on it (tests/test_philox_parity.py). */
 int chromo_ctx_set_batch_size(chromo_ctx *ctx, int64_t batch);
+/* fast_field = 1 of UniformDensityField (init_fast_field fields.pyx:577-671, get_change_in_density_quickly
+ * 1235-1368): the dE path bins positions quantised to n_points sub-bins per voxel edge (rounded up to an even
+ * number, as the reference does) and adds every term (no 1e-18 filter).  0 = exact binning (default).  The full
+ * recompute and compute_E are not affected (they are not in the reference either). */
+int chromo_ctx_set_fast_field(chromo_ctx *ctx, int64_t n_points);
 /* Attempts every replica has made so far = position of its production random
  * stream (counters[n] for replicas [first, first+n)).  Saved and restored with a
  * snapshot so that a resumed run continues the stream instead of replaying it. */

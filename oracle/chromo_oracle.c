@@ -225,6 +225,38 @@ static int64_t super_index(const oc_sim *s, int64_t ix, int64_t iy, int64_t iz)
 
 /* fields.pyx:1437-1462 (per-axis wrap/index/weight), 1524-1598 (8 weights),
  * 1600-1673 (8 super-indices).  Quirk 2: the weight uses the UNPATCHED ind. */
+/* fast_field = 1: init_fast_field fields.pyx:577-671 precomputes, for every sub-bin i of an axis (n_points per
+ * voxel edge), the lower voxel index and its weight from the sub-bin's LOWER EDGE
+ *   x_i = (i - n_points/2) * sub_bin_width,  ind = floor(x_i / d),  lower = (ind == -1 ? n-1 : ind),
+ *   lower_weight = 1 - (x_i / d - ind);
+ * get_change_in_density_quickly 1235-1368 looks a position up by
+ *   i = floor((x + W/2) / sub_bin_width) % (n_points * n)   (numpy floor, Python modulo),
+ * and adds the terms without the 1e-18 filters of the exact path.  Same quantities, computed on the fly. */
+static void bin_point_fast(const oc_sim *s, const double xyz[3], int64_t idx[8], double w[8])
+{
+    int64_t n3[3] = {s->nx, s->ny, s->nz};
+    int64_t ind3[3];
+    double w3[3];
+    int j, l;
+    for (j = 0; j < 3; j++) {
+        double sbw = s->dxyz[j] / (double)s->fast_n_points;
+        double nsub = (double)(s->fast_n_points * n3[j]);
+        double sub = py_mod(floor((xyz[j] + s->half_width[j]) / sbw), nsub);
+        double xi = ((double)((int64_t)sub - s->fast_n_points / 2) * sbw) / s->dxyz[j];
+        int64_t ind = (int64_t)floor(xi);
+        ind3[j] = (ind == -1) ? n3[j] - 1 : ind;
+        w3[j] = 1 - (xi - (double)ind);
+    }
+    for (l = 0; l < 8; l++) {
+        int bx = l & 1, by = (l >> 1) & 1, bz = (l >> 2) & 1;
+        double wx = bx ? (1 - w3[0]) : w3[0];
+        double wy = by ? (1 - w3[1]) : w3[1];
+        double wz = bz ? (1 - w3[2]) : w3[2];
+        w[l] = wx * wy * wz;
+        idx[l] = super_index(s, ind3[0] + bx, ind3[1] + by, ind3[2] + bz);
+    }
+}
+
 void oc_bin_point(const oc_sim *s, const double xyz[3], int64_t idx[8], double w[8])
 {
     int64_t n_m1[3] = {s->nx - 1, s->ny - 1, s->nz - 1};
@@ -561,9 +593,12 @@ static void change_in_density(oc_sim *s, const int64_t *inds, int64_t n, int sta
         int64_t idx[2][8];
         double w[2][8];
         int64_t bead = inds[i];
-        oc_bin_point(s, &s->r[3 * bead], idx[0], w[0]);
+        const int fast = s->fast_n_points > 0;
+        if (fast) bin_point_fast(s, &s->r[3 * bead], idx[0], w[0]);
+        else oc_bin_point(s, &s->r[3 * bead], idx[0], w[0]);
         if (state_change == 0) {
-            oc_bin_point(s, &s->r_trial[3 * bead], idx[1], w[1]);
+            if (fast) bin_point_fast(s, &s->r_trial[3 * bead], idx[1], w[1]);
+            else oc_bin_point(s, &s->r_trial[3 * bead], idx[1], w[1]);
         } else { /* quirk 4: trial coords = current coords */
             memcpy(idx[1], idx[0], sizeof idx[0]);
             memcpy(w[1], w[0], sizeof w[0]);
@@ -586,7 +621,10 @@ static void change_in_density(oc_sim *s, const int64_t *inds, int64_t n, int sta
                         dens = base * (double)st[bead * s->nb + m - 1];
                     }
                     temp = prefactor * dens;
-                    if (first)
+                    if (fast) { /* fields.pyx:1350-1366: no threshold in the fast path */
+                        if (first) s->density_trial[bin * ncol + m] = temp;
+                        else s->density_trial[bin * ncol + m] += temp;
+                    } else if (first)
                         s->density_trial[bin * ncol + m] = (fabs(temp) > 1E-18) ? temp : 0;
                     else if (fabs(temp) > 1E-18)
                         s->density_trial[bin * ncol + m] += temp;

@@ -119,6 +119,8 @@ typedef struct {
     double *twist0;                          /* [N-1] bead_length * NATURAL_TWIST_BARE / LENGTH_BP, 2088-2090 */
     /* --- production streams (crng.alt points here when in use) --- */
     oc_philox philox;
+    /* --- fast_field (fields.pyx:577-671, 1235-1368): sub-bins per voxel edge, 0 = exact binning --- */
+    int64_t fast_n_points;
 } oc_sim;
 
 /* RNG */

@@ -77,6 +77,7 @@ class Sim(C.Structure):
         ("last_accept", C.c_int64), ("last_u", C.c_double),
         ("eps_twist", _pd), ("twist0", _pd),
         ("philox", Philox),
+        ("fast_n_points", C.c_int64),
     ]
 
 
@@ -420,6 +421,9 @@ class OracleSim:
             s.confine_length = fld.get("confine_length", 0.0)
             s.chi = fld.get("chi", 1.0)
             s.vf_limit = fld.get("vf_limit", 0.5)
+            if fld.get("fast_field", 0) == 1:  # n_points is rounded up to an even number (fields.pyx:603)
+                npts = int(fld.get("n_points", 1000))
+                s.fast_n_points = npts + (npts % 2)
             pref, e_intra, xpref = field_prefactors(binders, s.vol_bin)
         else:
             s.field_active = 0
@@ -566,7 +570,8 @@ def ref_objects(spec: dict):
             [poly], df, f["x_width"], f["nx"], f["y_width"], f["ny"], f["z_width"], f["nz"],
             confine_type=f.get("confine_type", ""), confine_length=f.get("confine_length", 0.0),
             chi=f.get("chi", 1.0), vf_limit=f.get("vf_limit", 0.5),
-            assume_fully_accessible=f.get("assume_fully_accessible", 1))
+            assume_fully_accessible=f.get("assume_fully_accessible", 1),
+            fast_field=f.get("fast_field", 0), n_points=f.get("n_points", 1000))
     mods = dict(polymers=ply, binders=bnd, fields=fld,
                 mc_sim=importlib.import_module("chromo.mc.mc_sim"),
                 mc_controller=importlib.import_module("chromo.mc.mc_controller"),

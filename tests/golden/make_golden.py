@@ -164,6 +164,18 @@ def golden_csv(name, spec, polymer_name):
 
 if __name__ == "__main__":
     only = sys.argv[1:]  # e.g. `make_golden.py csv`: just the snapshot CSVs
+    if only == ["ff"]:
+        # fast_field = 1 (fields.pyx:577-671, 1235-1368): positions quantised to n_points sub-bins per voxel edge
+        ff = O.make_spec(N=300, nb=1, seed=51)
+        ff["field"] = dict(ff["field"], fast_field=1, n_points=1000)
+        ff2 = O.make_spec(N=200, nb=2, seed=52, cross_talk=-1.0, confine="", grid=6)
+        ff2["field"] = dict(ff2["field"], fast_field=1, n_points=37)  # odd: rounded up to 38; periodic box
+        golden_moves("moves_ff", ff, 300, 151)
+        golden_moves("moves_ff2", ff2, 250, 152)
+        ffs = O.make_spec(N=300, nb=1, seed=51, random_states=False)
+        ffs["field"] = dict(ffs["field"], fast_field=1, n_points=1000)
+        golden_mc_sim("mcsim_ff", ffs, 10, 26, 36)
+        sys.exit(0)
     if only == ["av"]:
         # per-voxel accessible volumes (assume_fully_accessible = 0, fields.pyx:714-951): the voxels cut by
         # the confining sphere are smaller, every w / V_access of the polymer's outer shell changes

@@ -32,6 +32,8 @@ def engine_from_spec(spec, R=1, device=0, chi=None, mu=None):
     if f is not None and f.get("assume_fully_accessible", 1) == 0:  # per-voxel accessible volumes (fields.pyx:714-951)
         from chromo_b200.fields import accessible_volumes
         e.set_access_volumes(accessible_volumes(f, 20, 0))
+    if f is not None and f.get("fast_field", 0) == 1:  # sub-bin quantised binning (fields.pyx:577-671)
+        e.set_fast_field(f.get("n_points", 1000))
     tile = lambda a: np.broadcast_to(np.asarray(a), (R,) + np.asarray(a).shape).copy()
     e.upload(tile(spec["r"]), tile(spec["t3"]), tile(spec["t2"]), tile(spec["states"]), tile(spec["mods"]))
     if f is not None and f["nx"] * f["ny"] * f["nz"] > 0:

@@ -38,7 +38,8 @@ def build(spec, lazy=False):
     field = fld.UniformDensityField([p], binders, f["x_width"], f["nx"], f["y_width"], f["ny"], f["z_width"],
                                     f["nz"], confine_type=f["confine_type"], confine_length=f["confine_length"],
                                     chi=f["chi"], vf_limit=f["vf_limit"],
-                                    assume_fully_accessible=f.get("assume_fully_accessible", 1))
+                                    assume_fully_accessible=f.get("assume_fully_accessible", 1),
+                                    fast_field=f.get("fast_field", 0), n_points=f.get("n_points", 1000))
     return p, binders, field
 
 
@@ -63,7 +64,7 @@ def test_construction_and_energies(backend, name):
             p._polymer_engine().set_twist_params(np.zeros(spec["N"] - 1), p.natural_twist)
 
 
-@pytest.mark.parametrize("name", ["mcsim_c2", "mcsim_c3", "mcsim_tw"])
+@pytest.mark.parametrize("name", ["mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_ff"])
 def test_mc_sim_drop_in(backend, name):
     """all_moves + SimpleControl + mc_sim, replaying the reference's RNG streams."""
     from chromo_b200.mc import get_amplitude_bounds, mc_controller as ctrl, set_rng_mode
@@ -279,3 +280,4 @@ def test_ensemble_from_polymers_coarse_grains_and_refines(backend):
     assert fine.N == spec["N"] + 1 and fine.assume_fully_accessible == 0 and np.isfinite(fine.field_energy()).all()
     for e in (fine, cg, ens):
         e.close()
+
