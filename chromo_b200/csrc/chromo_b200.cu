@@ -59,7 +59,7 @@ struct chromo_ctx {
     int64_t bytes = 0;
     // owned device buffers that can be replaced
     double *d_bond = nullptr, *d_twist = nullptr, *d_chi = nullptr, *d_mu = nullptr, *d_bindF = nullptr, *d_access = nullptr;
-    double *d_partial = nullptr, *d_out = nullptr;
+    double *d_partial = nullptr, *d_out = nullptr, *d_detailed = nullptr;
     int *d_dcount = nullptr;
     int *d_bad = nullptr; // set by the narrowing kernel when a state / mark is out of range
     // replica exchange (chromo_exchange_*): the chi ladder(s), the replica on every rung, counters
@@ -474,6 +474,21 @@ extern "C" int chromo_set_twist_params(chromo_ctx *c, int64_t n_sets, const doub
     if (rc) return rc;
     c->d.twist = c->d_twist;
     c->d.twist_stride = (n_sets == 1) ? 0 : (long long)nbonds * 2;
+    return CHROMO_OK;
+}
+
+extern "C" int chromo_set_detailed_nucleosomes(chromo_ctx *c, const double *consts20) {
+    if (!c) return fail(CHROMO_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    if (!consts20) {
+        c->d.detailed = nullptr;
+        return CHROMO_OK;
+    }
+    if (!c->d.twist) return fail(CHROMO_ERR_STATE, "DetailedChromatin is an SSTWLC: call chromo_set_twist_params first");
+    int rc = replace_buf(c, &c->d_detailed, consts20, (size_t)20);
+    if (rc) return rc;
+    c->d.detailed = c->d_detailed;
+    CK(cudaStreamSynchronize(c->stream));
     return CHROMO_OK;
 }
 

@@ -308,6 +308,99 @@ __device__ __forceinline__ double twist_energy(const double *tw, double omega) {
     return 0.5 * tw[0] * (d * d);
 }
 
+// ---- DetailedChromatin (polymers.pyx:2455-2607): the linker DNA leaves a nucleosome at its EXIT point with the
+// exit frame and arrives at the next one's ENTRY point with that nucleosome's own (t3, t2)
+// (DetailedNucleosome.update_configuration beads.py:536-574).  det[20] = t3_local[3] | t2_local[3] |
+// r_enter_unit[3] | r_enter_norm | r_exit_unit[3] | r_exit_norm | a3[3] | a1[3] (constants of one bp_wrap, built on
+// the host by chromo_b200.util.nucleo_geom).  The rotation local -> global is built exactly as the reference does:
+// align t3_local with t3, then the rotated t2_local with t2 (rotation_matrix_from_vectors linalg.pyx:478-510,
+// get_rotation_matrix 537-575 incl. its antiparallel fix-up).  Rare model, kept out of line.
+__device__ __forceinline__ void cb_cross3(const double a[3], const double b[3], double o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ void cb_mat3_vec(const double a[9], const double v[3], double o[3]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) o[i] = a[3 * i] * v[0] + a[3 * i + 1] * v[1] + a[3 * i + 2] * v[2];
+}
+__device__ __forceinline__ void cb_mat3_mul(const double a[9], const double b[9], double o[9]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) t += a[3 * i + k] * b[3 * k + j];
+            o[3 * i + j] = t;
+        }
+}
+__device__ __forceinline__ void cb_rot_from_vectors(const double v1[3], const double v2[3], double Rm[9]) {
+    const double n1 = sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
+    const double n2 = sqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
+    double a[3], b[3], v[3], K[9], K2[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++) a[i] = v1[i] / n1, b[i] = v2[i] / n2;
+    cb_cross3(a, b, v);
+#pragma unroll
+    for (int i = 0; i < 9; i++) Rm[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    if (v[0] != 0.0 || v[1] != 0.0 || v[2] != 0.0) {
+        const double c = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+        const double sn = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        const double f = (1.0 - c) / (sn * sn);
+        K[0] = 0.0, K[1] = -v[2], K[2] = v[1];
+        K[3] = v[2], K[4] = 0.0, K[5] = -v[0];
+        K[6] = -v[1], K[7] = v[0], K[8] = 0.0;
+        cb_mat3_mul(K, K, K2);
+#pragma unroll
+        for (int i = 0; i < 9; i++) Rm[i] = Rm[i] + K[i] + K2[i] * f;
+    }
+}
+// in place: (r, t3, t2) of a nucleosome -> exit point and exit frame (`exit` != 0) or entry point (frame unchanged)
+static __device__ CB_NOINLINE void nucleosome_frame(const double *det, double *r, double *t3, double *t2, int exit) {
+    const double *t3l = det, *t2l = det + 3, *ren = det + 6, *rex = det + 10, *a3 = det + 14, *a1 = det + 17;
+    double R1[9], R2[9], Rm[9], t2r[3], chk[3];
+    cb_rot_from_vectors(t3l, t3, R1);
+    cb_mat3_vec(R1, t2l, t2r);
+    cb_rot_from_vectors(t2r, t2, R2);
+    cb_mat3_mul(R2, R1, Rm);
+    cb_mat3_vec(Rm, t3l, chk);
+    bool anti = true; // np.allclose(R t3_local, -t3): |x - y| <= 1e-8 + 1e-5 |y|
+#pragma unroll
+    for (int i = 0; i < 3; i++) anti = anti && (fabs(chk[i] + t3[i]) <= 1e-8 + 1e-5 * fabs(t3[i]));
+    if (anti) { // get_arbitrary_axis_rotation_matrix(t2, pi) linalg.pyx:512-535
+        const double n = sqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]);
+        const double ux = t2[0] / n, uy = t2[1] / n, uz = t2[2] / n;
+        const double ct = -1.0, st = 1.2246467991473532e-16; // cos(pi), sin(pi) as libm returns them
+        double R3[9], Rn[9];
+        R3[0] = ct + ux * ux * (1 - ct), R3[1] = ux * uy * (1 - ct) - uz * st, R3[2] = uz * ux * (1 - ct) + uy * st;
+        R3[3] = ux * uy * (1 - ct) + uz * st, R3[4] = ct + uy * uy * (1 - ct), R3[5] = uy * uz * (1 - ct) - ux * st;
+        R3[6] = uz * ux * (1 - ct) - uy * st, R3[7] = uy * uz * (1 - ct) + ux * st, R3[8] = ct + uz * uz * (1 - ct);
+        cb_mat3_mul(R3, Rm, Rn);
+#pragma unroll
+        for (int i = 0; i < 9; i++) Rm[i] = Rn[i];
+    }
+    double v[3];
+    if (exit) {
+        double t1[3], t3e[3], t1e[3], t2e[3];
+        cb_cross3(t2, t3, t1);
+        cb_mat3_vec(Rm, rex, v);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            r[i] = v[i] * rex[3] + r[i];
+            t3e[i] = a3[0] * t3[i] + a3[1] * t2[i] + a3[2] * t1[i];
+            t1e[i] = a1[0] * t3[i] + a1[1] * t2[i] + a1[2] * t1[i];
+        }
+        cb_cross3(t3e, t1e, t2e);
+#pragma unroll
+        for (int i = 0; i < 3; i++) t3[i] = t3e[i], t2[i] = t2e[i];
+    } else {
+        cb_mat3_vec(Rm, ren, v);
+#pragma unroll
+        for (int i = 0; i < 3; i++) r[i] = v[i] * ren[3] + r[i];
+    }
+}
+
 __device__ __forceinline__ void load3(const double *p, double v[3]) {
     v[0] = p[0];
     v[1] = p[1];

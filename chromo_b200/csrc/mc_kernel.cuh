@@ -681,6 +681,7 @@ __device__ __forceinline__ double confinement_dE_segment(const DevCtx &C, const 
 struct TwistRows {
 #if CB_TWIST
     const double *T2, *tw;
+    const double *det; // DetailedChromatin: nucleosome constants, nullptr for a plain SSTWLC
 #endif
 };
 __device__ __forceinline__ TwistRows twist_rows(const DevCtx &C, int rep) {
@@ -688,6 +689,7 @@ __device__ __forceinline__ TwistRows twist_rows(const DevCtx &C, int rep) {
 #if CB_TWIST
     t.T2 = C.t2 + (long long)rep * C.N * 3;
     t.tw = C.twist + (long long)rep * C.twist_stride;
+    t.det = C.detailed;
 #endif
     return t;
 }
@@ -731,6 +733,10 @@ __device__ __forceinline__ double pair_energy_p(const double *Rr, const double *
     for (int j = 0; j < 3; j++) {
         u0[j] = moved == 1 ? t2n[j] : u0[j];
         u1[j] = moved == 2 ? t2n[j] : u1[j];
+    }
+    if (TW.det) { // DetailedChromatin.continuous_dE_poly polymers.pyx:2503-2607: exit of bead 0 -> entry of bead 1
+        nucleosome_frame(TW.det, r0, t0, u0, 1);
+        nucleosome_frame(TW.det, r1, t1, u1, 0);
     }
     return bond_energy(B, r0, r1, t0, t1) + twist_energy(TW.tw + 2 * bond, twist_omega(u0, t0, u1, t1));
 #else

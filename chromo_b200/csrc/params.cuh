@@ -36,6 +36,7 @@ struct DevCtx {
     long long bond_stride; // 0 (shared) or (N-1)*5
     const double *twist;   // SSTWLC: [sets][N-1][2] eps_twist, natural twist per bond; nullptr = no twist term
     long long twist_stride; // 0 (shared) or (N-1)*2
+    const double *detailed; // DetailedChromatin: 20 nucleosome constants (geometry.cuh nucleosome_frame), nullptr = off
     const double *chi;     // [R]
     const double *mu;      // [R][nb]
     double pref[CB_MAXNB], e_intra[CB_MAXNB], xpref[CB_MAXNB * CB_MAXNB];

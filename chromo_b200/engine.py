@@ -275,6 +275,15 @@ class Engine:
         """Attempts prepared at once by the production kernels (1..32; test knob, results do not depend on it)."""
         check(self._L.chromo_ctx_set_batch_size(self._h, int(batch)))
 
+    def set_detailed_nucleosomes(self, consts20=None) -> None:
+        """DetailedChromatin: the 20 nucleosome constants of `util.nucleo_geom.nucleosome_constants(bp_wrap)`
+        (None switches the entry / exit geometry off); set the twist parameters first."""
+        if consts20 is None:
+            check(self._L.chromo_set_detailed_nucleosomes(self._h, None))
+            return
+        a = _f64(np.asarray(consts20, dtype=float).reshape(20))
+        check(self._L.chromo_set_detailed_nucleosomes(self._h, _lib.dptr(a)))
+
     def set_fast_field(self, n_points: int) -> None:
         """fast_field = 1 of the reference's UniformDensityField: sub-bin quantised binning in the dE path
         (`n_points` sub-bins per voxel edge; 0 switches it off)."""

@@ -69,6 +69,8 @@ class ReplicaEnsemble:
                                     bond_params["gamma"], bond_params["eta"])
         if bond_params.get("eps_twist") is not None:  # SSTWLC replicas (polymers.pyx:1889-2319)
             self.engine.set_twist_params(bond_params["eps_twist"], bond_params["natural_twist"])
+            if bond_params.get("nucleosome_constants") is not None:  # DetailedChromatin replicas (polymers.pyx:2455-2607)
+                self.engine.set_detailed_nucleosomes(bond_params["nucleosome_constants"])
         self.assume_fully_accessible = assume_fully_accessible
         if access_vol is None and assume_fully_accessible != 1 and grid is not None and grid.get("nx", 0):
             from .fields import accessible_volumes
@@ -248,6 +250,9 @@ class ReplicaEnsemble:
         for k, v in self.bond_params.items():
             if v is None:
                 continue
+            if k == "nucleosome_constants":  # per model, not per bond
+                out[k] = v
+                continue
             v = np.asarray(v, dtype=float)
             if not np.all(v == v[..., :1]):
                 raise NotImplementedError("re-discretisation needs one bond length per chain")
@@ -338,6 +343,8 @@ class ReplicaEnsemble:
         bond = {k: np.stack([getattr(p, k) for p in polymers]) for k in keys}
         if all(np.array_equal(bond["eps_bend"][0], b) for b in bond["eps_bend"]):
             bond = {k: v[0] for k, v in bond.items()}
+        if getattr(p0, "nucleosome_constants", None) is not None:  # DetailedChromatin replicas share one bp_wrap
+            bond["nucleosome_constants"] = np.asarray(p0.nucleosome_constants, dtype=float)
         moves = None
         if controllers is not None:
             moves = np.stack([controllers_to_moves(c) for c in controllers])

@@ -111,6 +111,8 @@ class FieldBase:
             e.set_bond_params(poly.eps_bend, poly.eps_par, poly.eps_perp, poly.gamma, poly.eta)
             if getattr(poly, "eps_twist", None) is not None:  # SSTWLC
                 e.set_twist_params(poly.eps_twist, poly.natural_twist)
+                if getattr(poly, "nucleosome_constants", None) is not None:  # DetailedChromatin
+                    e.set_detailed_nucleosomes(poly.nucleosome_constants)
             self._engine, self._engine_poly = e, poly
         return self._engine
 

@@ -292,6 +292,8 @@ class SSWLC(PolymerBase):
             e.set_bond_params(self.eps_bend, self.eps_par, self.eps_perp, self.gamma, self.eta)
             if getattr(self, "eps_twist", None) is not None:  # SSTWLC
                 e.set_twist_params(self.eps_twist, self.natural_twist)
+                if getattr(self, "nucleosome_constants", None) is not None:  # DetailedChromatin
+                    e.set_detailed_nucleosomes(self.nucleosome_constants)
             self._engine = e
         return self._engine
 
@@ -373,6 +375,26 @@ class SSTWLC(SSWLC):
 
     def __str__(self):
         return f"Polymer_Class<SSTWLC>, {PolymerBase.__str__(self)}"
+
+
+class DetailedChromatin(SSTWLC):
+    """Chromatin fiber with detailed nucleosomes (polymers.pyx:2455-2607): an SSTWLC whose elastic dE runs every
+    linker from the EXIT point / frame of one nucleosome to the ENTRY point / frame of the next
+    (DetailedNucleosome, beads.py:448-574).  `bead_rad` is the nucleosome's radius (nucleo_geom R); `compute_E`
+    stays the SSTWLC one, as in the reference (only `continuous_dE_poly` is overridden there)."""
+
+    def __init__(self, name, r, *, bp_wrap, bead_length, lp, lt, t3=empty_2d, t2=empty_2d, states=mty_2d_int,
+                 binder_names=empty_1d, chemical_mods=mty_2d_int, chemical_mod_names=empty_1d, log_path="",
+                 max_binders=-1):
+        from .util import nucleo_geom
+        self.bp_wrap = float(bp_wrap)
+        self.nucleosome_constants = nucleo_geom.nucleosome_constants(self.bp_wrap)
+        super().__init__(name, r, bead_length=bead_length, lp=lp, lt=lt, bead_rad=nucleo_geom.consts_dict["R"], t3=t3,
+                         t2=t2, states=states, binder_names=binder_names, chemical_mods=chemical_mods,
+                         chemical_mod_names=chemical_mod_names, log_path=log_path, max_binders=max_binders)
+
+    def __str__(self):
+        return f"Polymer_Class<DetailedChromatin>, {PolymerBase.__str__(self)}"
 
 
 class Chromatin(SSWLC):

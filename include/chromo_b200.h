@@ -144,6 +144,12 @@ int chromo_ctx_set_replica_offset(chromo_ctx *ctx, int64_t offset);
  * is prepared at once by the lanes of a warp in the production kernels, 1..32
  * (default 32).  Results must not depend on it (tests/test_philox_parity.py). */
 int chromo_ctx_set_batch_size(chromo_ctx *ctx, int64_t batch);
+/* DetailedChromatin (polymers.pyx:2455-2607): nucleosomes with fixed entry / exit points and an exit frame
+ * (DetailedNucleosome beads.py:448-574).  consts20 = t3_local[3] | t2_local[3] | r_enter_unit[3] | r_enter_norm |
+ * r_exit_unit[3] | r_exit_norm | a3[3] | a1[3] for one bp_wrap (chromo_b200.util.nucleo_geom.nucleosome_constants):
+ * every bond energy of the elastic dE then runs from the exit of one bead to the entry of the next.  Needs the
+ * twist parameters (it is an SSTWLC); NULL switches it off.  compute_E is the SSTWLC one, as in the reference. */
+int chromo_set_detailed_nucleosomes(chromo_ctx *ctx, const double *consts20);
 /* fast_field = 1 of UniformDensityField (init_fast_field fields.pyx:577-671, get_change_in_density_quickly
  * 1235-1368): the dE path bins positions quantised to n_points sub-bins per voxel edge (rounded up to an even
  * number, as the reference does) and adds every term (no 1e-18 filter).  0 = exact binning (default).  The full

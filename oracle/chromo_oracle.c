@@ -464,10 +464,127 @@ static double pair_dE_reverse(const oc_sim *s, const double *r_0, const double *
            E_pair(s, bend, dr_par, dr_perp, b);
 }
 
+/* ---- DetailedChromatin: entry / exit frames of a nucleosome (DetailedNucleosome.update_configuration
+ * beads.py:536-574) ---- */
+static void mat3_mul(const double a[9], const double b[9], double o[9])
+{
+    int i, j, k;
+    for (i = 0; i < 3; i++)
+        for (j = 0; j < 3; j++) {
+            double t = 0;
+            for (k = 0; k < 3; k++) t += a[3 * i + k] * b[3 * k + j];
+            o[3 * i + j] = t;
+        }
+}
+static void mat3_vec(const double a[9], const double v[3], double o[3])
+{
+    int i;
+    for (i = 0; i < 3; i++) o[i] = a[3 * i] * v[0] + a[3 * i + 1] * v[1] + a[3 * i + 2] * v[2];
+}
+static void cross3(const double a[3], const double b[3], double o[3])
+{
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+/* rotation_matrix_from_vectors linalg.pyx:478-510 */
+static void rot_from_vectors(const double v1[3], const double v2[3], double R[9])
+{
+    double n1 = sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
+    double n2 = sqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
+    double a[3], b[3], v[3], K[9], K2[9];
+    int i;
+    for (i = 0; i < 3; i++) a[i] = v1[i] / n1, b[i] = v2[i] / n2;
+    cross3(a, b, v);
+    for (i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    if (v[0] != 0 || v[1] != 0 || v[2] != 0) {
+        double c = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+        double sn = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        double f = (1 - c) / (sn * sn);
+        K[0] = 0, K[1] = -v[2], K[2] = v[1];
+        K[3] = v[2], K[4] = 0, K[5] = -v[0];
+        K[6] = -v[1], K[7] = v[0], K[8] = 0;
+        mat3_mul(K, K, K2);
+        for (i = 0; i < 9; i++) R[i] = R[i] + K[i] + K2[i] * f;
+    }
+}
+static int allclose3(const double x[3], const double y[3])
+{ /* np.allclose defaults: |x - y| <= 1e-8 + 1e-5 |y| */
+    int i;
+    for (i = 0; i < 3; i++)
+        if (!(fabs(x[i] - y[i]) <= 1e-8 + 1e-5 * fabs(y[i]))) return 0;
+    return 1;
+}
+/* get_rotation_matrix linalg.pyx:537-575 */
+static void local_to_global(const oc_detailed *d, const double t3[3], const double t2[3], double R[9])
+{
+    double R1[9], R2[9], t2r[3], chk[3], neg[3];
+    int i;
+    rot_from_vectors(d->t3_local, t3, R1);
+    mat3_vec(R1, d->t2_local, t2r);
+    rot_from_vectors(t2r, t2, R2);
+    mat3_mul(R2, R1, R);
+    mat3_vec(R, d->t3_local, chk);
+    for (i = 0; i < 3; i++) neg[i] = -t3[i];
+    if (allclose3(chk, neg)) { /* get_arbitrary_axis_rotation_matrix(t2, pi) linalg.pyx:512-535 */
+        double n = sqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]);
+        double ux = t2[0] / n, uy = t2[1] / n, uz = t2[2] / n, ct = cos(M_PI), st = sin(M_PI);
+        double R3[9], Rn[9];
+        R3[0] = ct + ux * ux * (1 - ct), R3[1] = ux * uy * (1 - ct) - uz * st, R3[2] = uz * ux * (1 - ct) + uy * st;
+        R3[3] = ux * uy * (1 - ct) + uz * st, R3[4] = ct + uy * uy * (1 - ct), R3[5] = uy * uz * (1 - ct) - ux * st;
+        R3[6] = uz * ux * (1 - ct) - uy * st, R3[7] = uy * uz * (1 - ct) + ux * st, R3[8] = ct + uz * uz * (1 - ct);
+        mat3_mul(R3, R, Rn);
+        memcpy(R, Rn, sizeof Rn);
+    }
+}
+void oc_nucleosome_frames(const oc_detailed *d, const double r[3], const double t3[3], const double t2[3],
+                          double r_enter[3], double r_exit[3], double t3_exit[3], double t2_exit[3])
+{
+    double R[9], t1[3], v[3], t1_exit[3];
+    int i;
+    cross3(t2, t3, t1); /* beads.py:566 */
+    local_to_global(d, t3, t2, R);
+    mat3_vec(R, d->r_enter_unit, v);
+    for (i = 0; i < 3; i++) r_enter[i] = v[i] * d->r_enter_norm + r[i];
+    mat3_vec(R, d->r_exit_unit, v);
+    for (i = 0; i < 3; i++) r_exit[i] = v[i] * d->r_exit_norm + r[i];
+    for (i = 0; i < 3; i++) { /* nucleo_geom.get_T3 / get_T1 / get_T2 */
+        t3_exit[i] = d->a3[0] * t3[i] + d->a3[1] * t2[i] + d->a3[2] * t1[i];
+        t1_exit[i] = d->a1[0] * t3[i] + d->a1[1] * t2[i] + d->a1[2] * t1[i];
+    }
+    cross3(t3_exit, t1_exit, t2_exit);
+}
+
+/* DetailedChromatin.continuous_dE_poly polymers.pyx:2503-2607: the linker DNA runs from the EXIT point / frame
+ * of one nucleosome to the ENTRY point / frame (= the nucleosome's own t3, t2) of the next */
+static double continuous_dE_poly_detailed(const oc_sim *s, int64_t ind0, int64_t indf)
+{
+    const oc_detailed *d = s->detailed;
+    double dE = 0;
+    double ri0[3], ro0[3], t3o0[3], t2o0[3], ri1[3], ro1[3], t3o1[3], t2o1[3], rit[3], rot[3], t3ot[3], t2ot[3];
+    if (ind0 != 0) {
+        int64_t a = ind0 - 1, b = ind0;
+        oc_nucleosome_frames(d, &s->r[3 * a], &s->t3[3 * a], &s->t2[3 * a], ri0, ro0, t3o0, t2o0);
+        oc_nucleosome_frames(d, &s->r_trial[3 * b], &s->t3_trial[3 * b], &s->t2_trial[3 * b], rit, rot, t3ot, t2ot);
+        oc_nucleosome_frames(d, &s->r[3 * b], &s->t3[3 * b], &s->t2[3 * b], ri1, ro1, t3o1, t2o1);
+        dE += pair_dE_forward(s, ro0, ri1, rit, t3o0, &s->t3[3 * b], &s->t3_trial[3 * b], t2o0, &s->t2[3 * b],
+                              &s->t2_trial[3 * b], a);
+    }
+    if (indf != s->N) {
+        int64_t a = indf - 1, b = indf;
+        oc_nucleosome_frames(d, &s->r_trial[3 * a], &s->t3_trial[3 * a], &s->t2_trial[3 * a], rit, rot, t3ot, t2ot);
+        oc_nucleosome_frames(d, &s->r[3 * a], &s->t3[3 * a], &s->t2[3 * a], ri0, ro0, t3o0, t2o0);
+        oc_nucleosome_frames(d, &s->r[3 * b], &s->t3[3 * b], &s->t2[3 * b], ri1, ro1, t3o1, t2o1);
+        dE += pair_dE_reverse(s, ro0, rot, ri1, t3o0, t3ot, &s->t3[3 * b], t2o0, t2ot, &s->t2[3 * b], a);
+    }
+    return dE;
+}
+
 /* continuous_dE_poly polymers.pyx:1084-1146 */
 static double continuous_dE_poly(const oc_sim *s, int64_t ind0, int64_t indf)
 {
     double dE = 0;
+    if (s->detailed) return continuous_dE_poly_detailed(s, ind0, indf);
     if (ind0 != 0)
         dE += pair_dE_forward(s, &s->r[3 * (ind0 - 1)], &s->r[3 * ind0], &s->r_trial[3 * ind0],
                               &s->t3[3 * (ind0 - 1)], &s->t3[3 * ind0],

@@ -73,6 +73,16 @@ typedef struct {
     int64_t controller;       /* 0 = NoControl, 1 = SimpleControl */
 } oc_move;
 
+/* DetailedChromatin (polymers.pyx:2455-2607): every nucleosome has fixed entry / exit positions and an exit
+ * frame in its own frame (beads.py:448-574, util/nucleo_geom.py); constants of one value of bp_wrap */
+typedef struct {
+    double t3_local[3], t2_local[3];      /* beads.py:493-502 */
+    double r_enter_unit[3], r_enter_norm; /* beads.py:503-515 */
+    double r_exit_unit[3], r_exit_norm;
+    double a3[3];                         /* T3_exit = a3[0] T3 + a3[1] T2 + a3[2] T1   (nucleo_geom.get_T3) */
+    double a1[3];                         /* T1_exit = a1[0] T3 + a1[1] T2 + a1[2] T1   (nucleo_geom.get_T1) */
+} oc_detailed;
+
 /* polymer + field of ONE replica; all arrays caller-owned (numpy) */
 typedef struct {
     /* --- polymer (polymers.pxd:12-32) --- */
@@ -121,6 +131,8 @@ typedef struct {
     oc_philox philox;
     /* --- fast_field (fields.pyx:577-671, 1235-1368): sub-bins per voxel edge, 0 = exact binning --- */
     int64_t fast_n_points;
+    /* --- DetailedChromatin: NULL for every other polymer class --- */
+    const oc_detailed *detailed;
 } oc_sim;
 
 /* RNG */
@@ -144,6 +156,8 @@ double oc_poly_E(const oc_sim *s);
 double oc_field_dE(oc_sim *s, const int64_t *inds, int64_t n, int state_change);
 /* A7 */
 void oc_update_affected_densities(oc_sim *s);
+void oc_nucleosome_frames(const oc_detailed *d, const double r[3], const double t3[3], const double t2[3],
+                          double r_enter[3], double r_exit[3], double t3_exit[3], double t2_exit[3]);
 /* A9, A10 */
 double oc_poly_dE(oc_sim *s, int move, const int64_t *inds, int64_t n);
 double oc_binding_free_energy(int64_t Nn, int64_t Nm, int64_t s, double e_mod, double e_nomod);

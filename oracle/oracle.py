@@ -36,6 +36,12 @@ class Philox(C.Structure):
                 ("attempt", C.c_uint64), ("next_attempt", C.c_uint64), ("blk", C.c_uint32 * 4)]
 
 
+class Detailed(C.Structure):
+    _fields_ = [("t3_local", C.c_double * 3), ("t2_local", C.c_double * 3), ("r_enter_unit", C.c_double * 3),
+                ("r_enter_norm", C.c_double), ("r_exit_unit", C.c_double * 3), ("r_exit_norm", C.c_double),
+                ("a3", C.c_double * 3), ("a1", C.c_double * 3)]
+
+
 class MT19937(C.Structure):
     _fields_ = [("mt", C.c_uint32 * 624), ("pos", C.c_int)]
 
@@ -78,6 +84,7 @@ class Sim(C.Structure):
         ("eps_twist", _pd), ("twist0", _pd),
         ("philox", Philox),
         ("fast_n_points", C.c_int64),
+        ("detailed", C.POINTER(Detailed)),
     ]
 
 
@@ -223,6 +230,35 @@ def accessible_volumes(fld: dict, n_side: int = 20) -> np.ndarray:
         inside = np.sqrt(gx ** 2 + gy ** 2 + gz ** 2) < R
         vols[b] = vol_bin * (inside.sum() / float(n_side ** 3))
     return vols
+
+
+def nucleosome_constants(bp_wrap: float) -> dict:
+    """Geometry of a DetailedNucleosome (beads.py:448-515, util/nucleo_geom.py:17-245) for one bp_wrap, restated:
+    the local frame of the entering DNA, the entry / exit points on the nucleosome's super-helix and the
+    coefficients that give the exiting t3 / t1 in terms of the entering (t3, t2, t1)."""
+    LENGTH_BP, dens = 0.332, 10.17
+    Rn = 4.1899999999999995
+    h = 4.531142964071856 / 2
+    s_def = (147 - 1) * LENGTH_BP
+    w0 = 2 * np.pi / (dens * LENGTH_BP)
+    Lt = np.sqrt(4 * np.pi ** 2 * Rn ** 2 + h ** 2)
+    Phi = w0 - 2 * np.pi * h / (Lt ** 2)
+    t3f = lambda s: np.array([-2 * np.pi * Rn / Lt * np.sin(2 * np.pi * s / Lt),
+                              2 * np.pi * Rn / Lt * np.cos(2 * np.pi * s / Lt), h / Lt])
+    nrm = lambda s: np.array([-np.cos(2 * np.pi * s / Lt), -np.sin(2 * np.pi * s / Lt), 0])
+    bnm = lambda s: np.cross(t3f(s), nrm(s))
+    t1f = lambda s: np.cos(Phi * s) * nrm(s) + np.sin(Phi * s) * bnm(s)
+    t2f = lambda s: -np.sin(Phi * s) * nrm(s) + np.cos(Phi * s) * bnm(s)
+    s = (bp_wrap - 1) * LENGTH_BP
+    r_enter = np.array([Rn, 0, -(h * s_def / Lt) / 2])
+    r_exit = np.array([Rn * np.cos(2 * np.pi * s / Lt), Rn * np.sin(2 * np.pi * s / Lt), h * s / Lt - ((s_def / Lt * h) / 2)])
+    return dict(
+        bead_rad=Rn,
+        t3_local=np.array([0, 2 * np.pi * Rn / Lt, h / Lt]), t2_local=np.array([0, -h / Lt, 2 * np.pi * Rn / Lt]),
+        r_enter_norm=np.linalg.norm(r_enter), r_enter_unit=r_enter / np.linalg.norm(r_enter),
+        r_exit_norm=np.linalg.norm(r_exit), r_exit_unit=r_exit / np.linalg.norm(r_exit),
+        a3=np.array([np.dot(t3f(s), t3f(0)), np.dot(t3f(s), t2f(0)), np.dot(t3f(s), t1f(0))]),
+        a1=np.array([np.dot(t1f(s), t3f(0)), np.dot(t1f(s), t2f(0)), np.dot(t1f(s), t1f(0))]))
 
 
 def amplitude_bounds(N: int, min_spacing: float):
@@ -396,6 +432,13 @@ class OracleSim:
             self.eps_twist = f64(spec["lt"] / ((bl / spec["lp"]) * spec["lp"]))
             self.twist0 = f64(bl * (2 * np.pi / 10.5) / 0.332)
             s.eps_twist, s.twist0 = _p(self.eps_twist, _pd), _p(self.twist0, _pd)
+        if spec.get("bp_wrap") is not None:  # DetailedChromatin (polymers.pyx:2455-2607)
+            nc = nucleosome_constants(spec["bp_wrap"])
+            self._detailed = Detailed()
+            for k in ("t3_local", "t2_local", "r_enter_unit", "r_exit_unit", "a3", "a1"):
+                getattr(self._detailed, k)[:] = list(map(float, nc[k]))
+            self._detailed.r_enter_norm, self._detailed.r_exit_norm = float(nc["r_enter_norm"]), float(nc["r_exit_norm"])
+            s.detailed = C.pointer(self._detailed)
         s.max_binders = spec.get("max_binders", -1)
         s.mu_adjust_factor = mu_adjust_factor
         s.bead_vol = (4 / 3) * np.pi * spec["bead_rad"] ** 3  # beads.py:415
@@ -556,7 +599,11 @@ def ref_objects(spec: dict):
         max_binders=spec.get("max_binders", -1),
     )
     r = np.ascontiguousarray(spec["r"], dtype=float).copy()
-    if spec.get("lt") is not None:
+    if spec.get("bp_wrap") is not None:
+        kw.pop("bead_rad")  # fixed by the nucleosome geometry (consts_dict["R"])
+        poly = ply.DetailedChromatin("replica", r, bp_wrap=float(spec["bp_wrap"]), lp=float(spec["lp"]),
+                                     lt=float(spec["lt"]), **kw)
+    elif spec.get("lt") is not None:
         poly = ply.SSTWLC("replica", r, lp=float(spec["lp"]), lt=float(spec["lt"]), **kw)
     elif spec["lp"] == 53.0:
         poly = ply.Chromatin("replica", r, **kw)

@@ -27,6 +27,8 @@ def spec_to_npz(spec):
                 binders=spec["binders"], field=spec["field"], max_binders=spec["max_binders"])
     if spec.get("lt") is not None:
         meta["lt"] = spec["lt"]
+    if spec.get("bp_wrap") is not None:
+        meta["bp_wrap"] = spec["bp_wrap"]
     arrs = {k: np.asarray(spec[k]) for k in ("r", "t3", "t2", "states", "mods", "bead_length")}
     arrs["meta"] = np.array(json.dumps(meta))
     return arrs
@@ -164,6 +166,17 @@ def golden_csv(name, spec, polymer_name):
 
 if __name__ == "__main__":
     only = sys.argv[1:]  # e.g. `make_golden.py csv`: just the snapshot CSVs
+    if only == ["dc"]:
+        # DetailedChromatin (polymers.pyx:2455-2607): nucleosomes with entry / exit points and an exit frame.
+        # bead_rad is the nucleosome's (4.19 nm); linkers of 16.5 nm, 147 and 127 bp wrapped.
+        dc = dict(O.make_spec(N=60, nb=1, seed=71, bead_rad=4.1899999999999995), lt=100.0, bp_wrap=147.0)
+        dc2 = dict(O.make_spec(N=50, nb=2, seed=72, cross_talk=-1.0, bead_rad=4.1899999999999995), lt=60.0, bp_wrap=127.0)
+        golden_static("static_dc", dc)
+        golden_moves("moves_dc", dc, 200, 161)
+        golden_moves("moves_dc2", dc2, 150, 162)
+        golden_mc_sim("mcsim_dc", dict(O.make_spec(N=60, nb=1, seed=71, random_states=False, bead_rad=4.1899999999999995),
+                                       lt=100.0, bp_wrap=147.0), 4, 27, 37)
+        sys.exit(0)
     if only == ["ff"]:
         # fast_field = 1 (fields.pyx:577-671, 1235-1368): positions quantised to n_points sub-bins per voxel edge
         ff = O.make_spec(N=300, nb=1, seed=51)

@@ -30,7 +30,9 @@ def build(spec, lazy=False):
               binder_names=np.array([b["name"] for b in spec["binders"]]),
               chemical_mods=spec["mods"].reshape(N, nb).copy(),
               chemical_mod_names=np.array([f"m{j}" for j in range(nb)]))
-    if spec.get("lt") is not None:  # twist: polymers.pyx:1889
+    if spec.get("bp_wrap") is not None:  # detailed nucleosomes: polymers.pyx:2455
+        p = ply.DetailedChromatin("c", spec["r"].copy(), bp_wrap=spec["bp_wrap"], lp=spec["lp"], lt=spec["lt"], **kw)
+    elif spec.get("lt") is not None:  # twist: polymers.pyx:1889
         p = ply.SSTWLC("c", spec["r"].copy(), lp=spec["lp"], lt=spec["lt"], **kw)
     else:
         p = ply.Chromatin("c", spec["r"].copy(), **kw)
@@ -43,7 +45,7 @@ def build(spec, lazy=False):
     return p, binders, field
 
 
-@pytest.mark.parametrize("name", ["static_c2", "static_c3", "static_tw2", "static_av"])
+@pytest.mark.parametrize("name", ["static_c2", "static_c3", "static_tw2", "static_av", "static_dc"])
 def test_construction_and_energies(backend, name):
     spec, g = load_golden(name)
     p, binders, field = build(spec)
@@ -64,7 +66,7 @@ def test_construction_and_energies(backend, name):
             p._polymer_engine().set_twist_params(np.zeros(spec["N"] - 1), p.natural_twist)
 
 
-@pytest.mark.parametrize("name", ["mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_ff"])
+@pytest.mark.parametrize("name", ["mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_ff", "mcsim_dc"])
 def test_mc_sim_drop_in(backend, name):
     """all_moves + SimpleControl + mc_sim, replaying the reference's RNG streams."""
     from chromo_b200.mc import get_amplitude_bounds, mc_controller as ctrl, set_rng_mode
@@ -239,6 +241,45 @@ def test_against_live_reference(backend):
         assert np.allclose(p.r, np.asarray(rp.r), rtol=0, atol=tol)
         assert np.array_equal(p.states, np.asarray(rp.states))
         assert close(field.compute_E(p), rfield.compute_E(rp), 1e-9 if backend == "emu" else 1e-7)
+
+
+def test_nucleosome_constants_match_the_pinned_oracle():
+    """util.nucleo_geom (product) against the oracle's restatement, which the *_dc goldens pin to the reference."""
+    from chromo_b200.util.nucleo_geom import nucleosome_constants
+    for bp in (147, 146.5, 127, 1):
+        c, o = nucleosome_constants(bp), O.nucleosome_constants(bp)
+        want = np.concatenate([o["t3_local"], o["t2_local"], o["r_enter_unit"], [o["r_enter_norm"]], o["r_exit_unit"],
+                               [o["r_exit_norm"]], o["a3"], o["a1"]])
+        assert np.array_equal(c, want), bp
+
+
+def test_ensemble_from_detailed_chromatin(backend):
+    """ReplicaEnsemble.from_polymers on DetailedChromatin replicas keeps the entry / exit geometry: a crank-shaft
+    production mc_sim of the batched engine is the oracle's DetailedChromatin walk on the same Philox streams
+    (a plain SSTWLC would accept different moves)."""
+    from chromo_b200.ensemble import ReplicaEnsemble
+    spec, g = load_golden("static_dc")
+    built = [build(spec) for _ in range(2)]
+    ens = ReplicaEnsemble.from_polymers([b[0] for b in built], [b[2] for b in built])
+    assert np.array_equal(ens.bond_params["nucleosome_constants"], built[0][0].nucleosome_constants)
+    E = ens.elastic_energy()
+    assert close(E[0], float(g["E_poly"])) and E[0] == E[1]
+    mv0 = ens.moves.copy()
+    ens.mc_sim(2, 1.0, 77)
+    finals = {}
+    for detailed in (True, False):
+        o = O.OracleSim(spec if detailed else {k: v for k, v in spec.items() if k != "bp_wrap"})
+        o.use_production_streams(77, 1, 0)
+        omv = O.make_moves(spec["N"], float(np.min(spec["bead_length"])))
+        for i in range(5):
+            for f in ("amp_move", "amp_bead", "num_attempt", "num_success", "acceptance_rate"):
+                setattr(omv[i], f, type(getattr(omv[i], f))(mv0[f][1, i]))
+        o.mc_sim(omv, 2, 0)
+        finals[detailed] = (o.r.copy(), [m.num_success for m in omv])
+    assert [int(x) for x in ens.moves["num_success"][1]] == finals[True][1]
+    assert np.allclose(ens.r[1], finals[True][0], rtol=0, atol=1e-7)
+    assert not np.allclose(ens.r[1], finals[False][0], rtol=0, atol=1e-3)  # the geometry mattered
+    ens.close()
 
 
 def test_ensemble_from_twisted_polymers_keeps_the_twist_term(backend):
