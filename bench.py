@@ -465,7 +465,7 @@ def run_ours(args):
                           attempts_per_launch=attempts_launch,
                           bytes_per_attempt=bytes_launch / max(1.0, attempts_launch),
                           note="achieved = sum of algorithmic bytes of the timed launches / sum of their CUDA-event "
-                               "times; latency-bound (serial moves per replica); see DESIGN.md"),
+                               "times; the kernel is instruction-supply bound, not bandwidth-bound: DESIGN.md 4.1"),
             acceptance={k: round(float(v), 4) for k, v in acc.items()},
             amp_bead_mean=[round(x, 2) for x in amp_bead_mean],
             hbm_bytes=hbm_bytes,
