@@ -335,6 +335,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: chromo_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    from chromo_b200.parallel import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local) if world > 1 else dict(node=None, why="one rank")  # before the pinned buffers
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -456,6 +458,7 @@ def run_ours(args):
                      ms_per_step=e2e_ms / Ke, replica_chunks=e2e_chunks,
                      h2d_gbs_per_gpu=h2d / world / (e2e_ms / Ke * 1e-3) / 1e9,
                      d2h_gbs_per_gpu=d2h / world / (e2e_ms / Ke * 1e-3) / 1e9,
+                     host_numa_binding_rank0=numa,
                      path="chromo_mc_sim_host: pinned host arrays -> device -> kernel -> host, pipelined over replica chunks"),
             gpu_launches=K + 4 * e2e_chunks * Ke,  # e2e: per replica chunk 2 narrowing kernels, the MC kernel, 1 widening
             clocks=clocks,

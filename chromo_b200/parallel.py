@@ -30,6 +30,45 @@ def shard_indices(n_total: int, rank: int, world: int) -> np.ndarray:
     return np.arange(start, start + base + (1 if rank < extra else 0), dtype=np.int64)
 
 
+def _parse_cpulist(text: str) -> list:
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device: int, sysfs: str = "/sys", bdf: str = None) -> dict:
+    """Pin the calling process to the host cores of the NUMA node `device` hangs off, so that the pinned host
+    buffers allocated afterwards (first touch) and the threads that feed the copy engines are local to the GPU's
+    PCIe root: with one rank per GPU on a two-socket host the end-to-end path otherwise crosses the socket link
+    for half the ranks.  Call it before allocating pinned memory.  Returns what it did ({"node": n, "cpus": k}, or
+    {"node": None, "why": ...} when the platform does not say -- a VM without NUMA information, one node only)."""
+    import os
+    try:
+        if bdf is None:  # the GPU's PCI address
+            import torch
+            p = torch.cuda.get_device_properties(device)
+            bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"{sysfs}/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return dict(node=None, why="the platform reports no NUMA node for the GPU")
+        with open(f"{sysfs}/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return dict(node=node, why="none of the node's cores is in this process's cpuset")
+        if len(allowed) == len(os.sched_getaffinity(0)):
+            return dict(node=node, cpus=len(allowed), why="already local (one node)")
+        os.sched_setaffinity(0, allowed)
+        return dict(node=node, cpus=len(allowed))
+    except Exception as e:  # plumbing, never fatal
+        return dict(node=None, why=f"{type(e).__name__}: {e}")
+
+
 def shard_sizes(n_total: int, world: int) -> np.ndarray:
     return np.array([len(shard_indices(n_total, r, world)) for r in range(world)], dtype=np.int64)
 

@@ -5,14 +5,20 @@
 // into, shipped with, or loaded by the chromo_b200 package; the product library
 // is compiled by nvcc for sm_100a and has no CPU path.
 //
-// Model: each thread block runs as blockDim.x OS threads; warp collectives
+// Model: each thread block runs as blockDim.x cooperative FIBERS on the calling OS
+// thread (own stacks, a 10-instruction x86-64 context switch); warp collectives
 // (__shfl*_sync, __any_sync, __syncwarp) rendezvous on a per-warp barrier,
-// __syncthreads on a per-block barrier; blocks of a grid run one after another.
+// __syncthreads on a per-block barrier -- a fiber that has to wait hands the core to
+// the next fiber of the block; blocks of a grid run one after another.  (The first
+// version ran a block as OS threads on pthread barriers: the same semantics at ~10x
+// the wall time, nearly all of it in futex calls.)
 // All collectives in the kernels are called with warp-uniform control flow and a
 // full mask, which is what this model requires.
 #pragma once
-#include <pthread.h>
-#include <sched.h>
+#if !defined(__x86_64__)
+#error "cuda_emu.h switches fibers with x86-64 assembly"
+#endif
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <atomic>
@@ -44,27 +50,72 @@ struct emu_dim3 {
 typedef emu_dim3 dim3;
 inline thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim; // one instance across TUs
 
+struct EmuBarrier {
+    unsigned count = 0, need = 0, gen = 0;
+};
 struct EmuBlock {
-    pthread_barrier_t block_bar;
-    std::vector<pthread_barrier_t> warp_bar;
+    EmuBarrier block_bar;
+    std::vector<EmuBarrier> warp_bar;
     std::vector<uint64_t> slots; // one per thread
-    std::atomic<int> nb_count[16], nb_gen[16]; // named barriers (bar.sync id, count)
+    EmuBarrier named[16];        // named barriers (bar.sync id, count)
     unsigned char *dyn = nullptr;
+    // fibers
+    unsigned nt = 0, cur = 0, live = 0;
+    std::vector<void *> sp;          // saved stack pointers
+    std::vector<unsigned char> done;
+    void *main_sp = nullptr;
+    std::function<void()> body;
 };
 inline thread_local EmuBlock *emu_blk = nullptr;
 
-static inline void emu_warp_wait() { pthread_barrier_wait(&emu_blk->warp_bar[threadIdx.x >> 5]); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_wait(); }
-static inline void __syncthreads() { pthread_barrier_wait(&emu_blk->block_bar); }
-static inline void cb_bar_sync(int id, int count) {
+// save the callee-saved registers on the current stack, park its pointer in *from, continue on `to`
+static __attribute__((naked, noinline)) void emu_switch(void **from, void *to) {
+    asm volatile(
+        "pushq %rbp\n pushq %rbx\n pushq %r12\n pushq %r13\n pushq %r14\n pushq %r15\n"
+        "movq %rsp, (%rdi)\n movq %rsi, %rsp\n"
+        "popq %r15\n popq %r14\n popq %r13\n popq %r12\n popq %rbx\n popq %rbp\n ret\n");
+}
+// hand the core to the next unfinished fiber of the block (round robin)
+static inline void emu_yield() {
     EmuBlock *b = emu_blk;
-    const int gen = b->nb_gen[id].load();
-    if (b->nb_count[id].fetch_add(1) + 1 == count) {
-        b->nb_count[id].store(0);
-        b->nb_gen[id].fetch_add(1);
+    const unsigned me = b->cur;
+    unsigned n = me;
+    do n = n + 1 == b->nt ? 0 : n + 1; while (b->done[n]);
+    if (n == me) return;
+    b->cur = n;
+    emu_switch(&b->sp[me], b->sp[n]);
+    threadIdx.x = me; // back on this fiber
+}
+static inline void emu_barrier(EmuBarrier &bar) {
+    const unsigned gen = bar.gen;
+    if (++bar.count == bar.need) {
+        bar.count = 0;
+        bar.gen = gen + 1;
     } else {
-        while (b->nb_gen[id].load() == gen) sched_yield();
+        while (*(volatile unsigned *)&bar.gen == gen) emu_yield();
     }
+}
+static __attribute__((noinline)) void emu_fiber_entry() {
+    EmuBlock *b = emu_blk;
+    const unsigned me = b->cur;
+    threadIdx.x = me;
+    b->body();
+    b->done[me] = 1;
+    void *dummy;
+    if (--b->live == 0) emu_switch(&dummy, b->main_sp);
+    unsigned n = me;
+    do n = n + 1 == b->nt ? 0 : n + 1; while (b->done[n]);
+    b->cur = n;
+    emu_switch(&dummy, b->sp[n]);
+    abort(); // a finished fiber is never resumed
+}
+
+static inline void emu_warp_wait() { emu_barrier(emu_blk->warp_bar[threadIdx.x >> 5]); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_wait(); }
+static inline void __syncthreads() { emu_barrier(emu_blk->block_bar); }
+static inline void cb_bar_sync(int id, int count) {
+    emu_blk->named[id].need = (unsigned)count;
+    emu_barrier(emu_blk->named[id]);
 }
 
 template <class T>
@@ -163,7 +214,7 @@ static inline void cb_prefetch(const void *) {}
 typedef uintptr_t cb_saddr;
 static inline cb_saddr cb_shared_addr(const void *p) { return (cb_saddr)p; }
 static inline void cb_red_add_u32(cb_saddr a, uint32_t v) { __atomic_fetch_add((uint32_t *)a, v, __ATOMIC_SEQ_CST); }
-static inline void cb_backoff() { sched_yield(); }
+static inline void cb_backoff() { emu_yield(); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline double __longlong_as_double(long long v) {
     double d;
@@ -215,38 +266,67 @@ template <class K>
 static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return 0; }
 
 // ---- kernel launch ---------------------------------------------------------
+struct EmuStacks { // one region per OS thread, reused by every launch
+    unsigned char *base = nullptr;
+    size_t each = 0, n = 0;
+    ~EmuStacks() {
+        if (base) munmap(base, each * n);
+    }
+    unsigned char *top(unsigned t) { return base + each * (t + 1); }
+    void reserve(size_t threads) {
+        if (threads <= n) return;
+        if (base) munmap(base, each * n);
+        each = (size_t)1 << 20; // 1 MiB of address space per fiber, touched pages only are backed
+        n = threads;
+        void *p = mmap(nullptr, each * n, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (p == MAP_FAILED) {
+            perror("cuda_emu: mmap of the fiber stacks");
+            abort();
+        }
+        base = (unsigned char *)p;
+    }
+};
+inline thread_local EmuStacks emu_stacks;
+
 template <class K, class... A>
 static void emu_launch(K kernel, dim3 grid, dim3 block, size_t smem, A... args) {
     const unsigned nt = block.x;
     const unsigned nw = (nt + 31) / 32;
     EmuBlock blk;
+    EmuBlock *outer = emu_blk;
+    const emu_dim3 o_t = threadIdx, o_b = blockIdx, o_bd = blockDim, o_gd = gridDim;
     blk.slots.assign(nw * 32, 0);
-    for (int i = 0; i < 16; i++) {
-        blk.nb_count[i].store(0);
-        blk.nb_gen[i].store(0);
-    }
     blk.warp_bar.resize(nw);
     std::vector<unsigned char> dyn(smem + 64);
     blk.dyn = (unsigned char *)(((uintptr_t)dyn.data() + 15) & ~(uintptr_t)15);
-    pthread_barrier_init(&blk.block_bar, nullptr, nt);
-    for (unsigned w = 0; w < nw; w++) pthread_barrier_init(&blk.warp_bar[w], nullptr, std::min(32u, nt - 32 * w));
+    blk.nt = nt;
+    blk.sp.resize(nt);
+    blk.done.resize(nt);
+    blk.body = [&]() { kernel(args...); };
+    emu_stacks.reserve(nt);
+    emu_blk = &blk;
+    blockDim = block;
+    gridDim = grid;
     for (unsigned by = 0; by < grid.y; by++)
         for (unsigned bx = 0; bx < grid.x; bx++) {
-            std::vector<std::thread> th;
-            th.reserve(nt);
-            for (unsigned t = 0; t < nt; t++)
-                th.emplace_back([&, t]() {
-                    threadIdx = emu_dim3(t);
-                    blockIdx = emu_dim3(bx, by);
-                    blockDim = block;
-                    gridDim = grid;
-                    emu_blk = &blk;
-                    kernel(args...);
-                });
-            for (auto &x : th) x.join();
+            blk.block_bar = EmuBarrier{0, nt, 0};
+            for (unsigned w = 0; w < nw; w++) blk.warp_bar[w] = EmuBarrier{0, std::min(32u, nt - 32 * w), 0};
+            for (auto &b : blk.named) b = EmuBarrier{};
+            blockIdx = emu_dim3(bx, by);
+            for (unsigned t = 0; t < nt; t++) { // a fresh stack whose first `ret` enters emu_fiber_entry
+                void **top = (void **)((uintptr_t)emu_stacks.top(t) & ~(uintptr_t)15);
+                top[-1] = nullptr;                  // return address of the entry function (never used)
+                top[-2] = (void *)&emu_fiber_entry; // popped by emu_switch's ret
+                for (int k = 3; k <= 8; k++) top[-k] = nullptr; // rbp rbx r12 r13 r14 r15
+                blk.sp[t] = (void *)(top - 8);
+                blk.done[t] = 0;
+            }
+            blk.live = nt;
+            blk.cur = 0;
+            emu_switch(&blk.main_sp, blk.sp[0]); // returns when the last fiber has finished
         }
-    pthread_barrier_destroy(&blk.block_bar);
-    for (unsigned w = 0; w < nw; w++) pthread_barrier_destroy(&blk.warp_bar[w]);
+    emu_blk = outer;
+    threadIdx = o_t, blockIdx = o_b, blockDim = o_bd, gridDim = o_gd;
 }
 #define CB_LAUNCH(kernel, grid, block, smem, stream, ...) \
     emu_launch(kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)

@@ -122,3 +122,61 @@ def test_twisted_chains(backend, N):
                 mv["amp_bead"][:, i] = a
                 omv[i].amp_bead = a
     _replay_both(spec, 12, per_cycle=(8, 4, 8, 10, 3), move_on=(1, int(N >= 4), 1, 1, 1), tweak=wide, backend=backend)
+
+
+def test_metropolis_flips_exactly_at_the_accept_boundary(backend):
+    """north_star: accept / reject sequences must match "except where |dE - ln u| falls within" 1e-9.  A binder
+    move's dE is linear in mu_adjust_factor (polymers.pyx:1493-1517), its proposal and its uniform u are not touched
+    by it: solve for the factor a* that puts dE on the boundary dE = -ln u, then (i) a clear step to either side
+    (1e-6 relative, far outside the tolerance) must flip the decision on the kernel exactly as on the oracle, and
+    (ii) within the tolerance the two may disagree, but only there -- and a replay that follows the kernel's
+    decision stays in step with it."""
+    spec = O.make_spec(N=120, nb=1, seed=33, random_states=True)
+
+    def attempt(a, follow=None):
+        e = engine_from_spec(spec, R=1)
+        o = O.OracleSim(spec, mu_adjust_factor=a)
+        e.srand(8), o.srand(8), e.numpy_seed(4), o.np_seed(4)
+        out = e.mc_step(0, 4, 1.0, 40, a, REPLAY, 0, -1)
+        inds = o.propose(4, 1.0, 40)
+        assert np.array_equal(inds, out["inds"])
+        dE = o.poly_dE(4, inds) + o.field_dE(inds, True)[0]
+        u = O.lib().oc_rand(O.C.byref(o.s.crng)) / 2147483647.0  # `<double>rand() / RAND_MAX`, mc_sim.pyx:171
+        assert u == out["u"]
+        with np.errstate(over="ignore"):
+            o_acc = bool(u < np.exp(-dE))
+        k_dE = out["dE_poly"] + out["dE_field"]
+        if follow is not None:  # replay convention inside the tolerance: take the kernel's decision
+            mv = O.make_moves(spec["N"], 16.5)
+            ip = inds.ctypes.data_as(O._pl)
+            if out["accepted"]:
+                O.lib().oc_accept(O.C.byref(o.s), O.C.byref(mv[4]), 4, ip, len(inds))
+                o.commit_field()
+            else:
+                O.lib().oc_reject(O.C.byref(o.s), O.C.byref(mv[4]), 4, ip, len(inds))
+            st = e.download()[3]
+            assert np.array_equal(st[0], o.states)
+            assert np.allclose(e.density()[0], o.density, rtol=1e-9, atol=1e-9 / o.s.vol_bin)
+        e.close()
+        return dict(u=u, dE=dE, k_dE=k_dE, o_acc=o_acc, k_acc=out["accepted"])
+
+    a1, a2 = attempt(1.0), attempt(2.0)
+    assert a1["u"] == a2["u"] and a1["dE"] != a2["dE"]  # same proposal and uniform, dE moved with the factor
+    slope = a2["dE"] - a1["dE"]
+    target = -np.log(a1["u"])
+    a_star = 1.0 + (target - a1["dE"]) / slope
+    on = attempt(a_star, follow=True)
+    tol = 1e-9 * max(1.0, abs(target))
+    assert abs(on["dE"] - target) <= tol and abs(on["k_dE"] - target) <= tol  # both sit on the boundary
+    # (i) clear of the tolerance: kernel == oracle == the side of the boundary
+    step = 1e-6 * max(1.0, abs(target)) / abs(slope)
+    up, dn = attempt(a_star + step * np.sign(slope)), attempt(a_star - step * np.sign(slope))
+    assert abs(up["dE"] - target) > 100 * tol and abs(dn["dE"] - target) > 100 * tol
+    assert (up["k_acc"], up["o_acc"]) == (False, False)  # dE above -ln u: rejected
+    assert (dn["k_acc"], dn["o_acc"]) == (True, True)    # below: accepted
+    # (ii) inside the tolerance a disagreement is allowed, anywhere else it is not
+    for da in (0.0, 1e-13 / abs(slope), -1e-13 / abs(slope)):
+        w = attempt(a_star + da, follow=True)
+        assert abs(w["k_dE"] - w["dE"]) <= tol
+        if w["k_acc"] != w["o_acc"]:
+            assert abs(w["dE"] - target) <= tol

@@ -19,6 +19,30 @@ def test_sharding_partitions_all_replicas():
         assert par.shard_sizes(n, w).sum() == n
 
 
+def test_numa_binding_reads_the_gpus_node(tmp_path):
+    """bind_to_gpu_numa_node against a fake sysfs tree: it takes the cores of the GPU's node that this process may
+    use, leaves the process alone when the platform says nothing, and never raises."""
+    mine = sorted(os.sched_getaffinity(0))
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (tmp_path / "devices/system/node/node1").mkdir(parents=True)
+    try:
+        (dev / "numa_node").write_text("-1\n")
+        assert par.bind_to_gpu_numa_node(0, str(tmp_path), "0000:1b:00.0")["node"] is None
+        (dev / "numa_node").write_text("1\n")
+        (tmp_path / "devices/system/node/node1/cpulist").write_text(f"{mine[0]}\n")
+        got = par.bind_to_gpu_numa_node(0, str(tmp_path), "0000:1b:00.0")
+        assert got["node"] == 1 and got["cpus"] == 1
+        if len(mine) > 1:
+            assert sorted(os.sched_getaffinity(0)) == [mine[0]]
+        (tmp_path / "devices/system/node/node1/cpulist").write_text("100000-100003\n")  # cores we may not use
+        assert "cpuset" in par.bind_to_gpu_numa_node(0, str(tmp_path), "0000:1b:00.0")["why"]
+        assert par.bind_to_gpu_numa_node(0, str(tmp_path / "nowhere"), "0000:1b:00.0")["node"] is None
+        assert par._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    finally:
+        os.sched_setaffinity(0, mine)
+
+
 def test_swap_rule():
     chi = np.array([0.0, 1.0, 2.0, 3.0])
     # energy-lowering swaps are always accepted: pair (0,1) with Phi_1 < Phi_0
