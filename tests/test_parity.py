@@ -107,7 +107,7 @@ def test_mc_sim_replay(backend, name):
     final configuration."""
     exact = backend == "emu"
     spec, g = load_golden(name)
-    R = 1 if exact else 2  # (the CPU emulation runs ~1 ms per attempt and replica)
+    R = 2
     e = engine_from_spec(spec, R=R)
     mv = moves_array(spec, R, tuple(int(x) for x in g["per_cycle"]))
     e.srand(int(g["srand_seed"]))
@@ -256,8 +256,6 @@ def test_two_warps_per_replica_match_one(backend, oracle_mod, case):
         spec = O.make_spec(N=120, nb=1, seed=23, random_states=False)
         spec["field"] = dict(spec["field"], nx=0, ny=0, nz=0)
         sweeps, per_cycle = 6, (30, 1, 60, 60, 10)
-    if backend == "emu":  # the CPU emulation runs ~1 ms per attempt: fewer sweeps there, all of them on the GPU
-        sweeps = max(2, sweeps // 2)
     R = 3
     out = []
     dens0 = None

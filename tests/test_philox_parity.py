@@ -38,6 +38,8 @@ def _case(O, name):
         per_cycle = (30, 5, 60, 60, 30)
     elif name == "twist":    # SSTWLC builds of the kernels
         spec = dict(O.make_spec(N=300, nb=1, seed=33, random_states=True), lt=80.0)
+    elif name == "wide":     # the bench's stationary working point: bead windows at their upper bounds
+        spec = O.make_spec(N=700, nb=1, seed=35, random_states=True)
     elif name == "hp1":      # the bench's physics at a small size
         spec = O.make_spec(N=300, nb=1, seed=34, random_states=False)
     else:
@@ -57,8 +59,19 @@ def _dense_moves(mv_arr=None, omv=None):
         omv[4].amp_bead, omv[4].bead_amp_hi = 5, 5
 
 
+def _wide_moves(mv_arr=None, omv=None):
+    """SimpleControl's stationary state on the bench's workload (profiles/stationary_amplitudes.json): segments of
+    up to 150 beads (several 32-bead chunks per scatter pass), tangent rotations of ~14"""
+    amp = (150, 150, 150, 14, 1)
+    for i, a in enumerate(amp):
+        if mv_arr is not None:
+            mv_arr["amp_bead"][:, i] = a
+        if omv is not None:
+            omv[i].amp_bead = a
+
+
 def _compare_run(O, backend, spec, per_cycle, sweeps, R, seed, dense=False, rpb=None, warps=1, batch=None,
-                 offset=0, check=None):
+                 offset=0, check=None, wide=False):
     exact = backend == "emu"
     e = engine_from_spec(spec, R=R)
     if rpb is not None:
@@ -71,6 +84,8 @@ def _compare_run(O, backend, spec, per_cycle, sweeps, R, seed, dense=False, rpb=
     mv = moves_array(spec, R, per_cycle)
     if dense:
         _dense_moves(mv_arr=mv)
+    if wide:
+        _wide_moves(mv_arr=mv)
     e.mc_sim(sweeps, mv, 1.0, seed, PHILOX)
     r, t3, t2, st = e.download()
     dens = e.density()
@@ -82,6 +97,8 @@ def _compare_run(O, backend, spec, per_cycle, sweeps, R, seed, dense=False, rpb=
         omv = O.make_moves(spec["N"], float(np.min(spec["bead_length"])), per_cycle=per_cycle)
         if dense:
             _dense_moves(omv=omv)
+        if wide:
+            _wide_moves(omv=omv)
         o.mc_sim(omv, sweeps, 0)
         assert [int(x) for x in mv["num_attempt"][rep]] == [m.num_attempt for m in omv]
         assert [int(x) for x in mv["num_success"][rep]] == [m.num_success for m in omv], rep  # same accept sequence
@@ -98,16 +115,17 @@ def _compare_run(O, backend, spec, per_cycle, sweeps, R, seed, dense=False, rpb=
     return r, t3, t2, st, dens, mv
 
 
-@pytest.mark.parametrize("name", ["hp1", "mixed", "dense", "twist"])
+@pytest.mark.parametrize("name", ["hp1", "mixed", "dense", "twist", "wide"])
 def test_production_mc_sim_matches_oracle(backend, oracle_mod, name):
     """(a) whole mc_sim runs in production mode, seven replicas per block (the bench's launch shape)."""
     O = oracle_mod
     spec, per_cycle = _case(O, name)
     emu = backend == "emu"
-    sweeps = {"hp1": 3, "mixed": 2, "dense": 4, "twist": 2}[name] if emu else {"hp1": 12, "mixed": 8, "dense": 20, "twist": 8}[name]
-    R = 3 if emu else 14
-    _compare_run(O, backend, spec, per_cycle, sweeps, R, seed=20241 + len(name), dense=name == "dense",
-                 rpb=R if emu else 7, check=range(R) if emu else (0, 6, 7, 13))
+    sweeps = ({"hp1": 6, "mixed": 4, "dense": 10, "twist": 4, "wide": 3}[name] if emu else
+              {"hp1": 12, "mixed": 8, "dense": 20, "twist": 8, "wide": 10}[name])
+    R = 9 if emu else 14  # more than one block of 7 replicas: the default launch shape, move-type barrier included
+    _compare_run(O, backend, spec, per_cycle, sweeps, R, seed=20241 + len(name), dense=name == "dense", wide=name == "wide",
+                 rpb=7, check=range(R) if emu else (0, 6, 7, 13))
 
 
 def test_production_two_warps_and_offset(backend, oracle_mod):
@@ -123,7 +141,7 @@ def test_batch_of_one_is_bit_identical(backend, oracle_mod):
     nothing is ever prepared ahead: identical to the last bit on the case where nearly every look-ahead is stale"""
     O = oracle_mod
     spec, per_cycle = _case(O, "dense")
-    sweeps = 3 if backend == "emu" else 20
+    sweeps = 8 if backend == "emu" else 20
     outs = []
     for batch in (32, 1, 5):
         e = engine_from_spec(spec, R=2)
