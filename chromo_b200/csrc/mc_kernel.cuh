@@ -1822,7 +1822,12 @@ __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, CB_MIN_BLOCKS)
             // The block's replicas enter the next move type together.  (Measured on B200: skipping
             // the barrier before the short move types -- 1 end-pivot, 10 binding attempts -- costs
             // more in lost instruction-cache sharing than the wait for the slowest replica does.)
-#ifndef CB_NO_TYPE_BARRIER
+#if defined(CB_PAIR_BARRIER)
+            // experiment: only the warps that share an SM sub-partition (warp w and w + 4) wait for each other
+            if (NW == 1 && (int)blockDim.x == 32 * 7) {
+                if ((warp ^ 4) < 7) cb_bar_sync(1 + (warp & 3), 64);
+            } else __syncthreads();
+#elif !defined(CB_NO_TYPE_BARRIER)
             __syncthreads();
 #endif
         }
