@@ -383,18 +383,29 @@ class DetailedChromatin(SSTWLC):
     (DetailedNucleosome, beads.py:448-574).  `bead_rad` is the nucleosome's radius (nucleo_geom R); `compute_E`
     stays the SSTWLC one, as in the reference (only `continuous_dE_poly` is overridden there)."""
 
+    _with_diameter = True
+
     def __init__(self, name, r, *, bp_wrap, bead_length, lp, lt, t3=empty_2d, t2=empty_2d, states=mty_2d_int,
                  binder_names=empty_1d, chemical_mods=mty_2d_int, chemical_mod_names=empty_1d, log_path="",
                  max_binders=-1):
         from .util import nucleo_geom
         self.bp_wrap = float(bp_wrap)
-        self.nucleosome_constants = nucleo_geom.nucleosome_constants(self.bp_wrap)
+        self.nucleosome_constants = nucleo_geom.nucleosome_constants(self.bp_wrap, self._with_diameter)
         super().__init__(name, r, bead_length=bead_length, lp=lp, lt=lt, bead_rad=nucleo_geom.consts_dict["R"], t3=t3,
                          t2=t2, states=states, binder_names=binder_names, chemical_mods=chemical_mods,
                          chemical_mod_names=chemical_mod_names, log_path=log_path, max_binders=max_binders)
 
     def __str__(self):
         return f"Polymer_Class<DetailedChromatin>, {PolymerBase.__str__(self)}"
+
+
+class DetailedChromatin2(DetailedChromatin):
+    """`DetailedChromatin` without the nucleosome diameter (polymers.pyx:2627-2735): the linker runs between the
+    bead centres, only the exit frame of the nucleosome enters the bond energy (the kinked wormlike chain)."""
+    _with_diameter = False
+
+    def __str__(self):
+        return f"Polymer_Class<DetailedChromatin2>, {PolymerBase.__str__(self)}"
 
 
 class Chromatin(SSWLC):

@@ -50,8 +50,10 @@ def get_r(s):
     return np.array([R * np.cos(2 * np.pi * s / Lt), R * np.sin(2 * np.pi * s / Lt), h * s / Lt - ((s_default / Lt * h) / 2)])
 
 
-def nucleosome_constants(bp_wrap: float) -> np.ndarray:
-    """The 20 constants of one `bp_wrap`, in the order `chromo_set_detailed_nucleosomes` takes them."""
+def nucleosome_constants(bp_wrap: float, with_diameter: bool = True) -> np.ndarray:
+    """The 20 constants of one `bp_wrap`, in the order `chromo_set_detailed_nucleosomes` takes them.
+    `with_diameter=False` (DetailedChromatin2, polymers.pyx:2627-2735): entry / exit offsets of length zero -- the
+    bonds run between the bead centres and only the exit frame enters the energy."""
     s = (bp_wrap - 1) * LENGTH_BP
     R, Lt, h = R_default, Lt_default, h_default
     t3_local = np.array([0, 2 * np.pi * R / Lt, h / Lt])
@@ -59,6 +61,9 @@ def nucleosome_constants(bp_wrap: float) -> np.ndarray:
     r_enter = np.array([R, 0, -(h * s_default / Lt) / 2])
     r_exit = get_r(s)
     ne, nx = np.linalg.norm(r_enter), np.linalg.norm(r_exit)
+    r_enter, r_exit = r_enter / ne, r_exit / nx
+    if not with_diameter:
+        ne = nx = 0.0
     a3 = [np.dot(t3(s), t3(0)), np.dot(t3(s), t2(0)), np.dot(t3(s), t1(0))]
     a1 = [np.dot(t1(s), t3(0)), np.dot(t1(s), t2(0)), np.dot(t1(s), t1(0))]
-    return np.concatenate([t3_local, t2_local, r_enter / ne, [ne], r_exit / nx, [nx], a3, a1]).astype(float)
+    return np.concatenate([t3_local, t2_local, r_enter, [ne], r_exit, [nx], a3, a1]).astype(float)

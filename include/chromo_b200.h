@@ -148,7 +148,8 @@ int chromo_ctx_set_batch_size(chromo_ctx *ctx, int64_t batch);
  * (DetailedNucleosome beads.py:448-574).  consts20 = t3_local[3] | t2_local[3] | r_enter_unit[3] | r_enter_norm |
  * r_exit_unit[3] | r_exit_norm | a3[3] | a1[3] for one bp_wrap (chromo_b200.util.nucleo_geom.nucleosome_constants):
  * every bond energy of the elastic dE then runs from the exit of one bead to the entry of the next.  Needs the
- * twist parameters (it is an SSTWLC); NULL switches it off.  compute_E is the SSTWLC one, as in the reference. */
+ * twist parameters (it is an SSTWLC); NULL switches it off.  DetailedChromatin2 (polymers.pyx:2627-2735, bonds between
+ * the bead centres): the same constants with both norms 0.  compute_E is the SSTWLC one, as in the reference. */
 int chromo_set_detailed_nucleosomes(chromo_ctx *ctx, const double *consts20);
 /* fast_field = 1 of UniformDensityField (init_fast_field fields.pyx:577-671, get_change_in_density_quickly
  * 1235-1368): the dE path bins positions quantised to n_points sub-bins per voxel edge (rounded up to an even

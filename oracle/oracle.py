@@ -438,6 +438,8 @@ class OracleSim:
             for k in ("t3_local", "t2_local", "r_enter_unit", "r_exit_unit", "a3", "a1"):
                 getattr(self._detailed, k)[:] = list(map(float, nc[k]))
             self._detailed.r_enter_norm, self._detailed.r_exit_norm = float(nc["r_enter_norm"]), float(nc["r_exit_norm"])
+            if spec.get("no_diameter"):  # DetailedChromatin2 (polymers.pyx:2627-2735): bonds run between bead
+                self._detailed.r_enter_norm = self._detailed.r_exit_norm = 0.0  # centres, only the frames change
             s.detailed = C.pointer(self._detailed)
         s.max_binders = spec.get("max_binders", -1)
         s.mu_adjust_factor = mu_adjust_factor
@@ -601,8 +603,8 @@ def ref_objects(spec: dict):
     r = np.ascontiguousarray(spec["r"], dtype=float).copy()
     if spec.get("bp_wrap") is not None:
         kw.pop("bead_rad")  # fixed by the nucleosome geometry (consts_dict["R"])
-        poly = ply.DetailedChromatin("replica", r, bp_wrap=float(spec["bp_wrap"]), lp=float(spec["lp"]),
-                                     lt=float(spec["lt"]), **kw)
+        cls = ply.DetailedChromatin2 if spec.get("no_diameter") else ply.DetailedChromatin
+        poly = cls("replica", r, bp_wrap=float(spec["bp_wrap"]), lp=float(spec["lp"]), lt=float(spec["lt"]), **kw)
     elif spec.get("lt") is not None:
         poly = ply.SSTWLC("replica", r, lp=float(spec["lp"]), lt=float(spec["lt"]), **kw)
     elif spec["lp"] == 53.0:

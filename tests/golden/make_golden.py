@@ -29,6 +29,8 @@ def spec_to_npz(spec):
         meta["lt"] = spec["lt"]
     if spec.get("bp_wrap") is not None:
         meta["bp_wrap"] = spec["bp_wrap"]
+    if spec.get("no_diameter"):
+        meta["no_diameter"] = 1
     arrs = {k: np.asarray(spec[k]) for k in ("r", "t3", "t2", "states", "mods", "bead_length")}
     arrs["meta"] = np.array(json.dumps(meta))
     return arrs
@@ -176,6 +178,11 @@ if __name__ == "__main__":
         golden_moves("moves_dc2", dc2, 150, 162)
         golden_mc_sim("mcsim_dc", dict(O.make_spec(N=60, nb=1, seed=71, random_states=False, bead_rad=4.1899999999999995),
                                        lt=100.0, bp_wrap=147.0), 4, 27, 37)
+        # DetailedChromatin2 (polymers.pyx:2627-2735): the same frames, bonds between the bead centres
+        dc3 = dict(O.make_spec(N=60, nb=1, seed=73, bead_rad=4.1899999999999995), lt=100.0, bp_wrap=147.0, no_diameter=1)
+        golden_moves("moves_dc3", dc3, 200, 163)
+        golden_mc_sim("mcsim_dc3", dict(O.make_spec(N=60, nb=1, seed=73, random_states=False, bead_rad=4.1899999999999995),
+                                        lt=100.0, bp_wrap=147.0, no_diameter=1), 4, 28, 38)
         sys.exit(0)
     if only == ["ff"]:
         # fast_field = 1 (fields.pyx:577-671, 1235-1368): positions quantised to n_points sub-bins per voxel edge

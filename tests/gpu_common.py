@@ -29,7 +29,7 @@ def engine_from_spec(spec, R=1, device=0, chi=None, mu=None):
         e.set_twist_params(spec["lt"] / ((bl / spec["lp"]) * spec["lp"]), bl * (2 * np.pi / 10.5) / 0.332)
     if spec.get("bp_wrap") is not None:  # DetailedChromatin (polymers.pyx:2455-2607)
         from chromo_b200.util.nucleo_geom import nucleosome_constants
-        e.set_detailed_nucleosomes(nucleosome_constants(spec["bp_wrap"]))
+        e.set_detailed_nucleosomes(nucleosome_constants(spec["bp_wrap"], not spec.get("no_diameter")))
     e.set_replica_params(chi=(f["chi"] if f is not None else 1.0) if chi is None else chi,
                          mu=[b["chemical_potential"] for b in spec["binders"]] if mu is None else mu)
     if f is not None and f.get("assume_fully_accessible", 1) == 0:  # per-voxel accessible volumes (fields.pyx:714-951)

@@ -31,7 +31,8 @@ def build(spec, lazy=False):
               chemical_mods=spec["mods"].reshape(N, nb).copy(),
               chemical_mod_names=np.array([f"m{j}" for j in range(nb)]))
     if spec.get("bp_wrap") is not None:  # detailed nucleosomes: polymers.pyx:2455
-        p = ply.DetailedChromatin("c", spec["r"].copy(), bp_wrap=spec["bp_wrap"], lp=spec["lp"], lt=spec["lt"], **kw)
+        cls = ply.DetailedChromatin2 if spec.get("no_diameter") else ply.DetailedChromatin
+        p = cls("c", spec["r"].copy(), bp_wrap=spec["bp_wrap"], lp=spec["lp"], lt=spec["lt"], **kw)
     elif spec.get("lt") is not None:  # twist: polymers.pyx:1889
         p = ply.SSTWLC("c", spec["r"].copy(), lp=spec["lp"], lt=spec["lt"], **kw)
     else:
@@ -66,7 +67,7 @@ def test_construction_and_energies(backend, name):
             p._polymer_engine().set_twist_params(np.zeros(spec["N"] - 1), p.natural_twist)
 
 
-@pytest.mark.parametrize("name", ["mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_ff", "mcsim_dc"])
+@pytest.mark.parametrize("name", ["mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_ff", "mcsim_dc", "mcsim_dc3"])
 def test_mc_sim_drop_in(backend, name):
     """all_moves + SimpleControl + mc_sim, replaying the reference's RNG streams."""
     from chromo_b200.mc import get_amplitude_bounds, mc_controller as ctrl, set_rng_mode

@@ -20,8 +20,8 @@ from common import close, close_dE, huge_scale, load_golden, split
 from gpu_common import engine_from_spec, moves_array
 
 STATIC = ["static_c1", "static_c2", "static_c3", "static_c4", "static_tw", "static_tw2", "static_av", "static_av2", "static_dc"]
-MOVES = ["moves_c1", "moves_c2", "moves_c3", "moves_c4", "moves_tw", "moves_tw2", "moves_av", "moves_av2", "moves_ff", "moves_ff2", "moves_dc", "moves_dc2"]
-MCSIM = ["mcsim_c1", "mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_av", "mcsim_ff", "mcsim_dc"]
+MOVES = ["moves_c1", "moves_c2", "moves_c3", "moves_c4", "moves_tw", "moves_tw2", "moves_av", "moves_av2", "moves_ff", "moves_ff2", "moves_dc", "moves_dc2", "moves_dc3"]
+MCSIM = ["mcsim_c1", "mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_av", "mcsim_ff", "mcsim_dc", "mcsim_dc3"]
 REPLAY, PHILOX = 1, 0
 
 
