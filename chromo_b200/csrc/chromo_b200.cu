@@ -351,6 +351,29 @@ extern "C" int chromo_ctx_set_batch_size(chromo_ctx *c, int64_t batch) {
     c->d.batch = (int)batch;
     return CHROMO_OK;
 }
+// page-lock caller-owned host arrays so that chromo_mc_sim_host / upload / download run at link speed
+extern "C" int chromo_host_register(void *p, uint64_t bytes) {
+    if (!p || bytes == 0) return fail(CHROMO_ERR_ARG, "null or empty host range");
+    cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        (void)cudaGetLastError();
+        return fail(CHROMO_ERR_STATE, "host range is already page-locked");
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(CHROMO_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+    }
+    return CHROMO_OK;
+}
+extern "C" int chromo_host_unregister(void *p) {
+    if (!p) return fail(CHROMO_ERR_ARG, "null host pointer");
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(CHROMO_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e));
+    }
+    return CHROMO_OK;
+}
 extern "C" int chromo_ctx_set_fast_field(chromo_ctx *c, int64_t n_points) {
     if (!c) return fail(CHROMO_ERR_ARG, "null context");
     if (n_points < 0 || n_points > 1000000) return fail(CHROMO_ERR_ARG, "n_points out of range");

@@ -48,6 +48,24 @@ def binding_free_energy_table(binders: Sequence[dict]) -> np.ndarray:
     return F
 
 
+def host_register(a: np.ndarray) -> bool:
+    """Page-lock a C-contiguous host array (`chromo_host_register`) so that host-array calls move it at link
+    speed.  True: locked by this call (pair it with `host_unregister` before the array is freed); False: the
+    memory is already page-locked (e.g. a view of torch pinned memory)."""
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("host_register needs a C-contiguous array")
+    L = _lib.lib()
+    rc = L.chromo_host_register(a.ctypes.data, a.nbytes)
+    if rc == _lib.ERR_STATE:
+        return False
+    check(rc)
+    return True
+
+
+def host_unregister(a: np.ndarray) -> None:
+    check(_lib.lib().chromo_host_unregister(a.ctypes.data))
+
+
 class Engine:
     def __init__(self, n_replicas: int, num_beads: int, num_binders: int, *, grid: Optional[dict],
                  bead_vol: float, max_binders: int = -1, device: int = 0):

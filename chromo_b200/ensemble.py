@@ -48,7 +48,7 @@ class ReplicaEnsemble:
                  grid: Optional[dict], bead_vol: float, chi=1.0, mu=None, max_binders: int = -1,
                  moves: Optional[np.ndarray] = None, min_spacing: Optional[float] = None,
                  access_vol=None, device: int = 0, field_prefactors=None, assume_fully_accessible: int = 1,
-                 replica_offset: int = 0, fast_field_points: int = 0):
+                 replica_offset: int = 0, fast_field_points: int = 0, pin_host: Optional[bool] = None):
         self.r = np.ascontiguousarray(r, dtype=np.float64)
         self.R, self.N = self.r.shape[0], self.r.shape[1]
         self.t3 = np.ascontiguousarray(t3, dtype=np.float64)
@@ -57,6 +57,7 @@ class ReplicaEnsemble:
         self.nb = self.states.shape[2]
         self.chemical_mods = np.ascontiguousarray(chemical_mods, dtype=np.int64).reshape(self.R, self.N, self.nb)
         self.binders = [dict(b) for b in binders]
+        self._pinned = []
         self.grid = grid
         self.bead_vol, self.max_binders, self.bond_params = bead_vol, max_binders, dict(bond_params)
         self.min_spacing, self.device = min_spacing, device
@@ -93,6 +94,13 @@ class ReplicaEnsemble:
             moves = default_moves(self.R, self.N, 16.5 if min_spacing is None else min_spacing)
         self.moves = np.ascontiguousarray(moves, dtype=MOVE_DTYPE).reshape(self.R, NUM_MOVES)
         self.engine.set_moves(self.moves)
+        # host-in / host-out calls (mc_sim(sync_host=True), push, pull) copy these arrays every time: page-lock them
+        # once (pageable numpy memory moves at a third of the link speed).  Default: ensembles of >= 8 MiB.
+        if pin_host or (pin_host is None and self.r.nbytes >= (8 << 20)):
+            from .engine import host_register
+            for a in (self.r, self.t3, self.t2, self.states, self.chemical_mods):
+                if host_register(a):
+                    self._pinned.append(a)
         self.push()
         if grid is not None and grid.get("nx", 0):
             self.engine.field_recompute(clamp=True)  # UniformDensityField.__init__ fields.pyx:532
@@ -317,7 +325,19 @@ class ReplicaEnsemble:
         return ens
 
     def close(self):
+        if self._pinned:  # before the arrays can be freed
+            from .engine import host_unregister
+            self.engine.sync()
+            for a in self._pinned:
+                host_unregister(a)
+            self._pinned = []
         self.engine.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     # ---- construction helpers ----------------------------------------------
     @classmethod

@@ -151,6 +151,13 @@ int chromo_ctx_set_batch_size(chromo_ctx *ctx, int64_t batch);
  * twist parameters (it is an SSTWLC); NULL switches it off.  DetailedChromatin2 (polymers.pyx:2627-2735, bonds between
  * the bead centres): the same constants with both norms 0.  compute_E is the SSTWLC one, as in the reference. */
 int chromo_set_detailed_nucleosomes(chromo_ctx *ctx, const double *consts20);
+/* Page-lock (cudaHostRegister) a caller-owned host array -- the polymers' r / t3 / t2 / states buffers -- so that
+ * chromo_mc_sim_host, chromo_upload_state and chromo_download_state move it at link speed instead of staging it
+ * through the driver's bounce buffers (pageable numpy memory: ~3x slower).  The reference has no counterpart (its
+ * arrays never leave the host).  CHROMO_ERR_STATE if the range is already page-locked (e.g. torch pinned memory):
+ * nothing to do, and nothing to unregister.  Unregister before the array is freed. */
+int chromo_host_register(void *host_ptr, uint64_t bytes);
+int chromo_host_unregister(void *host_ptr);
 /* fast_field = 1 of UniformDensityField (init_fast_field fields.pyx:577-671, get_change_in_density_quickly
  * 1235-1368): the dE path bins positions quantised to n_points sub-bins per voxel edge (rounded up to an even
  * number, as the reference does) and adds every term (no 1e-18 filter).  0 = exact binning (default).  The full

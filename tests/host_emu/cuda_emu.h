@@ -262,6 +262,9 @@ static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cuda
     return 0;
 }
 static inline cudaError_t cudaGetLastError() { return 0; }
+enum { cudaHostRegisterDefault = 0, cudaErrorHostMemoryAlreadyRegistered = 712 };
+static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return 0; }
+static inline cudaError_t cudaHostUnregister(void *) { return 0; }
 template <class K>
 static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return 0; }
 

@@ -323,3 +323,38 @@ def test_ensemble_from_polymers_coarse_grains_and_refines(backend):
     for e in (fine, cg, ens):
         e.close()
 
+
+
+def test_ensemble_page_locks_its_host_arrays(backend):
+    """pin_host: the ensemble registers its r / t3 / t2 / states / chemical_mods buffers (chromo_host_register)
+    for the host-in / host-out path and releases them on close; results do not depend on it."""
+    from chromo_b200.ensemble import ReplicaEnsemble, default_moves
+    spec = O.make_spec(N=80, nb=1, seed=5)
+    st = lambda k: np.stack([spec[k]] * 3)
+    out = []
+    for pin in (True, False):
+        ens = ReplicaEnsemble(st("r"), st("t3"), st("t2"), st("states"), st("mods"), binders=spec["binders"],
+                              bond_params=O.bond_params(spec["bead_length"], 53.0), grid=spec["field"],
+                              bead_vol=(4 / 3) * np.pi * 125.0, moves=default_moves(3, 80, 16.5), pin_host=pin)
+        assert len(ens._pinned) == (5 if pin else 0)
+        ens.mc_sim(2, 1.0, 9)
+        out.append((ens.r.copy(), ens.states.copy()))
+        ens.close()
+        assert ens._pinned == []
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.gpu
+def test_host_register_on_the_gpu():
+    """cudaHostRegister for real: a numpy array is locked once (a second registration is refused), memory torch
+    already pinned is reported as such."""
+    import torch
+    from chromo_b200.engine import host_register, host_unregister
+    a = np.zeros(1 << 20)
+    assert host_register(a) is True
+    assert host_register(a) is False          # already page-locked: nothing to do
+    host_unregister(a)
+    t = torch.empty(1 << 20, dtype=torch.float64, pin_memory=True)
+    assert host_register(t.numpy()) is False
+    with pytest.raises(Exception):
+        host_unregister(np.zeros(16))         # never registered
