@@ -354,6 +354,12 @@ extern "C" int chromo_ctx_set_batch_size(chromo_ctx *c, int64_t batch) {
 // page-lock caller-owned host arrays so that chromo_mc_sim_host / upload / download run at link speed
 extern "C" int chromo_host_register(void *p, uint64_t bytes) {
     if (!p || bytes == 0) return fail(CHROMO_ERR_ARG, "null or empty host range");
+#ifndef CHROMO_HOST_EMU
+    cudaPointerAttributes at; // memory from cudaHostAlloc (torch pinned tensors) or an earlier registration
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered)
+        return fail(CHROMO_ERR_STATE, "host range is already page-locked");
+    (void)cudaGetLastError();
+#endif
     cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault);
     if (e == cudaErrorHostMemoryAlreadyRegistered) {
         (void)cudaGetLastError();
