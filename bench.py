@@ -411,6 +411,17 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
     barrier()
+    # the link alone: every rank uploads / downloads its whole state at the same time (what the e2e path
+    # contends for at N > 1); r, t3, t2 as f64, states (and, on upload, marks) as int64
+    link = []
+    for fn, nbytes in ((ens.push, 3 * R * N * 24 + 2 * R * N * 8), (ens.pull, 3 * R * N * 24 + R * N * 8)):
+        eng.sync()
+        barrier()
+        t0 = time.perf_counter()
+        fn()
+        eng.sync()
+        link.append(nbytes / (time.perf_counter() - t0) / 1e9)
+    barrier()
 
     # ---- extra legs: strong scaling of C2 and the C5 replica-exchange ladder ---------------
     extra = {}
@@ -420,10 +431,11 @@ def run_ours(args):
         extra = extra_legs(args, rank, world, local, dist, (r, t3, t2, states, mods, grid))
 
     # ---- reduce over ranks --------------------------------------------------
-    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
+    t = torch.tensor([ms_total, e2e_ms, -link[0], -link[1]], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms = float(t[0]), float(t[1])
+    link = [-float(t[2]), -float(t[3])]  # the slowest rank's
     attempts_step = R * S * ATTEMPTS_PER_SWEEP * world
     value = attempts_step * K / (ms_total * 1e-3)
     e2e = attempts_step * Ke / (e2e_ms * 1e-3)
@@ -456,8 +468,7 @@ def run_ours(args):
             launch=dict(warps_per_replica=warps, replicas_per_block=rpb, table_slots=cap, rng="philox4x32-10"),
             e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=Ke,
                      ms_per_step=e2e_ms / Ke, replica_chunks=e2e_chunks,
-                     h2d_gbs_per_gpu=h2d / world / (e2e_ms / Ke * 1e-3) / 1e9,
-                     d2h_gbs_per_gpu=d2h / world / (e2e_ms / Ke * 1e-3) / 1e9,
+                     h2d_link_gbs_per_gpu=link[0], d2h_link_gbs_per_gpu=link[1],  # whole-state copies alone, all ranks at once, slowest rank
                      host_numa_binding_rank0=numa,
                      path="chromo_mc_sim_host: pinned host arrays -> device -> kernel -> host, pipelined over replica chunks"),
             gpu_launches=K + 4 * e2e_chunks * Ke,  # e2e: per replica chunk 2 narrowing kernels, the MC kernel, 1 widening
