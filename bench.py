@@ -396,7 +396,7 @@ def run_ours(args):
     d2h = (3 * R * N * 24 + R * N * 1 * 8) * world
     Ke = max(1, min(K, args.e2e_steps))
     nblk = -(-R // rpb)
-    e2e_chunks = 4
+    e2e_chunks = 8  # (the library's own rule for n_chunks = 0, repeated here to count launches)
     while e2e_chunks > 1 and e2e_chunks * -(-nblk // e2e_chunks) > torch.cuda.get_device_properties(local).multi_processor_count:
         e2e_chunks -= 1
     ens.mc_sim(S, 1.0, 5000, sync_host=True)  # (refreshes the host arrays from the device first)
@@ -471,7 +471,7 @@ def run_ours(args):
                      h2d_link_gbs_per_gpu=link[0], d2h_link_gbs_per_gpu=link[1],  # whole-state copies alone, all ranks at once, slowest rank
                      host_numa_binding_rank0=numa,
                      path="chromo_mc_sim_host: pinned host arrays -> device -> kernel -> host, pipelined over replica chunks"),
-            gpu_launches=K + 4 * e2e_chunks * Ke,  # e2e: per replica chunk 2 narrowing kernels, the MC kernel, 1 widening
+            gpu_launches=K + 3 * e2e_chunks * Ke,  # e2e: per replica chunk 1 narrowing kernel (states; the marks stay resident), the MC kernel, 1 widening
             clocks=clocks,
             roofline=dict(bound="hbm", achieved=achieved, peak=peaks, unit="GB/s", frac=achieved / peaks,
                           traffic=traffic, peak_source=peak_src, kernel=f"mc_sim_kernel<PhiloxRng,1,{warps}>",

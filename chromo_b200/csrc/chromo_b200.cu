@@ -963,11 +963,11 @@ extern "C" int chromo_mc_sim_host(chromo_ctx *c, int64_t num_mc_steps, chromo_mo
     if (moves && (rc = chromo_set_moves(c, moves))) return rc;
     if (rng_mode == CHROMO_RNG_REPLAY && numpy_seeds && (rc = chromo_numpy_seed(c, numpy_seeds))) return rc;
     CK(cudaStreamSynchronize(c->stream)); // everything queued on the context's own stream comes first
-    // chunks are whole thread blocks; automatic = as many (<= 4) as keep every chunk's blocks resident at once
+    // chunks are whole thread blocks; automatic = as many (<= 8) as keep every chunk's blocks resident at once
     const int rpb = c->rpb, nblk = (d.R + rpb - 1) / rpb;
     int chunks = (int)n_chunks;
     if (chunks == 0) {
-        chunks = 4;
+        chunks = 8; // the call ends with the LAST chunk's kernel + download: the finer, the less is left exposed
         while (chunks > 1 && chunks * ((nblk + chunks - 1) / chunks) > c->sm_count) chunks--;
     }
     chunks = std::max(1, std::min(chunks, nblk));

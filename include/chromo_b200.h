@@ -285,7 +285,7 @@ int chromo_set_moves(chromo_ctx *ctx, const chromo_move_state *moves /* [R][5] *
  * [R][N][nb] int64, in the reference's layouts; states and the three coordinate
  * arrays are overwritten with the result, mods is only read.  The replicas are
  * processed in `n_chunks` chunks (0 = automatic: as many as keep every chunk's thread
- * blocks resident at once, at most 4), each on its own stream: while chunk k runs,
+ * blocks resident at once, at most 8), each on its own stream: while chunk k runs,
  * chunk k+1 is still arriving over PCIe and chunk k-1 is already on its way back.
  * Pinned (page-locked) host arrays make the copies asynchronous; pageable ones work,
  * serialised by the driver.  The voxel densities are the field's state, not the
