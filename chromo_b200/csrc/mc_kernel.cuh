@@ -1827,6 +1827,8 @@ __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, CB_MIN_BLOCKS)
             if (NW == 1 && (int)blockDim.x == 32 * 7) {
                 if ((warp ^ 4) < 7) cb_bar_sync(1 + (warp & 3), 64);
             } else __syncthreads();
+#elif defined(CB_SKIP_BARRIER_AFTER)
+            if (m != CB_SKIP_BARRIER_AFTER) __syncthreads();
 #elif !defined(CB_NO_TYPE_BARRIER)
             __syncthreads();
 #endif
