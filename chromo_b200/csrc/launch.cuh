@@ -43,7 +43,9 @@ static inline __host__ __device__ size_t cb_replica_smem(int cap, int ncol, int 
 }
 // replicas that share one thread block (one block per SM; their warps go through the move types
 // of a sweep together, see mc_sim_kernel)
+#ifndef CB_MAX_RPB
 #define CB_MAX_RPB 7
+#endif
 #include "params.cuh"
 
 struct McSimArgs {
