@@ -60,7 +60,7 @@ _vp = C.c_void_p
 SYMBOLS = [
     "chromo_last_error", "chromo_version", "chromo_ctx_create", "chromo_ctx_destroy",
     "chromo_ctx_sync", "chromo_ctx_stream", "chromo_ctx_bytes", "chromo_ctx_set_table_capacity",
-    "chromo_ctx_set_warps_per_replica", "chromo_ctx_set_replicas_per_block", "chromo_ctx_set_replica_offset", "chromo_ctx_set_batch_size", "chromo_host_register", "chromo_host_unregister", "chromo_ctx_set_fast_field", "chromo_set_detailed_nucleosomes",
+    "chromo_ctx_set_warps_per_replica", "chromo_ctx_set_replicas_per_block", "chromo_ctx_set_replica_offset", "chromo_ctx_set_batch_size", "chromo_ctx_set_move_order", "chromo_host_register", "chromo_host_unregister", "chromo_ctx_set_fast_field", "chromo_set_detailed_nucleosomes",
     "chromo_get_rng_counters", "chromo_set_rng_counters", "chromo_set_binders",
     "chromo_set_replica_params", "chromo_set_bond_params", "chromo_set_twist_params", "chromo_set_access_volumes",
     "chromo_upload_state", "chromo_download_state", "chromo_download_density",
@@ -89,6 +89,7 @@ def _declare(L):
     L.chromo_ctx_set_replica_offset.argtypes = [_vp, C.c_int64]
     L.chromo_ctx_set_batch_size.argtypes = [_vp, C.c_int64]
     L.chromo_ctx_set_fast_field.argtypes = [_vp, C.c_int64]
+    L.chromo_ctx_set_move_order.argtypes = [_vp, C.POINTER(C.c_int32)]
     L.chromo_host_register.argtypes = [_vp, C.c_uint64]
     L.chromo_host_unregister.argtypes = [_vp]
     L.chromo_set_detailed_nucleosomes.argtypes = [_vp, _pd]

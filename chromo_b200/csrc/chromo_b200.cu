@@ -231,6 +231,7 @@ extern "C" int chromo_ctx_create(chromo_ctx **out, int device, const chromo_shap
     if ((rc = dev_alloc(c, &c->d_bad, (size_t)1))) return rc;
     d.rep_offset = 0u;
     d.batch = 32;
+    for (int i = 0; i < CHROMO_NUM_MOVES; i++) d.move_order[i] = i;
     if ((rc = dev_alloc(c, &d.tan_inds, RN))) return rc;
     if ((rc = dev_alloc(c, &d.sel_bits, (size_t)d.R * ((d.N + 31) / 32)))) return rc;
     if ((rc = dev_alloc(c, &d.st_new, RN))) return rc;
@@ -343,6 +344,17 @@ extern "C" int chromo_ctx_set_replica_offset(chromo_ctx *c, int64_t offset) {
     if (!c) return fail(CHROMO_ERR_ARG, "null context");
     if (offset < 0 || offset > 0xffffffffLL - c->d.R) return fail(CHROMO_ERR_ARG, "replica offset out of range");
     c->d.rep_offset = (unsigned)offset;
+    return CHROMO_OK;
+}
+extern "C" int chromo_ctx_set_move_order(chromo_ctx *c, const int32_t *order) {
+    if (!c || !order) return fail(CHROMO_ERR_ARG, "null argument");
+    unsigned seen = 0;
+    for (int i = 0; i < CHROMO_NUM_MOVES; i++) {
+        if (order[i] < 0 || order[i] >= CHROMO_NUM_MOVES || (seen >> order[i] & 1u))
+            return fail(CHROMO_ERR_ARG, "move order must be a permutation of 0..%d", CHROMO_NUM_MOVES - 1);
+        seen |= 1u << order[i];
+    }
+    for (int i = 0; i < CHROMO_NUM_MOVES; i++) c->d.move_order[i] = order[i];
     return CHROMO_OK;
 }
 extern "C" int chromo_ctx_set_batch_size(chromo_ctx *c, int64_t batch) {

@@ -1802,7 +1802,8 @@ __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, CB_MIN_BLOCKS)
         for (int m = 0; m < CHROMO_NUM_MOVES; m++) a0 += B.mv[m].num_attempt;
     const int BS = Rng::kBatched ? C.batch : 1;
     for (long long k = 0; k < num_mc_steps; k++)
-        for (int m = 0; m < CHROMO_NUM_MOVES; m++) {
+        for (int mi = 0; mi < CHROMO_NUM_MOVES; mi++) {
+            const int m = C.move_order[mi]; // (the same for every replica: the block stays in one move type)
             if (active) {
                 if (B.mv[m].move_on == 1) {
                     const int npc = B.mv[m].num_per_cycle;

@@ -289,6 +289,12 @@ class Engine:
         (seed, global replica, attempt), so the shards of one ensemble draw different numbers."""
         check(self._L.chromo_ctx_set_replica_offset(self._h, int(offset)))
 
+    def set_move_order(self, order) -> None:
+        """Order of the move types within one MC step (a permutation of the move ids; the reference walks its
+        controller list, mc_sim.pyx:92-103)."""
+        a = np.ascontiguousarray(order, dtype=np.int32).reshape(NUM_MOVES)
+        check(self._L.chromo_ctx_set_move_order(self._h, a.ctypes.data_as(C.POINTER(C.c_int32))))
+
     def set_batch_size(self, batch: int) -> None:
         """Attempts prepared at once by the production kernels (1..32; test knob, results do not depend on it)."""
         check(self._L.chromo_ctx_set_batch_size(self._h, int(batch)))

@@ -376,4 +376,10 @@ class ReplicaEnsemble:
                   device=device, field_prefactors=pre,
                   assume_fully_accessible=getattr(f0, "assume_fully_accessible", 1),
                   fast_field_points=int(getattr(f0, "n_points", 0)) if getattr(f0, "fast_field", 0) == 1 else 0)
+        if controllers is not None:  # every replica goes through the move types in its controller list's order
+            from .mc.mc_sim import controller_order
+            orders = {tuple(controller_order(c)) for c in controllers}
+            if len(orders) != 1:
+                raise ValueError("the replicas of one ensemble must list their move controllers in the same order")
+            ens.engine.set_move_order(orders.pop())
         return ens

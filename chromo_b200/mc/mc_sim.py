@@ -55,11 +55,15 @@ def controllers_to_moves(controllers):
         r["num_attempt"], r["num_success"] = m.num_attempt, m.num_success
         r["num_per_cycle"], r["move_on"] = m.num_per_cycle, int(m.move_on)
         r["controller"] = getattr(c, "device_code", 0)
-    order = [MOVE_ID[c.move.name] for c in controllers]
-    if order != sorted(order):
-        raise NotImplementedError("controllers must be listed in the canonical move order "
-                                  "(crank_shaft, end_pivot, slide, tangent_rotation, change_binding_state)")
     return row
+
+
+def controller_order(controllers):
+    """Move ids in the order the reference would go through them within one MC step: its controller list as
+    given (`for controller in mc_move_controllers`, mc_sim.pyx:92-103), then the move types without a
+    controller (they are off)."""
+    order = [MOVE_ID[c.move.name] for c in controllers]
+    return order + [i for i in range(NUM_MOVES) if i not in order]
 
 
 def moves_to_controllers(row, controllers):
@@ -85,6 +89,7 @@ def mc_sim(polymers, readerproteins, num_mc_steps, mc_move_controllers, field, m
     poly._field = field
     e = field._push(poly)
     mv = controllers_to_moves(mc_move_controllers).reshape(1, NUM_MOVES).copy()
+    e.set_move_order(controller_order(mc_move_controllers))
     mode = rng_mode()
     e.mc_sim(int(num_mc_steps), mv, float(mu_adjust_factor), int(random_seed), mode,
              numpy_seeds=int(random_seed) & 0xFFFFFFFF if mode == RNG_REPLAY else None)

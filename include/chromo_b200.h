@@ -151,6 +151,10 @@ int chromo_ctx_set_batch_size(chromo_ctx *ctx, int64_t batch);
  * twist parameters (it is an SSTWLC); NULL switches it off.  DetailedChromatin2 (polymers.pyx:2627-2735, bonds between
  * the bead centres): the same constants with both norms 0.  compute_E is the SSTWLC one, as in the reference. */
 int chromo_set_detailed_nucleosomes(chromo_ctx *ctx, const double *consts20);
+/* Order in which chromo_mc_sim goes through the move types within one MC step: the reference walks its
+ * controller LIST (`for controller in mc_move_controllers`, mc_sim.pyx:92-103), whatever order the caller built
+ * it in.  `order` is a permutation of the CHROMO_* move ids; default 0,1,2,3,4 (mc_controller.all_moves). */
+int chromo_ctx_set_move_order(chromo_ctx *ctx, const int32_t order[CHROMO_NUM_MOVES]);
 /* Page-lock (cudaHostRegister) a caller-owned host array -- the polymers' r / t3 / t2 / states buffers -- so that
  * chromo_mc_sim_host, chromo_upload_state and chromo_download_state move it at link speed instead of staging it
  * through the driver's bounce buffers (pageable numpy memory: ~3x slower).  The reference has no counterpart (its

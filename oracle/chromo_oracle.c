@@ -1267,16 +1267,23 @@ int oc_mc_step(oc_sim *s, oc_move *mv, int move, int64_t *inds)
 }
 
 /* mc_sim mc_sim.pyx:26-103 (one polymer; np.random.seed(random_seed) at :81) */
-void oc_mc_sim(oc_sim *s, oc_move mv[OC_NMOVES], int64_t num_mc_steps, uint32_t mt_seed,
-               int64_t *inds)
+void oc_mc_sim_ordered(oc_sim *s, oc_move mv[OC_NMOVES], int64_t num_mc_steps, uint32_t mt_seed,
+                       int64_t *inds, const int32_t *order)
 {
     int64_t k, j;
-    int c;
+    int ci, c;
     oc_mt_seed(&s->mt, mt_seed);
     for (k = 0; k < num_mc_steps; k++)
-        for (c = 0; c < OC_NMOVES; c++) {
+        for (ci = 0; ci < OC_NMOVES; ci++) { /* `for controller in mc_move_controllers` mc_sim.pyx:92 */
+            c = order ? order[ci] : ci;
             if (mv[c].move_on == 1)
                 for (j = 0; j < mv[c].num_per_cycle; j++) (void)oc_mc_step(s, &mv[c], c, inds);
             oc_update_amplitudes(&mv[c]); /* quirk 15: also for moves that are off */
         }
+}
+
+void oc_mc_sim(oc_sim *s, oc_move mv[OC_NMOVES], int64_t num_mc_steps, uint32_t mt_seed,
+               int64_t *inds)
+{
+    oc_mc_sim_ordered(s, mv, num_mc_steps, mt_seed, inds, 0);
 }

@@ -175,6 +175,8 @@ void oc_accept(oc_sim *s, oc_move *mv, int move, const int64_t *inds, int64_t n)
 void oc_reject(oc_sim *s, oc_move *mv, int move, const int64_t *inds, int64_t n);
 void oc_update_amplitudes(oc_move *mv);
 int oc_mc_step(oc_sim *s, oc_move *mv, int move, int64_t *inds_scratch);
+void oc_mc_sim_ordered(oc_sim *s, oc_move mv[OC_NMOVES], int64_t num_mc_steps, uint32_t mt_seed,
+                       int64_t *inds, const int32_t *order); /* order: the controller list's move ids, or NULL */
 void oc_mc_sim(oc_sim *s, oc_move mv[OC_NMOVES], int64_t num_mc_steps, uint32_t mt_seed,
                int64_t *inds_scratch);
 

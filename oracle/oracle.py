@@ -141,6 +141,7 @@ def lib():
         L.oc_mc_step.argtypes = [ps, pm, C.c_int, _pl]
         L.oc_mc_step.restype = C.c_int
         L.oc_mc_sim.argtypes = [ps, pm, C.c_int64, C.c_uint32, _pl]
+        L.oc_mc_sim_ordered.argtypes = [ps, pm, C.c_int64, C.c_uint32, _pl, C.POINTER(C.c_int32)]
         _LIB = L
     return _LIB
 
@@ -552,8 +553,13 @@ class OracleSim:
     def mc_step(self, mv, move):
         return self.L.oc_mc_step(C.byref(self.s), C.byref(mv), move, _p(self.inds, _pl))
 
-    def mc_sim(self, moves, num_mc_steps, np_seed):
-        self.L.oc_mc_sim(C.byref(self.s), moves, num_mc_steps, np_seed, _p(self.inds, _pl))
+    def mc_sim(self, moves, num_mc_steps, np_seed, order=None):
+        """`order`: move ids in the order of the reference's controller list (default: the canonical one)."""
+        if order is None:
+            self.L.oc_mc_sim(C.byref(self.s), moves, num_mc_steps, np_seed, _p(self.inds, _pl))
+        else:
+            o = (C.c_int32 * 5)(*[int(x) for x in order])
+            self.L.oc_mc_sim_ordered(C.byref(self.s), moves, num_mc_steps, np_seed, _p(self.inds, _pl), o)
 
 
 # --------------------------------------------------------------------------

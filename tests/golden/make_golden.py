@@ -124,7 +124,7 @@ def golden_moves(name, spec, nmoves, seed):
     print(name, "moves", nmoves, "accepted", int(np.sum(rec["accept"])))
 
 
-def golden_mc_sim(name, spec, steps, srand_seed, np_seed, mu_adjust=1.0, per_cycle=None):
+def golden_mc_sim(name, spec, steps, srand_seed, np_seed, mu_adjust=1.0, per_cycle=None, order=None):
     """A whole mc_sim call under pinned libc/numpy seeds."""
     poly, df, field, M = O.ref_objects(spec)
     sh, ctrl, mc, mcs = M["shim"], M["mc_controller"], M["mc"], M["mc_sim"]
@@ -133,11 +133,14 @@ def golden_mc_sim(name, spec, steps, srand_seed, np_seed, mu_adjust=1.0, per_cyc
     if per_cycle is not None:
         for c, k in zip(cs, per_cycle):
             c.move.num_per_cycle = k
+    run = cs if order is None else [cs[i] for i in order]  # the controller list as the caller ordered it
     sh.c_srand(srand_seed)
-    mcs.mc_sim([poly], df, steps, cs, field, mu_adjust, np_seed)
+    mcs.mc_sim([poly], df, steps, run, field, mu_adjust, np_seed)
     out = spec_to_npz(spec)
     out["steps"], out["srand_seed"], out["np_seed"], out["mu_adjust"] = steps, srand_seed, np_seed, mu_adjust
     out["per_cycle"] = np.array([c.move.num_per_cycle for c in cs])
+    if order is not None:
+        out["order"] = np.array(order)
     out["final_r"] = np.asarray(poly.r).copy()
     out["final_t3"] = np.asarray(poly.t3).copy()
     out["final_t2"] = np.asarray(poly.t2).copy()
@@ -183,6 +186,11 @@ if __name__ == "__main__":
         golden_moves("moves_dc3", dc3, 200, 163)
         golden_mc_sim("mcsim_dc3", dict(O.make_spec(N=60, nb=1, seed=73, random_states=False, bead_rad=4.1899999999999995),
                                         lt=100.0, bp_wrap=147.0, no_diameter=1), 4, 28, 38)
+        sys.exit(0)
+    if only == ["order"]:
+        # a controller list that is not in all_moves' order (mc_sim.pyx:92 walks the list as given)
+        golden_mc_sim("mcsim_order", O.make_spec(N=200, nb=1, seed=81, random_states=False), 5, 29, 39,
+                      order=[4, 2, 0, 3, 1])
         sys.exit(0)
     if only == ["ff"]:
         # fast_field = 1 (fields.pyx:577-671, 1235-1368): positions quantised to n_points sub-bins per voxel edge

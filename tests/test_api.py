@@ -67,7 +67,7 @@ def test_construction_and_energies(backend, name):
             p._polymer_engine().set_twist_params(np.zeros(spec["N"] - 1), p.natural_twist)
 
 
-@pytest.mark.parametrize("name", ["mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_ff", "mcsim_dc", "mcsim_dc3"])
+@pytest.mark.parametrize("name", ["mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_ff", "mcsim_dc", "mcsim_dc3", "mcsim_order"])
 def test_mc_sim_drop_in(backend, name):
     """all_moves + SimpleControl + mc_sim, replaying the reference's RNG streams."""
     from chromo_b200.mc import get_amplitude_bounds, mc_controller as ctrl, set_rng_mode
@@ -81,7 +81,8 @@ def test_mc_sim_drop_in(backend, name):
     set_rng_mode("replay")
     try:
         field._engine_for(p).srand(int(g["srand_seed"]))
-        mc_sim([p], binders, int(g["steps"]), cs, field, float(g["mu_adjust"]), int(g["np_seed"]))
+        run = [cs[i] for i in g["order"]] if "order" in g else cs  # a controller list in the caller's own order
+        mc_sim([p], binders, int(g["steps"]), run, field, float(g["mu_adjust"]), int(g["np_seed"]))
     finally:
         set_rng_mode("philox")
     tol = 0 if backend == "emu" else 1e-7

@@ -13,7 +13,7 @@ from common import close, close_dE, huge_scale, load_golden, split
 
 STATIC = ["static_c1", "static_c2", "static_c3", "static_c4", "static_tw", "static_tw2", "static_av", "static_av2", "static_dc"]
 MOVES = ["moves_c1", "moves_c2", "moves_c3", "moves_c4", "moves_tw", "moves_tw2", "moves_av", "moves_av2", "moves_ff", "moves_ff2", "moves_dc", "moves_dc2", "moves_dc3"]
-MCSIM = ["mcsim_c1", "mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_av", "mcsim_ff", "mcsim_dc", "mcsim_dc3"]
+MCSIM = ["mcsim_c1", "mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_av", "mcsim_ff", "mcsim_dc", "mcsim_dc3", "mcsim_order"]
 
 
 @pytest.mark.parametrize("name", STATIC)
@@ -88,7 +88,7 @@ def test_mc_sim_replay(oracle_mod, name):
     s = O.OracleSim(spec, mu_adjust_factor=float(g["mu_adjust"]))
     mv = O.make_moves(spec["N"], float(np.min(spec["bead_length"])), per_cycle=[int(x) for x in g["per_cycle"]])
     s.srand(int(g["srand_seed"]))
-    s.mc_sim(mv, int(g["steps"]), int(g["np_seed"]))
+    s.mc_sim(mv, int(g["steps"]), int(g["np_seed"]), order=g["order"] if "order" in g else None)
     assert np.array_equal(s.r, g["final_r"])
     assert np.array_equal(s.t3, g["final_t3"])
     assert np.array_equal(s.t2, g["final_t2"])

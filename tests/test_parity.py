@@ -21,7 +21,7 @@ from gpu_common import engine_from_spec, moves_array
 
 STATIC = ["static_c1", "static_c2", "static_c3", "static_c4", "static_tw", "static_tw2", "static_av", "static_av2", "static_dc"]
 MOVES = ["moves_c1", "moves_c2", "moves_c3", "moves_c4", "moves_tw", "moves_tw2", "moves_av", "moves_av2", "moves_ff", "moves_ff2", "moves_dc", "moves_dc2", "moves_dc3"]
-MCSIM = ["mcsim_c1", "mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_av", "mcsim_ff", "mcsim_dc", "mcsim_dc3"]
+MCSIM = ["mcsim_c1", "mcsim_c2", "mcsim_c3", "mcsim_tw", "mcsim_av", "mcsim_ff", "mcsim_dc", "mcsim_dc3", "mcsim_order"]
 REPLAY, PHILOX = 1, 0
 
 
@@ -111,6 +111,8 @@ def test_mc_sim_replay(backend, name):
     e = engine_from_spec(spec, R=R)
     mv = moves_array(spec, R, tuple(int(x) for x in g["per_cycle"]))
     e.srand(int(g["srand_seed"]))
+    if "order" in g:  # the reference's controller list was not in all_moves' order
+        e.set_move_order(g["order"])
     e.mc_sim(int(g["steps"]), mv, float(g["mu_adjust"]), 0, REPLAY, numpy_seeds=int(g["np_seed"]))
     r, t3, t2, st = e.download()
     for rep in range(R):
