@@ -60,6 +60,7 @@ struct chromo_ctx {
     // owned device buffers that can be replaced
     double *d_bond = nullptr, *d_twist = nullptr, *d_chi = nullptr, *d_mu = nullptr, *d_bindF = nullptr, *d_access = nullptr;
     double *d_partial = nullptr, *d_out = nullptr, *d_detailed = nullptr;
+    int move_order[CHROMO_NUM_MOVES] = {0, 1, 2, 3, 4}; // chromo_ctx_set_move_order
     int *d_dcount = nullptr;
     int *d_bad = nullptr; // set by the narrowing kernel when a state / mark is out of range
     // replica exchange (chromo_exchange_*): the chi ladder(s), the replica on every rung, counters
@@ -106,7 +107,7 @@ static void refresh_fx_base(chromo_ctx *c) {
 
 // kernel instantiation for (rng mode, number of binders, twist); the twist (SSTWLC) kernels are their own
 // translation units, built for one or two binders
-static int launch_sim(const McSimArgs &a, int rng_mode) {
+static int launch_sim_once(const McSimArgs &a, int rng_mode) {
     const DevCtx &d = a.d;
     if (d.twist) {
         if (d.nb > 2) return -1000;
@@ -114,6 +115,28 @@ static int launch_sim(const McSimArgs &a, int rng_mode) {
     }
     if (rng_mode == CHROMO_RNG_REPLAY) return d.nb <= 2 ? cb_mc_sim_replay_12(a) : cb_mc_sim_replay_34(a);
     return d.nb <= 2 ? cb_mc_sim_philox_12(a) : cb_mc_sim_philox_34(a);
+}
+// One launch runs every MC step with the move types in all_moves' order (the kernel's loop).  A controller list
+// in another order (mc_sim.pyx:92-103 walks the list as given) becomes one launch per (MC step, move type) with
+// only that type enabled -- the replicas' RNG streams, controller state and densities carry over on the device,
+// the counters of chromo_last_attempts / _algo_bytes accumulate.  (A run-time order inside the kernel's loop cost
+// the common case 1.4-2.3 % on B200; the order is rare.)
+static int launch_sim(const McSimArgs &a, int rng_mode) {
+    bool canonical = true;
+    for (int i = 0; i < CHROMO_NUM_MOVES; i++) canonical = canonical && (!a.order || a.order[i] == i);
+    McSimArgs b = a;
+    b.d.type_mask = (1 << CHROMO_NUM_MOVES) - 1;
+    b.d.accumulate = 0;
+    if (canonical || a.num_mc_steps == 0) return launch_sim_once(b, rng_mode);
+    b.num_mc_steps = 1;
+    for (long long k = 0; k < a.num_mc_steps; k++)
+        for (int i = 0; i < CHROMO_NUM_MOVES; i++) {
+            b.d.type_mask = 1 << a.order[i];
+            const int e = launch_sim_once(b, rng_mode);
+            if (e) return e;
+            b.d.accumulate = 1;
+        }
+    return 0;
 }
 static int launch_step(const McStepArgs &a, int rng_mode) {
     const DevCtx &d = a.d;
@@ -231,7 +254,9 @@ extern "C" int chromo_ctx_create(chromo_ctx **out, int device, const chromo_shap
     if ((rc = dev_alloc(c, &c->d_bad, (size_t)1))) return rc;
     d.rep_offset = 0u;
     d.batch = 32;
-    for (int i = 0; i < CHROMO_NUM_MOVES; i++) d.move_order[i] = i;
+    d.type_mask = (1 << CHROMO_NUM_MOVES) - 1;
+    d.accumulate = 0;
+    for (int i = 0; i < CHROMO_NUM_MOVES; i++) c->move_order[i] = i;
     if ((rc = dev_alloc(c, &d.tan_inds, RN))) return rc;
     if ((rc = dev_alloc(c, &d.sel_bits, (size_t)d.R * ((d.N + 31) / 32)))) return rc;
     if ((rc = dev_alloc(c, &d.st_new, RN))) return rc;
@@ -354,7 +379,7 @@ extern "C" int chromo_ctx_set_move_order(chromo_ctx *c, const int32_t *order) {
             return fail(CHROMO_ERR_ARG, "move order must be a permutation of 0..%d", CHROMO_NUM_MOVES - 1);
         seen |= 1u << order[i];
     }
-    for (int i = 0; i < CHROMO_NUM_MOVES; i++) c->d.move_order[i] = order[i];
+    for (int i = 0; i < CHROMO_NUM_MOVES; i++) c->move_order[i] = order[i];
     return CHROMO_OK;
 }
 extern "C" int chromo_ctx_set_batch_size(chromo_ctx *c, int64_t batch) {
@@ -944,6 +969,7 @@ extern "C" int chromo_mc_sim(chromo_ctx *c, int64_t num_mc_steps, chromo_move_st
     if (moves && (rc = chromo_set_moves(c, moves))) return rc;
     if (rng_mode == CHROMO_RNG_REPLAY && numpy_seeds && (rc = chromo_numpy_seed(c, numpy_seeds))) return rc;
     McSimArgs a{d, (long long)num_mc_steps, mu_adjust_factor, (unsigned long long)seed, c->cap, c->warps, c->rpb, c->stream};
+    a.order = c->move_order;
     if (rng_mode != CHROMO_RNG_REPLAY && rng_mode != CHROMO_RNG_PHILOX) return fail(CHROMO_ERR_ARG, "unknown rng_mode %d", rng_mode);
     const int e = launch_sim(a, rng_mode);
     if (e) return fail(CHROMO_ERR_CUDA, "mc_sim launch failed: %s", launch_error(e));
@@ -1042,6 +1068,7 @@ extern "C" int chromo_mc_sim_host(chromo_ctx *c, int64_t num_mc_steps, chromo_mo
         CB_MARK(0);
         McSimArgs a{d, (long long)num_mc_steps, mu_adjust_factor, (unsigned long long)seed, c->cap, c->warps, c->rpb, st,
                     (int)first, (int)n};
+        a.order = c->move_order;
         const int e = launch_sim(a, rng_mode);
         if (e) return fail(CHROMO_ERR_CUDA, "mc_sim launch failed: %s", launch_error(e));
         CB_MARK(1);

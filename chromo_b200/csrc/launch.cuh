@@ -58,6 +58,7 @@ struct McSimArgs {
     int rpb;   // replicas per block (1..CB_MAX_RPB)
     cudaStream_t stream;
     int rep0 = 0, nrep = -1; // replica sub-range [rep0, rep0 + nrep) (nrep < 0: all of the context's)
+    const int *order = nullptr; // move ids in the controller list's order (host; nullptr = all_moves' order)
 };
 struct McStepArgs {
     DevCtx d;

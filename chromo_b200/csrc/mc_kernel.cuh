@@ -1802,9 +1802,12 @@ __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, CB_MIN_BLOCKS)
         for (int m = 0; m < CHROMO_NUM_MOVES; m++) a0 += B.mv[m].num_attempt;
     const int BS = Rng::kBatched ? C.batch : 1;
     for (long long k = 0; k < num_mc_steps; k++)
-        for (int mi = 0; mi < CHROMO_NUM_MOVES; mi++) {
-            const int m = C.move_order[mi]; // (the same for every replica: the block stays in one move type)
+        for (int m = 0; m < CHROMO_NUM_MOVES; m++) {
+#ifdef CB_NO_TYPE_MASK // (A/B knob: what the per-type mask costs)
             if (active) {
+#else
+            if (active && (C.type_mask >> m & 1)) {
+#endif
                 if (B.mv[m].move_on == 1) {
                     const int npc = B.mv[m].num_per_cycle;
 #pragma unroll 1
@@ -1838,8 +1841,8 @@ __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, CB_MIN_BLOCKS)
     long long a1 = 0;
     for (int m = 0; m < CHROMO_NUM_MOVES; m++) a1 += B.mv[m].num_attempt;
     if (rtid == 0) {
-        C.attempts[rep] = (unsigned long long)(a1 - a0);
-        C.algo_bytes[rep] = B.algo_bytes;
+        C.attempts[rep] = (C.accumulate ? C.attempts[rep] : 0ull) + (unsigned long long)(a1 - a0);
+        C.algo_bytes[rep] = (C.accumulate ? C.algo_bytes[rep] : 0ull) + B.algo_bytes;
     }
     if (rtid < CHROMO_NUM_MOVES) C.moves[(long long)rep * CHROMO_NUM_MOVES + rtid] = B.mv[rtid];
     rng_store<Rng>(C, B, rep, rtid, W.abase);

@@ -53,7 +53,8 @@ struct DevCtx {
     double fast_sbw[3];              // fast_field: sub-bin widths dx / n_points (fields.pyx:604-606)
     unsigned rep_offset;             // global index of replica 0 (key of the production streams)
     int batch;                       // attempts prepared at once in the production kernels (1..32)
-    int move_order[CHROMO_NUM_MOVES]; // move types in the order the controller list names them (mc_sim.pyx:92-103)
+    int type_mask;                   // bit m: mc_sim_kernel runs move type m (31 = all; see launch_sim, chromo_b200.cu)
+    int accumulate;                  // add this launch's attempt / byte counters to the stored ones
     int *tan_inds;                   // [R][N]   tangent-rotation large path
     uint32_t *sel_bits;              // [R][ceil(N/32)]
     signed char *st_new;             // [R][N]   binding large path
