@@ -97,10 +97,15 @@ class ReplicaEnsemble:
         # host-in / host-out calls (mc_sim(sync_host=True), push, pull) copy these arrays every time: page-lock them
         # once (pageable numpy memory moves at a third of the link speed).  Default: ensembles of >= 8 MiB.
         if pin_host or (pin_host is None and self.r.nbytes >= (8 << 20)):
+            from ._lib import ChromoError
             from .engine import host_register
-            for a in (self.r, self.t3, self.t2, self.states, self.chemical_mods):
-                if host_register(a):
-                    self._pinned.append(a)
+            try:
+                for a in (self.r, self.t3, self.t2, self.states, self.chemical_mods):
+                    if host_register(a):
+                        self._pinned.append(a)
+            except ChromoError:  # e.g. the locked-memory limit: the copies still work, through the driver's staging
+                if pin_host:
+                    raise
         self.push()
         if grid is not None and grid.get("nx", 0):
             self.engine.field_recompute(clamp=True)  # UniformDensityField.__init__ fields.pyx:532
