@@ -34,8 +34,14 @@ static inline __host__ __device__ size_t cb_table_bytes(int cap, int ncol) {
 }
 // shared memory of the MC kernel per replica / per warp (>= sizeof(ReplicaSh), sizeof(WarpSh);
 // checked in mc_kernel.cuh) and the largest number of warps per replica that is instantiated
-#define CB_REPLICA_SH_BYTES 8576
-#define CB_WARP_SH_BYTES 1280
+#ifndef CB_KSEL
+// tangent rotations of up to this many beads take the prepared (lane-parallel) path; <= 32.  SimpleControl settles
+// the window at 14-18 beads on the reference workloads: with 16 the ~6 % of attempts above it went down the
+// sequential path (bead set and axis draws by one lane, index scratch in HBM) and cost 6 % of the whole step.
+#define CB_KSEL 24
+#endif
+#define CB_REPLICA_SH_BYTES (6528 + 128 * CB_KSEL)
+#define CB_WARP_SH_BYTES ((368 + 52 * CB_KSEL + 127) / 128 * 128)
 #define CB_MAX_WARPS 2
 // shared memory of one replica: ReplicaSh | WarpSh x warps | table x warps
 static inline __host__ __device__ size_t cb_replica_smem(int cap, int ncol, int warps) {

@@ -60,8 +60,8 @@ __device__ unsigned long long cb_phase_acc[CHROMO_NUM_MOVES][CB_NPHASE];
 #define CB_UNIT_UNROLL 1 // voxel-contribution loop of scatter_pass (A/B knob)
 #endif
 constexpr int cb_unit_unroll = CB_UNIT_UNROLL;
-#define CB_KSEL 16      // tangent rotation: bead sets up to this size are drawn in the batched prepare
-#define CB_TAN_SMALL 16 // tangent rotation: new tangents of up to this many beads are staged in shared memory
+// CB_KSEL (launch.cuh): tangent rotation: bead sets up to this size are drawn in the batched prepare
+#define CB_TAN_SMALL CB_KSEL // tangent rotation: new tangents of up to this many beads are staged in shared memory
 #define CB_NEWST 128    // binding: new states of up to this many beads are staged in shared memory
 
 // one prepared attempt (see McWarp::prepare)
@@ -989,11 +989,11 @@ struct McWarp {
             } else if (Q.n > CB_KSEL) {
                 hit = true; // its bead set was drawn at execute time: assume the worst
             } else {
-                // lanes: a = lane % 16 walks this attempt's beads, the halves split the other's
-                const int a = lane & 15;
+                // lane a walks this attempt's beads against all of the other's
+                const int a = lane;
                 if (a < P.n) {
                     const int mine = P.n == 1 ? P.aux : B.tsel[slot][a];
-                    for (int q = lane >> 4; q < Q.n; q += 2) {
+                    for (int q = 0; q < Q.n; q++) {
                         const int other = Q.n == 1 ? Q.aux : B.tsel[j][q];
                         hit |= (other - mine <= 1) && (mine - other <= 1);
                     }

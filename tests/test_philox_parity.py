@@ -48,14 +48,14 @@ def _case(O, name):
 
 
 def _dense_moves(mv_arr=None, omv=None):
-    """tangent rotations of up to 12 beads growing past the prepared-set limit of 16; binding windows of 5"""
+    """tangent rotations of up to 26 beads, on both sides of the prepared-set limit of 24; binding windows of 5"""
     if mv_arr is not None:
-        mv_arr["amp_bead"][:, 3] = 12
-        mv_arr["bead_amp_hi"][:, 3] = 24
+        mv_arr["amp_bead"][:, 3] = 26
+        mv_arr["bead_amp_hi"][:, 3] = 36
         mv_arr["amp_bead"][:, 4] = 5
         mv_arr["bead_amp_hi"][:, 4] = 5
     if omv is not None:
-        omv[3].amp_bead, omv[3].bead_amp_hi = 12, 24
+        omv[3].amp_bead, omv[3].bead_amp_hi = 26, 36
         omv[4].amp_bead, omv[4].bead_amp_hi = 5, 5
 
 
