@@ -272,8 +272,8 @@ def test_two_warps_per_replica_match_one(backend, oracle_mod, case):
             e.upload_density(dens0)
         mv = moves_array(spec, R, per_cycle)
         if case == "dense":
-            mv["amp_bead"][:, 3] = 12  # tangent rotation: bead sets of up to 12 (prepared) ...
-            mv["bead_amp_hi"][:, 3] = 24  # ... growing past CB_KSEL = 16 (sequential path)
+            mv["amp_bead"][:, 3] = 26  # tangent rotation: bead sets on both sides of CB_KSEL = 24 (prepared /
+            mv["bead_amp_hi"][:, 3] = 36  # sequential path)
             mv["amp_bead"][:, 4] = 5
             mv["bead_amp_hi"][:, 4] = 5
         e.mc_sim(sweeps, mv, 1.0, 4242, PHILOX)
