@@ -704,25 +704,40 @@ static int launch_recompute(chromo_ctx *c, int clamp) {
     if (!d.field_active) return fail(CHROMO_ERR_STATE, "context has no field");
     if (!c->have_state) return fail(CHROMO_ERR_STATE, "upload the polymer state first");
     size_t n = (size_t)d.R * d.n_bins * d.ncol;
-    const size_t priv_bytes = (size_t)d.n_bins * 16;
-    if (priv_bytes <= c->smem_optin && !c->force_l2_density) {
-        // the grid fits one block's shared memory: privatised, bit-reproducible accumulation (field_kernels.cuh)
+    const size_t col_bytes = (size_t)d.n_bins * 12; // three 32-bit words per voxel and column
+    if (col_bytes <= c->smem_optin && !c->force_l2_density) {
+        // the grid fits one block's shared memory: privatised, bit-reproducible accumulation (field_kernels.cuh).
+        // A term w / V (x state) is an integer of 3p bits spread over three 32-bit words that collect p bits each;
+        // the 32 - p bits above are head room for the adds of one chunk of beads (a voxel receives at most one
+        // term per bead and column, two / four / eight on a grid with one / two / three dimensions of a single
+        // voxel), after which the carries are folded.  p = 21 (63-bit terms) for chains of up to 2,048 beads,
+        // 18 (54-bit terms, quantum ~5e-21 nm^-3 at C2: 1/200 of the 1e-18 below which the reference itself
+        // zeroes a density) without a fold up to 16,384, folds every 16,384 beads beyond.
+        int kdeg = 1;
+        for (int n1 : {d.nx, d.ny, d.nz}) kdeg *= (n1 == 1 ? 2 : 1);
+        int hbits = 11;
+        while (hbits < 14 && (1LL << hbits) < (long long)d.N * kdeg) hbits++;
+        const int pbits = 32 - hbits, fold_beads = std::max(1, (1 << hbits) / kdeg);
         double vmin = (d.access_vol && c->min_access_vol > 0.0) ? c->min_access_vol : d.vol_bin;
         int smax = 1;
         for (int a = 0; a < d.nb; a++) smax = std::max(smax, d.sites[a]);
         int sbits = 0;
         while ((1 << sbits) < smax) sbits++;
-        const long long chunks = ((long long)d.N + 65535) / 65536;
-        int cbits = 0;
-        while ((1LL << cbits) < chunks) cbits++;
-        const int fx_e = 61 - sbits - std::max(0, cbits - 2) + (int)ilogb(vmin);
-        dim3 grid(d.R, d.ncol);
+        // (w / V) * state <= 2^(sbits - ilogb(vmin)) must stay below 2^(3p - 1); the top word is never folded, so
+        // the terms of ALL beads must fit its 32 bits: chains beyond 2^(33 - p) beads give up a bit per doubling
+        int tot_bits = 0;
+        while ((1LL << tot_bits) < (long long)d.N * kdeg) tot_bits++;
+        const int extra = std::max(0, pbits - 1 + tot_bits - 32);
+        const int fx_e = 3 * pbits - 1 - extra - sbits + (int)ilogb(vmin);
+        const int cpb = (int)std::min<size_t>((size_t)d.ncol, c->smem_optin / col_bytes); // columns per block
+        const size_t priv_bytes = col_bytes * (size_t)cpb;
+        dim3 grid(d.R, (d.ncol + cpb - 1) / cpb);
         int lrc = 0;
         DISPATCH_NB(d.nb, {
             auto k = density_private_kernel<NB>;
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)priv_bytes);
             if (e != cudaSuccess) lrc = (int)e;
-            else CB_LAUNCH(k, grid, FK_PRIV_THREADS, priv_bytes, c->stream, d, clamp, fx_e);
+            else CB_LAUNCH(k, grid, FK_PRIV_THREADS, priv_bytes, c->stream, d, clamp, fx_e, pbits, fold_beads, cpb);
         });
         if (lrc) return fail(CHROMO_ERR_CUDA, "density_private_kernel: %s", cudaGetErrorString((cudaError_t)lrc));
         CK(cudaGetLastError());

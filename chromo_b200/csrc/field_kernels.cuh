@@ -66,67 +66,82 @@ __global__ void __launch_bounds__(FK_THREADS) density_scatter_kernel(DevCtx C) {
 // the correctly rounded value of its exact fixed-point sum.
 #define FK_PRIV_THREADS 1024
 template <int NB>
-__global__ void __launch_bounds__(FK_PRIV_THREADS, 1) density_private_kernel(DevCtx C, int clamp, int fx_e) {
+__global__ void __launch_bounds__(FK_PRIV_THREADS, 1)
+    density_private_kernel(DevCtx C, int clamp, int fx_e, int pbits, int fold_beads, int cols_per_block) {
     constexpr int NCOL = NB + 1;
     CB_DYN_SMEM(dyn);
-    // [4][n_bins], word-major: the 32 lanes' adds to word w of their voxels fall on banks bin % 32 (with the
-    // four words of a voxel side by side only 8 banks are ever used by one instruction: 4-way conflicts)
+    // cells[column][word][bin], word-major: the 32 lanes' adds to one word of their voxels fall on banks bin % 32
+    // (with a voxel's words side by side one instruction only ever touched a quarter of the banks)
     uint32_t *cells = (uint32_t *)dyn;
     const int nbw = C.n_bins;
     const cb_saddr cells_s = cb_shared_addr(dyn);
-    const int rep = blockIdx.x, col = blockIdx.y, tid = threadIdx.x;
+    const int rep = blockIdx.x, tid = threadIdx.x;
+    const int col0 = blockIdx.y * cols_per_block, ncb = min(cols_per_block, NCOL - col0); // this block's columns
+    const uint32_t pmask = (1u << pbits) - 1u;
     const double scale = __hiloint2double((1023 + fx_e) << 20, 0), inv_scale = __hiloint2double((1023 - fx_e) << 20, 0);
-    for (int i = tid; i < C.n_bins * 4; i += blockDim.x) cells[i] = 0u;
+    for (int i = tid; i < nbw * 3 * ncb; i += blockDim.x) cells[i] = 0u;
     __syncthreads();
     const double *R = C.r + (long long)rep * C.N * 3;
     const signed char *ST = C.states + (long long)rep * C.N * NB;
-    for (int chunk = 0; chunk < C.N; chunk += 65536) {
-        const int end = min(C.N, chunk + 65536);
+    for (int chunk = 0; chunk < C.N; chunk += fold_beads) {
+        const int end = min(C.N, chunk + fold_beads);
         // blocked assignment: a thread walks k CONSECUTIVE beads, so the lanes of a warp are k beads (~6 voxels
         // at C2) apart and rarely meet in a voxel -- with one bead per lane neighbouring lanes hit the same
-        // 16-byte cells and the shared-memory atomics serialise 8-fold (ncu: 7.6 wavefronts per instruction)
+        // cells and the shared-memory atomics serialise 8-fold (ncu: 7.6 wavefronts per instruction)
         const int k = (end - chunk + (int)blockDim.x - 1) / (int)blockDim.x;
         for (int j = 0; j < k; j++) {
             const int bead = chunk + tid * k + j;
             if (bead >= end) break;
-            const unsigned long long s = col == 0 ? 1ull : (unsigned long long)ST[bead * NB + col - 1];
-            if (s == 0ull) continue;
+            unsigned long long mult[NCOL]; // column c of this block receives (w / V) * mult[c]
+            bool any = false;
+#pragma unroll
+            for (int c = 0; c < NCOL; c++) {
+                const int col = col0 + c;
+                mult[c] = (c >= ncb) ? 0ull : (col == 0 ? 1ull : (unsigned long long)ST[bead * NB + col - 1]);
+                any = any || mult[c] != 0ull;
+            }
+            if (!any) continue;
             int idx[8];
             double w[8];
             bin_point(C, R[3 * bead], R[3 * bead + 1], R[3 * bead + 2], idx, w);
 #pragma unroll
             for (int l = 0; l < 8; l++) {
                 const double d = C.access_vol ? w[l] / C.access_vol[idx[l]] : div_const(w[l], C.vol_bin, C.inv_vol_bin);
-                const unsigned long long t = (unsigned long long)__double2ll_rn(d * scale) * s;
-                const cb_saddr a = cells_s + (cb_saddr)idx[l] * 4;
-                cb_red_add_u32(a, (uint32_t)t & 0xFFFFu);
-                cb_red_add_u32(a + 4 * nbw, (uint32_t)(t >> 16) & 0xFFFFu);
-                cb_red_add_u32(a + 8 * nbw, (uint32_t)(t >> 32) & 0xFFFFu);
-                cb_red_add_u32(a + 12 * nbw, (uint32_t)(t >> 48));
+                const unsigned long long t1 = (unsigned long long)__double2ll_rn(d * scale);
+#pragma unroll
+                for (int c = 0; c < NCOL; c++) {
+                    if (mult[c] == 0ull) continue;
+                    const unsigned long long t = t1 * mult[c];
+                    const cb_saddr a = cells_s + 4u * (cb_saddr)(c * 3 * nbw + idx[l]);
+                    cb_red_add_u32(a, (uint32_t)t & pmask);
+                    cb_red_add_u32(a + 4 * nbw, (uint32_t)(t >> pbits) & pmask);
+                    cb_red_add_u32(a + 8 * nbw, (uint32_t)(t >> (2 * pbits)));
+                }
             }
         }
         __syncthreads();
-        if (end < C.N) { // more beads to come: fold the carries so that the 16-bit lanes start empty again
-            for (int bin = tid; bin < C.n_bins; bin += blockDim.x) {
-                uint32_t *c = cells + bin;
-                uint32_t w0 = c[0], w1 = c[nbw], w2 = c[2 * nbw], w3 = c[3 * nbw];
-                w1 += w0 >> 16, w0 &= 0xFFFFu;
-                w2 += w1 >> 16, w1 &= 0xFFFFu;
-                w3 += w2 >> 16, w2 &= 0xFFFFu;
-                c[0] = w0, c[nbw] = w1, c[2 * nbw] = w2, c[3 * nbw] = w3;
+        if (end < C.N) { // more beads to come: fold the carries so that the payload lanes start empty again
+            for (int i = tid; i < nbw * ncb; i += blockDim.x) {
+                uint32_t *c = cells + (i / nbw) * 3 * nbw + (i % nbw);
+                uint32_t w0 = c[0], w1 = c[nbw], w2 = c[2 * nbw];
+                w1 += w0 >> pbits, w0 &= pmask;
+                w2 += w1 >> pbits, w1 &= pmask;
+                c[0] = w0, c[nbw] = w1, c[2 * nbw] = w2;
             }
             __syncthreads();
         }
     }
-    double *dens = C.density + (long long)rep * C.n_bins * NCOL + col;
-    for (int bin = tid; bin < C.n_bins; bin += blockDim.x) {
-        const uint32_t *c = cells + bin;
-        // exact value = (w3 2^48 + w2 2^32 + w1 2^16 + w0) 2^-E: two exactly representable halves, one rounding
-        const unsigned long long lo = (unsigned long long)c[0] + ((unsigned long long)c[nbw] << 16);
-        const unsigned long long hi = (unsigned long long)c[2 * nbw] + ((unsigned long long)c[3 * nbw] << 16);
-        double v = ((double)hi * 4294967296.0 + (double)lo) * inv_scale;
+    for (int i = tid; i < nbw * ncb; i += blockDim.x) {
+        const int c = i / nbw, bin = i % nbw;
+        const uint32_t *q = cells + c * 3 * nbw + bin;
+        // exact value = (w2 2^(2p) + w1 2^p + w0) 2^-E, written as B 2^32 + A with A < 2^32 and B < 2^53: two
+        // exactly representable halves, one rounding
+        const unsigned long long low = ((unsigned long long)q[nbw] << pbits) + (unsigned long long)q[0];
+        const unsigned long long A = low & 0xFFFFFFFFull;
+        const unsigned long long B = (low >> 32) + ((unsigned long long)q[2 * nbw] << (2 * pbits - 32));
+        double v = ((double)B * 4294967296.0 + (double)A) * inv_scale;
         if (clamp && fabs(v) < 1E-18) v = 0.0; // update_all_densities_for_all_polymers fields.pyx:2101-2105
-        dens[(long long)bin * NCOL] = v;
+        C.density[((long long)rep * nbw + bin) * NCOL + col0 + c] = v;
     }
 }
 
