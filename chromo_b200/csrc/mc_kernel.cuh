@@ -383,7 +383,14 @@ __device__ __forceinline__ int2 scatter_pass(const DevCtx &C, HashTable &H, Warp
             unsigned left = __ballot_sync(FULL_MASK, active && !merged && sub == 0);
 #pragma unroll 1
             while (left) {
-                const int owner = (int)__fns(left, 0, (lane >> 3) + 1); // the (lane / 8)-th bead of this round
+                // the (lane / 8)-th set bit of `left` (the beads of this round): peel the lowest set bit q times
+                // (__fns is a software loop of ~30 instructions)
+                unsigned peel = left;
+                const int q = lane >> 3;
+                if (q > 0) peel &= peel - 1;
+                if (q > 1) peel &= peel - 1;
+                if (q > 2) peel &= peel - 1;
+                const int owner = peel ? (int)__ffs((int)peel) - 1 : -1;
                 const bool has = owner >= 0 && owner < 32;
                 const int src = has ? owner : 0;
                 int qlo[3], qhi[3], qm[NB];
@@ -1562,9 +1569,10 @@ struct McWarp {
             if (DEBUG && force_accept >= 0) {
                 acc = force_accept;
             } else {
-                double e = exp(-dE);
                 u = BATCH ? P.u : u01(rng.next31());
-                acc = (u < e) ? 1 : 0;
+                // mc_sim.pyx:163-171: accept iff u < exp(-dE).  dE < 0: exp(-dE) > 1 >= u whatever u is -- the same
+                // decision without the exponential (about half of the attempts)
+                acc = (dE < 0.0) ? 1 : ((u < exp(-dE)) ? 1 : 0);
             }
             if (DEBUG) {
                 dbg->u = u;

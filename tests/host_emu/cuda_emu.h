@@ -168,6 +168,7 @@ static inline unsigned __fns(unsigned mask, unsigned base, int offset) {
     return 0xffffffffu;
 }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 
 static inline int atomicCAS(int *a, int cmp, int val) {
     __atomic_compare_exchange_n(a, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
