@@ -114,6 +114,7 @@ struct HashTable {
     uint32_t *vals; // [cap][ncol][2]  delta-rho in fixed point (two words per cell, see Fx)
     cb_saddr vals_s; // the same as a shared-state-space address
     int cap, limit; // cap: any size >= 128 (not necessarily a power of two)
+    bool prefetch;  // prefetch the density row of a voxel that joins the table (a compile-time fact of the kernel)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -260,7 +261,10 @@ __device__ __forceinline__ void unit_add(const DevCtx &C, HashTable &H, WarpSh &
     bool fresh; // the voxel joins the touched set even when its term is zero (fields.pyx:1499-1520)
     const int slot = table_claim(H, S, bin, checked, fresh);
     if (slot < 0) return;
-    if (fresh) cb_prefetch(dens_rows + (long long)bin * NCOL); // the density row is needed by table_energy
+    // the density row is needed by table_energy: worth a prefetch when the replica has the SM to itself (the
+    // two-warp kernels, C4: +3 %); with seven replicas per SM it costs 3 % (the rows of all seven compete for
+    // 60 KB of L1)
+    if (H.prefetch && fresh) cb_prefetch(dens_rows + (long long)bin * NCOL);
     if (GEN && v == 0) return;
     uint32_t *cell = H.vals + (size_t)slot * NCOL * 2;
     const cb_saddr cell_s = H.vals_s + (cb_saddr)slot * (NCOL * 8);
@@ -1623,47 +1627,6 @@ struct McWarp {
 #endif
     }
 
-    // pull the rows a later attempt will read towards the SM while this one runs
-    __device__ __forceinline__ void prefetch_attempt(int mtype, const Prop &P, int slot) {
-        const int N = C.N;
-        int first, count;
-        if (mtype == CHROMO_TANGENT_ROTATION) {
-            if (P.n != 1) {
-                if (BATCH && P.n <= CB_KSEL && lane < P.n) { // prepared bead set: the bead's line (+ neighbours)
-                    const long long o = 3ll * max(B.tsel[slot][lane] - 1, 0);
-                    cb_prefetch(R_() + o);
-                    cb_prefetch(T3_() + o);
-                    cb_prefetch(T2_() + o);
-                    cb_prefetch(T3_() + min(o + 6, 3ll * N - 1));
-                    cb_prefetch(R_() + min(o + 6, 3ll * N - 1));
-                }
-                return;
-            }
-            first = max(P.aux - 1, 0);
-            count = min(P.aux + 1, N - 1) - first + 1;
-        } else {
-            if (P.n <= 0) return;
-            first = max(P.ind0 - 1, 0);
-            count = min(P.indf, N - 1) - first + 1;
-        }
-        // 24 bytes per bead and array: one prefetch per 128-byte line
-        const int lines = (count * 24 + 127) / 128 + 1;
-        if (lane < min(lines, 32)) {
-            const long long off = (long long)first * 3 + (long long)lane * 16;
-            if (off < (long long)N * 3) {
-                cb_prefetch(R_() + off);
-                if (mtype == CHROMO_CHANGE_BINDING_STATE) {
-                    if (lane == 0) {
-                        cb_prefetch(ST_() + (long long)P.ind0 * NB);
-                        cb_prefetch(MOD_() + (long long)P.ind0 * NB);
-                    }
-                } else cb_prefetch(T3_() + off);
-                if (mtype == CHROMO_TANGENT_ROTATION || mtype == CHROMO_CRANK_SHAFT || mtype == CHROMO_END_PIVOT)
-                    cb_prefetch(T2_() + off);
-            }
-        }
-    }
-
     // a batch of `cnt` attempts of one move type: prepare (lanes of warp 0), then the warps take
     // the attempts round-robin
     __device__ __forceinline__ void run(int mtype, int cnt) {
@@ -1681,7 +1644,6 @@ struct McWarp {
 #pragma unroll 1
         for (int j = wid; j < cnt; j += NW) {
             CB_T0();
-            if (j + NW < cnt) prefetch_attempt(mtype, B.prop[j + NW], j + NW);
             CB_LAP(0);
             attempt(mtype, j);
         }
@@ -1791,6 +1753,7 @@ __global__ void __launch_bounds__(32 * NW * CB_MAX_RPB, CB_MIN_BLOCKS)
     WarpSh &S = *(WarpSh *)(base + CB_REPLICA_SH_BYTES + (size_t)wid * CB_WARP_SH_BYTES);
     HashTable H = carve_table(base + CB_REPLICA_SH_BYTES + (size_t)NW * CB_WARP_SH_BYTES +
                                   (size_t)wid * cb_table_bytes(cap, C.ncol), cap, C.ncol);
+    H.prefetch = NW > 1;
     Rng rng;
     unsigned long long abase0 = 0;
     if (active) {
@@ -1867,6 +1830,7 @@ __global__ void __launch_bounds__(32) mc_step_kernel(const CB_GRID_CONSTANT DevC
     __shared__ WarpSh S;
     const int lane = threadIdx.x;
     HashTable H = carve_table(dyn, cap, C.ncol);
+    H.prefetch = false;
     table_reset_all(H, S, C.ncol, lane);
     if (lane < CHROMO_NUM_MOVES) B.mv[lane] = C.moves[(long long)rep * CHROMO_NUM_MOVES + lane];
     __syncwarp();

@@ -120,7 +120,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out-dir", default=None)
+    ap.add_argument("--lib", default=None, help="another build of the C-ABI library (tools/build_variant.sh), for A/B runs")
     a = ap.parse_args()
+    if a.lib:
+        sys.path.insert(0, str(ROOT / "tests"))
+        import devlib
+        devlib.use_library(a.lib)
     for name in a.configs:
         line = run(name, a.steps, a.warmup)
         s = json.dumps(line)
