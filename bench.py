@@ -349,6 +349,8 @@ def run_ours(args):
                           moves=stationary_moves(R, N, first=rank * R), device=local,
                           replica_offset=rank * R)  # every rank's replicas draw their own random streams
     eng = ens.engine
+    if args.batch:
+        eng.set_batch_size(args.batch)
     warps = eng.set_warps_per_replica(args.warps)
     rpb = eng.set_replicas_per_block(args.rpb)
     cap = eng.set_table_capacity(args.table_slots)
@@ -667,6 +669,7 @@ def main():
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0, help="warps per replica in the MC kernel (0 = library default)")
     ap.add_argument("--rpb", type=int, default=0, help="replicas per thread block (0 = library default)")
+    ap.add_argument("--batch", type=int, default=0, help="attempts prepared at once (1..32; 0 = library default, 32)")
     ap.add_argument("--lt", type=float, default=None, help="twist persistence length: run the SSTWLC kernels "
                     "(not the headline configuration; the reference arm ignores it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
