@@ -1256,13 +1256,16 @@ struct McWarp {
                 double x[3], y[3];
                 load3(Rr + o, x);
                 if (kind == 0) {
+                    // all three rows first: the arrays could alias as far as the compiler knows, so a load placed
+                    // after a store waits for it -- three trips to HBM in a row instead of one
+                    double a[3], b[3];
+                    load3(T3 + o, a);
+                    load3(T2 + o, b);
                     apply_affine(S.M, x, y);
                     store3(Rr + o, y);
-                    load3(T3 + o, x);
-                    apply_rot(S.M, x, y);
+                    apply_rot(S.M, a, y);
                     store3(T3 + o, y);
-                    load3(T2 + o, x);
-                    apply_rot(S.M, x, y);
+                    apply_rot(S.M, b, y);
                     store3(T2 + o, y);
                 } else {
 #pragma unroll
