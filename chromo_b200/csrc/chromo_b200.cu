@@ -183,10 +183,13 @@ static int choose_table(chromo_ctx *c) {
     // The shared-memory carve-out comes in steps (..., 164, 196, 228 KB of the SM's 256 KB; the rest is L1, which
     // holds the bead rows of the attempts in flight): a block that needs a byte more than 196 KB (its 1 KB of
     // static and the 1 KB the driver reserves included) leaves 28 KB of L1 instead of 60.  Measured at the
-    // stationary working point: 704 slots inside the 196 KB step beat 736 / 768 slots outside it by 3 %.
+    // stationary working point: 704 slots inside the 196 KB step beat 736 / 768 slots outside it by 3 % (v17
+    // layout); with the prepared tangent sets overlaid on Prop::M the step holds 832 slots (+0.8 % over 768).
     const size_t step = (size_t)196 * 1024 - 2048;
-    int inside = cap;
-    while (inside > 512 && (size_t)rpb * cb_replica_smem(inside, ncol, c->warps) > step) inside -= 32;
+    int inside = rpb > 1 ? 1024 : cap;
+    while (inside > 512 && ((size_t)rpb * cb_replica_smem(inside, ncol, c->warps) > step ||
+                            cb_replica_smem(inside, ncol, c->warps) > per_replica))
+        inside -= 32;
     if ((size_t)rpb * cb_replica_smem(inside, ncol, c->warps) <= step) cap = inside;
     c->cap = cap;
     c->rpb = rpb;

@@ -40,7 +40,7 @@ static inline __host__ __device__ size_t cb_table_bytes(int cap, int ncol) {
 // sequential path (bead set and axis draws by one lane, index scratch in HBM) and cost 6 % of the whole step.
 #define CB_KSEL 24
 #endif
-#define CB_REPLICA_SH_BYTES (6528 + 128 * CB_KSEL)
+#define CB_REPLICA_SH_BYTES 6528
 #define CB_WARP_SH_BYTES ((368 + 52 * CB_KSEL + 127) / 128 * 128)
 #define CB_MAX_WARPS 2
 // shared memory of one replica: ReplicaSh | WarpSh x warps | table x warps

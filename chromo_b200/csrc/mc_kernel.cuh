@@ -100,13 +100,18 @@ struct ReplicaSh {
     unsigned long long algo_bytes;   // SURVEY 8(d) algorithmic bytes, accumulated under the commit token
     int token;                       // attempt of the batch whose turn it is to evaluate the field and commit
     unsigned accepted;               // bit j: attempt j of the batch was accepted
-    int tsel[32][CB_KSEL];           // tangent rotation: bead sets drawn by the batched prepare
+    // (tangent rotation: the bead set drawn by the batched prepare lives in the attempt's own Prop::M, which only
+    // segment moves use -- see tsel())
     uint32_t grs[CB_GLIBC_WORDS];    // ReplayRng state
     uint32_t rng_save[CB_GLIBC_WORDS];
     uint32_t rng_after[CB_GLIBC_WORDS];
 };
 static_assert(sizeof(ReplicaSh) <= CB_REPLICA_SH_BYTES && sizeof(WarpSh) <= CB_WARP_SH_BYTES, "update launch.cuh");
 static_assert(CB_KSEL <= CB_TAN_SMALL, "prepared bead sets are staged in shared memory");
+static_assert(CB_KSEL * sizeof(int) <= sizeof(Prop::M), "the prepared bead set of a tangent rotation overlays Prop::M");
+// prepared bead set of tangent-rotation attempt `slot` of the batch
+__device__ __forceinline__ int *tsel(ReplicaSh &B, int slot) { return reinterpret_cast<int *>(B.prop[slot].M); }
+__device__ __forceinline__ const int *tsel(const ReplicaSh &B, int slot) { return reinterpret_cast<const int *>(B.prop[slot].M); }
 
 struct HashTable {
     int *keys;      // [cap]
@@ -1003,9 +1008,9 @@ struct McWarp {
                 // lane a walks this attempt's beads against all of the other's
                 const int a = lane;
                 if (a < P.n) {
-                    const int mine = P.n == 1 ? P.aux : B.tsel[slot][a];
+                    const int mine = P.n == 1 ? P.aux : tsel(B, slot)[a];
                     for (int q = 0; q < Q.n; q++) {
-                        const int other = Q.n == 1 ? Q.aux : B.tsel[j][q];
+                        const int other = Q.n == 1 ? Q.aux : tsel(B, j)[q];
                         hit |= (other - mine <= 1) && (mine - other <= 1);
                     }
                 }
@@ -1090,7 +1095,7 @@ struct McWarp {
             } else if (BATCH && k <= CB_KSEL) {
                 // get_inds move_funcs.pyx:552-582: k distinct draws, duplicates redrawn; the per-bead
                 // axis draws follow in the attempt's stream and are made at execute time
-                int *sel = B.tsel[lane];
+                int *sel = tsel(B, lane);
                 for (int i = 0; i < k; i++) {
                     int c;
                     bool dup;
@@ -1517,7 +1522,7 @@ struct McWarp {
                 __syncwarp();
                 dE_poly = tangent_chunk(S.tinds, 1, nullptr, P.ax, P.sn, P.cs, S.tan_new, false, 0, 0.0);
             } else if (presel) {
-                tinds = B.tsel[slot];
+                tinds = tsel(B, slot);
                 dE_poly = tangent_eval_multi(tinds, n, P.sn, P.cs, true, false, true, att, P.used);
             } else {
                 if (BATCH && lane == 0) rng.seek_attempt(att, P.used);
